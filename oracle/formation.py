@@ -1,0 +1,378 @@
+"""Float64 PyTorch CPU oracle of the CasualHDRSplat image-formation model.
+
+TEST INFRASTRUCTURE ONLY — never imported by the product path (``casualhdrsplat_b200``).
+Allowed users: ``tests/``, ``__graft_entry__.smoke()``, ``bench.py``'s ``cpu_baseline`` leg and
+``bench.py --impl reference``.
+
+PARITY UNPINNED: ``/root/reference`` contains a README and two figures, no code, no tests and no
+golden vectors (``/root/reference/Readme.md:57``: "Still working on....").  This file restates the
+model that ``/root/reference/Readme.md:54`` and ``/root/reference/assets/pipeline.png`` describe
+("unified model based on the physical image formation process, integrating camera motion blur and
+exposure-induced brightness variations ... joint estimation of camera motion, exposure time, and
+camera response curve"), with every hole filled by SURVEY.md Appendix A (decisions D0-D9).  The
+oracle is pinned only by its own closed-form known-answer tests (tests/test_oracle_*.py) and by
+the committed goldens it generated (tests/golden/, tests/golden/make_golden.py).
+
+Pipeline:
+    spline -> viewmats -> project (EWA) -> bin (64-bit keys, stable sort) -> blend (front to back,
+    linear HDR) -> mean over virtual poses -> x exposure -> CRF -> blurred LDR frame.
+All gradients come from torch autograd.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import se3
+
+TILE = 16
+ALPHA_MIN = 1.0 / 255.0
+ALPHA_MAX = 0.999
+T_STOP = 1e-4
+CRF_IDENTITY = 0
+CRF_MLP = 1
+CRF_EPS = 1e-5
+
+
+def _f64(x):
+    return None if x is None else torch.as_tensor(x).to(torch.float64)
+
+
+# ----------------------------------------------------------------------------------------------
+# A.3 projection + EWA
+# ----------------------------------------------------------------------------------------------
+def project(means, quats, scales, viewmats, Ks, width, height, near=0.01, far=1e10, eps2d=0.3,
+            radius_sigmas=3.0):
+    """Per (camera, Gaussian) projection. Returns dict of [C,N,...] float64 tensors + int32 radii.
+
+    Follows SURVEY.md A.3 [D5]: pinhole, EWA Jacobian with the frustum clamp, +eps2d*I blur,
+    conic = inverse 2D covariance, radius = ceil(3 sqrt(lambda_max)), off-screen cull.
+    """
+    means, quats, scales, viewmats, Ks = map(_f64, (means, quats, scales, viewmats, Ks))
+    C, N = viewmats.shape[0], means.shape[0]
+    R = viewmats[:, :3, :3]
+    t = viewmats[:, :3, 3]
+    p = torch.einsum("cij,nj->cni", R, means) + t[:, None, :]
+    x, y, z = p.unbind(-1)
+    valid = (z >= near) & (z <= far)
+    zs = torch.where(valid, z, torch.ones_like(z))
+
+    Rq = se3.quat_to_rotmat(quats)
+    M = Rq * scales[:, None, :]
+    Sigma = M @ M.transpose(-1, -2)
+    Sc = R[:, None] @ Sigma[None] @ R[:, None].transpose(-1, -2)
+
+    fx, fy, cx, cy = Ks[:, 0, 0], Ks[:, 1, 1], Ks[:, 0, 2], Ks[:, 1, 2]
+    W, H = float(width), float(height)
+    lim_xp = ((W - cx) / fx + 0.3 * (W / (2 * fx)))[:, None]
+    lim_xm = (cx / fx + 0.3 * (W / (2 * fx)))[:, None]
+    lim_yp = ((H - cy) / fy + 0.3 * (H / (2 * fy)))[:, None]
+    lim_ym = (cy / fy + 0.3 * (H / (2 * fy)))[:, None]
+    xt = zs * torch.minimum(lim_xp, torch.maximum(-lim_xm, x / zs))
+    yt = zs * torch.minimum(lim_yp, torch.maximum(-lim_ym, y / zs))
+    fxc, fyc = fx[:, None], fy[:, None]
+    zero = torch.zeros_like(zs)
+    J = torch.stack(
+        [fxc / zs, zero, -fxc * xt / (zs * zs), zero, fyc / zs, -fyc * yt / (zs * zs)], dim=-1
+    ).reshape(C, N, 2, 3)
+    cov2 = J @ Sc @ J.transpose(-1, -2)
+    a = cov2[..., 0, 0] + eps2d
+    b = cov2[..., 0, 1]
+    c = cov2[..., 1, 1] + eps2d
+    det = a * c - b * b
+    valid = valid & (det > 0)
+    dets = torch.where(valid, det, torch.ones_like(det))
+    conics = torch.stack([c / dets, -b / dets, a / dets], dim=-1)
+    means2d = torch.stack([fxc * x / zs + cx[:, None], fyc * y / zs + cy[:, None]], dim=-1)
+    m = 0.5 * (a + c)
+    lam = m + torch.sqrt(torch.clamp(m * m - det, min=0.01))
+    radius = torch.ceil(radius_sigmas * torch.sqrt(lam))
+    r = radius.detach()
+    mx, my = means2d[..., 0].detach(), means2d[..., 1].detach()
+    valid = valid & ~((mx + r <= 0) | (mx - r >= W) | (my + r <= 0) | (my - r >= H))
+    radii = torch.where(valid, r, torch.zeros_like(r)).to(torch.int32)
+    return {"means2d": means2d, "depths": z, "conics": conics, "radii": radii, "valid": valid}
+
+
+# ----------------------------------------------------------------------------------------------
+# A.4 binning: integer function of fp32 (means2d, radii, depths) — bit-exact contract [D9]
+# ----------------------------------------------------------------------------------------------
+def tile_grid(width, height, tile=TILE):
+    tile_w = (width + tile - 1) // tile
+    tile_h = (height + tile - 1) // tile
+    return tile_w, tile_h
+
+
+def key_bits(n_cams, width, height, tile=TILE):
+    tile_w, tile_h = tile_grid(width, height, tile)
+    tile_bits = int(tile_w * tile_h).bit_length()
+    cam_bits = int(n_cams).bit_length()
+    return tile_bits, cam_bits
+
+
+def tile_bounds(means2d_f32, radii_i32, width, height, tile=TILE):
+    """fp32, round-to-nearest, no FMA: lo = mx/16 - r/16, hi = mx/16 + r/16 (the /16 scalings are exact)."""
+    assert means2d_f32.dtype == torch.float32 and radii_i32.dtype == torch.int32
+    tile_w, tile_h = tile_grid(width, height, tile)
+    inv = torch.tensor(1.0 / tile, dtype=torch.float32)
+    tr = radii_i32.to(torch.float32) * inv
+    tx = means2d_f32[..., 0] * inv
+    ty = means2d_f32[..., 1] * inv
+    zero = torch.tensor(0.0, dtype=torch.float32)
+
+    def lo(v, n):
+        return torch.minimum(torch.maximum(torch.floor(v - tr), zero), torch.tensor(float(n))).to(torch.int32)
+
+    def hi(v, n):
+        return torch.minimum(torch.maximum(torch.ceil(v + tr), zero), torch.tensor(float(n))).to(torch.int32)
+
+    min_x, max_x = lo(tx, tile_w), hi(tx, tile_w)
+    min_y, max_y = lo(ty, tile_h), hi(ty, tile_h)
+    touched = (max_x - min_x) * (max_y - min_y)
+    touched = torch.where(radii_i32 > 0, touched, torch.zeros_like(touched))
+    return min_x, min_y, max_x, max_y, touched
+
+
+def bin_tiles(means2d_f32, radii_i32, depths_f32, width, height, tile=TILE):
+    """Tile binning, 64-bit key generation, stable sort, per-(camera, tile) offsets.
+
+    key = cam << (32 + tile_bits) | tile << 32 | float_as_uint(depth);  val = c * N + g.
+    Returns dict with tiles_touched [C,N] i32, offsets [C*N] i64 (exclusive scan, c-major), keys /
+    vals in emission order and sorted, tile_offsets [C*tiles + 1] i64 (last entry = M).
+    """
+    C, N = radii_i32.shape
+    tile_w, tile_h = tile_grid(width, height, tile)
+    tiles = tile_w * tile_h
+    tile_bits, cam_bits = key_bits(C, width, height, tile)
+    min_x, min_y, max_x, max_y, touched = tile_bounds(means2d_f32, radii_i32, width, height, tile)
+    counts = touched.reshape(-1).to(torch.int64)
+    offsets = torch.cumsum(counts, 0) - counts
+    M = int(counts.sum())
+    ids = torch.arange(C * N, dtype=torch.int64)
+    rep = torch.repeat_interleave(ids, counts)
+    local = torch.arange(M, dtype=torch.int64) - offsets[rep]
+    bw = (max_x - min_x).reshape(-1).to(torch.int64)[rep]
+    ti = min_y.reshape(-1).to(torch.int64)[rep] + local // torch.clamp(bw, min=1)
+    tj = min_x.reshape(-1).to(torch.int64)[rep] + local % torch.clamp(bw, min=1)
+    tile_id = ti * tile_w + tj
+    cam = rep // N
+    depth_bits = depths_f32.contiguous().view(torch.int32).reshape(-1).to(torch.int64)[rep] & 0xFFFFFFFF
+    keys = (cam << (32 + tile_bits)) | (tile_id << 32) | depth_bits
+    vals = rep.to(torch.int32)
+    keys_sorted, perm = torch.sort(keys, stable=True)
+    vals_sorted = vals[perm]
+    bucket = keys_sorted >> 32  # cam << tile_bits | tile
+    wanted = (torch.arange(C, dtype=torch.int64)[:, None] << tile_bits) | torch.arange(tiles, dtype=torch.int64)[None, :]
+    tile_offsets = torch.searchsorted(bucket, wanted.reshape(-1), right=False)
+    tile_offsets = torch.cat([tile_offsets, torch.tensor([M], dtype=torch.int64)])
+    return {
+        "tiles_touched": touched,
+        "offsets": offsets,
+        "n_isect": M,
+        "keys": keys,
+        "vals": vals,
+        "keys_sorted": keys_sorted,
+        "vals_sorted": vals_sorted,
+        "tile_offsets": tile_offsets,
+        "tile_bits": tile_bits,
+        "cam_bits": cam_bits,
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# A.5 blend forward (vectorised per tile; validated against the literal loop in tests)
+# ----------------------------------------------------------------------------------------------
+def blend(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss, width, height,
+          background=None, tile=TILE, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP):
+    """Front-to-back alpha blending of every camera's sorted tile lists in linear HDR radiance.
+
+    means2d [C,N,2], conics [C,N,3], opacities [N], colors [N,3] float64.
+    Returns hdr [C,H,W,3], alpha [C,H,W], last_id [C,H,W] (sorted index of the last accumulated
+    Gaussian, -1 if none).  ``tile_subset``: optional iterable of (c, tile_id) to restrict work
+    (used for the bounded CPU-baseline timing); other pixels stay at background.
+    """
+    means2d, conics, opacities, colors = map(_f64, (means2d, conics, opacities, colors))
+    C = means2d.shape[0]
+    N = n_gauss
+    tile_w, tile_h = tile_grid(width, height, tile)
+    tiles = tile_w * tile_h
+    bg = torch.zeros(3, dtype=torch.float64) if background is None else _f64(background)
+    last_id = torch.full((C, height, width), -1, dtype=torch.int64)
+    hdr = bg.expand(C, height, width, 3).clone()
+    alpha = torch.zeros(C, height, width, dtype=torch.float64)
+    todo = tile_subset if tile_subset is not None else ((c, t) for c in range(C) for t in range(tiles))
+    to = tile_offsets.tolist()
+    pieces = []
+    for c, tid in todo:
+        start, end = to[c * tiles + tid], to[c * tiles + tid + 1]
+        if end <= start:
+            continue
+        ty, tx = divmod(tid, tile_w)
+        y0, x0 = ty * tile, tx * tile
+        y1, x1 = min(y0 + tile, height), min(x0 + tile, width)
+        py = torch.arange(y0, y1, dtype=torch.float64) + 0.5
+        px = torch.arange(x0, x1, dtype=torch.float64) + 0.5
+        PY, PX = torch.meshgrid(py, px, indexing="ij")
+        PX, PY = PX.reshape(-1), PY.reshape(-1)
+        ids = vals_sorted[start:end].to(torch.int64)
+        g = ids - c * N
+        m = means2d[c, g]
+        q = conics[c, g]
+        o = opacities[g]
+        col = colors[g]
+        dx = m[:, 0, None] - PX[None, :]
+        dy = m[:, 1, None] - PY[None, :]
+        sigma = 0.5 * (q[:, 0, None] * dx * dx + q[:, 2, None] * dy * dy) + q[:, 1, None] * dx * dy
+        a = torch.clamp(o[:, None] * torch.exp(-sigma), max=ALPHA_MAX)
+        skip = (sigma < 0) | (a < alpha_min)
+        a_eff = torch.where(skip, torch.zeros_like(a), a)
+        t_after = torch.cumprod(1 - a_eff.detach(), dim=0)
+        stopped = t_after <= t_stop
+        contrib = ~skip & ~stopped
+        a_c = torch.where(contrib, a, torch.zeros_like(a))
+        t_incl = torch.cumprod(1 - a_c, dim=0)
+        t_before = torch.cat([torch.ones_like(t_incl[:1]), t_incl[:-1]], dim=0)
+        w = a_c * t_before
+        t_final = t_incl[-1]
+        pix = w.transpose(0, 1) @ col + t_final[:, None] * bg[None, :]
+        idx = torch.arange(end - start, dtype=torch.int64)[:, None].expand_as(contrib)
+        last = torch.where(contrib, idx, torch.full_like(idx, -1)).max(dim=0).values
+        last = torch.where(last >= 0, last + start, last)
+        pieces.append((c, y0, y1, x0, x1, pix, 1 - t_final, last))
+    # scatter with index_put on a flat view so autograd sees one op per tile (no in-place on leaves)
+    if pieces:
+        flat_idx, flat_pix, flat_alpha = [], [], []
+        for c, y0, y1, x0, x1, pix, al, last in pieces:
+            yy, xx = torch.meshgrid(torch.arange(y0, y1), torch.arange(x0, x1), indexing="ij")
+            lin = (c * height + yy.reshape(-1)) * width + xx.reshape(-1)
+            flat_idx.append(lin)
+            flat_pix.append(pix)
+            flat_alpha.append(al)
+            last_id.view(-1)[lin] = last
+        lin = torch.cat(flat_idx)
+        hdr = hdr.reshape(-1, 3).index_put((lin,), torch.cat(flat_pix)).reshape(C, height, width, 3)
+        alpha = alpha.reshape(-1).index_put((lin,), torch.cat(flat_alpha)).reshape(C, height, width)
+    return hdr, alpha, last_id
+
+
+def blend_pixel_loop(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss, width, height,
+                     c, i, j, background=None, tile=TILE):
+    """Literal sequential A.5 loop for one pixel (i = row, j = column). Test helper, no autograd needed."""
+    tile_w, _ = tile_grid(width, height, tile)
+    tiles = tile_w * ((height + tile - 1) // tile)
+    tid = (i // tile) * tile_w + (j // tile)
+    start, end = int(tile_offsets[c * tiles + tid]), int(tile_offsets[c * tiles + tid + 1])
+    bg = [0.0, 0.0, 0.0] if background is None else [float(v) for v in background]
+    T, acc, last = 1.0, [0.0, 0.0, 0.0], -1
+    px, py = j + 0.5, i + 0.5
+    for s in range(start, end):
+        g = int(vals_sorted[s]) - c * n_gauss
+        dx = float(means2d[c, g, 0]) - px
+        dy = float(means2d[c, g, 1]) - py
+        q = conics[c, g]
+        sigma = 0.5 * (float(q[0]) * dx * dx + float(q[2]) * dy * dy) + float(q[1]) * dx * dy
+        if sigma < 0:
+            continue
+        a = min(ALPHA_MAX, float(opacities[g]) * math.exp(-sigma))
+        if a < ALPHA_MIN:
+            continue
+        Tn = T * (1 - a)
+        if Tn <= T_STOP:
+            break
+        for ch in range(3):
+            acc[ch] += a * T * float(colors[g, ch])
+        T = Tn
+        last = s
+    return [acc[ch] + T * bg[ch] for ch in range(3)], 1 - T, last
+
+
+# ----------------------------------------------------------------------------------------------
+# A.7 blur, exposure, CRF
+# ----------------------------------------------------------------------------------------------
+def crf_apply(X, crf_kind, crf_params=None):
+    """Camera response F_theta, shared by all cameras. IDENTITY: F(X)=X. MLP [D6]: per channel
+    z=ln(X+1e-5), h=relu(w1 z + b1), y=sigmoid(w2.h + b2); params [3, 3*Hd+1] = [w1|b1|w2|b2]."""
+    if crf_kind == CRF_IDENTITY:
+        return X
+    if crf_kind != CRF_MLP:
+        raise ValueError(f"unknown crf_kind {crf_kind}")
+    P = _f64(crf_params)
+    hd = (P.shape[1] - 1) // 3
+    w1, b1, w2, b2 = P[:, :hd], P[:, hd:2 * hd], P[:, 2 * hd:3 * hd], P[:, 3 * hd]
+    z = torch.log(X + CRF_EPS)
+    h = torch.relu(z[..., None] * w1 + b1)
+    return torch.sigmoid((h * w2).sum(-1) + b2)
+
+
+def formation(hdr_cams, alpha_cams, exposure, n_virtual, crf_kind, crf_params=None, crf_before_average=False):
+    """hdr_cams [C,H,W,3] (C = B*n, camera c = i*n + k) -> (ldr [B,H,W,3], alpha [B,H,W,1], hdr_mean [B,H,W,3])."""
+    C, Hh, Ww, _ = hdr_cams.shape
+    B = C // n_virtual
+    Hk = hdr_cams.reshape(B, n_virtual, Hh, Ww, 3)
+    dt = _f64(exposure).reshape(B, 1, 1, 1)
+    hdr_mean = Hk.mean(dim=1)
+    if crf_before_average:
+        ldr = crf_apply(dt[:, None] * Hk, crf_kind, crf_params).mean(dim=1)
+    else:
+        ldr = crf_apply(dt * hdr_mean, crf_kind, crf_params)
+    alpha = alpha_cams.reshape(B, n_virtual, Hh, Ww).mean(dim=1)[..., None]
+    return ldr, alpha, hdr_mean
+
+
+# ----------------------------------------------------------------------------------------------
+# Full path, product-shaped signature
+# ----------------------------------------------------------------------------------------------
+def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, width=0, height=0,
+              exposure_times=None, n_virtual=1, crf_kind=CRF_IDENTITY, crf_params=None, *, spline=None,
+              background=None, near=0.01, far=1e10, eps2d=0.3, tile_size=TILE, crf_before_average=False,
+              projection_override=None, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP,
+              radius_sigmas=3.0):
+    """Oracle of ``casualhdrsplat_b200.rasterize`` (same arguments and meaning; float64 CPU).
+
+    ``spline`` = dict(knots [K,7], knot_t0, knot_dt, frame_times [B], kind) or explicit
+    ``viewmats [C,4,4]`` with C = B*n_virtual and c = i*n + k.
+    ``projection_override`` = dict(means2d, conics, depths (fp32 [C,N,...]), radii i32) lets a test
+    feed the CUDA kernel's own fp32 projection so binning can be compared bit-for-bit (A.4/D9);
+    those tensors then carry no gradient to the Gaussian geometry.
+    ``alpha_min`` / ``t_stop`` / ``radius_sigmas`` default to the model's constants (1/255, 1e-4, 3);
+    tests override them only to obtain a discontinuity-free variant for finite-difference checks.
+    Returns (ldr [B,H,W,3], alpha [B,H,W,1], meta dict).
+    """
+    means, quats, scales, opacities, colors = map(_f64, (means, quats, scales, opacities, colors))
+    exposure = _f64(exposure_times)
+    B = exposure.shape[0]
+    if spline is not None:
+        knots = _f64(spline["knots"])
+        frame_times = _f64(spline["frame_times"])
+        viewmats = se3.spline_viewmats(knots, float(spline["knot_t0"]), float(spline["knot_dt"]), frame_times,
+                                       exposure, n_virtual, int(spline["kind"]))
+    else:
+        viewmats = _f64(viewmats)
+    C = viewmats.shape[0]
+    if C != B * n_virtual:
+        raise ValueError(f"viewmats has {C} cameras, expected B*n_virtual = {B * n_virtual}")
+    Ks = _f64(Ks)
+    if Ks.shape[0] == B and C != B:
+        Ks = Ks.repeat_interleave(n_virtual, dim=0)
+    N = means.shape[0]
+    if projection_override is None:
+        proj = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas)
+        m2d_f32 = proj["means2d"].detach().to(torch.float32)
+        dep_f32 = proj["depths"].detach().to(torch.float32)
+        radii = proj["radii"]
+        m2d, con = proj["means2d"], proj["conics"]
+    else:
+        m2d_f32 = projection_override["means2d"].to(torch.float32)
+        dep_f32 = projection_override["depths"].to(torch.float32)
+        radii = projection_override["radii"].to(torch.int32)
+        m2d, con = _f64(m2d_f32), _f64(projection_override["conics"])
+        proj = {"means2d": m2d, "conics": con, "depths": _f64(dep_f32), "radii": radii}
+    bins = bin_tiles(m2d_f32, radii, dep_f32, width, height, tile_size)
+    hdr, alpha_c, last_id = blend(m2d, con, opacities, colors, bins["vals_sorted"], bins["tile_offsets"], N,
+                                  width, height, background, tile_size, tile_subset, alpha_min, t_stop)
+    ldr, alpha, hdr_mean = formation(hdr, alpha_c, exposure, n_virtual, crf_kind, crf_params, crf_before_average)
+    meta = {"viewmats": viewmats, "proj": proj, "bins": bins, "hdr_cams": hdr, "alpha_cams": alpha_c,
+            "last_id": last_id, "hdr_mean": hdr_mean, "n_isect": bins["n_isect"]}
+    return ldr, alpha, meta
