@@ -1,0 +1,109 @@
+"""ctypes binding of libchs.so (the C ABI declared in include/chs.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C casualhdrsplat_b200/csrc``.
+There is no fallback: if the shared library is missing, :func:`lib` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libchs.so")
+
+CHS_CRF_IDENTITY, CHS_CRF_MLP = 0, 1
+CHS_SPLINE_LINEAR, CHS_SPLINE_CUBIC = 0, 1
+CHS_SORT_KEY64, CHS_SORT_DEPTH_PRESORT = 0, 1
+
+
+class ChsConfig(ctypes.Structure):
+    _fields_ = [
+        ("n_gauss", c_int32), ("n_frames", c_int32), ("n_virtual", c_int32), ("width", c_int32), ("height", c_int32),
+        ("tile_size", c_int32), ("near_plane", c_float), ("far_plane", c_float), ("eps2d", c_float),
+        ("crf_kind", c_int32), ("crf_hidden", c_int32), ("crf_before_average", c_int32), ("ks_per_camera", c_int32),
+        ("sort_mode", c_int32), ("background", c_float * 3), ("reserved", c_int32 * 4),
+    ]
+
+
+class ChsWorkspaceSizes(ctypes.Structure):
+    _fields_ = [("bin_count_bytes", c_uint64), ("bin_sort_bytes", c_uint64), ("reduce_bytes", c_uint64)]
+
+
+# name -> (restype, argtypes); every symbol include/chs.h declares
+P = c_void_p
+CFG = POINTER(ChsConfig)
+SIGNATURES = {
+    "chs_version": (ctypes.c_int, []),
+    "chs_last_error": (c_char_p, []),
+    "chs_workspace_query": (ctypes.c_int, [CFG, c_int64, c_int32, POINTER(ChsWorkspaceSizes)]),
+    "chs_spline_fwd": (ctypes.c_int, [c_int32, P, c_int32, c_double, c_double, P, P, c_int32, c_int32, P, P]),
+    "chs_spline_bwd": (ctypes.c_int, [c_int32, P, c_int32, c_double, c_double, P, P, c_int32, c_int32, P, P, P, P, P, c_uint64, P]),
+    "chs_project_fwd": (ctypes.c_int, [CFG] + [P] * 14),
+    "chs_project_bwd": (ctypes.c_int, [CFG] + [P] * 12 + [c_uint64, P]),
+    "chs_bin_count": (ctypes.c_int, [CFG, P, P, P, P, P, POINTER(c_int64), P, c_uint64, P]),
+    "chs_bin_sort": (ctypes.c_int, [CFG, c_int64] + [P] * 9 + [c_uint64, P]),
+    "chs_bin_emit_keys": (ctypes.c_int, [CFG, c_int64] + [P] * 8),
+    "chs_blend_fwd": (ctypes.c_int, [CFG] + [P] * 13),
+    "chs_crf_bwd": (ctypes.c_int, [CFG] + [P] * 8 + [c_uint64, P]),
+    "chs_blend_bwd": (ctypes.c_int, [CFG] + [P] * 13),
+    "chs_comm_unique_id": (ctypes.c_int, [P]),
+    "chs_comm_init": (ctypes.c_int, [P, c_int32, c_int32, POINTER(c_void_p)]),
+    "chs_allreduce_grads": (ctypes.c_int, [P, P, c_uint64, P]),
+    "chs_comm_destroy": (ctypes.c_int, [P]),
+}
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libchs.so (once). Raises if it has not been built — there is no CPU path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C casualhdrsplat_b200/csrc`. casualhdrsplat_b200 has no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = l
+    return _LIB
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().chs_last_error()
+        raise RuntimeError(f"libchs {what} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) tensor, or NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "libchs needs contiguous tensors"
+    return c_void_p(t.data_ptr())
+
+
+def make_config(n_gauss, n_frames, n_virtual, width, height, *, near=0.01, far=1e10, eps2d=0.3, tile_size=16,
+                crf_kind=CHS_CRF_IDENTITY, crf_hidden=0, crf_before_average=False, ks_per_camera=False,
+                sort_mode=CHS_SORT_DEPTH_PRESORT, background=None) -> ChsConfig:
+    cfg = ChsConfig()
+    cfg.n_gauss, cfg.n_frames, cfg.n_virtual = int(n_gauss), int(n_frames), int(n_virtual)
+    cfg.width, cfg.height, cfg.tile_size = int(width), int(height), int(tile_size)
+    cfg.near_plane, cfg.far_plane, cfg.eps2d = float(near), float(far), float(eps2d)
+    cfg.crf_kind, cfg.crf_hidden = int(crf_kind), int(crf_hidden)
+    cfg.crf_before_average = int(bool(crf_before_average))
+    cfg.ks_per_camera = int(bool(ks_per_camera))
+    cfg.sort_mode = int(sort_mode)
+    bg = (0.0, 0.0, 0.0) if background is None else tuple(float(v) for v in background)
+    cfg.background[0], cfg.background[1], cfg.background[2] = bg
+    return cfg
+
+
+def workspace_sizes(cfg: ChsConfig, n_isect: int = 0, n_knots: int = 0) -> ChsWorkspaceSizes:
+    out = ChsWorkspaceSizes()
+    check(lib().chs_workspace_query(byref(cfg), int(n_isect), int(n_knots), byref(out)), "chs_workspace_query")
+    return out

@@ -1,0 +1,163 @@
+// chs_api.cu — version, error string, configuration validation, workspace query and the NCCL
+// communicator of libchs (include/chs.h).
+#include <dlfcn.h>
+#include <string.h>
+
+#include "chs_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void chs_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int chs_version(void) { return CHS_VERSION; }
+extern "C" const char* chs_last_error(void) { return g_err; }
+
+int chs_make_dims(const chs_config* cfg, ChsDims* d) {
+  CHS_REQUIRE(cfg && d, "null chs_config");
+  CHS_REQUIRE(cfg->tile_size == CHS_TILE, "tile_size must be %d (got %d)", CHS_TILE, cfg->tile_size);
+  CHS_REQUIRE(cfg->n_gauss >= 0 && cfg->n_frames >= 0 && cfg->n_virtual >= 1, "bad n_gauss / n_frames / n_virtual");
+  CHS_REQUIRE(cfg->width >= 1 && cfg->height >= 1, "bad image size %d x %d", cfg->width, cfg->height);
+  CHS_REQUIRE(cfg->crf_kind == CHS_CRF_IDENTITY || cfg->crf_kind == CHS_CRF_MLP, "unknown crf_kind %d", cfg->crf_kind);
+  CHS_REQUIRE(cfg->crf_kind != CHS_CRF_MLP || (cfg->crf_hidden >= 1 && cfg->crf_hidden <= 128), "crf_hidden must be in [1,128]");
+  CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || cfg->sort_mode == CHS_SORT_DEPTH_PRESORT, "unknown sort_mode %d", cfg->sort_mode);
+  d->N = cfg->n_gauss; d->B = cfg->n_frames; d->n = cfg->n_virtual;
+  d->C = d->B * d->n;
+  d->W = cfg->width; d->H = cfg->height;
+  d->tile_w = (d->W + CHS_TILE - 1) / CHS_TILE;
+  d->tile_h = (d->H + CHS_TILE - 1) / CHS_TILE;
+  d->tiles = d->tile_w * d->tile_h;
+  d->tile_bits = chs_bit_length((uint64_t)d->tiles);
+  d->cam_bits = chs_bit_length((uint64_t)d->C);
+  d->CN = (int64_t)d->C * d->N;
+  d->P = (int64_t)d->W * d->H;
+  CHS_REQUIRE(d->C <= 4096, "too many cameras in one call (%d)", d->C);
+  CHS_REQUIRE(d->CN < ((int64_t)1 << 31), "C*N = %lld exceeds int32 ids; split the frame batch", (long long)d->CN);
+  CHS_REQUIRE((int64_t)d->C * d->tiles < ((int64_t)1 << 31), "C*tiles exceeds int32");
+  CHS_REQUIRE(32 + d->tile_bits + d->cam_bits <= 64, "key does not fit 64 bits");
+  return CHS_OK;
+}
+
+int chs_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes);
+int chs_bin_sort_bytes(const ChsDims& d, int sort_mode, int64_t M, uint64_t* bytes);
+
+extern "C" int chs_workspace_query(const chs_config* cfg, int64_t n_isect, int32_t n_knots, chs_workspace_sizes* out) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(out, "chs_workspace_query: null output");
+  memset(out, 0, sizeof(*out));
+  if (d.CN > 0) {
+    st = chs_bin_count_bytes(d, cfg->sort_mode, &out->bin_count_bytes);
+    if (st) return st;
+  }
+  out->bin_count_bytes += 256;
+  if (n_isect > 0) {
+    st = chs_bin_sort_bytes(d, cfg->sort_mode, n_isect, &out->bin_sort_bytes);
+    if (st) return st;
+  }
+  out->bin_sort_bytes += 256;
+  uint64_t crf = cfg->crf_kind == CHS_CRF_MLP ? (uint64_t)3 * (3 * cfg->crf_hidden + 1) : 0;
+  uint64_t a = crf + d.B, b = (uint64_t)d.C * 12, c = (uint64_t)(n_knots > 0 ? n_knots : 0) * 7 + 2 * (uint64_t)d.B;
+  uint64_t m = a > b ? a : b;
+  m = m > c ? m : c;
+  out->reduce_bytes = chs_align_up(m * sizeof(double), 256) + 256;
+  return CHS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10: NCCL all-reduce of the flat gradient buffer.  libnccl is resolved at run time (the copy
+// already mapped into the process — e.g. the one PyTorch bundles — or the system one), so libchs
+// has no link-time NCCL dependency and cannot clash with the host application's NCCL.
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return CHS_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    chs_set_error("NCCL: cannot dlopen libnccl.so.2: %s", dlerror());
+    return CHS_ERR_NCCL;
+  }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    chs_set_error("NCCL: missing symbols in libnccl.so.2");
+    return CHS_ERR_NCCL;
+  }
+  g_nccl.handle = h;
+  return CHS_OK;
+}
+
+int nccl_fail(const char* what, ncclResult_t r) {
+  chs_set_error("NCCL: %s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return CHS_ERR_NCCL;
+}
+}  // namespace
+
+struct chs_comm {
+  ncclComm_t comm;
+  int rank, world;
+};
+
+extern "C" int chs_comm_unique_id(void* unique_id_host_128) {
+  CHS_REQUIRE(unique_id_host_128, "chs_comm_unique_id: null output");
+  int st = load_nccl();
+  if (st) return st;
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r) return nccl_fail("ncclGetUniqueId", r);
+  memcpy(unique_id_host_128, &id, 128);
+  return CHS_OK;
+}
+
+extern "C" int chs_comm_init(const void* unique_id_host_128, int32_t rank, int32_t world, chs_comm** out) {
+  CHS_REQUIRE(unique_id_host_128 && out, "chs_comm_init: null pointer");
+  CHS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "chs_comm_init: bad rank %d / world %d", rank, world);
+  int st = load_nccl();
+  if (st) return st;
+  ncclUniqueId id;
+  memcpy(&id, unique_id_host_128, 128);
+  ncclComm_t c;
+  ncclResult_t r = g_nccl.CommInitRank(&c, world, id, rank);
+  if (r) return nccl_fail("ncclCommInitRank", r);
+  chs_comm* h = new chs_comm{c, rank, world};
+  *out = h;
+  return CHS_OK;
+}
+
+extern "C" int chs_allreduce_grads(chs_comm* comm, float* buf, uint64_t count, void* stream) {
+  CHS_REQUIRE(comm && buf, "chs_allreduce_grads: null pointer");
+  if (count == 0) return CHS_OK;
+  // ncclFloat32 = 7, ncclSum = 0
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, (size_t)count, 7, 0, comm->comm, (cudaStream_t)stream);
+  if (r) return nccl_fail("ncclAllReduce", r);
+  return CHS_OK;
+}
+
+extern "C" int chs_comm_destroy(chs_comm* comm) {
+  if (!comm) return CHS_OK;
+  if (g_nccl.CommDestroy) g_nccl.CommDestroy(comm->comm);
+  delete comm;
+  return CHS_OK;
+}

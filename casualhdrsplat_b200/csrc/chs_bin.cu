@@ -1,0 +1,313 @@
+// chs_bin.cu — K2 intersection count, K3 key generation, K4 radix sort, K5 tile offsets
+// (SURVEY.md section 2.4, Appendix A.4).  Integer work, bit-exact against the oracle.
+//
+// Two sort strategies with identical outputs:
+//   CHS_SORT_KEY64          the literal algorithm: one 64-bit key cam|tile|depth per intersection,
+//                           stable LSD radix sort of the low 32+tile_bits+cam_bits bits
+//                           (~7 passes x 24 B per intersection at 1080p).
+//   CHS_SORT_DEPTH_PRESORT  depth is a property of the (camera, Gaussian) pair, not of the
+//                           intersection: sort the C*N pairs by (cam, depth) once (C*N << M), emit
+//                           intersections in that order, then a *stable* sort on the cam|tile bits
+//                           alone (2-3 passes x 16 B) leaves every tile list depth-ordered with
+//                           ties in Gaussian order — the same permutation as the 64-bit sort.
+// The radix passes themselves are cub::DeviceRadixSort (onesweep); everything around them
+// (key construction, ordering trick, offsets) is hand-written.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "chs_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct GatherTouched {
+  const int32_t* touched;
+  const int32_t* order;
+  __host__ __device__ uint32_t operator()(int64_t i) const { return (uint32_t)touched[order ? order[i] : i]; }
+};
+struct GatherTouched64 {
+  const int32_t* touched;
+  __host__ __device__ int64_t operator()(int64_t i) const { return (int64_t)touched[i]; }
+};
+
+__global__ void depth_keys_kernel(const int32_t* __restrict__ touched, const float* __restrict__ depths, int64_t CN, int N,
+                                  uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CN) return;
+  uint64_t c = (uint64_t)(i / N);
+  uint32_t d = touched[i] > 0 ? __float_as_uint(depths[i]) : 0xFFFFFFFFu;
+  keys[i] = (c << 32) | d;
+  vals[i] = (int32_t)i;
+}
+
+// One thread per (camera, Gaussian) in emission order. MODE 0: 64-bit keys; MODE 1: 32-bit linear
+// (cam * tiles + tile) keys.
+template <int MODE>
+__global__ void emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits, const float4* __restrict__ geom,
+                            const int32_t* __restrict__ radii, const float* __restrict__ depths,
+                            const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order, uint64_t* __restrict__ keys64,
+                            uint32_t* __restrict__ keys32, int32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CN) return;
+  const int32_t id = order ? order[i] : (int32_t)i;
+  const int radius = radii[id];
+  if (radius <= 0) return;
+  const float4 gm = geom[id];
+  const ChsTileRect r = chs_tile_bounds(gm.x, gm.y, radius, tile_w, tile_h);
+  const uint32_t c = (uint32_t)(id / N);
+  uint64_t out = offsets[i];
+  if (MODE == 0) {
+    const uint64_t hi = ((uint64_t)c << (32 + tile_bits));
+    const uint64_t d = __float_as_uint(depths[id]);
+    for (int ty = r.y0; ty < r.y1; ++ty)
+      for (int tx = r.x0; tx < r.x1; ++tx) {
+        keys64[out] = hi | ((uint64_t)(ty * tile_w + tx) << 32) | d;
+        vals[out] = id;
+        ++out;
+      }
+  } else {
+    const uint32_t base = c * (uint32_t)tiles;
+    for (int ty = r.y0; ty < r.y1; ++ty)
+      for (int tx = r.x0; tx < r.x1; ++tx) {
+        keys32[out] = base + (uint32_t)(ty * tile_w + tx);
+        vals[out] = id;
+        ++out;
+      }
+  }
+}
+
+__device__ __forceinline__ uint32_t lin_of_key64(uint64_t key, int tile_bits, int tiles) {
+  uint32_t b = (uint32_t)(key >> 32);
+  return (b >> tile_bits) * (uint32_t)tiles + (b & ((1u << tile_bits) - 1u));
+}
+
+// tile_offsets[lin] = first sorted index whose (cam, tile) >= lin; tile_offsets[C*tiles] = M.
+template <int MODE>
+__global__ void tile_offsets_kernel(int64_t M, int n_lin, int tile_bits, int tiles, const uint64_t* __restrict__ keys64,
+                                    const uint32_t* __restrict__ keys32, uint32_t* __restrict__ tile_offsets) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  uint32_t cur = MODE == 0 ? lin_of_key64(keys64[i], tile_bits, tiles) : keys32[i];
+  if (i == 0) {
+    for (uint32_t b = 0; b <= cur; ++b) tile_offsets[b] = 0;
+  } else {
+    uint32_t prev = MODE == 0 ? lin_of_key64(keys64[i - 1], tile_bits, tiles) : keys32[i - 1];
+    for (uint32_t b = prev + 1; b <= cur; ++b) tile_offsets[b] = (uint32_t)i;
+  }
+  if (i == M - 1)
+    for (uint32_t b = cur + 1; b <= (uint32_t)n_lin; ++b) tile_offsets[b] = (uint32_t)M;
+}
+
+__global__ void rebuild_keys_kernel(int64_t M, int tiles, int tile_bits, const uint32_t* __restrict__ lin_sorted,
+                                    const int32_t* __restrict__ vals_sorted, const float* __restrict__ depths,
+                                    uint64_t* __restrict__ keys_sorted) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  uint32_t lin = lin_sorted[i];
+  uint64_t c = lin / (uint32_t)tiles, t = lin % (uint32_t)tiles;
+  keys_sorted[i] = (c << (32 + tile_bits)) | (t << 32) | (uint64_t)__float_as_uint(depths[vals_sorted[i]]);
+}
+
+__global__ void store_total_kernel(const int64_t* total, int64_t* n_isect_dev) { *n_isect_dev = *total; }
+
+inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+
+// CUB temp-storage sizes (need a CUDA context).
+struct CountTemp {
+  size_t scan, reduce, sort;
+};
+int count_temp_sizes(const ChsDims& d, int sort_mode, CountTemp* t) {
+  t->scan = t->reduce = t->sort = 0;
+  GatherTouched gt{nullptr, nullptr};
+  cub::TransformInputIterator<uint32_t, GatherTouched, cub::CountingInputIterator<int64_t>> it(cub::CountingInputIterator<int64_t>(0), gt);
+  CHS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t->scan, it, (uint32_t*)nullptr, d.CN));
+  GatherTouched64 g64{nullptr};
+  cub::TransformInputIterator<int64_t, GatherTouched64, cub::CountingInputIterator<int64_t>> it64(cub::CountingInputIterator<int64_t>(0), g64);
+  CHS_CUDA(cub::DeviceReduce::Sum(nullptr, t->reduce, it64, (int64_t*)nullptr, d.CN));
+  if (sort_mode == CHS_SORT_DEPTH_PRESORT)
+    CHS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t->sort, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
+                                             (int32_t*)nullptr, d.CN, 0, 32 + d.cam_bits));
+  return CHS_OK;
+}
+
+int sort_temp_size(const ChsDims& d, int sort_mode, int64_t M, size_t* bytes) {
+  *bytes = 0;
+  if (M <= 0) return CHS_OK;
+  if (sort_mode == CHS_SORT_KEY64)
+    CHS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
+                                             (int32_t*)nullptr, M, 0, 32 + d.tile_bits + d.cam_bits));
+  else
+    CHS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                             (int32_t*)nullptr, M, 0, chs_bit_length((uint64_t)d.C * d.tiles)));
+  return CHS_OK;
+}
+
+}  // namespace
+
+// exported to chs_api.cu
+int chs_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes) {
+  CountTemp t;
+  int st = count_temp_sizes(d, sort_mode, &t);
+  if (st) return st;
+  uint64_t b = chs_align_up(t.scan, 256) + chs_align_up(t.reduce, 256) + 256;
+  if (sort_mode == CHS_SORT_DEPTH_PRESORT)
+    b += chs_align_up(t.sort, 256) + 2 * chs_align_up((uint64_t)d.CN * 8, 256) + chs_align_up((uint64_t)d.CN * 4, 256);
+  *bytes = b;
+  return CHS_OK;
+}
+
+int chs_bin_sort_bytes(const ChsDims& d, int sort_mode, int64_t M, uint64_t* bytes) {
+  size_t t;
+  int st = sort_temp_size(d, sort_mode, M, &t);
+  if (st) return st;
+  uint64_t m = (uint64_t)(M > 0 ? M : 0);
+  uint64_t b = chs_align_up(t, 256) + chs_align_up(m * 4, 256);  // vals_in
+  if (sort_mode == CHS_SORT_KEY64)
+    b += 2 * chs_align_up(m * 8, 256);  // keys_in + keys_out (when the caller does not want the keys)
+  else
+    b += 2 * chs_align_up(m * 4, 256);  // lin_in + lin_out
+  *bytes = b;
+  return CHS_OK;
+}
+
+extern "C" int chs_bin_count(const chs_config* cfg, const int32_t* tiles_touched, const float* depths, uint32_t* isect_offsets,
+                             int32_t* order, int64_t* n_isect_dev, int64_t* n_isect_host, void* workspace,
+                             uint64_t workspace_bytes, void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(tiles_touched && depths && isect_offsets && n_isect_dev && workspace, "chs_bin_count: null pointer");
+  CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || order, "chs_bin_count: order buffer required for CHS_SORT_DEPTH_PRESORT");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d.CN == 0) {
+    CHS_CUDA(cudaMemsetAsync(n_isect_dev, 0, sizeof(int64_t), s));
+    if (n_isect_host) *n_isect_host = 0;
+    return CHS_OK;
+  }
+  CountTemp t;
+  st = count_temp_sizes(d, cfg->sort_mode, &t);
+  if (st) return st;
+  ChsArena ar(workspace, workspace_bytes);
+  char* scan_tmp = ar.take<char>(t.scan);
+  char* red_tmp = ar.take<char>(t.reduce);
+  int64_t* total = ar.take<int64_t>(1);
+  const int32_t* ord = nullptr;
+  if (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT) {
+    char* sort_tmp = ar.take<char>(t.sort);
+    uint64_t* k_in = ar.take<uint64_t>(d.CN);
+    uint64_t* k_out = ar.take<uint64_t>(d.CN);
+    int32_t* v_in = ar.take<int32_t>(d.CN);
+    if (!ar.ok) {
+      chs_set_error("chs_bin_count: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+      return CHS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    depth_keys_kernel<<<grid_for(d.CN), kThreads, 0, s>>>(tiles_touched, depths, d.CN, d.N, k_in, v_in);
+    CHS_LAUNCH_CHECK();
+    size_t tb = t.sort;
+    CHS_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, tb, (const uint64_t*)k_in, k_out, (const int32_t*)v_in, order, d.CN, 0,
+                                             32 + d.cam_bits, s));
+    ord = order;
+  }
+  if (!ar.ok) {
+    chs_set_error("chs_bin_count: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+    return CHS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  GatherTouched gt{tiles_touched, ord};
+  cub::TransformInputIterator<uint32_t, GatherTouched, cub::CountingInputIterator<int64_t>> it(cub::CountingInputIterator<int64_t>(0), gt);
+  size_t sb = t.scan;
+  CHS_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, sb, it, isect_offsets, d.CN, s));
+  GatherTouched64 g64{tiles_touched};
+  cub::TransformInputIterator<int64_t, GatherTouched64, cub::CountingInputIterator<int64_t>> it64(cub::CountingInputIterator<int64_t>(0), g64);
+  size_t rb = t.reduce;
+  CHS_CUDA(cub::DeviceReduce::Sum(red_tmp, rb, it64, total, d.CN, s));
+  store_total_kernel<<<1, 1, 0, s>>>(total, n_isect_dev);
+  CHS_LAUNCH_CHECK();
+  if (n_isect_host) {
+    CHS_CUDA(cudaMemcpyAsync(n_isect_host, n_isect_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CHS_CUDA(cudaStreamSynchronize(s));
+    if (*n_isect_host >= ((int64_t)1 << 31)) {
+      chs_set_error("chs_bin_count: %lld intersections exceed the 2^31 limit of one launch; split the frame batch",
+                    (long long)*n_isect_host);
+      return CHS_ERR_UNSUPPORTED;
+    }
+  }
+  return CHS_OK;
+}
+
+extern "C" int chs_bin_emit_keys(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii, const float* depths,
+                                 const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys, int32_t* vals, void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(geom && radii && depths && isect_offsets, "chs_bin_emit_keys: null input");
+  if (n_isect == 0 || d.CN == 0) return CHS_OK;
+  CHS_REQUIRE(keys && vals, "chs_bin_emit_keys: null output");
+  emit_kernel<0><<<grid_for(d.CN), kThreads, 0, (cudaStream_t)stream>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits,
+                                                                         (const float4*)geom, radii, depths, isect_offsets, order, keys,
+                                                                         nullptr, vals);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}
+
+extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii, const float* depths,
+                            const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted,
+                            uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(geom && radii && depths && isect_offsets && tile_offsets, "chs_bin_sort: null pointer");
+  CHS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 31), "chs_bin_sort: n_isect out of range");
+  CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || order, "chs_bin_sort: order required for CHS_SORT_DEPTH_PRESORT");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_lin = d.C * d.tiles;
+  const int64_t M = n_isect;
+  if (M == 0) {
+    CHS_CUDA(cudaMemsetAsync(tile_offsets, 0, ((size_t)n_lin + 1) * sizeof(uint32_t), s));
+    return CHS_OK;
+  }
+  CHS_REQUIRE(vals_sorted && workspace, "chs_bin_sort: null output/workspace");
+  size_t tb;
+  st = sort_temp_size(d, cfg->sort_mode, M, &tb);
+  if (st) return st;
+  ChsArena ar(workspace, workspace_bytes);
+  char* tmp = ar.take<char>(tb);
+  int32_t* v_in = ar.take<int32_t>(M);
+  if (cfg->sort_mode == CHS_SORT_KEY64) {
+    uint64_t* k_in = ar.take<uint64_t>(M);
+    uint64_t* k_out = keys_sorted ? keys_sorted : ar.take<uint64_t>(M);
+    if (!ar.ok) {
+      chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+      return CHS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    emit_kernel<0><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom, radii,
+                                                       depths, isect_offsets, nullptr, k_in, nullptr, v_in);
+    CHS_LAUNCH_CHECK();
+    CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_in, k_out, (const int32_t*)v_in, vals_sorted, M, 0,
+                                             32 + d.tile_bits + d.cam_bits, s));
+    tile_offsets_kernel<0><<<grid_for(M), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, k_out, nullptr, tile_offsets);
+    CHS_LAUNCH_CHECK();
+  } else {
+    uint32_t* l_in = ar.take<uint32_t>(M);
+    uint32_t* l_out = ar.take<uint32_t>(M);
+    if (!ar.ok) {
+      chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+      return CHS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    emit_kernel<1><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom, radii,
+                                                       depths, isect_offsets, order, nullptr, l_in, v_in);
+    CHS_LAUNCH_CHECK();
+    CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)l_in, l_out, (const int32_t*)v_in, vals_sorted, M, 0,
+                                             chs_bit_length((uint64_t)n_lin), s));
+    tile_offsets_kernel<1><<<grid_for(M), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr, l_out, tile_offsets);
+    CHS_LAUNCH_CHECK();
+    if (keys_sorted) {
+      rebuild_keys_kernel<<<grid_for(M), kThreads, 0, s>>>(M, d.tiles, d.tile_bits, l_out, vals_sorted, depths, keys_sorted);
+      CHS_LAUNCH_CHECK();
+    }
+  }
+  return CHS_OK;
+}

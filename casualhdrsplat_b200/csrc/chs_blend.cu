@@ -1,0 +1,387 @@
+// chs_blend.cu — K6 blend_fwd (+ fused formation epilogue) and K8 blend_bwd
+// (SURVEY.md section 2.4, Appendix A.5 / A.6 / A.7).
+//
+// Layout of one CTA: 256 threads = one 16x16 pixel tile; warp w owns the 8x4 pixel block at
+// ((w & 1) * 8, (w >> 1) * 4), lane l the pixel (l & 7, l >> 3) inside it.
+//
+// Per batch of up to 256 tile-list entries the CTA gathers the per-(camera, Gaussian) records
+// (three 128-bit loads each) into shared memory, pre-scaling the conic for exp2 and computing the
+// half extents of the alpha >= 1/255 ellipse.  Each warp then *culls the batch against its own 8x4
+// block*: 32 lanes test 32 Gaussians, a ballot yields the survivors, and only those are evaluated
+// for the warp's 32 pixels.  Skipped pairs are exactly pairs with alpha < 1/255, so results are
+// unchanged, but most of the 256 pair evaluations per intersection of a naive tile kernel vanish.
+// Early termination is warp-granular (ballot of per-pixel "done") and CTA-granular
+// (__syncthreads_and) per batch.
+//
+// Forward fuses the whole formation epilogue: the CTA loops over the n virtual poses of its frame,
+// accumulates sum_k H_k in registers, and writes B = F(dt/n * sum_k H_k) once (decision D0 order).
+//
+// Backward walks each pixel's list back to front from last_id; the nine per-Gaussian partials are
+// reduced across the warp with a transposing butterfly (14 shuffles instead of 45) that leaves
+// value j on lane 4j, so a single predicated vector-of-lanes RED instruction adds all nine numbers
+// into the three [C,N] gradient planes.
+#include "chs_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBatch = 256;
+#define CHS_LOG2_ALPHA_MIN (-7.994353436858858f) /* log2(1/255) */
+
+struct SplatSmem {
+  float4 a[kBatch];  // mx, my, qa, qb
+  float4 b[kBatch];  // qc, lo, ex, ey
+  float4 c[kBatch];  // r, g, b, opacity
+};
+
+__device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
+                                            const float* __restrict__ conic_c, const float4* __restrict__ rgbo) {
+  const float4 gm = __ldg(geom + val);
+  const float cc = __ldg(conic_c + val);
+  const float4 col = __ldg(rgbo + (val - cam_base));
+  ChsSplat<float> s;
+  chs_make_splat(gm.x, gm.y, gm.z, gm.w, cc, col.w, col.x, col.y, col.z, s);
+  if (s.ex < 0.f) s.ex = s.ey = -1e30f;
+  sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.qb);
+  sm.b[slot] = make_float4(s.qc, s.lo, s.ex, s.ey);
+  sm.c[slot] = make_float4(s.r, s.g, s.b, s.opac);
+}
+
+// does the alpha >= 1/255 region of staged splat `slot` reach the warp's pixel-centre rectangle?
+__device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
+  const float4 a = sm.a[slot];
+  const float4 b = sm.b[slot];
+  return (a.x + b.z >= bx0) && (a.x - b.z <= bx1) && (a.y + b.w >= by0) && (a.y - b.w <= by1);
+}
+
+__device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, int slot) {
+  const float4 a = sm.a[slot];
+  const float4 b = sm.b[slot];
+  ChsSplat<float> s;
+  s.mx = a.x; s.my = a.y; s.qa = a.z; s.qb = a.w;
+  s.qc = b.x; s.lo = b.y; s.ex = b.z; s.ey = b.w;
+  return s;
+}
+
+struct BlendFwdArgs {
+  int N, n_virtual, W, H, tile_w, tiles;
+  int crf_kind, crf_hidden;
+  float bg[3];
+  const float4* geom;
+  const float* conic_c;
+  const float4* rgbo;
+  const int32_t* vals;
+  const uint32_t* tile_offsets;
+  const float* exposure;
+  const float* crf_params;
+  float *ldr, *alpha, *hdr_mean, *final_T;
+  int32_t* last_id;
+};
+
+__global__ void __launch_bounds__(kThreads) blend_fwd_kernel(BlendFwdArgs a) {
+  __shared__ SplatSmem sm;
+  extern __shared__ float s_crf[];  // 3 * (3 Hd + 1) floats when the CRF is the MLP
+
+  const int tile = blockIdx.x, frame = blockIdx.y;
+  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 4;
+  const int ix = bx + (lane & 7), iy = by + (lane >> 3);
+  const bool inside = ix < a.W && iy < a.H;
+  const float px = ix + 0.5f, py = iy + 0.5f;
+  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 3.5f;
+  const int64_t P = (int64_t)a.W * a.H;
+  const int64_t pix = (int64_t)iy * a.W + ix;
+
+  if (a.crf_kind == CHS_CRF_MLP)
+    for (int i = tid; i < 3 * (3 * a.crf_hidden + 1); i += kThreads) s_crf[i] = a.crf_params[i];
+
+  float sum_r = 0.f, sum_g = 0.f, sum_b = 0.f, sum_alpha = 0.f;
+  for (int k = 0; k < a.n_virtual; ++k) {
+    const int c = frame * a.n_virtual + k;
+    const int cam_base = c * a.N;
+    const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
+    const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
+    float T = 1.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+    int last = 0;
+    bool done = !inside;
+    bool warp_done = __all_sync(CHS_FULL_MASK, done);
+    for (uint32_t base = start; base < end; base += kBatch) {
+      // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
+      if (__syncthreads_and(done)) break;
+      const int cnt = min((uint32_t)kBatch, end - base);
+      if (tid < cnt) stage_splat(sm, tid, a.vals[base + tid], cam_base, a.geom, a.conic_c, a.rgbo);
+      __syncthreads();
+      if (warp_done) continue;
+      for (int sub = 0; sub < cnt; sub += 32) {
+        const int j = sub + lane;
+        const bool hit = (j < cnt) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
+        unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+        while (mask) {
+          const int jj = sub + __ffs(mask) - 1;
+          mask &= mask - 1;
+          const ChsSplat<float> s = read_splat_ab(sm, jj);
+          float dx, dy;
+          const float power = chs_pair_power(s, px, py, dx, dy);
+          if (!done && power >= CHS_LOG2_ALPHA_MIN) {
+            const float alpha = fminf(CHS_ALPHA_MAX, chs_exp2_fast(power));
+            const float Tn = T * (1.f - alpha);
+            if (Tn <= CHS_T_STOP) {
+              done = true;
+            } else {
+              const float4 col = sm.c[jj];
+              const float w = alpha * T;
+              acc_r += w * col.x;
+              acc_g += w * col.y;
+              acc_b += w * col.z;
+              T = Tn;
+              last = (int)(base - start) + jj + 1;
+            }
+          }
+        }
+        if (__all_sync(CHS_FULL_MASK, done)) {
+          warp_done = true;
+          break;
+        }
+      }
+    }
+    __syncthreads();  // the next pose restages shared memory
+    if (inside) {
+      a.final_T[(int64_t)c * P + pix] = T;
+      a.last_id[(int64_t)c * P + pix] = last;
+      sum_r += acc_r + T * a.bg[0];
+      sum_g += acc_g + T * a.bg[1];
+      sum_b += acc_b + T * a.bg[2];
+      sum_alpha += 1.f - T;
+    }
+  }
+  if (!inside) return;
+  // formation epilogue (A.7, decision D0): mean over poses, x exposure, CRF
+  const float inv_n = 1.f / (float)a.n_virtual;
+  const float hr = sum_r * inv_n, hg = sum_g * inv_n, hb = sum_b * inv_n;
+  const float dt = a.exposure[frame];
+  float o0 = dt * hr, o1 = dt * hg, o2 = dt * hb;
+  if (a.crf_kind == CHS_CRF_MLP) {
+    const int stride = 3 * a.crf_hidden + 1;
+    o0 = chs_crf_mlp_fwd(o0, s_crf, a.crf_hidden);
+    o1 = chs_crf_mlp_fwd(o1, s_crf + stride, a.crf_hidden);
+    o2 = chs_crf_mlp_fwd(o2, s_crf + 2 * stride, a.crf_hidden);
+  }
+  const int64_t o = ((int64_t)frame * P + pix) * 3;
+  a.ldr[o] = o0; a.ldr[o + 1] = o1; a.ldr[o + 2] = o2;
+  a.hdr_mean[o] = hr; a.hdr_mean[o + 1] = hg; a.hdr_mean[o + 2] = hb;
+  a.alpha[(int64_t)frame * P + pix] = sum_alpha * inv_n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct BlendBwdArgs {
+  int N, n_virtual, W, H, tile_w, tiles;
+  float bg[3];
+  const float4* geom;
+  const float* conic_c;
+  const float4* rgbo;
+  const int32_t* vals;
+  const uint32_t* tile_offsets;
+  const float* final_T;
+  const int32_t* last_id;
+  const float* v_hdr;    // [B,H,W,3] gradient w.r.t. each pose's HDR image
+  const float* v_alpha;  // [B,H,W] or null (gradient w.r.t. the pose-averaged alpha)
+  float4* v_geom;        // [C,N] (v_mx, v_my, v_A, v_B)
+  float4* v_cogr;        // [C,N] (v_C, v_opacity, v_r, v_g)
+  float* v_blue;         // [C,N]  v_b
+};
+
+// Transposing butterfly: on entry every lane holds its pixel's 8 partials v[0..7]; on exit lane l
+// holds, in the return value, the warp total of v[l >> 2] (all four lanes of a quad hold the same).
+__device__ __forceinline__ float warp_transpose_reduce8(float v[8], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 4);
+  }
+  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 2);
+  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 1);
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
+  __shared__ SplatSmem sm;
+  __shared__ int32_t s_vals[kBatch];
+  __shared__ int s_max_last;
+
+  const int tile = blockIdx.x, c = blockIdx.y;
+  const int frame = c / a.n_virtual;
+  const int cam_base = c * a.N;
+  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 4;
+  const int ix = bx + (lane & 7), iy = by + (lane >> 3);
+  const bool inside = ix < a.W && iy < a.H;
+  const float px = ix + 0.5f, py = iy + 0.5f;
+  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 3.5f;
+  const int64_t P = (int64_t)a.W * a.H;
+  const int64_t pix = (int64_t)iy * a.W + ix;
+  const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
+  const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
+  if (end <= start) return;
+
+  float Tr = 1.f, vh[3] = {0.f, 0.f, 0.f}, va_t = 0.f;
+  int my_last = 0;
+  if (inside) {
+    const float T_final = a.final_T[(int64_t)c * P + pix];
+    my_last = a.last_id[(int64_t)c * P + pix];
+    const int64_t o = ((int64_t)frame * P + pix) * 3;
+    vh[0] = a.v_hdr[o]; vh[1] = a.v_hdr[o + 1]; vh[2] = a.v_hdr[o + 2];
+    const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] / (float)a.n_virtual : 0.f;
+    va_t = T_final * (v_al - (a.bg[0] * vh[0] + a.bg[1] * vh[1] + a.bg[2] * vh[2]));
+    Tr = T_final;
+  }
+  if (tid == 0) s_max_last = 0;
+  __syncthreads();
+  {
+    int m = my_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(CHS_FULL_MASK, m, o));
+    if (lane == 0 && m > 0) atomicMax(&s_max_last, m);
+  }
+  __syncthreads();
+  const int n_walk = s_max_last;  // entries [0, n_walk) of the tile list can matter
+  int warp_last = my_last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(CHS_FULL_MASK, warp_last, o));
+
+  float buf[3] = {0.f, 0.f, 0.f};
+  for (int hi = n_walk; hi > 0; hi -= kBatch) {
+    const int lo = max(0, hi - kBatch);
+    const int cnt = hi - lo;
+    __syncthreads();
+    if (tid < cnt) {
+      const int32_t val = a.vals[start + lo + tid];
+      s_vals[tid] = val;
+      stage_splat(sm, tid, val, cam_base, a.geom, a.conic_c, a.rgbo);
+    }
+    __syncthreads();
+    if (warp_last <= lo) continue;  // none of this warp's pixels reaches into this batch
+    for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
+      const int sub_lo = max(0, sub_hi - 32);
+      if (warp_last <= lo + sub_lo) continue;
+      const int j = sub_lo + lane;
+      const bool hit = (j < sub_hi) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
+      unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+      while (mask) {
+        const int bit = 31 - __clz(mask);
+        mask &= ~(1u << bit);
+        const int jj = sub_lo + bit;
+        const int rel = lo + jj + 1;  // 1-based index in the tile list
+        ChsSplat<float> s = read_splat_ab(sm, jj);
+        float dx, dy;
+        const float power = chs_pair_power(s, px, py, dx, dy);
+        const bool valid = (rel <= my_last) && power >= CHS_LOG2_ALPHA_MIN;
+        if (!__any_sync(CHS_FULL_MASK, valid)) continue;
+        float g[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g[i] = 0.f;
+        if (valid) {
+          const float4 col = sm.c[jj];
+          s.r = col.x; s.g = col.y; s.b = col.z; s.opac = col.w;
+          const float au = chs_exp2_fast(power);
+          chs_pair_bwd(s, dx, dy, au, fminf(CHS_ALPHA_MAX, au), Tr, buf, vh, va_t, g);
+        }
+        const float blue = chs_warp_sum(g[8]);
+        const float r8 = warp_transpose_reduce8(g, lane);
+        // lane 4j holds total j (j = 0..7): [v_mx, v_my, v_A, v_B | v_C, v_o, v_r, v_g]; lane 1 adds blue
+        const int64_t val = s_vals[jj];
+        float* dst = nullptr;
+        float add = r8;
+        if ((lane & 3) == 0) {
+          const int j8 = lane >> 2;
+          dst = (j8 < 4) ? reinterpret_cast<float*>(a.v_geom + val) + j8 : reinterpret_cast<float*>(a.v_cogr + val) + (j8 - 4);
+        } else if (lane == 1) {
+          dst = a.v_blue + val;
+          add = blue;
+        }
+        if (dst && add != 0.f) atomicAdd(dst, add);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+static size_t crf_smem_bytes(const chs_config* cfg) {
+  return cfg->crf_kind == CHS_CRF_MLP ? (size_t)3 * (3 * cfg->crf_hidden + 1) * sizeof(float) : 0;
+}
+
+extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const float* conic_c, const float* rgbo,
+                             const int32_t* vals_sorted, const uint32_t* tile_offsets, const float* exposure,
+                             const float* crf_params, float* ldr, float* alpha, float* hdr_mean, float* final_T, int32_t* last_id,
+                             void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(geom && conic_c && rgbo && tile_offsets && exposure, "chs_blend_fwd: null input");
+  CHS_REQUIRE(ldr && alpha && hdr_mean && final_T && last_id, "chs_blend_fwd: null output");
+  CHS_REQUIRE(cfg->crf_kind == CHS_CRF_IDENTITY || crf_params, "chs_blend_fwd: crf_params required for the MLP CRF");
+  if (cfg->crf_before_average) {
+    chs_set_error("chs_blend_fwd: crf_before_average=1 (figure order) is not implemented in CUDA yet (SURVEY.md section 8(f) row f3)");
+    return CHS_ERR_UNSUPPORTED;
+  }
+  if (d.B == 0 || d.P == 0) return CHS_OK;
+  BlendFwdArgs a;
+  a.N = d.N; a.n_virtual = d.n; a.W = d.W; a.H = d.H; a.tile_w = d.tile_w; a.tiles = d.tiles;
+  a.crf_kind = cfg->crf_kind; a.crf_hidden = cfg->crf_hidden;
+  a.bg[0] = cfg->background[0]; a.bg[1] = cfg->background[1]; a.bg[2] = cfg->background[2];
+  a.geom = (const float4*)geom; a.conic_c = conic_c; a.rgbo = (const float4*)rgbo; a.vals = vals_sorted; a.tile_offsets = tile_offsets;
+  a.exposure = exposure; a.crf_params = crf_params;
+  a.ldr = ldr; a.alpha = alpha; a.hdr_mean = hdr_mean; a.final_T = final_T; a.last_id = last_id;
+  dim3 grid(d.tiles, d.B);
+  blend_fwd_kernel<<<grid, kThreads, crf_smem_bytes(cfg), (cudaStream_t)stream>>>(a);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}
+
+extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const float* conic_c, const float* rgbo,
+                             const int32_t* vals_sorted, const uint32_t* tile_offsets, const float* final_T, const int32_t* last_id,
+                             const float* v_hdr, const float* v_alpha, float* v_geom, float* v_cogr, float* v_blue, void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(geom && conic_c && rgbo && tile_offsets && final_T && last_id && v_hdr, "chs_blend_bwd: null input");
+  CHS_REQUIRE(v_geom && v_cogr && v_blue, "chs_blend_bwd: null output");
+  cudaStream_t s = (cudaStream_t)stream;
+  CHS_CUDA(cudaMemsetAsync(v_geom, 0, (size_t)d.CN * 16, s));
+  CHS_CUDA(cudaMemsetAsync(v_cogr, 0, (size_t)d.CN * 16, s));
+  CHS_CUDA(cudaMemsetAsync(v_blue, 0, (size_t)d.CN * 4, s));
+  if (d.C == 0 || d.P == 0) return CHS_OK;
+  BlendBwdArgs a;
+  a.N = d.N; a.n_virtual = d.n; a.W = d.W; a.H = d.H; a.tile_w = d.tile_w; a.tiles = d.tiles;
+  a.bg[0] = cfg->background[0]; a.bg[1] = cfg->background[1]; a.bg[2] = cfg->background[2];
+  a.geom = (const float4*)geom; a.conic_c = conic_c; a.rgbo = (const float4*)rgbo; a.vals = vals_sorted; a.tile_offsets = tile_offsets;
+  a.final_T = final_T; a.last_id = last_id; a.v_hdr = v_hdr; a.v_alpha = v_alpha;
+  a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
+  dim3 grid(d.tiles, d.C);
+  blend_bwd_kernel<<<grid, kThreads, 0, s>>>(a);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}

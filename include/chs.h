@@ -1,0 +1,194 @@
+/* chs.h — C ABI of the B200-native CasualHDRSplat image-formation library (libchs.so).
+ *
+ * Drop-in boundary (decision D1).  The reference repository defines no
+ * FFI / plugin / operator interface for this path — it ships no code at all
+ * (/root/reference/Readme.md:57 "Still working on....") — so each entry point below cites the
+ * statement of the reference that *requires* the function instead of an interface it replaces:
+ *
+ *   chs_spline_*    "Trajectory control knots", "Camera motion spline", "Virtual camera pose",
+ *                   "Exposure time range"        /root/reference/assets/pipeline.png (Readme.md:50)
+ *   chs_project_*   "train 3DGS ... HDR scene"   /root/reference/Readme.md:54
+ *   chs_bin_*       tile binning, 64-bit depth|tile keys, radix sort (BASELINE.json north_star part 3)
+ *   chs_blend_*     "Virtual sharp HDR Image", "Blur from virtual sharp images", "Auto exposure
+ *                   time", "implicit CRF"        /root/reference/assets/pipeline.png
+ *   chs_crf_bwd     "joint estimation of camera motion, exposure time, and camera response curve"
+ *                                                /root/reference/Readme.md:54
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its name
+ *    ends in _host.  All float tensors are contiguous fp32, all index tensors int32/uint32.
+ *  - The caller owns every buffer (inputs, outputs, scratch); the library never allocates device
+ *    memory.  Scratch sizes come from chs_workspace_query().
+ *  - Every function returns 0 on success or a negative chs_status; chs_last_error() returns a
+ *    thread-local message.  Nothing throws or exits.
+ *  - Functions are stream-ordered on the cudaStream_t passed as `stream` (void* to keep CUDA headers
+ *    out of this file) and re-entrant.  There is no CPU fallback: without a CUDA device every compute
+ *    entry point returns CHS_ERR_CUDA.
+ *  - Shapes: N Gaussians, B frames, n virtual poses per frame, C = B*n cameras, camera c = i*n + k,
+ *    P = width*height, tiles = ceil(W/16)*ceil(H/16), M = number of (camera, tile, Gaussian)
+ *    intersections (data dependent, < 2^31).
+ */
+#ifndef CHS_H_
+#define CHS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHS_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define CHS_API __attribute__((visibility("default")))
+#else
+#define CHS_API
+#endif
+
+typedef enum chs_status {
+  CHS_OK = 0,
+  CHS_ERR_INVALID_ARG = -1,
+  CHS_ERR_CUDA = -2,
+  CHS_ERR_NCCL = -3,
+  CHS_ERR_WORKSPACE_TOO_SMALL = -4,
+  CHS_ERR_UNSUPPORTED = -5
+} chs_status;
+
+enum { CHS_CRF_IDENTITY = 0, CHS_CRF_MLP = 1 };
+enum { CHS_SPLINE_LINEAR = 0, CHS_SPLINE_CUBIC = 1 };
+/* CHS_SORT_KEY64: emit 64-bit cam|tile|depth keys and radix-sort them (the literal A.4 algorithm).
+ * CHS_SORT_DEPTH_PRESORT: sort the C*N Gaussians by (cam, depth) once, emit intersections in that
+ * order and stable-radix-sort only the cam|tile bits.  Both produce bit-identical outputs. */
+enum { CHS_SORT_KEY64 = 0, CHS_SORT_DEPTH_PRESORT = 1 };
+
+typedef struct chs_config {
+  int32_t n_gauss;            /* N */
+  int32_t n_frames;           /* B (frames handled by this call / this GPU) */
+  int32_t n_virtual;          /* n virtual poses per frame */
+  int32_t width, height;
+  int32_t tile_size;          /* must be 16 */
+  float near_plane, far_plane, eps2d;
+  int32_t crf_kind;           /* CHS_CRF_* */
+  int32_t crf_hidden;         /* Hd of the MLP CRF (params are [3, 3*Hd+1]); <= 128 */
+  int32_t crf_before_average; /* 0 = F(dt * mean_k H_k) (default, D0); 1 = mean_k F(dt * H_k) */
+  int32_t ks_per_camera;      /* 0: Ks is [B,3,3]; 1: Ks is [C,3,3] */
+  int32_t sort_mode;          /* CHS_SORT_* */
+  float background[3];
+  int32_t reserved[4];
+} chs_config;
+
+typedef struct chs_workspace_sizes {
+  uint64_t bin_count_bytes; /* scratch for chs_bin_count */
+  uint64_t bin_sort_bytes;  /* scratch for chs_bin_sort at the queried M */
+  uint64_t reduce_bytes;    /* fp64 accumulators for chs_crf_bwd / chs_project_bwd / chs_spline_bwd */
+} chs_workspace_sizes;
+
+CHS_API int chs_version(void);
+CHS_API const char* chs_last_error(void);
+
+/* Scratch sizes for a configuration and an intersection count M (pass 0 if not yet known:
+ * bin_sort_bytes is then 0). n_knots is only used for reduce_bytes. */
+CHS_API int chs_workspace_query(const chs_config* cfg, int64_t n_isect, int32_t n_knots, chs_workspace_sizes* out);
+
+/* ---- K0: SE(3) spline -> virtual camera poses (fp64 arithmetic on device) ---------------------
+ * knots [K,7] camera-to-world (t, q wxyz); sample times t_i + (k/(n-1) - 1/2) dt_i.
+ * viewmats [C,4,4] world-to-camera, row major. */
+CHS_API int chs_spline_fwd(int32_t kind, const float* knots, int32_t n_knots, double knot_t0, double knot_dt,
+                   const float* frame_times, const float* exposure, int32_t n_frames, int32_t n_virtual,
+                   float* viewmats, void* stream);
+/* v_viewmats [C,4,4] -> v_knots [K,7], v_frame_times [B], v_exposure [B] (window path only; the
+ * brightness path comes from chs_crf_bwd).  Outputs are overwritten.  workspace: reduce_bytes. */
+CHS_API int chs_spline_bwd(int32_t kind, const float* knots, int32_t n_knots, double knot_t0, double knot_dt,
+                   const float* frame_times, const float* exposure, int32_t n_frames, int32_t n_virtual,
+                   const float* v_viewmats, float* v_knots, float* v_frame_times, float* v_exposure,
+                   void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ---- K1: projection + EWA ------------------------------------------------------------------------
+ * Outputs, all [C,N] (camera major):
+ *   geom          float4 (mean2d.x, mean2d.y, conic.A, conic.B)
+ *   conic_c       float  conic.C
+ *   depths        float  camera-space z
+ *   radii         int32  ceil(3 sqrt(lambda_max)), 0 = culled
+ *   tiles_touched int32
+ *   rgbo [N]      float4 (r, g, b, opacity) — the per-Gaussian record the blend kernels gather */
+CHS_API int chs_project_fwd(const chs_config* cfg, const float* means, const float* quats, const float* scales,
+                    const float* opacities, const float* colors, const float* viewmats, const float* Ks,
+                    float* geom, float* conic_c, float* depths, int32_t* radii, int32_t* tiles_touched,
+                    float* rgbo, void* stream);
+
+/* ---- K9: projection backward -------------------------------------------------------------------
+ * v_geom float4 [C,N] = (v_mx, v_my, v_A, v_B); v_cogr float4 [C,N] = (v_C, v_opacity, v_r, v_g);
+ * v_blue float [C,N] = v_b  (all written by chs_blend_bwd).
+ * grads_flat [14*N] = sections [means 3N | quats 4N | scales 3N | opacities N | colors 3N]; the one
+ * buffer that is all-reduced across GPUs.  v_viewmats [C,4,4] (last row zero).  workspace: reduce_bytes. */
+CHS_API int chs_project_bwd(const chs_config* cfg, const float* means, const float* quats, const float* scales,
+                    const float* viewmats, const float* Ks, const int32_t* radii, const float* v_geom,
+                    const float* v_cogr, const float* v_blue, float* grads_flat, float* v_viewmats,
+                    void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ---- K2: intersection count --------------------------------------------------------------------
+ * isect_offsets uint32 [C*N]: exclusive scan of tiles_touched in emission order.
+ * order int32 [C*N]: emission order (identity for CHS_SORT_KEY64; the (cam, depth)-sorted
+ * permutation of c*N+g for CHS_SORT_DEPTH_PRESORT).
+ * n_isect_dev: device int64 receiving M.  If n_isect_host != NULL the call synchronises the stream
+ * and also stores M there (the one host sync of a step, needed to size the M-length buffers). */
+CHS_API int chs_bin_count(const chs_config* cfg, const int32_t* tiles_touched, const float* depths,
+                  uint32_t* isect_offsets, int32_t* order, int64_t* n_isect_dev, int64_t* n_isect_host,
+                  void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ---- K3 + K4 + K5: key generation, radix sort, per-(camera, tile) offsets ------------------------
+ * keys_sorted uint64 [M] (may be NULL with CHS_SORT_DEPTH_PRESORT — only tests need it),
+ * vals_sorted int32 [M] (= c*N + g), tile_offsets uint32 [C*tiles + 1] (last entry = M).
+ * Bit-exact contract: identical to a stable ascending sort of
+ *   key = cam << (32 + tile_bits) | tile << 32 | float_as_uint(depth). */
+CHS_API int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii,
+                 const float* depths, const uint32_t* isect_offsets, const int32_t* order,
+                 uint64_t* keys_sorted, int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace,
+                 uint64_t workspace_bytes, void* stream);
+
+/* ---- K6: blend forward + formation epilogue -----------------------------------------------------
+ * Per (frame, tile): for each virtual pose, front-to-back alpha blending in linear HDR; then
+ * mean over poses, x exposure, CRF.  Outputs: ldr [B,H,W,3], alpha [B,H,W], hdr_mean [B,H,W,3]
+ * (saved for the backward / return_hdr), final_T [C,H,W], last_id [C,H,W] int32 (1-based index
+ * into the pixel's tile list of the last accumulated Gaussian, 0 = none). */
+CHS_API int chs_blend_fwd(const chs_config* cfg, const float* geom, const float* conic_c, const float* rgbo,
+                  const int32_t* vals_sorted, const uint32_t* tile_offsets, const float* exposure,
+                  const float* crf_params, float* ldr, float* alpha, float* hdr_mean, float* final_T,
+                  int32_t* last_id, void* stream);
+
+/* ---- K7: CRF / exposure backward -----------------------------------------------------------------
+ * v_ldr [B,H,W,3] -> v_hdr [B,H,W,3] (gradient w.r.t. each pose's HDR image, = dt_i/n * v_X),
+ * v_crf_params [3, 3*Hd+1], v_exposure [B] (brightness path).  Outputs overwritten.
+ * workspace: reduce_bytes. */
+CHS_API int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const float* exposure, const float* crf_params,
+                const float* v_ldr, float* v_hdr, float* v_crf_params, float* v_exposure, void* workspace,
+                uint64_t workspace_bytes, void* stream);
+
+/* ---- K8: blend backward ------------------------------------------------------------------------
+ * v_alpha [B,H,W] may be NULL.  v_geom / v_cogr / v_blue are zeroed by the call, then accumulated
+ * with warp-reduced vector atomics (see chs_project_bwd for their layout). */
+CHS_API int chs_blend_bwd(const chs_config* cfg, const float* geom, const float* conic_c, const float* rgbo,
+                  const int32_t* vals_sorted, const uint32_t* tile_offsets, const float* final_T,
+                  const int32_t* last_id, const float* v_hdr, const float* v_alpha, float* v_geom,
+                  float* v_cogr, float* v_blue, void* stream);
+
+/* ---- test / verification helper: unpack 64-bit keys in emission order (CHS_SORT_KEY64 layout) ---- */
+CHS_API int chs_bin_emit_keys(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii,
+                      const float* depths, const uint32_t* isect_offsets, const int32_t* order,
+                      uint64_t* keys, int32_t* vals, void* stream);
+
+/* ---- K10: gradient all-reduce over NCCL (one process per GPU) ----------------------------------
+ * The NCCL library already loaded in the process is used (dlopen of libnccl.so.2).  unique_id is
+ * the 128-byte ncclUniqueId created by rank 0 with chs_comm_unique_id() and distributed by the
+ * caller. */
+typedef struct chs_comm chs_comm;
+CHS_API int chs_comm_unique_id(void* unique_id_host_128);
+CHS_API int chs_comm_init(const void* unique_id_host_128, int32_t rank, int32_t world, chs_comm** out);
+CHS_API int chs_allreduce_grads(chs_comm* comm, float* buf, uint64_t count, void* stream);
+CHS_API int chs_comm_destroy(chs_comm* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHS_H_ */

@@ -1,0 +1,216 @@
+// hostsim.cpp — TEST-ONLY host harness around casualhdrsplat_b200/csrc/chs_math.cuh and
+// chs_spline.cuh.  It compiles the exact per-element arithmetic the CUDA kernels use with g++ and
+// runs it in plain serial loops so tests/test_hostsim_*.py can compare it with the float64 oracle
+// in this GPU-less container.  It is NOT part of the product: libchs.so never contains or calls
+// this code, and casualhdrsplat_b200 has no CPU path.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../casualhdrsplat_b200/csrc/chs_math.cuh"
+#include "../../casualhdrsplat_b200/csrc/chs_spline.cuh"
+
+template <class T> static void load_cam(const T* viewmats, const T* Ks, int c, ChsCam<T>& cam) {
+  const T* v = viewmats + c * 16;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) cam.R[i * 3 + j] = v[i * 4 + j];
+    cam.t[i] = v[i * 4 + 3];
+  }
+  const T* K = Ks + c * 9;
+  cam.fx = K[0]; cam.fy = K[4]; cam.cx = K[2]; cam.cy = K[5];
+}
+
+template <class T>
+static void project_fwd_impl(int N, int C, int W, int H, T near_p, T far_p, T eps2d, const T* means, const T* quats, const T* scales,
+                             const T* viewmats, const T* Ks, T* means2d, T* depths, T* conics, int32_t* radii, int32_t* touched) {
+  int tile_w = (W + 15) / 16, tile_h = (H + 15) / 16;
+  for (int g = 0; g < N; ++g) {
+    T S[6];
+    chs_cov3d(quats + g * 4, scales + g * 3, S);
+    for (int c = 0; c < C; ++c) {
+      ChsCam<T> cam;
+      load_cam(viewmats, Ks, c, cam);
+      ChsProj<T> pr;
+      int r = chs_project_fwd(means + g * 3, S, cam, (T)W, (T)H, near_p, far_p, eps2d, pr);
+      size_t o = (size_t)c * N + g;
+      means2d[o * 2] = pr.mx; means2d[o * 2 + 1] = pr.my;
+      depths[o] = pr.depth;
+      conics[o * 3] = pr.ca; conics[o * 3 + 1] = pr.cb; conics[o * 3 + 2] = pr.cc;
+      radii[o] = r;
+      int t = 0;
+      if (r > 0) {
+        ChsTileRect tr = chs_tile_bounds((float)pr.mx, (float)pr.my, r, tile_w, tile_h);
+        t = (tr.x1 - tr.x0) * (tr.y1 - tr.y0);
+      }
+      touched[o] = t;
+    }
+  }
+}
+
+template <class T>
+static void project_bwd_impl(int N, int C, int W, int H, T eps2d, const T* means, const T* quats, const T* scales, const T* viewmats,
+                             const T* Ks, const int32_t* radii, const T* v_means2d, const T* v_conics, T* v_means, T* v_quats,
+                             T* v_scales, T* v_viewmats /* [C,12]: R(9), t(3) */) {
+  std::memset(v_viewmats, 0, sizeof(T) * C * 12);
+  for (int g = 0; g < N; ++g) {
+    T S[6];
+    chs_cov3d(quats + g * 4, scales + g * 3, S);
+    T v_mu[3] = {0, 0, 0}, G[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < C; ++c) {
+      size_t o = (size_t)c * N + g;
+      if (radii[o] <= 0) continue;
+      ChsCam<T> cam;
+      load_cam(viewmats, Ks, c, cam);
+      chs_project_bwd(means + g * 3, S, cam, (T)W, (T)H, eps2d, v_means2d[o * 2], v_means2d[o * 2 + 1], v_conics[o * 3],
+                      v_conics[o * 3 + 1], v_conics[o * 3 + 2], v_mu, G, v_viewmats + c * 12, v_viewmats + c * 12 + 9);
+    }
+    T vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0};
+    chs_cov3d_bwd(quats + g * 4, scales + g * 3, G, vq, vs);
+    for (int k = 0; k < 3; ++k) { v_means[g * 3 + k] = v_mu[k]; v_scales[g * 3 + k] = vs[k]; }
+    for (int k = 0; k < 4; ++k) v_quats[g * 4 + k] = vq[k];
+  }
+}
+
+// One tile list blended over a set of pixels, forward then backward, the way the kernels walk it.
+// splat params per list entry: mean2d (2), conic (3), opacity, rgb (3) = 9 numbers.
+template <class T>
+static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, const T* bg, const T* v_hdr, const T* v_alpha,
+                       T* out_hdr, T* out_alpha, int32_t* out_last, T* v_params) {
+  std::vector<ChsSplat<T>> sp(n_list);
+  for (int j = 0; j < n_list; ++j) {
+    const T* p = params + j * 9;
+    chs_make_splat(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], sp[j]);
+  }
+  const T thr = (T)log2(1.0 / 255.0);
+  std::memset(v_params, 0, sizeof(T) * n_list * 9);
+  for (int p = 0; p < n_pix; ++p) {
+    T px = pix_xy[p * 2], py = pix_xy[p * 2 + 1];
+    T Tr = 1, acc[3] = {0, 0, 0};
+    int last = 0;
+    for (int j = 0; j < n_list; ++j) {
+      // sub-tile cull, applied per pixel here: must never drop a contributing pair
+      bool reach = (sp[j].mx + sp[j].ex >= px) && (sp[j].mx - sp[j].ex <= px) && (sp[j].my + sp[j].ey >= py) && (sp[j].my - sp[j].ey <= py);
+      T dx, dy;
+      T power = chs_pair_power(sp[j], px, py, dx, dy);
+      if (!(power >= thr)) continue;
+      if (!reach) { out_last[p] = -1000000; }  // flag: the cull would have dropped a live pair
+      T alpha = chs_min(ChsK<T>::alpha_max, chs_exp2_fast(power));
+      T Tn = Tr * (1 - alpha);
+      if (Tn <= ChsK<T>::t_stop) break;
+      T w = alpha * Tr;
+      acc[0] += w * sp[j].r; acc[1] += w * sp[j].g; acc[2] += w * sp[j].b;
+      Tr = Tn;
+      last = j + 1;
+    }
+    for (int ch = 0; ch < 3; ++ch) out_hdr[p * 3 + ch] = acc[ch] + Tr * bg[ch];
+    out_alpha[p] = 1 - Tr;
+    if (out_last[p] != -1000000) out_last[p] = last;
+    // backward
+    const T vh[3] = {v_hdr[p * 3], v_hdr[p * 3 + 1], v_hdr[p * 3 + 2]};
+    T va_t = Tr * (v_alpha[p] - (bg[0] * vh[0] + bg[1] * vh[1] + bg[2] * vh[2]));
+    T buf[3] = {0, 0, 0};
+    for (int j = last - 1; j >= 0; --j) {
+      T dx, dy;
+      T power = chs_pair_power(sp[j], px, py, dx, dy);
+      if (!(power >= thr)) continue;
+      T au = chs_exp2_fast(power);
+      T g[9];
+      chs_pair_bwd(sp[j], dx, dy, au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, g);
+      // g = [v_mx, v_my, v_A, v_B, v_C, v_o, v_r, v_g, v_b] -> params order (mx,my,A,B,C,o,r,g,b)
+      for (int k = 0; k < 9; ++k) v_params[j * 9 + k] += g[k];
+    }
+  }
+}
+
+extern "C" {
+
+void hs_project_fwd_f64(int N, int C, int W, int H, double near_p, double far_p, double eps2d, const double* means, const double* quats,
+                        const double* scales, const double* viewmats, const double* Ks, double* means2d, double* depths, double* conics,
+                        int32_t* radii, int32_t* touched) {
+  project_fwd_impl<double>(N, C, W, H, near_p, far_p, eps2d, means, quats, scales, viewmats, Ks, means2d, depths, conics, radii, touched);
+}
+void hs_project_fwd_f32(int N, int C, int W, int H, float near_p, float far_p, float eps2d, const float* means, const float* quats,
+                        const float* scales, const float* viewmats, const float* Ks, float* means2d, float* depths, float* conics,
+                        int32_t* radii, int32_t* touched) {
+  project_fwd_impl<float>(N, C, W, H, near_p, far_p, eps2d, means, quats, scales, viewmats, Ks, means2d, depths, conics, radii, touched);
+}
+void hs_project_bwd_f64(int N, int C, int W, int H, double eps2d, const double* means, const double* quats, const double* scales,
+                        const double* viewmats, const double* Ks, const int32_t* radii, const double* v_means2d, const double* v_conics,
+                        double* v_means, double* v_quats, double* v_scales, double* v_viewmats) {
+  project_bwd_impl<double>(N, C, W, H, eps2d, means, quats, scales, viewmats, Ks, radii, v_means2d, v_conics, v_means, v_quats, v_scales,
+                           v_viewmats);
+}
+void hs_project_bwd_f32(int N, int C, int W, int H, float eps2d, const float* means, const float* quats, const float* scales,
+                        const float* viewmats, const float* Ks, const int32_t* radii, const float* v_means2d, const float* v_conics,
+                        float* v_means, float* v_quats, float* v_scales, float* v_viewmats) {
+  project_bwd_impl<float>(N, C, W, H, eps2d, means, quats, scales, viewmats, Ks, radii, v_means2d, v_conics, v_means, v_quats, v_scales,
+                          v_viewmats);
+}
+void hs_blend_f64(int n_list, const double* params, int n_pix, const double* pix_xy, const double* bg, const double* v_hdr,
+                  const double* v_alpha, double* out_hdr, double* out_alpha, int32_t* out_last, double* v_params) {
+  blend_impl<double>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params);
+}
+void hs_blend_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
+                  const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
+  blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params);
+}
+void hs_tile_bounds(int n, const float* mx, const float* my, const int32_t* radius, int tile_w, int tile_h, int32_t* rect) {
+  for (int i = 0; i < n; ++i) {
+    ChsTileRect r = chs_tile_bounds(mx[i], my[i], radius[i], tile_w, tile_h);
+    rect[i * 4] = r.x0; rect[i * 4 + 1] = r.y0; rect[i * 4 + 2] = r.x1; rect[i * 4 + 3] = r.y1;
+  }
+}
+// CRF MLP: y and dy/dX per value, parameter gradient accumulated with weights v_y
+void hs_crf_f64(int n, const double* X, const double* params, int hd, const double* v_y, double* y, double* dydx, double* v_params) {
+  std::memset(v_params, 0, sizeof(double) * (3 * hd + 1));
+  for (int i = 0; i < n; ++i) {
+    y[i] = chs_crf_mlp_fwd(X[i], params, hd);
+    dydx[i] = chs_crf_mlp_bwd(X[i], params, hd, v_y[i], v_params);
+  }
+}
+// spline: viewmats [C,16] fp64 and the backward contraction, mirroring chs_spline.cu
+void hs_spline_fwd(int kind, const float* knots, int n_knots, double t0, double dt, const float* frame_times, const float* exposure,
+                   int B, int n, double* viewmats) {
+  for (int c = 0; c < B * n; ++c) {
+    int i = c / n, kk = c % n;
+    double w = chs_sample_weight(kk, n);
+    double time = (double)frame_times[i] + w * (double)exposure[i];
+    int s; double u;
+    chs_spline_segment(kind, n_knots, t0, dt, time, s, u);
+    int first = kind == CHS_SPLINE_LINEAR ? s : s - 1, nk = kind == CHS_SPLINE_LINEAR ? 2 : 4;
+    double k[4][7];
+    for (int j = 0; j < nk; ++j) for (int e = 0; e < 7; ++e) k[j][e] = knots[(first + j) * 7 + e];
+    double vm[12];
+    chs_spline_viewmat<double>(kind, k, u, vm);
+    for (int e = 0; e < 12; ++e) viewmats[c * 16 + e] = vm[e];
+    viewmats[c * 16 + 12] = viewmats[c * 16 + 13] = viewmats[c * 16 + 14] = 0; viewmats[c * 16 + 15] = 1;
+  }
+}
+void hs_spline_bwd(int kind, const float* knots, int n_knots, double t0, double dt, const float* frame_times, const float* exposure,
+                   int B, int n, const double* v_viewmats, double* v_knots, double* v_ft, double* v_ex) {
+  std::memset(v_knots, 0, sizeof(double) * n_knots * 7);
+  std::memset(v_ft, 0, sizeof(double) * B);
+  std::memset(v_ex, 0, sizeof(double) * B);
+  int nk = kind == CHS_SPLINE_LINEAR ? 2 : 4, n_in = nk * 7 + 1;
+  for (int c = 0; c < B * n; ++c) {
+    int i = c / n, kk = c % n;
+    double w = chs_sample_weight(kk, n);
+    double time = (double)frame_times[i] + w * (double)exposure[i];
+    int s; double u;
+    chs_spline_segment(kind, n_knots, t0, dt, time, s, u);
+    int first = kind == CHS_SPLINE_LINEAR ? s : s - 1;
+    for (int in = 0; in < n_in; ++in) {
+      ChsDual k[4][7];
+      for (int j = 0; j < nk; ++j) for (int e = 0; e < 7; ++e) k[j][e] = ChsDual(knots[(first + j) * 7 + e], (j * 7 + e == in) ? 1.0 : 0.0);
+      ChsDual ud(u, in == nk * 7 ? 1.0 : 0.0);
+      ChsDual vm[12];
+      chs_spline_viewmat<ChsDual>(kind, k, ud, vm);
+      double dot = 0;
+      for (int e = 0; e < 12; ++e) dot += v_viewmats[c * 16 + e] * vm[e].d;
+      if (in < nk * 7) v_knots[(first + in / 7) * 7 + in % 7] += dot;
+      else { v_ft[i] += dot / dt; v_ex[i] += dot / dt * w; }
+    }
+  }
+}
+}

@@ -1,0 +1,223 @@
+"""The kernels' per-element arithmetic (csrc/chs_math.cuh, chs_spline.cuh) compiled for the host by
+tests/hostsim and compared with the float64 oracle.  CPU-only; validates every hand-derived
+forward/backward formula before a GPU is involved."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from casualhdrsplat_b200.scene import make_config, make_scene
+from oracle import se3
+from tests.hostsim.loader import load
+
+torch.set_default_dtype(torch.float64)
+HS = load()
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _scene_cams(name="small", **kw):
+    sc = make_config(name, **kw)
+    vm = se3.spline_viewmats(sc.knots.double(), sc.knot_t0, sc.knot_dt, sc.frame_times.double(), sc.exposure_times.double(),
+                             sc.n_virtual, sc.spline_kind)
+    Ks = sc.Ks.double().repeat_interleave(sc.n_virtual, dim=0)
+    return sc, vm, Ks
+
+
+def _hs_project(sc, vm, Ks, dtype):
+    N, C = sc.means.shape[0], vm.shape[0]
+    np_t = np.float64 if dtype == "f64" else np.float32
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np_t))
+    m2d = np.zeros((C, N, 2), np_t); dep = np.zeros((C, N), np_t); con = np.zeros((C, N, 3), np_t)
+    rad = np.zeros((C, N), np.int32); tou = np.zeros((C, N), np.int32)
+    fn = getattr(HS, f"hs_project_fwd_{dtype}")
+    ct = ctypes.c_double if dtype == "f64" else ctypes.c_float
+    a = [arr(sc.means), arr(sc.quats), arr(sc.scales), arr(vm), arr(Ks)]
+    fn(N, C, sc.width, sc.height, ct(0.01), ct(1e10), ct(0.3), *[_p(x) for x in a], _p(m2d), _p(dep), _p(con), _p(rad), _p(tou))
+    return m2d, dep, con, rad, tou
+
+
+def test_project_fwd_f64_matches_oracle():
+    sc, vm, Ks = _scene_cams()
+    m2d, dep, con, rad, tou = _hs_project(sc, vm, Ks, "f64")
+    ref = oracle.project(sc.means, sc.quats, sc.scales, vm, Ks, sc.width, sc.height)
+    vis = ref["radii"].numpy() > 0
+    assert vis.sum() > 1000
+    assert np.array_equal(rad, ref["radii"].numpy())
+    assert np.allclose(m2d[vis], ref["means2d"].numpy()[vis], rtol=1e-11, atol=1e-9)
+    assert np.allclose(con[vis], ref["conics"].numpy()[vis], rtol=1e-9, atol=1e-12)
+    assert np.allclose(dep, ref["depths"].numpy(), rtol=1e-12)
+    b = oracle.bin_tiles(torch.from_numpy(m2d).float(), torch.from_numpy(rad), torch.from_numpy(dep).float(), sc.width, sc.height)
+    assert np.array_equal(tou, b["tiles_touched"].numpy())
+
+
+def test_project_fwd_f32_close_and_binning_bit_exact():
+    sc, vm, Ks = _scene_cams()
+    m2d, dep, con, rad, tou = _hs_project(sc, vm.float(), Ks.float(), "f32")
+    ref = oracle.project(sc.means, sc.quats, sc.scales, vm.float(), Ks.float(), sc.width, sc.height)
+    rr = ref["radii"].numpy()
+    both = (rad > 0) & (rr > 0)
+    assert (rad != rr).mean() < 1e-3  # ceil() flips between fp32 and fp64 are a counted, tiny set
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(m2d[both], ref["means2d"].numpy()[both]) < 1e-6
+    assert rel(con[both], ref["conics"].numpy()[both]) < 1e-4
+    # A.4 contract: tiles_touched is an integer function of the fp32 outputs
+    b = oracle.bin_tiles(torch.from_numpy(m2d), torch.from_numpy(rad), torch.from_numpy(dep), sc.width, sc.height)
+    assert np.array_equal(tou, b["tiles_touched"].numpy())
+
+
+def test_tile_bounds_bit_exact_random():
+    g = torch.Generator().manual_seed(0)
+    n = 20000
+    mx = ((torch.rand(n, generator=g) * 2400 - 200)).float()
+    my = ((torch.rand(n, generator=g) * 1500 - 200)).float()
+    mx[:100] = torch.arange(100).float() * 16.0  # exact tile boundaries
+    r = torch.randint(0, 300, (n,), generator=g, dtype=torch.int32)
+    rect = np.zeros((n, 4), np.int32)
+    HS.hs_tile_bounds(n, _p(mx.numpy()), _p(my.numpy()), _p(r.numpy()), 120, 68, _p(rect))
+    x0, y0, x1, y1, _ = oracle.tile_bounds(torch.stack([mx, my], -1), torch.clamp(r, min=1), 1920, 1080)
+    x0r, y0r, x1r, y1r, _ = oracle.tile_bounds(torch.stack([mx, my], -1), r, 1920, 1080)
+    assert np.array_equal(rect[:, 0], x0r.numpy()) and np.array_equal(rect[:, 2], x1r.numpy())
+    assert np.array_equal(rect[:, 1], y0r.numpy()) and np.array_equal(rect[:, 3], y1r.numpy())
+
+
+def test_project_bwd_f64_matches_autograd():
+    sc, vm, Ks = _scene_cams("tiny")
+    N, C = sc.means.shape[0], vm.shape[0]
+    leaves = [sc.means.double().requires_grad_(True), sc.quats.double().mul(1.3).requires_grad_(True),
+              sc.scales.double().requires_grad_(True), vm.clone().requires_grad_(True)]
+    ref = oracle.project(leaves[0], leaves[1], leaves[2], leaves[3], Ks, sc.width, sc.height)
+    g = torch.Generator().manual_seed(1)
+    vis = (ref["radii"] > 0)
+    vm2 = torch.randn(C, N, 2, generator=g) * vis[..., None]
+    vc = torch.randn(C, N, 3, generator=g) * vis[..., None]
+    loss = (ref["means2d"] * vm2).sum() + (ref["conics"] * vc).sum()
+    gm, gq, gs, gv = torch.autograd.grad(loss, leaves)
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np.float64))
+    o_m = np.zeros((N, 3)); o_q = np.zeros((N, 4)); o_s = np.zeros((N, 3)); o_v = np.zeros((C, 12))
+    a = [arr(leaves[0]), arr(leaves[1]), arr(leaves[2]), arr(vm), arr(Ks)]
+    rad = np.ascontiguousarray(ref["radii"].numpy())
+    HS.hs_project_bwd_f64(N, C, sc.width, sc.height, ctypes.c_double(0.3), *[_p(x) for x in a], _p(rad), _p(arr(vm2)), _p(arr(vc)),
+                          _p(o_m), _p(o_q), _p(o_s), _p(o_v))
+    assert np.allclose(o_m, gm.numpy(), rtol=1e-8, atol=1e-9 * np.abs(gm.numpy()).max())
+    assert np.allclose(o_q, gq.numpy(), rtol=1e-8, atol=1e-9 * np.abs(gq.numpy()).max())
+    assert np.allclose(o_s, gs.numpy(), rtol=1e-8, atol=1e-9 * np.abs(gs.numpy()).max())
+    gvR = gv[:, :3, :3].reshape(C, 9).numpy()
+    gvt = gv[:, :3, 3].numpy()
+    assert np.allclose(o_v[:, :9], gvR, rtol=1e-8, atol=1e-9 * np.abs(gvR).max())
+    assert np.allclose(o_v[:, 9:], gvt, rtol=1e-8, atol=1e-9 * np.abs(gvt).max())
+
+
+def test_project_bwd_clamped_jacobian_branch():
+    # Gaussians far off-axis exercise the frustum clamp of the EWA Jacobian (x~ = z * lim)
+    W = H = 64
+    K = torch.tensor([[30.0, 0, 32], [0, 30.0, 32], [0, 0, 1]])[None]
+    vm = torch.eye(4)[None].clone()
+    means = torch.tensor([[9.0, 0.2, 2.0], [-0.3, -8.0, 2.5], [0.1, 0.1, 3.0]])
+    quats = torch.tensor([[1.0, 0.1, 0.2, 0.3], [0.5, 0.5, -0.5, 0.1], [1.0, 0, 0, 0]])
+    scales = torch.tensor([[3.0, 2.5, 2.0], [2.0, 3.0, 2.2], [0.3, 0.2, 0.1]])
+    leaves = [means.clone().requires_grad_(True), quats.clone().requires_grad_(True), scales.clone().requires_grad_(True),
+              vm.clone().requires_grad_(True)]
+    ref = oracle.project(*leaves, K, W, H)
+    assert (ref["radii"] > 0).all()
+    g = torch.Generator().manual_seed(2)
+    vm2, vc = torch.randn(1, 3, 2, generator=g), torch.randn(1, 3, 3, generator=g)
+    gm, gq, gs, gv = torch.autograd.grad((ref["means2d"] * vm2).sum() + (ref["conics"] * vc).sum(), leaves)
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np.float64))
+    o_m = np.zeros((3, 3)); o_q = np.zeros((3, 4)); o_s = np.zeros((3, 3)); o_v = np.zeros((1, 12))
+    HS.hs_project_bwd_f64(3, 1, W, H, ctypes.c_double(0.3), _p(arr(means)), _p(arr(quats)), _p(arr(scales)), _p(arr(vm)), _p(arr(K)),
+                          _p(np.ascontiguousarray(ref["radii"].numpy())), _p(arr(vm2)), _p(arr(vc)), _p(o_m), _p(o_q), _p(o_s), _p(o_v))
+    assert np.allclose(o_m, gm.numpy(), rtol=1e-9) and np.allclose(o_q, gq.numpy(), rtol=1e-8, atol=1e-12)
+    assert np.allclose(o_s, gs.numpy(), rtol=1e-9)
+    assert np.allclose(o_v[:, :9], gv[:, :3, :3].reshape(1, 9).numpy(), rtol=1e-9)
+    assert np.allclose(o_v[:, 9:], gv[:, :3, 3].numpy(), rtol=1e-9)
+
+
+def _tile_case(seed=0, n_list=60, bg=(0.1, 0.3, 0.2)):
+    g = torch.Generator().manual_seed(seed)
+    m = torch.rand(n_list, 2, generator=g) * 24 - 4
+    L = torch.randn(n_list, 2, 2, generator=g) * 0.35 + torch.eye(2) * 0.5
+    con = L @ L.transpose(1, 2) * 0.2 + 0.01 * torch.eye(2)
+    conic = torch.stack([con[:, 0, 0], con[:, 0, 1], con[:, 1, 1]], 1)
+    o = torch.rand(n_list, generator=g) * 0.95 + 0.02
+    o[::7] = 0.9995  # exercise the 0.999 clamp
+    col = torch.exp(torch.randn(n_list, 3, generator=g))
+    yy, xx = torch.meshgrid(torch.arange(16.0), torch.arange(16.0), indexing="ij")
+    pix = torch.stack([xx.reshape(-1) + 0.5, yy.reshape(-1) + 0.5], 1)
+    return m, conic, o, col, pix, torch.tensor(bg)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_blend_pair_math_matches_oracle(dtype):
+    m, conic, o, col, pix, bg = _tile_case()
+    n_list, n_pix = m.shape[0], pix.shape[0]
+    leaves = [t.clone().requires_grad_(True) for t in (m, conic, o, col)]
+    vals = torch.arange(n_list, dtype=torch.int32)
+    to = torch.tensor([0, n_list])
+    hdr, alpha, last = oracle.blend(leaves[0][None], leaves[1][None], leaves[2], leaves[3], vals, to, n_list, 16, 16, background=bg)
+    g = torch.Generator().manual_seed(3)
+    vh, va = torch.randn(16, 16, 3, generator=g), torch.randn(16, 16, generator=g)
+    grads = torch.autograd.grad((hdr[0] * vh).sum() + (alpha[0] * va).sum(), leaves)
+    np_t = np.float64 if dtype == "f64" else np.float32
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np_t))
+    params = arr(torch.cat([m, conic, o[:, None], col], 1))
+    o_h = np.zeros((n_pix, 3), np_t); o_a = np.zeros(n_pix, np_t); o_l = np.zeros(n_pix, np.int32); o_v = np.zeros((n_list, 9), np_t)
+    getattr(HS, f"hs_blend_{dtype}")(n_list, _p(params), n_pix, _p(arr(pix)), _p(arr(bg)), _p(arr(vh.reshape(-1, 3))),
+                                     _p(arr(va.reshape(-1))), _p(o_h), _p(o_a), _p(o_l), _p(o_v))
+    assert (o_l > -1000000).all(), "sub-tile cull dropped a contributing pair"
+    tol = 1e-11 if dtype == "f64" else 2e-5
+    rel = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+    assert rel(o_h, hdr[0].reshape(-1, 3).detach().numpy()) < tol
+    assert rel(o_a, alpha[0].reshape(-1).detach().numpy()) < tol
+    want_last = (last[0].reshape(-1) + 1).numpy()
+    assert (o_l != want_last).mean() <= (0 if dtype == "f64" else 0.01)
+    ref = torch.cat([grads[0], grads[1], grads[2][:, None], grads[3]], 1).numpy()
+    gtol = 1e-9 if dtype == "f64" else 1e-3
+    for k in range(9):
+        assert rel(o_v[:, k], ref[:, k]) < gtol, (k, rel(o_v[:, k], ref[:, k]))
+
+
+def test_crf_mlp_fwd_bwd():
+    from casualhdrsplat_b200.scene import gamma_crf_params
+    P = gamma_crf_params(32).double()
+    g = torch.Generator().manual_seed(4)
+    X = torch.exp(torch.randn(500, generator=g) * 2 - 3)
+    for ch in range(3):
+        p = P[ch].clone().requires_grad_(True)
+        Xl = X.clone().requires_grad_(True)
+        y = oracle.crf_apply(Xl[:, None].expand(-1, 3), oracle.CRF_MLP, torch.stack([p, p, p]))[:, 0]
+        vy = torch.randn(500, generator=g)
+        gx, gp = torch.autograd.grad((y * vy).sum(), [Xl, p])
+        o_y = np.zeros(500); o_d = np.zeros(500); o_p = np.zeros(3 * 32 + 1)
+        HS.hs_crf_f64(500, _p(X.numpy()), _p(np.ascontiguousarray(p.detach().numpy())), 32, _p(vy.numpy()), _p(o_y), _p(o_d), _p(o_p))
+        assert np.allclose(o_y, y.detach().numpy(), rtol=1e-12)
+        assert np.allclose(o_d * vy.numpy(), gx.numpy(), rtol=1e-10, atol=1e-14)
+        assert np.allclose(o_p, gp.numpy(), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,name", [(se3.SPLINE_LINEAR, "c2"), (se3.SPLINE_CUBIC, "tiny")])
+def test_spline_fwd_bwd_matches_oracle(kind, name):
+    sc = make_config(name, n_gauss=4) if name == "c2" else make_config(name)
+    B, n, K = sc.n_frames, sc.n_virtual, sc.knots.shape[0]
+    knots = sc.knots.double().requires_grad_(True)
+    ft = sc.frame_times.double().requires_grad_(True)
+    ex = sc.exposure_times.double().requires_grad_(True)
+    vm = se3.spline_viewmats(knots, sc.knot_t0, sc.knot_dt, ft, ex, n, kind)
+    out = np.zeros((B * n, 16))
+    f32 = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np.float32))
+    args = (kind, _p(f32(sc.knots)), K, ctypes.c_double(sc.knot_t0), ctypes.c_double(sc.knot_dt), _p(f32(sc.frame_times)),
+            _p(f32(sc.exposure_times)), B, n)
+    HS.hs_spline_fwd(*args, _p(out))
+    assert np.allclose(out.reshape(-1, 4, 4), vm.detach().numpy(), rtol=0, atol=1e-12)
+    g = torch.Generator().manual_seed(5)
+    vv = torch.randn(B * n, 4, 4, generator=g)
+    gk, gf, ge = torch.autograd.grad((vm * vv).sum(), [knots, ft, ex])
+    o_k = np.zeros((K, 7)); o_f = np.zeros(B); o_e = np.zeros(B)
+    HS.hs_spline_bwd(*args, _p(np.ascontiguousarray(vv.numpy())), _p(o_k), _p(o_f), _p(o_e))
+    assert np.allclose(o_k, gk.numpy(), rtol=1e-8, atol=1e-9 * np.abs(gk.numpy()).max())
+    assert np.allclose(o_f, gf.numpy(), rtol=1e-8, atol=1e-12)
+    assert np.allclose(o_e, ge.numpy(), rtol=1e-8, atol=1e-12)

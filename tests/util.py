@@ -1,0 +1,71 @@
+"""Shared helpers for the parity tests: run the oracle / the CUDA path on a Scene, error norms."""
+import torch
+
+import oracle
+
+LEAF_NAMES = ["means", "quats", "scales", "opacities", "colors", "knots", "exposure_times", "frame_times", "crf_params"]
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    """||a - b||_2 / max(||b||_2, 1e-30) over the whole tensor, b = oracle."""
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, **kw):
+    """float64 oracle on the scene's fp32 inputs (upcast). Returns (ldr, alpha, meta, grads dict)."""
+    leaves = {}
+    for k in LEAF_NAMES:
+        v = getattr(sc, k)
+        if v is None:
+            continue
+        leaves[k] = v.detach().cpu().double().requires_grad_(with_grad)
+    sp = dict(knots=leaves["knots"], knot_t0=sc.knot_t0, knot_dt=sc.knot_dt, frame_times=leaves["frame_times"], kind=sc.spline_kind)
+    ldr, alpha, meta = oracle.rasterize(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"],
+                                        None, sc.Ks.cpu(), sc.width, sc.height, leaves["exposure_times"], sc.n_virtual, sc.crf_kind,
+                                        leaves.get("crf_params"), spline=sp, projection_override=projection_override, **kw)
+    grads = {}
+    if with_grad:
+        loss = (ldr * sc.v_ldr.cpu().double()).sum()
+        if v_alpha is not None:
+            loss = loss + (alpha * v_alpha.cpu().double()).sum()
+        names = [k for k in leaves]
+        gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+        grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, gs)}
+    return ldr.detach(), alpha.detach(), meta, grads
+
+
+def cuda_run(sc, with_grad=True, v_alpha=None, sort_mode="presort", debug_keys=False, **kw):
+    """The product path on cuda:0. Returns (ldr, alpha, meta, grads dict)."""
+    from casualhdrsplat_b200 import rasterize
+
+    dev = torch.device("cuda:0")
+    leaves = {}
+    for k in LEAF_NAMES:
+        v = getattr(sc, k)
+        if v is None:
+            continue
+        leaves[k] = v.detach().to(dev).requires_grad_(with_grad)
+    sp = dict(knots=leaves["knots"], knot_t0=sc.knot_t0, knot_dt=sc.knot_dt, frame_times=leaves["frame_times"], kind=sc.spline_kind)
+    ldr, alpha, meta = rasterize(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"], None,
+                                 sc.Ks.to(dev), sc.width, sc.height, leaves["exposure_times"], sc.n_virtual, sc.crf_kind,
+                                 leaves.get("crf_params"), spline=sp, sort_mode=sort_mode, debug_keys=debug_keys, **kw)
+    grads = {}
+    if with_grad:
+        loss = (ldr * sc.v_ldr.to(dev)).sum()
+        if v_alpha is not None:
+            loss = loss + (alpha * v_alpha.to(dev)).sum()
+        names = [k for k in leaves]
+        gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+        grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, gs)}
+    torch.cuda.synchronize()
+    return ldr.detach(), alpha.detach(), meta, grads
+
+
+def cuda_projection(meta):
+    """Unpack the CUDA path's fp32 projection outputs as the oracle's projection_override."""
+    st = meta["state"]
+    geom = st.geom.cpu()
+    return {"means2d": geom[..., :2].contiguous(), "conics": torch.cat([geom[..., 2:4], st.conic_c.cpu()[..., None]], -1),
+            "depths": st.depths.cpu(), "radii": st.radii.cpu()}
