@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the CasualHDRSplat formation path on B200.
+
+Metric (BASELINE.json): blurred-LDR frames/s, forward+backward, 1M Gaussians, 1920x1080, 8 virtual
+poses per frame, on 1/2/4/8 B200.  Workload = BASELINE.json configs[3] ("c4"): a global batch of 8
+frames, sharded by frames across the ranks (strong scaling: the batch is fixed), replicated
+Gaussians, one NCCL all-reduce of the flat gradient buffer per step.  At N=1 the 8 frames run as 8
+micro-batches on the one GPU (this is configs[2] repeated per frame).
+
+A step = fwd+bwd of the whole batch (K0..K9 of SURVEY.md section 3.1) + the all-reduce.
+    value : frames/s with every input resident in HBM (upstream gradient = the fixed seed-2 v_B)
+    e2e   : the same step through the public step API with HOST (pinned) buffers: H2D of all
+            parameters and of the batch's target frames, L2 loss on device, D2H of the flat gradient
+            buffer and the loss — copies inside the timed region
+    roofline : blend_bwd (K8), the dominant kernel; algorithmic bytes over its
+            CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json
+    cpu_baseline : the float64 oracle on the host cores, on a bounded sample (stated), extrapolated
+`--impl reference` times that CPU oracle alone (the reference ships no implementation to run).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "blurred-LDR frames/sec fwd+bwd (1M G, 1080p, 8 poses) @1/2/4/8 B200; % HBM roofline"
+UNIT = "frames/s"
+WORKLOAD = "c4"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD, help="scene config name (casualhdrsplat_b200.scene.CONFIGS)")
+    ap.add_argument("--sort-mode", default="presort", choices=["presort", "key64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-tiles", type=int, default=48, help="tiles in the CPU-oracle sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle sample (cpu_baseline leg and --impl reference): the only place bench.py touches oracle/
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_sample(sc, n_tiles, seed=0):
+    """Time the float64 oracle on a bounded sample of the workload and extrapolate to one frame.
+
+    Sample: virtual pose 0 of frame 0 — full projection fwd+bwd and full binning/sort for that camera,
+    blend fwd+bwd on `n_tiles` random non-empty tiles.  Extrapolation (linear in tiles and poses):
+        t_frame = n * (t_proj_fwd + t_proj_bwd + t_bin + tiles_nonempty/n_tiles * (t_blend_fwd + t_blend_bwd))
+    """
+    import torch
+
+    import oracle
+    from oracle import se3
+
+    t = {}
+    f64 = torch.float64
+    leaves = [getattr(sc, k).double().requires_grad_(True) for k in ["means", "quats", "scales", "opacities", "colors"]]
+    vm = se3.spline_viewmats(sc.knots.double(), sc.knot_t0, sc.knot_dt, sc.frame_times[:1].double(), sc.exposure_times[:1].double(),
+                             sc.n_virtual, sc.spline_kind)[:1]
+    K = sc.Ks[:1].double()
+    t0 = time.perf_counter()
+    proj = oracle.project(leaves[0], leaves[1], leaves[2], vm, K, sc.width, sc.height)
+    t["proj_fwd"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    torch.autograd.grad(proj["means2d"].sum() + proj["conics"].sum(), leaves[:3], retain_graph=True)
+    t["proj_bwd"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = oracle.bin_tiles(proj["means2d"].detach().float(), proj["radii"], proj["depths"].detach().float(), sc.width, sc.height)
+    t["bin"] = time.perf_counter() - t0
+    to = b["tile_offsets"]
+    counts = to[1:] - to[:-1]
+    nonempty = torch.nonzero(counts > 0).reshape(-1)
+    g = torch.Generator().manual_seed(seed)
+    pick = nonempty[torch.randperm(nonempty.numel(), generator=g)[:n_tiles]].tolist()
+    t0 = time.perf_counter()
+    hdr, alpha, _ = oracle.blend(proj["means2d"], proj["conics"], leaves[3], leaves[4], b["vals_sorted"], to, sc.means.shape[0],
+                                 sc.width, sc.height, tile_subset=[(0, tid) for tid in pick])
+    ldr, _, _ = oracle.formation(hdr, alpha, sc.exposure_times[:1], 1, sc.crf_kind, sc.crf_params)
+    t["blend_fwd"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    torch.autograd.grad((ldr * sc.v_ldr[:1].double()).sum(), [proj["means2d"], proj["conics"], leaves[3], leaves[4]])
+    t["blend_bwd"] = time.perf_counter() - t0
+    scale = float(nonempty.numel()) / max(len(pick), 1)
+    t_frame = sc.n_virtual * (t["proj_fwd"] + t["proj_bwd"] + t["bin"] + scale * (t["blend_fwd"] + t["blend_bwd"]))
+    return t_frame, t, int(b["n_isect"]), len(pick), int(nonempty.numel())
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own implementation of the path does not exist (the repository ships a
+    README and two figures), so this arm times the CPU oracle (kind "port") on the host cores."""
+    if rank != 0:
+        return
+    import torch
+
+    from casualhdrsplat_b200.scene import make_config
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sc = make_config(args.workload, n_frames=1)
+    times = []
+    detail = None
+    for it in range(args.warmup + args.steps):
+        t_frame, detail, m1, n_pick, n_nonempty = cpu_oracle_sample(sc, args.cpu_tiles, seed=it)
+        if it >= args.warmup:
+            times.append(t_frame)
+    t_frame = sorted(times)[len(times) // 2]
+    value = 1.0 / t_frame
+    sample = (f"per step: pose 0 of frame 0, full projection fwd+bwd + binning ({m1} isects) and blend fwd+bwd on {n_pick} of "
+              f"{n_nonempty} non-empty tiles; extrapolated linearly to {sc.n_virtual} poses x all tiles")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_frame * 8 * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: 1M Gaussians, 1920x1080, 8 virtual poses, global batch 8 frames (CPU oracle, extrapolated)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                             "phase_seconds": {k: round(v, 3) for k, v in detail.items()}},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from casualhdrsplat_b200 import _lib
+    from casualhdrsplat_b200.parallel import ChsComm, TorchComm, formation_step, shard_frames
+    from casualhdrsplat_b200.scene import make_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: casualhdrsplat_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        comm = TorchComm() if os.environ.get("CHS_COMM", "cabi") == "torch" else ChsComm(rank, world, dev)
+    L = _lib.lib()
+
+    sc = make_config(args.workload)
+    B, n, N, W, H = sc.n_frames, sc.n_virtual, sc.means.shape[0], sc.width, sc.height
+    ids = list(shard_frames(B, rank, world))
+    names = ["means", "quats", "scales", "opacities", "colors", "knots", "frame_times", "exposure_times", "Ks", "crf_params"]
+    host = {k: getattr(sc, k).contiguous().pin_memory() for k in names if getattr(sc, k) is not None}
+    P = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    v_ldr_local = {i: sc.v_ldr[i].to(dev) for i in ids}
+    spline_meta = {"knot_t0": sc.knot_t0, "knot_dt": sc.knot_dt, "kind": sc.spline_kind}
+
+    def upstream_fixed(fids, ldr):
+        return torch.stack([v_ldr_local[i] for i in fids])
+
+    stats = {"count_pairs": True}
+    flat = None
+
+    def step(upstream, st=None):
+        nonlocal flat
+        layout, flat = formation_step(P, spline_meta, W, H, n, sc.crf_kind, ids, upstream, micro_batch=1, sort_mode=args.sort_mode,
+                                      comm=comm, out=flat, stats=st)
+        return layout
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (also collects M and M_g) ----
+    for _ in range(max(args.warmup, 3)):
+        layout = step(upstream_fixed, stats)
+    stats["count_pairs"] = False
+
+    # ---- per-kernel events for the dominant kernel (K8 blend_bwd), recorded on the launching stream ----
+    bwd_events = []
+    stage_events = {}
+    orig = {}
+    for name_ in ["chs_spline_fwd", "chs_project_fwd", "chs_bin_count", "chs_bin_sort", "chs_blend_fwd", "chs_crf_bwd", "chs_blend_bwd",
+                  "chs_project_bwd", "chs_spline_bwd"]:
+        orig[name_] = getattr(L, name_)
+        stage_events[name_] = []
+
+        def make(nm):
+            f = orig[nm]
+
+            def g(*a):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = f(*a)
+                e1.record()
+                stage_events[nm].append((e0, e1))
+                return r
+            return g
+        setattr(L, name_, make(name_))
+
+    # ---- timed region: value ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = L.chs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(upstream_fixed)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    launches = L.chs_launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms / args.steps
+    value = B / (ms_per_step / 1e3)
+    stage_ms = {k[4:]: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in stage_events.items()}
+    bwd_calls = stage_events["chs_blend_bwd"]
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_calls) / max(len(bwd_calls), 1)
+    for k, f in orig.items():
+        setattr(L, k, f)
+
+    # ---- e2e: host buffers in, host gradients out ----
+    e2e = None
+    if not args.no_e2e:
+        targets_host = {i: (sc.v_ldr[i] * 0.05 + 0.2).contiguous().pin_memory() for i in ids}  # synthetic "captured" frames
+        grads_host = torch.empty(layout.total, dtype=torch.float32).pin_memory()
+        loss_dev = torch.zeros((), device=dev)
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(v.numel() * 4 for v in targets_host.values())
+        d2h = layout.total * 4 + 4
+
+        def e2e_step():
+            for k, v in host.items():
+                P[k].copy_(v, non_blocking=True)
+            tg = {i: targets_host[i].to(dev, non_blocking=True) for i in ids}
+            loss_dev.zero_()
+
+            def upstream_l2(fids, ldr):
+                d = ldr - torch.stack([tg[i] for i in fids])
+                loss_dev.add_(0.5 * (d * d).sum())
+                return d
+            step(upstream_l2)
+            grads_host.copy_(flat, non_blocking=True)
+            return loss_dev.item()  # D2H read of the step's loss (synchronises)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        s1.record()
+        barrier()
+        e2e_ms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+        e2e = {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_ms}
+
+    # ---- roofline of the dominant kernel (one launch = one frame = n cameras) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    n_local = max(len(ids), 1)
+    M_f = stats["n_isect"] / n_local
+    Mg_f = stats["m_g"] / n_local
+    Ppix = W * H
+    bwd_bytes = 40 * M_f + 36 * Mg_f + 8 * n * Ppix + 12 * 1 * Ppix
+    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "blend_bwd_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "blend_bwd_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
+                "launch_ms": bwd_ms, "isects_per_launch": M_f}
+    # whole-step algorithmic bytes, per frame
+    Cn = n
+    key_passes = 2 if args.sort_mode == "presort" else 7
+    step_bytes = {"K1": 44 * N + 32 * Cn * N, "K2": 8 * Cn * N, "K3": 12 * M_f + 20 * Cn * N,
+                  "K4": 8 * M_f + 24 * M_f * 7, "K5": 8 * M_f + 4 * Cn * 8160, "K6": 40 * M_f + 8 * Cn * Ppix + 24 * Ppix,
+                  "K7": 36 * Ppix, "K8": bwd_bytes, "K9": 68 * Cn * N + 100 * N}
+    frame_bytes = float(sum(step_bytes.values()))
+    step_frac = (frame_bytes * n_local) / (ms_per_step * 1e-3) / 1e9 / peak
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sc1 = make_config(args.workload, n_frames=1)
+        t_frame, detail, m1, n_pick, n_nonempty = cpu_oracle_sample(sc1, args.cpu_tiles)
+        cpu_baseline = {"value": 1.0 / t_frame, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": (f"float64 torch oracle: pose 0 of frame 0, full projection fwd+bwd + binning ({m1} isects), blend "
+                                   f"fwd+bwd on {n_pick} of {n_nonempty} non-empty tiles; extrapolated linearly to {n} poses x all tiles"),
+                        "phase_seconds": {k: round(v, 3) for k, v in detail.items()}}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: BASELINE.json configs[3] — {N} Gaussians, {W}x{H}, {n} virtual poses/frame, "
+                                       f"global batch {B} frames sharded by frame, fwd+bwd incl. pose/exposure/CRF grads",
+                           "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode,
+                           "isects_per_frame": M_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
+                           "collective": None if world == 1 else ("ncclAllReduce via libchs C ABI" if isinstance(comm, ChsComm) else "torch.distributed all_reduce"),
+                           "parallelism": f"dp{world} over frames"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline,
+                "cpu_baseline": cpu_baseline,
+                "extra": {"stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
+                          "step_algorithmic_bytes_per_frame": frame_bytes, "step_roofline_frac": step_frac,
+                          "sort_passes_actual": key_passes, "mem_GB": torch.cuda.max_memory_allocated() / 1e9}}
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

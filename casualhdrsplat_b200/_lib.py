@@ -36,6 +36,7 @@ CFG = POINTER(ChsConfig)
 SIGNATURES = {
     "chs_version": (ctypes.c_int, []),
     "chs_last_error": (c_char_p, []),
+    "chs_launch_count": (c_uint64, []),
     "chs_workspace_query": (ctypes.c_int, [CFG, c_int64, c_int32, POINTER(ChsWorkspaceSizes)]),
     "chs_spline_fwd": (ctypes.c_int, [c_int32, P, c_int32, c_double, c_double, P, P, c_int32, c_int32, P, P]),
     "chs_spline_bwd": (ctypes.c_int, [c_int32, P, c_int32, c_double, c_double, P, P, c_int32, c_int32, P, P, P, P, P, c_uint64, P]),

@@ -1,6 +1,8 @@
 // chs_api.cu — version, error string, configuration validation, workspace query and the NCCL
 // communicator of libchs (include/chs.h).
 #include <dlfcn.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "chs_common.cuh"
@@ -13,6 +15,10 @@ void chs_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<uint64_t> g_launches{0};
+void chs_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" uint64_t chs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int chs_version(void) { return CHS_VERSION; }
 extern "C" const char* chs_last_error(void) { return g_err; }

@@ -31,7 +31,14 @@ void chs_set_error(const char* fmt, ...);
     }                                                                                           \
   } while (0)
 
-#define CHS_LAUNCH_CHECK() CHS_CUDA(cudaGetLastError())
+// every hand-written kernel launch is followed by CHS_LAUNCH_CHECK(), which also counts it
+// (chs_launch_count() — the bench reports it as gpu_launches; CUB and memsets are not counted)
+void chs_count_launch();
+#define CHS_LAUNCH_CHECK()          \
+  do {                              \
+    chs_count_launch();             \
+    CHS_CUDA(cudaGetLastError());   \
+  } while (0)
 
 struct ChsDims {
   int N, B, n, C, W, H;

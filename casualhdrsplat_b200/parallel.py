@@ -1,0 +1,160 @@
+"""Data-parallel training step of the formation path.
+
+Work shards by training frames: Gaussians, CRF parameters and spline knots are replicated on every
+GPU; the batch of B frames is split B/G per GPU with all n virtual poses of a frame on one GPU, so
+the blur average / CRF epilogue needs no communication.  The one exchange step is a sum all-reduce
+of the flat gradient buffer
+
+    [ means 3N | quats 4N | scales 3N | opacities N | colors 3N | knots 7K | crf P | exposure B | frame_times B ]
+
+over NCCL (NVLink 5 / NVSwitch).  One process per GPU; ``torch.distributed`` is used for
+rendezvous only (or as the collective backend when asked), the data path can go through the C ABI
+(``chs_allreduce_grads``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .api import _stream, backward_stages, forward_stages
+
+_SORT = {"key64": _lib.CHS_SORT_KEY64, "presort": _lib.CHS_SORT_DEPTH_PRESORT}
+
+
+def shard_frames(n_frames: int, rank: int, world: int) -> range:
+    """Contiguous block of frame indices owned by ``rank`` (blocks differ by at most one frame)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} for world {world}")
+    base, extra = divmod(n_frames, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+class GradLayout:
+    """Offsets of every section of the flat gradient buffer (in floats)."""
+
+    def __init__(self, n_gauss: int, n_knots: int, n_crf: int, n_frames: int):
+        self.N, self.K, self.P, self.B = n_gauss, n_knots, n_crf, n_frames
+        self.off_knots = 14 * n_gauss
+        self.off_crf = self.off_knots + 7 * n_knots
+        self.off_exposure = self.off_crf + n_crf
+        self.off_frame_times = self.off_exposure + n_frames
+        self.total = self.off_frame_times + n_frames
+
+    def views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+        N = self.N
+        return {
+            "means": buf[0:3 * N].view(N, 3), "quats": buf[3 * N:7 * N].view(N, 4), "scales": buf[7 * N:10 * N].view(N, 3),
+            "opacities": buf[10 * N:11 * N], "colors": buf[11 * N:14 * N].view(N, 3),
+            "knots": buf[self.off_knots:self.off_crf].view(self.K, 7), "crf_params": buf[self.off_crf:self.off_exposure],
+            "exposure_times": buf[self.off_exposure:self.off_frame_times], "frame_times": buf[self.off_frame_times:self.total],
+        }
+
+
+class ChsComm:
+    """NCCL communicator owned by libchs (C ABI). The 128-byte unique id travels over torch.distributed."""
+
+    def __init__(self, rank: int, world: int, device: torch.device):
+        import torch.distributed as dist
+
+        L = _lib.lib()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_char * 128)()
+            _lib.check(L.chs_comm_unique_id(buf), "chs_comm_unique_id")
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.to(device)
+        dist.broadcast(uid, src=0)
+        raw = bytes(uid.cpu().tolist())
+        self._handle = ctypes.c_void_p()
+        self._raw = ctypes.create_string_buffer(raw, 128)
+        _lib.check(L.chs_comm_init(self._raw, rank, world, ctypes.byref(self._handle)), "chs_comm_init")
+        self.rank, self.world = rank, world
+
+    def allreduce_(self, buf: torch.Tensor) -> None:
+        _lib.check(_lib.lib().chs_allreduce_grads(self._handle, _lib.ptr(buf), buf.numel(), _stream()), "chs_allreduce_grads")
+
+    def close(self) -> None:
+        if self._handle:
+            _lib.lib().chs_comm_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+
+class TorchComm:
+    """Collective through torch.distributed (NCCL on GPUs; gloo in the CPU tests of the sharding logic)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self._dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allreduce_(self, buf: torch.Tensor) -> None:
+        self._dist.all_reduce(buf, op=self._dist.ReduceOp.SUM, group=self.group)
+
+    def close(self) -> None:
+        pass
+
+
+def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: int, height: int, n_virtual: int, crf_kind: int,
+                   frame_ids: Sequence[int], upstream: Callable[[Sequence[int], torch.Tensor], torch.Tensor], *,
+                   micro_batch: int = 1, sort_mode: str = "presort", comm=None, background=None, out: Optional[torch.Tensor] = None,
+                   stats: Optional[dict] = None):
+    """One fwd+bwd training step over this rank's frames, then the gradient all-reduce.
+
+    params: CUDA fp32 tensors means [N,3], quats [N,4], scales [N,3], opacities [N], colors [N,3], knots [K,7],
+            frame_times [B], exposure_times [B], Ks [B,3,3], crf_params [3,3Hd+1] (or absent for the identity CRF);
+            B is the GLOBAL batch.  spline_meta: knot_t0, knot_dt, kind.
+    frame_ids: the frames this rank renders (``shard_frames``).  ``upstream(ids, ldr[len(ids),H,W,3])`` returns the
+            gradient of the loss w.r.t. those LDR frames (same shape).
+    Returns (GradLayout, flat gradient buffer summed over all ranks).
+    """
+    means, quats, scales = params["means"], params["quats"], params["scales"]
+    opacities, colors, knots = params["opacities"], params["colors"], params["knots"]
+    crf_params = params.get("crf_params") if crf_kind == _lib.CHS_CRF_MLP else None
+    N, K = means.shape[0], knots.shape[0]
+    B_total = params["frame_times"].shape[0]
+    n_crf = crf_params.numel() if crf_params is not None else 0
+    layout = GradLayout(N, K, n_crf, B_total)
+    dev = means.device
+    flat = out if out is not None else torch.empty(layout.total, dtype=torch.float32, device=dev)
+    flat[layout.off_knots:].zero_()
+    v = layout.views(flat)
+    first = True
+    ids_all = list(frame_ids)
+    n_isect_total, m_g_total = 0, 0
+    for s in range(0, len(ids_all), micro_batch):
+        ids = ids_all[s:s + micro_batch]
+        idx = torch.as_tensor(ids, device=dev)
+        ft, ex, Ks = params["frame_times"][idx].contiguous(), params["exposure_times"][idx].contiguous(), params["Ks"][idx].contiguous()
+        cfg = _lib.make_config(N, len(ids), n_virtual, width, height, crf_kind=crf_kind,
+                               crf_hidden=(crf_params.shape[1] - 1) // 3 if crf_params is not None else 0,
+                               sort_mode=_SORT[sort_mode], background=background)
+        spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
+        st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline)
+        v_ldr = upstream(ids, st.ldr).contiguous()
+        g = backward_stages(st, means, quats, scales, ex, crf_params, v_ldr, None)
+        if first:
+            flat[:14 * N].copy_(g["grads_flat"])
+            first = False
+        else:
+            flat[:14 * N].add_(g["grads_flat"])
+        v["knots"].add_(g["v_knots"])
+        if crf_params is not None:
+            v["crf_params"].add_(g["v_crf"].reshape(-1))
+        v["exposure_times"][idx] = g["v_exposure"]
+        v["frame_times"][idx] = g["v_frame_times"]
+        n_isect_total += st.n_isect
+        if stats is not None and stats.get("count_pairs"):
+            m_g_total += int((st.tiles_touched > 0).sum())
+    if first:
+        flat[:14 * N].zero_()
+    if comm is not None and comm.world > 1:
+        comm.allreduce_(flat)
+    if stats is not None:
+        stats["n_isect"] = n_isect_total
+        stats["m_g"] = m_g_total
+    return layout, flat

@@ -86,6 +86,8 @@ typedef struct chs_workspace_sizes {
 
 CHS_API int chs_version(void);
 CHS_API const char* chs_last_error(void);
+/* Number of hand-written kernels this process has launched so far (CUB passes and memsets excluded). */
+CHS_API uint64_t chs_launch_count(void);
 
 /* Scratch sizes for a configuration and an intersection count M (pass 0 if not yet known:
  * bin_sort_bytes is then 0). n_knots is only used for reduce_bytes. */

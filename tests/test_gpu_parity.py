@@ -149,7 +149,7 @@ def test_forward_parity_end_to_end(name):
 def test_gradient_parity_end_to_end(name):
     sc = make_config(name)
     g = torch.Generator().manual_seed(11)
-    v_alpha = torch.randn(sc.n_frames, sc.height, sc.width, 1, generator=g)
+    v_alpha = torch.randn(sc.n_frames, sc.height, sc.width, 1, generator=g, dtype=torch.float32)
     _, _, _, grads = cuda_run(sc, v_alpha=v_alpha)
     _, _, _, o_grads = oracle_run(sc, v_alpha=v_alpha)
     errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
@@ -172,8 +172,8 @@ def test_blend_backward_stage_parity():
     hdr, alpha_c, _ = oracle.blend(m2d, con, op, col, b["vals_sorted"], b["tile_offsets"], sc.means.shape[0], sc.width, sc.height, bg)
     g = torch.Generator().manual_seed(5)
     B, n = sc.n_frames, sc.n_virtual
-    v_hdr = torch.randn(B, sc.height, sc.width, 3, generator=g)
-    v_al = torch.randn(B, sc.height, sc.width, generator=g)
+    v_hdr = torch.randn(B, sc.height, sc.width, 3, generator=g, dtype=torch.float32)
+    v_al = torch.randn(B, sc.height, sc.width, generator=g, dtype=torch.float32)
     loss = (hdr.reshape(B, n, sc.height, sc.width, 3) * v_hdr[:, None].double()).sum() \
         + (alpha_c.reshape(B, n, sc.height, sc.width).mean(1) * v_al.double()).sum()
     gm, gc, go, gcol = torch.autograd.grad(loss, [m2d, con, op, col])
@@ -183,7 +183,8 @@ def test_blend_backward_stage_parity():
 
     dev = st.geom.device
     C, N = st.radii.shape
-    v_geom = torch.empty(C, N, 4, device=dev); v_cogr = torch.empty(C, N, 4, device=dev); v_blue = torch.empty(C, N, device=dev)
+    f32 = torch.float32
+    v_geom = torch.empty(C, N, 4, device=dev, dtype=f32); v_cogr = torch.empty(C, N, 4, device=dev, dtype=f32); v_blue = torch.empty(C, N, device=dev, dtype=f32)
     _lib.check(_lib.lib().chs_blend_bwd(byref(st.cfg), _lib.ptr(st.geom), _lib.ptr(st.conic_c), _lib.ptr(st.rgbo), _lib.ptr(st.vals_sorted),
                                         _lib.ptr(st.tile_offsets), _lib.ptr(st.final_T), _lib.ptr(st.last_id),
                                         _lib.ptr(v_hdr.to(dev).contiguous()), _lib.ptr(v_al.to(dev).contiguous()), _lib.ptr(v_geom),
@@ -234,7 +235,7 @@ def test_empty_and_fully_culled_scene():
                                  spline={k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in sc.spline().items()},
                                  background=[0.5, 0.25, 0.125])
     assert meta["n_isect"] == 0
-    want = sc.exposure_times.to(dev)[:, None, None, None] * torch.tensor([0.5, 0.25, 0.125], device=dev)
+    want = sc.exposure_times.to(dev)[:, None, None, None] * torch.tensor([0.5, 0.25, 0.125], device=dev, dtype=torch.float32)
     assert torch.allclose(ldr, want.expand_as(ldr), rtol=1e-6)
     assert float(alpha.abs().max()) == 0.0
     (g,) = torch.autograd.grad(ldr.sum(), [m])

@@ -12,7 +12,13 @@ from casualhdrsplat_b200.scene import make_config, make_scene
 from oracle import se3
 from tests.hostsim.loader import load
 
-torch.set_default_dtype(torch.float64)
+@pytest.fixture(autouse=True)
+def _float64_default():
+    """These tests build float64 tensors implicitly; keep that local to the module's tests."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
 HS = load()
 
 

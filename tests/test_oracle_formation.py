@@ -8,7 +8,13 @@ import oracle
 from casualhdrsplat_b200.scene import make_config, make_scene, gamma_crf_params
 from oracle import se3
 
-torch.set_default_dtype(torch.float64)
+@pytest.fixture(autouse=True)
+def _float64_default():
+    """These tests build float64 tensors implicitly; keep that local to the module's tests."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
 
 
 def _run(sc, leaves=None, **kw):

@@ -6,7 +6,13 @@ import torch
 
 from oracle import se3
 
-torch.set_default_dtype(torch.float64)
+@pytest.fixture(autouse=True)
+def _float64_default():
+    """These tests build float64 tensors implicitly; keep that local to the module's tests."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
 
 
 def _rand_pose(g, scale=0.5):
