@@ -44,39 +44,70 @@ __global__ void depth_keys_kernel(const int32_t* __restrict__ touched, const flo
   vals[i] = (int32_t)i;
 }
 
-// One thread per (camera, Gaussian) in emission order. MODE 0: 64-bit keys; MODE 1: 32-bit linear
-// (cam * tiles + tile) keys.
+// Key emission (K3), warp-cooperative: a warp takes 32 consecutive (camera, Gaussian) entries of the
+// emission order; their intersections occupy one contiguous output range (the exclusive scan is in
+// the same order), which the 32 lanes write fully coalesced.  The owner of each output slot is found
+// by a 5-step binary search over the lanes' start offsets (shuffles), its tile rectangle fetched by
+// shuffle.  MODE 0: 64-bit cam|tile|depth keys; MODE 1: 32-bit linear (cam * tiles + tile) keys.
 template <int MODE>
-__global__ void emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits, const float4* __restrict__ geom,
-                            const int32_t* __restrict__ radii, const float* __restrict__ depths,
-                            const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order, uint64_t* __restrict__ keys64,
-                            uint32_t* __restrict__ keys32, int32_t* __restrict__ vals) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= CN) return;
-  const int32_t id = order ? order[i] : (int32_t)i;
-  const int radius = radii[id];
-  if (radius <= 0) return;
-  const float4 gm = geom[id];
-  const ChsTileRect r = chs_tile_bounds(gm.x, gm.y, radius, tile_w, tile_h);
-  const uint32_t c = (uint32_t)(id / N);
-  uint64_t out = offsets[i];
-  if (MODE == 0) {
-    const uint64_t hi = ((uint64_t)c << (32 + tile_bits));
-    const uint64_t d = __float_as_uint(depths[id]);
-    for (int ty = r.y0; ty < r.y1; ++ty)
-      for (int tx = r.x0; tx < r.x1; ++tx) {
-        keys64[out] = hi | ((uint64_t)(ty * tile_w + tx) << 32) | d;
-        vals[out] = id;
-        ++out;
-      }
-  } else {
-    const uint32_t base = c * (uint32_t)tiles;
-    for (int ty = r.y0; ty < r.y1; ++ty)
-      for (int tx = r.x0; tx < r.x1; ++tx) {
-        keys32[out] = base + (uint32_t)(ty * tile_w + tx);
-        vals[out] = id;
-        ++out;
-      }
+__global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits,
+                                                        const float4* __restrict__ geom, const int32_t* __restrict__ radii,
+                                                        const float* __restrict__ depths, const uint32_t* __restrict__ offsets,
+                                                        const int32_t* __restrict__ order, uint64_t* __restrict__ keys64,
+                                                        uint32_t* __restrict__ keys32, int32_t* __restrict__ vals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t id = 0;
+  int x0 = 0, y0 = 0, w = 1, cnt = 0;
+  uint32_t off = 0, dbits = 0;
+  if (i < CN) {
+    id = order ? order[i] : (int32_t)i;
+    off = offsets[i];
+    const int radius = radii[id];
+    if (radius > 0) {
+      const float4 gm = geom[id];
+      const ChsTileRect r = chs_tile_bounds(gm.x, gm.y, radius, tile_w, tile_h);
+      x0 = r.x0; y0 = r.y0;
+      w = max(r.x1 - r.x0, 1);
+      cnt = (r.x1 - r.x0) * (r.y1 - r.y0);
+      if (MODE == 0) dbits = __float_as_uint(depths[id]);
+    }
+  }
+  // lanes past CN (or culled) own empty ranges that start where the previous lane's range ends
+  const uint32_t end_prev = __shfl_up_sync(CHS_FULL_MASK, off + (uint32_t)cnt, 1);
+  if (i >= CN && lane > 0) off = end_prev;
+  // a tail lane's `off` must be >= every earlier end; propagate with a max-scan over invalid lanes
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o2 = __shfl_up_sync(CHS_FULL_MASK, off + (uint32_t)cnt, d);
+    if (i >= CN && lane >= d) off = max(off, o2);
+  }
+  const uint32_t w_begin = __shfl_sync(CHS_FULL_MASK, off, 0);
+  const uint32_t w_end = __shfl_sync(CHS_FULL_MASK, off + (uint32_t)cnt, 31);
+  for (uint32_t o = w_begin + lane; __any_sync(CHS_FULL_MASK, o < w_end); o += 32) {
+    int lo_l = 0, hi_l = 31;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int mid = (lo_l + hi_l + 1) >> 1;
+      const uint32_t v = __shfl_sync(CHS_FULL_MASK, off, mid);
+      if (v <= o) lo_l = mid; else hi_l = mid - 1;
+    }
+    const uint32_t o_off = __shfl_sync(CHS_FULL_MASK, off, lo_l);
+    const int o_x0 = __shfl_sync(CHS_FULL_MASK, x0, lo_l);
+    const int o_y0 = __shfl_sync(CHS_FULL_MASK, y0, lo_l);
+    const int o_w = __shfl_sync(CHS_FULL_MASK, w, lo_l);
+    const int32_t o_id = __shfl_sync(CHS_FULL_MASK, id, lo_l);
+    const uint32_t o_d = __shfl_sync(CHS_FULL_MASK, dbits, lo_l);
+    if (o < w_end) {
+      const int local = (int)(o - o_off);
+      const int ty = o_y0 + local / o_w, tx = o_x0 + local % o_w;
+      const uint32_t c = (uint32_t)(o_id / N);
+      if (MODE == 0)
+        keys64[o] = ((uint64_t)c << (32 + tile_bits)) | ((uint64_t)(ty * tile_w + tx) << 32) | (uint64_t)o_d;
+      else
+        keys32[o] = c * (uint32_t)tiles + (uint32_t)(ty * tile_w + tx);
+      vals[o] = o_id;
+    }
   }
 }
 
@@ -85,21 +116,37 @@ __device__ __forceinline__ uint32_t lin_of_key64(uint64_t key, int tile_bits, in
   return (b >> tile_bits) * (uint32_t)tiles + (b & ((1u << tile_bits) - 1u));
 }
 
-// tile_offsets[lin] = first sorted index whose (cam, tile) >= lin; tile_offsets[C*tiles] = M.
+// K5: tile_offsets[lin] = first sorted index whose (cam, tile) >= lin; tile_offsets[C*tiles] = M.
+// Four sorted entries per thread.
 template <int MODE>
-__global__ void tile_offsets_kernel(int64_t M, int n_lin, int tile_bits, int tiles, const uint64_t* __restrict__ keys64,
-                                    const uint32_t* __restrict__ keys32, uint32_t* __restrict__ tile_offsets) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
-  uint32_t cur = MODE == 0 ? lin_of_key64(keys64[i], tile_bits, tiles) : keys32[i];
-  if (i == 0) {
-    for (uint32_t b = 0; b <= cur; ++b) tile_offsets[b] = 0;
+__global__ void __launch_bounds__(kThreads) tile_offsets_kernel(int64_t M, int n_lin, int tile_bits, int tiles,
+                                                                const uint64_t* __restrict__ keys64, const uint32_t* __restrict__ keys32,
+                                                                uint32_t* __restrict__ tile_offsets) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= M) return;
+  uint32_t lin[4];
+  const int nv = (int)min((int64_t)4, M - i0);
+  if (MODE == 0) {
+    for (int k = 0; k < nv; ++k) lin[k] = lin_of_key64(keys64[i0 + k], tile_bits, tiles);
+  } else if (nv == 4) {
+    const uint4 v = *reinterpret_cast<const uint4*>(keys32 + i0);
+    lin[0] = v.x; lin[1] = v.y; lin[2] = v.z; lin[3] = v.w;
   } else {
-    uint32_t prev = MODE == 0 ? lin_of_key64(keys64[i - 1], tile_bits, tiles) : keys32[i - 1];
-    for (uint32_t b = prev + 1; b <= cur; ++b) tile_offsets[b] = (uint32_t)i;
+    for (int k = 0; k < nv; ++k) lin[k] = keys32[i0 + k];
   }
-  if (i == M - 1)
-    for (uint32_t b = cur + 1; b <= (uint32_t)n_lin; ++b) tile_offsets[b] = (uint32_t)M;
+  uint32_t prev;
+  if (i0 == 0) {
+    for (uint32_t b = 0; b <= lin[0]; ++b) tile_offsets[b] = 0;
+    prev = lin[0];
+  } else {
+    prev = MODE == 0 ? lin_of_key64(keys64[i0 - 1], tile_bits, tiles) : keys32[i0 - 1];
+  }
+  for (int k = 0; k < nv; ++k) {
+    for (uint32_t b = prev + 1; b <= lin[k]; ++b) tile_offsets[b] = (uint32_t)(i0 + k);
+    prev = lin[k];
+  }
+  if (i0 + nv == M)
+    for (uint32_t b = prev + 1; b <= (uint32_t)n_lin; ++b) tile_offsets[b] = (uint32_t)M;
 }
 
 __global__ void rebuild_keys_kernel(int64_t M, int tiles, int tile_bits, const uint32_t* __restrict__ lin_sorted,
@@ -288,7 +335,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
     CHS_LAUNCH_CHECK();
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_in, k_out, (const int32_t*)v_in, vals_sorted, M, 0,
                                              32 + d.tile_bits + d.cam_bits, s));
-    tile_offsets_kernel<0><<<grid_for(M), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, k_out, nullptr, tile_offsets);
+    tile_offsets_kernel<0><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, k_out, nullptr, tile_offsets);
     CHS_LAUNCH_CHECK();
   } else {
     uint32_t* l_in = ar.take<uint32_t>(M);
@@ -302,7 +349,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
     CHS_LAUNCH_CHECK();
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)l_in, l_out, (const int32_t*)v_in, vals_sorted, M, 0,
                                              chs_bit_length((uint64_t)n_lin), s));
-    tile_offsets_kernel<1><<<grid_for(M), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr, l_out, tile_offsets);
+    tile_offsets_kernel<1><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr, l_out, tile_offsets);
     CHS_LAUNCH_CHECK();
     if (keys_sorted) {
       rebuild_keys_kernel<<<grid_for(M), kThreads, 0, s>>>(M, d.tiles, d.tile_bits, l_out, vals_sorted, depths, keys_sorted);

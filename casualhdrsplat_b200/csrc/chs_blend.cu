@@ -30,8 +30,8 @@ constexpr int kBatch = 256;
 
 struct SplatSmem {
   float4 a[kBatch];  // mx, my, qa, qb
-  float4 b[kBatch];  // qc, lo, ex, ey
-  float4 c[kBatch];  // r, g, b, opacity
+  float4 b[kBatch];  // qc, lo, rbc, rba
+  float4 c[kBatch];  // r, g, b, 1/opacity
 };
 
 __device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
@@ -41,17 +41,9 @@ __device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val
   const float4 col = __ldg(rgbo + (val - cam_base));
   ChsSplat<float> s;
   chs_make_splat(gm.x, gm.y, gm.z, gm.w, cc, col.w, col.x, col.y, col.z, s);
-  if (s.ex < 0.f) s.ex = s.ey = -1e30f;
   sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.qb);
-  sm.b[slot] = make_float4(s.qc, s.lo, s.ex, s.ey);
-  sm.c[slot] = make_float4(s.r, s.g, s.b, s.opac);
-}
-
-// does the alpha >= 1/255 region of staged splat `slot` reach the warp's pixel-centre rectangle?
-__device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
-  const float4 a = sm.a[slot];
-  const float4 b = sm.b[slot];
-  return (a.x + b.z >= bx0) && (a.x - b.z <= bx1) && (a.y + b.w >= by0) && (a.y - b.w <= by1);
+  sm.b[slot] = make_float4(s.qc, s.lo, s.rbc, s.rba);
+  sm.c[slot] = make_float4(s.r, s.g, s.b, s.inv_opac);
 }
 
 __device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, int slot) {
@@ -59,8 +51,14 @@ __device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, in
   const float4 b = sm.b[slot];
   ChsSplat<float> s;
   s.mx = a.x; s.my = a.y; s.qa = a.z; s.qb = a.w;
-  s.qc = b.x; s.lo = b.y; s.ex = b.z; s.ey = b.w;
+  s.qc = b.x; s.lo = b.y; s.rbc = b.z; s.rba = b.w;
   return s;
+}
+
+// can staged splat `slot` reach alpha >= 1/255 anywhere in the warp's rectangle of pixel centres?
+__device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
+  const ChsSplat<float> s = read_splat_ab(sm, slot);
+  return chs_block_max_power(s, bx0, bx1, by0, by1) >= CHS_LOG2_ALPHA_MIN - 1e-3f;
 }
 
 struct BlendFwdArgs {
@@ -193,35 +191,35 @@ struct BlendBwdArgs {
   float* v_blue;         // [C,N]  v_b
 };
 
-// Transposing butterfly: on entry every lane holds its pixel's 8 partials v[0..7]; on exit lane l
-// holds, in the return value, the warp total of v[l >> 2] (all four lanes of a quad hold the same).
+// Transposing butterfly: on entry every lane holds its pixel's 8 partials v[0..7]; on exit every
+// lane l holds the warp total of v[l & 7].  9 shuffles instead of 40.
 __device__ __forceinline__ float warp_transpose_reduce8(float v[8], int lane) {
   {
-    const bool up = lane & 16;
+    const bool odd = lane & 1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float send = up ? v[i] : v[i + 4];
-      const float keep = up ? v[i + 4] : v[i];
-      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 16);
+      const float send = odd ? v[2 * i] : v[2 * i + 1];
+      const float keep = odd ? v[2 * i + 1] : v[2 * i];
+      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 1);  // v[i] = value 2i + bit0
     }
   }
   {
-    const bool up = lane & 8;
+    const bool odd = lane & 2;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const float send = up ? v[i] : v[i + 2];
-      const float keep = up ? v[i + 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 8);
+      const float send = odd ? v[2 * i] : v[2 * i + 1];
+      const float keep = odd ? v[2 * i + 1] : v[2 * i];
+      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 2);  // v[i] = value 4i + 2 bit1 + bit0
     }
   }
   {
-    const bool up = lane & 4;
-    const float send = up ? v[0] : v[1];
-    const float keep = up ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 4);
+    const bool odd = lane & 4;
+    const float send = odd ? v[0] : v[1];
+    const float keep = odd ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 4);  // value lane & 7
   }
-  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 2);
-  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 1);
+  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 8);
+  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 16);
   return v[0];
 }
 
@@ -271,6 +269,21 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(CHS_FULL_MASK, warp_last, o));
 
+  // lanes 0..7 own the eight totals of the butterfly, lane 8 the ninth (blue): one RED instruction
+  // with nine active lanes adds a Gaussian's whole gradient record
+  char* lane_base = nullptr;
+  int lane_stride = 0;
+  if (lane < 4) {
+    lane_base = reinterpret_cast<char*>(a.v_geom) + lane * 4;
+    lane_stride = 16;
+  } else if (lane < 8) {
+    lane_base = reinterpret_cast<char*>(a.v_cogr) + (lane - 4) * 4;
+    lane_stride = 16;
+  } else if (lane == 8) {
+    lane_base = reinterpret_cast<char*>(a.v_blue);
+    lane_stride = 4;
+  }
+
   float buf[3] = {0.f, 0.f, 0.f};
   for (int hi = n_walk; hi > 0; hi -= kBatch) {
     const int lo = max(0, hi - kBatch);
@@ -287,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
       const int sub_lo = max(0, sub_hi - 32);
       if (warp_last <= lo + sub_lo) continue;
       const int j = sub_lo + lane;
-      const bool hit = (j < sub_hi) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
+      const bool hit = (j < sub_hi) && (lo + j < warp_last) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
       unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
       while (mask) {
         const int bit = 31 - __clz(mask);
@@ -304,24 +317,14 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
         for (int i = 0; i < 9; ++i) g[i] = 0.f;
         if (valid) {
           const float4 col = sm.c[jj];
-          s.r = col.x; s.g = col.y; s.b = col.z; s.opac = col.w;
+          s.r = col.x; s.g = col.y; s.b = col.z; s.inv_opac = col.w;
           const float au = chs_exp2_fast(power);
           chs_pair_bwd(s, dx, dy, au, fminf(CHS_ALPHA_MAX, au), Tr, buf, vh, va_t, g);
         }
         const float blue = chs_warp_sum(g[8]);
         const float r8 = warp_transpose_reduce8(g, lane);
-        // lane 4j holds total j (j = 0..7): [v_mx, v_my, v_A, v_B | v_C, v_o, v_r, v_g]; lane 1 adds blue
-        const int64_t val = s_vals[jj];
-        float* dst = nullptr;
-        float add = r8;
-        if ((lane & 3) == 0) {
-          const int j8 = lane >> 2;
-          dst = (j8 < 4) ? reinterpret_cast<float*>(a.v_geom + val) + j8 : reinterpret_cast<float*>(a.v_cogr + val) + (j8 - 4);
-        } else if (lane == 1) {
-          dst = a.v_blue + val;
-          add = blue;
-        }
-        if (dst && add != 0.f) atomicAdd(dst, add);
+        const float add = lane == 8 ? blue : r8;
+        if (lane < 9 && add != 0.f) atomicAdd(reinterpret_cast<float*>(lane_base + (int64_t)s_vals[jj] * lane_stride), add);
       }
     }
   }

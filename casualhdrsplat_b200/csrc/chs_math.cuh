@@ -62,7 +62,9 @@ CHS_HD double chs_fma(double a, double b, double c) { return fma(a, b, c); }
 
 CHS_HD float chs_rcp_fast(float x) {
 #if defined(__CUDA_ARCH__)
-  return __frcp_rn(x);
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 #else
   return 1.0f / x;
 #endif
@@ -347,8 +349,8 @@ CHS_HD ChsTileRect chs_tile_bounds(float mx, float my, int radius, int tile_w, i
 // ---------------------------------------------------------------------------------------------
 template <class T> struct ChsSplat {
   T mx, my, qa, qb;
-  T qc, lo, ex, ey;  // ex, ey: half extents of the alpha >= 1/255 region (for sub-tile culling)
-  T r, g, b, opac;
+  T qc, lo, rbc, rba;  // rbc = -B/C, rba = -B/A: minimisers of the exponent along a vertical / horizontal line
+  T r, g, b, inv_opac;
 };
 
 template <class T>
@@ -358,20 +360,27 @@ CHS_HD void chs_make_splat(T mx, T my, T ca, T cb, T cc, T opac, T r, T g, T b, 
   s.qb = -ChsK<T>::log2e * cb;
   s.qc = T(-0.5) * ChsK<T>::log2e * cc;
   s.lo = log2(opac);
-  s.r = r; s.g = g; s.b = b; s.opac = opac;
-  // alpha >= 1/255  <=>  sigma <= tau = ln(255 o).  The ellipse {sigma <= tau} has half extents
-  // sqrt(2 tau Sxx), sqrt(2 tau Syy) with S = conic^-1.  Inflated slightly so the cull is conservative.
-  T tau = log(T(255) * opac);
-  T det = ca * cc - cb * cb;
-  if (tau > T(0) && det > T(0)) {
-    T k = T(2) * tau / det;
-    s.ex = sqrt(k * cc) * T(1.0005) + T(0.01);
-    s.ey = sqrt(k * ca) * T(1.0005) + T(0.01);
-  } else if (tau > T(0)) {
-    s.ex = s.ey = T(1e30);  // degenerate conic: never cull
-  } else {
-    s.ex = s.ey = T(-1);  // opacity below 1/255: can never contribute
-  }
+  s.r = r; s.g = g; s.b = b;
+  s.inv_opac = T(1) / opac;
+  s.rbc = cc > T(0) ? -cb / cc : T(0);
+  s.rba = ca > T(0) ? -cb / ca : T(0);
+}
+
+// Sub-tile culling.  Upper bound of log2(alpha) over the axis-aligned rectangle of pixel centres
+// [x0,x1] x [y0,y1]: the exponent is a concave quadratic of d = p - mean, so its maximum over the
+// rectangle is attained either at the mean (inside the rectangle) or on one of the two edges that
+// face the mean, at the 1-D maximiser clamped to the edge.  (With x or y at a far edge the KKT
+// conditions would need B^2 >= AC, impossible for a positive-definite conic.)  A warp skips a
+// staged Gaussian when this bound is below log2(1/255): exactly the pairs A.5 skips anyway.
+template <class T> CHS_HD T chs_block_max_power(const ChsSplat<T>& s, T x0, T x1, T y0, T y1) {
+  T ax0 = x0 - s.mx, ax1 = x1 - s.mx, ay0 = y0 - s.my, ay1 = y1 - s.my;
+  T cx = chs_min(chs_max(T(0), ax0), ax1);
+  T cy = chs_min(chs_max(T(0), ay0), ay1);
+  T dy1 = chs_min(chs_max(s.rbc * cx, ay0), ay1);
+  T dx2 = chs_min(chs_max(s.rba * cy, ax0), ax1);
+  T p1 = (s.qa * cx + s.qb * dy1) * cx + s.qc * dy1 * dy1;
+  T p2 = (s.qa * dx2 + s.qb * cy) * dx2 + s.qc * cy * cy;
+  return chs_min(chs_max(p1, p2), T(0)) + s.lo;
 }
 
 // log2(alpha) before the 0.999 clamp
@@ -390,7 +399,7 @@ template <class T> CHS_HD T chs_pair_power(const ChsSplat<T>& s, T px, T py, T& 
 template <class T>
 CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T alpha_unclamped, T alpha, T& Tr, T buf[3],
                          const T vh[3], T va_t, T g[9]) {
-  T ra = T(1) / (T(1) - alpha);
+  T ra = chs_rcp_fast(T(1) - alpha);
   Tr = Tr * ra;  // transmittance before this Gaussian
   T f = alpha * Tr;
   g[6] = f * vh[0];
@@ -409,7 +418,7 @@ CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T alpha_unclamped, T 
     g[2] = T(0.5) * v_sigma * dx * dx;
     g[3] = v_sigma * dx * dy;
     g[4] = T(0.5) * v_sigma * dy * dy;
-    g[5] = alpha_unclamped / s.opac * v_alpha;
+    g[5] = alpha_unclamped * s.inv_opac * v_alpha;
   } else {
     g[0] = g[1] = g[2] = g[3] = g[4] = g[5] = T(0);
   }

@@ -89,8 +89,10 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
     T Tr = 1, acc[3] = {0, 0, 0};
     int last = 0;
     for (int j = 0; j < n_list; ++j) {
-      // sub-tile cull, applied per pixel here: must never drop a contributing pair
-      bool reach = (sp[j].mx + sp[j].ex >= px) && (sp[j].mx - sp[j].ex <= px) && (sp[j].my + sp[j].ey >= py) && (sp[j].my - sp[j].ey <= py);
+      // sub-tile cull exactly as the kernels apply it (8x4 pixel block of this pixel's warp): must never
+      // drop a contributing pair
+      T bx0 = floor((px - T(0.5)) / 8) * 8 + T(0.5), by0 = floor((py - T(0.5)) / 4) * 4 + T(0.5);
+      bool reach = chs_block_max_power(sp[j], bx0, bx0 + 7, by0, by0 + 3) >= thr - T(1e-3);
       T dx, dy;
       T power = chs_pair_power(sp[j], px, py, dx, dy);
       if (!(power >= thr)) continue;
@@ -154,6 +156,23 @@ void hs_blend_f64(int n_list, const double* params, int n_pix, const double* pix
 void hs_blend_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
                   const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
   blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params);
+}
+// brute-force check helper: the culling bound for a block vs the true maximum over its pixel centres
+void hs_block_bound_f32(int n, const float* params /* mx,my,A,B,C,o */, const float* rect /* x0,x1,y0,y1 */, float* bound, float* brute) {
+  for (int i = 0; i < n; ++i) {
+    ChsSplat<float> s;
+    const float* p = params + i * 6;
+    chs_make_splat(p[0], p[1], p[2], p[3], p[4], p[5], 0.f, 0.f, 0.f, s);
+    const float* r = rect + i * 4;
+    bound[i] = chs_block_max_power(s, r[0], r[1], r[2], r[3]);
+    float best = -1e30f;
+    for (float y = r[2]; y <= r[3] + 1e-3f; y += 1.f)
+      for (float x = r[0]; x <= r[1] + 1e-3f; x += 1.f) {
+        float dx, dy;
+        best = fmaxf(best, chs_pair_power(s, x, y, dx, dy));
+      }
+    brute[i] = best;
+  }
 }
 void hs_tile_bounds(int n, const float* mx, const float* my, const int32_t* radius, int tile_w, int tile_h, int32_t* rect) {
   for (int i = 0; i < n; ++i) {

@@ -2,6 +2,7 @@
 tests/hostsim and compared with the float64 oracle.  CPU-only; validates every hand-derived
 forward/backward formula before a GPU is involved."""
 import ctypes
+import math
 
 import numpy as np
 import pytest
@@ -185,6 +186,37 @@ def test_blend_pair_math_matches_oracle(dtype):
     gtol = 1e-9 if dtype == "f64" else 1e-3
     for k in range(9):
         assert rel(o_v[:, k], ref[:, k]) < gtol, (k, rel(o_v[:, k], ref[:, k]))
+
+
+def test_block_cull_bound_is_conservative_and_tight():
+    """chs_block_max_power >= max over the block's pixel centres (never culls a live pair) and is tight."""
+    g = torch.Generator().manual_seed(9)
+    n = 200000
+    th = torch.rand(n, generator=g) * math.pi
+    l1 = torch.exp(torch.rand(n, generator=g) * 6 - 3)          # eigenvalues of the conic, 0.05 .. 20
+    l2 = l1 * torch.exp(-torch.rand(n, generator=g) * 5)        # anisotropy up to e^5
+    c, s_ = torch.cos(th), torch.sin(th)
+    A = l1 * c * c + l2 * s_ * s_
+    B = (l1 - l2) * c * s_
+    C = l1 * s_ * s_ + l2 * c * c
+    bx = torch.randint(0, 8, (n,), generator=g).double() * 8 + 0.5
+    by = torch.randint(0, 8, (n,), generator=g).double() * 4 + 0.5
+    mx = bx + torch.rand(n, generator=g) * 40 - 16
+    my = by + torch.rand(n, generator=g) * 30 - 13
+    o = torch.rand(n, generator=g) * 0.98 + 0.01
+    params = np.ascontiguousarray(torch.stack([mx, my, A, B, C, o], 1).numpy().astype(np.float32))
+    rect = np.ascontiguousarray(torch.stack([bx, bx + 7, by, by + 3], 1).numpy().astype(np.float32))
+    bound = np.zeros(n, np.float32); brute = np.zeros(n, np.float32)
+    HS.hs_block_bound_f32(n, _p(params), _p(rect), _p(bound), _p(brute))
+    thr = math.log2(1 / 255)
+    live = brute >= thr
+    assert live.sum() > 1000
+    # conservative: whenever some pixel of the block is live the bound (minus the kernel's margin) keeps it
+    assert (bound[live] >= thr - 1e-3).all()
+    assert (bound >= brute - 1e-3 * np.maximum(1, np.abs(brute))).all()
+    # tight: blocks the bound keeps but that have no live pixel are a small fraction
+    kept = bound >= thr - 1e-3
+    assert (kept & ~live).sum() < 0.35 * kept.sum()
 
 
 def test_crf_mlp_fwd_bwd():
