@@ -5,10 +5,10 @@
 // ((w & 1) * 8, (w >> 1) * 4), lane l the pixel (l & 7, l >> 3) inside it.
 //
 // Per batch of up to 256 tile-list entries the CTA gathers the per-(camera, Gaussian) records
-// (three 128-bit loads each) into shared memory, pre-scaling the conic for exp2 and computing the
-// half extents of the alpha >= 1/255 ellipse.  Each warp then *culls the batch against its own 8x4
-// block*: 32 lanes test 32 Gaussians, a ballot yields the survivors, and only those are evaluated
-// for the warp's 32 pixels.  Skipped pairs are exactly pairs with alpha < 1/255, so results are
+// (three 128-bit loads each) into shared memory, pre-scaling the conic for exp2.  Each warp then
+// *culls the batch against its own 8x4 block* with an exact ellipse-vs-rectangle bound
+// (chs_block_max_power): 32 lanes test 32 Gaussians, a ballot yields the survivors, and only those
+// are evaluated for the warp's 32 pixels.  Skipped pairs are exactly pairs with alpha < 1/255, so results are
 // unchanged, but most of the 256 pair evaluations per intersection of a naive tile kernel vanish.
 // Early termination is warp-granular (ballot of per-pixel "done") and CTA-granular
 // (__syncthreads_and) per batch.
@@ -18,7 +18,7 @@
 //
 // Backward walks each pixel's list back to front from last_id; the nine per-Gaussian partials are
 // reduced across the warp with a transposing butterfly (14 shuffles instead of 45) that leaves
-// value j on lane 4j, so a single predicated vector-of-lanes RED instruction adds all nine numbers
+// value j on lane j, so a single RED instruction with nine active lanes adds all nine numbers
 // into the three [C,N] gradient planes.
 #include "chs_common.cuh"
 
@@ -30,8 +30,9 @@ constexpr int kBatch = 256;
 
 struct SplatSmem {
   float4 a[kBatch];  // mx, my, qa, qb
-  float4 b[kBatch];  // qc, lo, rbc, rba
+  float4 b[kBatch];  // qc, lo, val (int bits; c * N + g), unused
   float4 c[kBatch];  // r, g, b, 1/opacity
+  float2 r[kBatch];  // rbc, rba (culling test only)
 };
 
 __device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
@@ -42,8 +43,9 @@ __device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val
   ChsSplat<float> s;
   chs_make_splat(gm.x, gm.y, gm.z, gm.w, cc, col.w, col.x, col.y, col.z, s);
   sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.qb);
-  sm.b[slot] = make_float4(s.qc, s.lo, s.rbc, s.rba);
+  sm.b[slot] = make_float4(s.qc, s.lo, __int_as_float(val), 0.f);
   sm.c[slot] = make_float4(s.r, s.g, s.b, s.inv_opac);
+  sm.r[slot] = make_float2(s.rbc, s.rba);
 }
 
 __device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, int slot) {
@@ -51,13 +53,15 @@ __device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, in
   const float4 b = sm.b[slot];
   ChsSplat<float> s;
   s.mx = a.x; s.my = a.y; s.qa = a.z; s.qb = a.w;
-  s.qc = b.x; s.lo = b.y; s.rbc = b.z; s.rba = b.w;
+  s.qc = b.x; s.lo = b.y;
   return s;
 }
 
 // can staged splat `slot` reach alpha >= 1/255 anywhere in the warp's rectangle of pixel centres?
 __device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
-  const ChsSplat<float> s = read_splat_ab(sm, slot);
+  ChsSplat<float> s = read_splat_ab(sm, slot);
+  const float2 r = sm.r[slot];
+  s.rbc = r.x; s.rba = r.y;
   return chs_block_max_power(s, bx0, bx1, by0, by1) >= CHS_LOG2_ALPHA_MIN - 1e-3f;
 }
 
@@ -225,7 +229,6 @@ __device__ __forceinline__ float warp_transpose_reduce8(float v[8], int lane) {
 
 __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
   __shared__ SplatSmem sm;
-  __shared__ int32_t s_vals[kBatch];
   __shared__ int s_max_last;
 
   const int tile = blockIdx.x, c = blockIdx.y;
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
   // lanes 0..7 own the eight totals of the butterfly, lane 8 the ninth (blue): one RED instruction
   // with nine active lanes adds a Gaussian's whole gradient record
   char* lane_base = nullptr;
-  int lane_stride = 0;
+  uint32_t lane_stride = 0;
   if (lane < 4) {
     lane_base = reinterpret_cast<char*>(a.v_geom) + lane * 4;
     lane_stride = 16;
@@ -290,9 +293,7 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
     const int cnt = hi - lo;
     __syncthreads();
     if (tid < cnt) {
-      const int32_t val = a.vals[start + lo + tid];
-      s_vals[tid] = val;
-      stage_splat(sm, tid, val, cam_base, a.geom, a.conic_c, a.rgbo);
+      stage_splat(sm, tid, a.vals[start + lo + tid], cam_base, a.geom, a.conic_c, a.rgbo);
     }
     __syncthreads();
     if (warp_last <= lo) continue;  // none of this warp's pixels reaches into this batch
@@ -307,24 +308,25 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
         mask &= ~(1u << bit);
         const int jj = sub_lo + bit;
         const int rel = lo + jj + 1;  // 1-based index in the tile list
-        ChsSplat<float> s = read_splat_ab(sm, jj);
+        const float4 sa = sm.a[jj];
+        const float4 sb = sm.b[jj];
+        ChsSplat<float> s;
+        s.mx = sa.x; s.my = sa.y; s.qa = sa.z; s.qb = sa.w;
+        s.qc = sb.x; s.lo = sb.y;
+        const uint32_t val = (uint32_t)__float_as_int(sb.z);
         float dx, dy;
         const float power = chs_pair_power(s, px, py, dx, dy);
         const bool valid = (rel <= my_last) && power >= CHS_LOG2_ALPHA_MIN;
         if (!__any_sync(CHS_FULL_MASK, valid)) continue;
+        const float4 col = sm.c[jj];
+        s.r = col.x; s.g = col.y; s.b = col.z; s.inv_opac = col.w;
+        const float au = valid ? chs_exp2_fast(power) : 0.f;
         float g[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) g[i] = 0.f;
-        if (valid) {
-          const float4 col = sm.c[jj];
-          s.r = col.x; s.g = col.y; s.b = col.z; s.inv_opac = col.w;
-          const float au = chs_exp2_fast(power);
-          chs_pair_bwd(s, dx, dy, au, fminf(CHS_ALPHA_MAX, au), Tr, buf, vh, va_t, g);
-        }
+        chs_pair_bwd(s, dx, dy, au, fminf(CHS_ALPHA_MAX, au), Tr, buf, vh, va_t, g);
         const float blue = chs_warp_sum(g[8]);
         const float r8 = warp_transpose_reduce8(g, lane);
         const float add = lane == 8 ? blue : r8;
-        if (lane < 9 && add != 0.f) atomicAdd(reinterpret_cast<float*>(lane_base + (int64_t)s_vals[jj] * lane_stride), add);
+        if (lane < 9 && add != 0.f) atomicAdd(reinterpret_cast<float*>(lane_base + (uint64_t)val * (uint32_t)lane_stride), add);
       }
     }
   }

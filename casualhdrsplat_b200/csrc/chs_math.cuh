@@ -396,6 +396,8 @@ template <class T> CHS_HD T chs_pair_power(const ChsSplat<T>& s, T px, T py, T& 
 // Gaussian, buf = colour accumulated behind it. vh = v_H (3), va_t = T_final * (v_alpha - bg.v_H).
 // Outputs the 9 per-Gaussian partials for this pixel in g[9] =
 //   [v_mx, v_my, v_A, v_B, v_C, v_opacity, v_r, v_g, v_b]   (zero where the clamp is active).
+// Branch-free: a pair that does not contribute is passed with alpha_unclamped = alpha = 0, which
+// leaves T and buf untouched and yields g = 0.
 template <class T>
 CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T alpha_unclamped, T alpha, T& Tr, T buf[3],
                          const T vh[3], T va_t, T g[9]) {
@@ -409,19 +411,18 @@ CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T alpha_unclamped, T 
   buf[0] += s.r * f;
   buf[1] += s.g * f;
   buf[2] += s.b * f;
-  if (alpha_unclamped <= ChsK<T>::alpha_max) {
-    T v_sigma = -alpha_unclamped * v_alpha;
-    // A dx + B dy = -(2 qa dx + qb dy) / log2e ;  B dx + C dy = -(qb dx + 2 qc dy) / log2e
-    const T k = T(-1) / ChsK<T>::log2e;
-    g[0] = v_sigma * k * (T(2) * s.qa * dx + s.qb * dy);
-    g[1] = v_sigma * k * (s.qb * dx + T(2) * s.qc * dy);
-    g[2] = T(0.5) * v_sigma * dx * dx;
-    g[3] = v_sigma * dx * dy;
-    g[4] = T(0.5) * v_sigma * dy * dy;
-    g[5] = alpha_unclamped * s.inv_opac * v_alpha;
-  } else {
-    g[0] = g[1] = g[2] = g[3] = g[4] = g[5] = T(0);
-  }
+  // no gradient through the 0.999 clamp
+  T v_sigma = alpha_unclamped <= ChsK<T>::alpha_max ? -alpha_unclamped * v_alpha : T(0);
+  // A dx + B dy = -(2 qa dx + qb dy) / log2e ;  B dx + C dy = -(qb dx + 2 qc dy) / log2e
+  const T k = T(-1) / ChsK<T>::log2e;
+  T vk = v_sigma * k;
+  T hx = T(0.5) * v_sigma * dx, hy = T(0.5) * v_sigma * dy;
+  g[0] = vk * (T(2) * s.qa * dx + s.qb * dy);
+  g[1] = vk * (s.qb * dx + T(2) * s.qc * dy);
+  g[2] = hx * dx;
+  g[3] = T(2) * hx * dy;
+  g[4] = hy * dy;
+  g[5] = -v_sigma * s.inv_opac;
 }
 
 // ---------------------------------------------------------------------------------------------
