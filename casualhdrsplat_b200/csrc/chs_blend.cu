@@ -20,21 +20,23 @@
 // reduced across the warp with a transposing butterfly (14 shuffles instead of 45) that leaves
 // value j on lane j, so a single RED instruction with nine active lanes adds all nine numbers
 // into the three [C,N] gradient planes.
+#include <stdlib.h>
+
 #include "chs_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kBatch = 256;
 #define CHS_LOG2_ALPHA_MIN (-7.994353436858858f) /* log2(1/255) */
 
-struct SplatSmem {
+template <int kBatch> struct SplatSmemT {
   float4 a[kBatch];  // mx, my, qa, qb
   float4 b[kBatch];  // qc, lo, val (int bits; c * N + g), unused
   float4 c[kBatch];  // r, g, b, 1/opacity
   float2 r[kBatch];  // rbc, rba (culling test only)
 };
 
+template <class SplatSmem>
 __device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
                                             const float* __restrict__ conic_c, const float4* __restrict__ rgbo) {
   const float4 gm = __ldg(geom + val);
@@ -48,6 +50,7 @@ __device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val
   sm.r[slot] = make_float2(s.rbc, s.rba);
 }
 
+template <class SplatSmem>
 __device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, int slot) {
   const float4 a = sm.a[slot];
   const float4 b = sm.b[slot];
@@ -58,6 +61,7 @@ __device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, in
 }
 
 // can staged splat `slot` reach alpha >= 1/255 anywhere in the warp's rectangle of pixel centres?
+template <class SplatSmem>
 __device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
   ChsSplat<float> s = read_splat_ab(sm, slot);
   const float2 r = sm.r[slot];
@@ -80,8 +84,9 @@ struct BlendFwdArgs {
   int32_t* last_id;
 };
 
-__global__ void __launch_bounds__(kThreads) blend_fwd_kernel(BlendFwdArgs a) {
-  __shared__ SplatSmem sm;
+template <int kBatch, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFwdArgs a) {
+  __shared__ SplatSmemT<kBatch> sm;
   extern __shared__ float s_crf[];  // 3 * (3 Hd + 1) floats when the CRF is the MLP
 
   const int tile = blockIdx.x, frame = blockIdx.y;
@@ -227,8 +232,9 @@ __device__ __forceinline__ float warp_transpose_reduce8(float v[8], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
-  __shared__ SplatSmem sm;
+template <int kBatch, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd_kernel(BlendBwdArgs a) {
+  __shared__ SplatSmemT<kBatch> sm;
   __shared__ int s_max_last;
 
   const int tile = blockIdx.x, c = blockIdx.y;
@@ -334,6 +340,12 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdArgs a) {
 
 }  // namespace
 
+// tuning knob (development): selects a (batch size, min blocks/SM) instantiation of the blend kernels
+static int blend_variant(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+
 static size_t crf_smem_bytes(const chs_config* cfg) {
   return cfg->crf_kind == CHS_CRF_MLP ? (size_t)3 * (3 * cfg->crf_hidden + 1) * sizeof(float) : 0;
 }
@@ -361,7 +373,14 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   a.exposure = exposure; a.crf_params = crf_params;
   a.ldr = ldr; a.alpha = alpha; a.hdr_mean = hdr_mean; a.final_T = final_T; a.last_id = last_id;
   dim3 grid(d.tiles, d.B);
-  blend_fwd_kernel<<<grid, kThreads, crf_smem_bytes(cfg), (cudaStream_t)stream>>>(a);
+  const size_t dyn = crf_smem_bytes(cfg);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (blend_variant("CHS_BLEND_FWD_VARIANT")) {
+    case 1: blend_fwd_kernel<256, 1><<<grid, kThreads, dyn, s>>>(a); break;
+    case 2: blend_fwd_kernel<128, 6><<<grid, kThreads, dyn, s>>>(a); break;
+    case 4: blend_fwd_kernel<256, 4><<<grid, kThreads, dyn, s>>>(a); break;
+    default: blend_fwd_kernel<256, 5><<<grid, kThreads, dyn, s>>>(a); break;  // measured best on c3 (r1 sweep)
+  }
   CHS_LAUNCH_CHECK();
   return CHS_OK;
 }
@@ -386,7 +405,11 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.final_T = final_T; a.last_id = last_id; a.v_hdr = v_hdr; a.v_alpha = v_alpha;
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
-  blend_bwd_kernel<<<grid, kThreads, 0, s>>>(a);
+  switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {
+    case 1: blend_bwd_kernel<256, 5><<<grid, kThreads, 0, s>>>(a); break;
+    case 2: blend_bwd_kernel<128, 5><<<grid, kThreads, 0, s>>>(a); break;
+    default: blend_bwd_kernel<256, 1><<<grid, kThreads, 0, s>>>(a); break;  // all variants within 1% (r1 sweep)
+  }
   CHS_LAUNCH_CHECK();
   return CHS_OK;
 }

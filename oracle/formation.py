@@ -327,7 +327,7 @@ def formation(hdr_cams, alpha_cams, exposure, n_virtual, crf_kind, crf_params=No
 def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, width=0, height=0,
               exposure_times=None, n_virtual=1, crf_kind=CRF_IDENTITY, crf_params=None, *, spline=None,
               background=None, near=0.01, far=1e10, eps2d=0.3, tile_size=TILE, crf_before_average=False,
-              projection_override=None, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP,
+              projection_override=None, binning_override=None, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP,
               radius_sigmas=3.0):
     """Oracle of ``casualhdrsplat_b200.rasterize`` (same arguments and meaning; float64 CPU).
 
@@ -336,6 +336,11 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     ``projection_override`` = dict(means2d, conics, depths (fp32 [C,N,...]), radii i32) lets a test
     feed the CUDA kernel's own fp32 projection so binning can be compared bit-for-bit (A.4/D9);
     those tensors then carry no gradient to the Gaussian geometry.
+    ``binning_override`` = dict(means2d, depths (fp32), radii i32): only the *binning* (A.4, an integer function of
+    fp32 projection outputs) uses these; projection values and all gradients stay the oracle's own float64 ones.  This
+    is how end-to-end gradient parity is defined: last-ulp differences between an fp32 and an fp64
+    projection can flip a ceil() or swap two nearly equal depths, which changes a handful of tile lists and would
+    otherwise dominate the error norm (discrete decisions carry no gradient, A.6).
     ``alpha_min`` / ``t_stop`` / ``radius_sigmas`` default to the model's constants (1/255, 1e-4, 3);
     tests override them only to obtain a discontinuity-free variant for finite-difference checks.
     Returns (ldr [B,H,W,3], alpha [B,H,W,1], meta dict).
@@ -369,6 +374,10 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         radii = projection_override["radii"].to(torch.int32)
         m2d, con = _f64(m2d_f32), _f64(projection_override["conics"])
         proj = {"means2d": m2d, "conics": con, "depths": _f64(dep_f32), "radii": radii}
+    if binning_override is not None:
+        m2d_f32 = binning_override["means2d"].to(torch.float32)
+        dep_f32 = binning_override["depths"].to(torch.float32)
+        radii = binning_override["radii"].to(torch.int32)
     bins = bin_tiles(m2d_f32, radii, dep_f32, width, height, tile_size)
     hdr, alpha_c, last_id = blend(m2d, con, opacities, colors, bins["vals_sorted"], bins["tile_offsets"], N,
                                   width, height, background, tile_size, tile_subset, alpha_min, t_stop)

@@ -13,7 +13,7 @@ def rel(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).norm() / b.norm().clamp(min=1e-30))
 
 
-def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, **kw):
+def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, binning_override=None, **kw):
     """float64 oracle on the scene's fp32 inputs (upcast). Returns (ldr, alpha, meta, grads dict)."""
     leaves = {}
     for k in LEAF_NAMES:
@@ -24,7 +24,8 @@ def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, **kw)
     sp = dict(knots=leaves["knots"], knot_t0=sc.knot_t0, knot_dt=sc.knot_dt, frame_times=leaves["frame_times"], kind=sc.spline_kind)
     ldr, alpha, meta = oracle.rasterize(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"],
                                         None, sc.Ks.cpu(), sc.width, sc.height, leaves["exposure_times"], sc.n_virtual, sc.crf_kind,
-                                        leaves.get("crf_params"), spline=sp, projection_override=projection_override, **kw)
+                                        leaves.get("crf_params"), spline=sp, projection_override=projection_override,
+                                        binning_override=binning_override, **kw)
     grads = {}
     if with_grad:
         loss = (ldr * sc.v_ldr.cpu().double()).sum()
@@ -69,3 +70,12 @@ def cuda_projection(meta):
     geom = st.geom.cpu()
     return {"means2d": geom[..., :2].contiguous(), "conics": torch.cat([geom[..., 2:4], st.conic_c.cpu()[..., None]], -1),
             "depths": st.depths.cpu(), "radii": st.radii.cpu()}
+
+
+def robust_grad_report(a: torch.Tensor, b: torch.Tensor):
+    """Per-row relative errors of a gradient tensor against the oracle: (median, fraction of rows off by > 1e-2)."""
+    a = a.detach().double().cpu().reshape(a.shape[0], -1)
+    b = b.detach().double().cpu().reshape(b.shape[0], -1)
+    nz = b.norm(dim=1) > 0
+    e = (a - b).norm(dim=1)[nz] / b.norm(dim=1)[nz]
+    return float(e.median()), float((e > 1e-2).double().mean())
