@@ -17,13 +17,22 @@ struct CrfBwdArgs {
   double* acc_exposure;  // [B]
 };
 
+// Phase 1 (pixel-parallel): each thread recomputes the CRF of kPix pixels, writes v_hdr, and leaves
+// z = ln(X + eps) and gy = v_y * y * (1 - y) of every (pixel, channel) in shared memory.
+// Phase 2 (hidden-unit-parallel): lane <-> hidden unit.  A warp walks its 128 pixels reading (z, gy)
+// by shared-memory broadcast; every lane accumulates the three parameter gradients of its own
+// units in registers, so no cross-lane reduction is needed at all.
+constexpr int kMaxUnitsPerLane = 4;  // crf_hidden <= 128
+
 __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
   extern __shared__ float smem[];
   const int stride = 3 * a.hd + 1;
-  float* s_p = smem;                // parameters [3, stride]
-  float* s_g = smem + 3 * stride;   // block-partial parameter gradients [3, stride]
+  float* s_p = smem;                         // parameters [3, stride]
+  float* s_g = s_p + 3 * stride;             // block-partial parameter gradients [3, stride]
+  float* s_z = s_g + 3 * stride;             // [3][kThreads * kPix]
+  float* s_gy = s_z + 3 * kThreads * kPix;   // [3][kThreads * kPix]
   const int frame = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool mlp = a.crf_kind == CHS_CRF_MLP;
   if (mlp)
     for (int i = tid; i < 3 * stride; i += kThreads) {
@@ -33,78 +42,96 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
   __syncthreads();
   const float dt = a.exposure[frame];
   const float scale = dt / (float)a.n_virtual;
-  float z[kPix][3], gy[kPix][3];
   float v_dt = 0.f;
 #pragma unroll
   for (int q = 0; q < kPix; ++q) {
-    const int64_t pix = ((int64_t)blockIdx.x * kPix + q) * kThreads + tid;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) z[q][ch] = gy[q][ch] = 0.f;
-    if (pix >= a.P) continue;
-    const int64_t o = ((int64_t)frame * a.P + pix) * 3;
+    const int slot = q * kThreads + tid;
+    const int64_t pix = (int64_t)blockIdx.x * (kPix * kThreads) + slot;
+    const bool live = pix < a.P;
+    const int64_t o = ((int64_t)frame * a.P + (live ? pix : 0)) * 3;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      const float h = a.hdr_mean[o + ch];
-      const float vy = a.v_ldr[o + ch];
-      float vx;
-      if (mlp) {
-        const float* p = s_p + ch * stride;
-        const float xe = dt * h + CHS_CRF_EPS;
-        const float zz = logf(xe);
-        float acc = p[3 * a.hd], dz = 0.f;
-        for (int j = 0; j < a.hd; ++j) {
-          const float pre = fmaf(p[j], zz, p[a.hd + j]);
-          if (pre > 0.f) {
-            acc = fmaf(p[2 * a.hd + j], pre, acc);
-            dz = fmaf(p[2 * a.hd + j], p[j], dz);
+      float zz = 0.f, g = 0.f;
+      if (live) {
+        const float h = a.hdr_mean[o + ch];
+        const float vy = a.v_ldr[o + ch];
+        float vx;
+        if (mlp) {
+          const float* p = s_p + ch * stride;
+          const float xe = dt * h + CHS_CRF_EPS;
+          zz = logf(xe);
+          float acc = p[3 * a.hd], dz = 0.f;
+          for (int j = 0; j < a.hd; ++j) {
+            const float pre = fmaf(p[j], zz, p[a.hd + j]);
+            if (pre > 0.f) {
+              acc = fmaf(p[2 * a.hd + j], pre, acc);
+              dz = fmaf(p[2 * a.hd + j], p[j], dz);
+            }
           }
+          const float y = 1.f / (1.f + expf(-acc));
+          g = vy * y * (1.f - y);
+          vx = g * dz / xe;
+        } else {
+          vx = vy;
         }
-        const float y = 1.f / (1.f + expf(-acc));
-        const float g = vy * y * (1.f - y);
-        z[q][ch] = zz;
-        gy[q][ch] = g;
-        vx = g * dz / xe;
-      } else {
-        vx = vy;
+        v_dt = fmaf(vx, h, v_dt);
+        a.v_hdr[o + ch] = vx * scale;
       }
-      v_dt = fmaf(vx, h, v_dt);
-      a.v_hdr[o + ch] = vx * scale;
+      if (mlp) {
+        s_z[ch * (kThreads * kPix) + slot] = zz;
+        s_gy[ch * (kThreads * kPix) + slot] = g;  // 0 for pixels past the end: they add nothing below
+      }
     }
   }
   // exposure (brightness path): block reduce -> one fp64 atomic
   v_dt = chs_warp_sum(v_dt);
   __shared__ float s_dt[kThreads / 32];
-  if (lane == 0) s_dt[tid >> 5] = v_dt;
+  if (lane == 0) s_dt[warp] = v_dt;
+  __syncthreads();
   if (mlp) {
+    const int upl = (a.hd + 31) / 32;  // units per lane
+    const int p0 = warp * (kThreads * kPix / 8), p1 = p0 + kThreads * kPix / 8;
     for (int ch = 0; ch < 3; ++ch) {
       const float* p = s_p + ch * stride;
+      float w1[kMaxUnitsPerLane], b1[kMaxUnitsPerLane], w2[kMaxUnitsPerLane];
+      float g_w1[kMaxUnitsPerLane], g_b1[kMaxUnitsPerLane], g_w2[kMaxUnitsPerLane];
+#pragma unroll
+      for (int u = 0; u < kMaxUnitsPerLane; ++u) {
+        const int j = u * 32 + lane;
+        const bool on = u < upl && j < a.hd;
+        w1[u] = on ? p[j] : 0.f;
+        b1[u] = on ? p[a.hd + j] : -1.f;  // pre = -1 < 0: inactive unit contributes nothing
+        w2[u] = on ? p[2 * a.hd + j] : 0.f;
+        g_w1[u] = g_b1[u] = g_w2[u] = 0.f;
+      }
       float g_b2 = 0.f;
+      const float* zc = s_z + ch * (kThreads * kPix);
+      const float* gc = s_gy + ch * (kThreads * kPix);
+      for (int q = p0; q < p1; ++q) {
+        const float zz = zc[q], g = gc[q];
+        g_b2 += g;
 #pragma unroll
-      for (int q = 0; q < kPix; ++q) g_b2 += gy[q][ch];
-      g_b2 = chs_warp_sum(g_b2);
-      if (lane == 0) atomicAdd(&s_g[ch * stride + 3 * a.hd], g_b2);
-      for (int j = 0; j < a.hd; ++j) {
-        const float w1 = p[j], b1 = p[a.hd + j], w2 = p[2 * a.hd + j];
-        float g_w1 = 0.f, g_b1 = 0.f, g_w2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < kPix; ++q) {
-          const float pre = fmaf(w1, z[q][ch], b1);
-          if (pre > 0.f) {
-            g_w2 = fmaf(gy[q][ch], pre, g_w2);
-            const float dh = gy[q][ch] * w2;
-            g_w1 = fmaf(dh, z[q][ch], g_w1);
-            g_b1 += dh;
+        for (int u = 0; u < kMaxUnitsPerLane; ++u) {
+          if (u < upl) {
+            const float pre = fmaf(w1[u], zz, b1[u]);
+            const float gate = pre > 0.f ? g : 0.f;
+            g_w2[u] = fmaf(gate, pre, g_w2[u]);
+            const float dh = gate * w2[u];
+            g_w1[u] = fmaf(dh, zz, g_w1[u]);
+            g_b1[u] += dh;
           }
         }
-        g_w1 = chs_warp_sum(g_w1);
-        g_b1 = chs_warp_sum(g_b1);
-        g_w2 = chs_warp_sum(g_w2);
-        if (lane == 0) {
-          atomicAdd(&s_g[ch * stride + j], g_w1);
-          atomicAdd(&s_g[ch * stride + a.hd + j], g_b1);
-          atomicAdd(&s_g[ch * stride + 2 * a.hd + j], g_w2);
+      }
+#pragma unroll
+      for (int u = 0; u < kMaxUnitsPerLane; ++u) {
+        const int j = u * 32 + lane;
+        if (u < upl && j < a.hd) {
+          atomicAdd(&s_g[ch * stride + j], g_w1[u]);
+          atomicAdd(&s_g[ch * stride + a.hd + j], g_b1[u]);
+          atomicAdd(&s_g[ch * stride + 2 * a.hd + j], g_w2[u]);
         }
       }
+      if (lane == 0) atomicAdd(&s_g[ch * stride + 3 * a.hd], g_b2);
     }
   }
   __syncthreads();
@@ -153,7 +180,7 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
     a.hdr_mean = hdr_mean; a.exposure = exposure; a.crf_params = crf_params; a.v_ldr = v_ldr; a.v_hdr = v_hdr;
     a.acc_crf = acc; a.acc_exposure = acc + n_par;
     dim3 grid((unsigned)((d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix)), d.B);
-    size_t smem = mlp ? (size_t)2 * n_par * sizeof(float) : 16;
+    size_t smem = mlp ? ((size_t)2 * n_par + (size_t)6 * kThreads * kPix) * sizeof(float) : 16;
     crf_bwd_kernel<<<grid, kThreads, smem, s>>>(a);
     CHS_LAUNCH_CHECK();
   }

@@ -327,7 +327,7 @@ def formation(hdr_cams, alpha_cams, exposure, n_virtual, crf_kind, crf_params=No
 def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, width=0, height=0,
               exposure_times=None, n_virtual=1, crf_kind=CRF_IDENTITY, crf_params=None, *, spline=None,
               background=None, near=0.01, far=1e10, eps2d=0.3, tile_size=TILE, crf_before_average=False,
-              projection_override=None, binning_override=None, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP,
+              projection_override=None, binning_override=None, straight_through=False, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP,
               radius_sigmas=3.0):
     """Oracle of ``casualhdrsplat_b200.rasterize`` (same arguments and meaning; float64 CPU).
 
@@ -336,6 +336,12 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     ``projection_override`` = dict(means2d, conics, depths (fp32 [C,N,...]), radii i32) lets a test
     feed the CUDA kernel's own fp32 projection so binning can be compared bit-for-bit (A.4/D9);
     those tensors then carry no gradient to the Gaussian geometry.
+    ``projection_override`` with ``straight_through=True``: the forward *values* of means2d / conics are the
+    overriding fp32 ones (so every discrete decision — tile lists, alpha >= 1/255, early stop — is taken on exactly the
+    numbers the kernel saw), while gradients flow through the oracle's own float64 projection (x + (x_fp32 - x).detach()).
+    This is the end-to-end gradient parity definition: the model is discontinuous at those decisions, and
+    with heavy-tailed HDR colours a single boundary pixel that flips on a very bright Gaussian moves the gradient norm by
+    ~1e-3, so derivatives are only comparable at identical decisions.
     ``binning_override`` = dict(means2d, depths (fp32), radii i32): only the *binning* (A.4, an integer function of
     fp32 projection outputs) uses these; projection values and all gradients stay the oracle's own float64 ones.  This
     is how end-to-end gradient parity is defined: last-ulp differences between an fp32 and an fp64
@@ -373,6 +379,11 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         dep_f32 = projection_override["depths"].to(torch.float32)
         radii = projection_override["radii"].to(torch.int32)
         m2d, con = _f64(m2d_f32), _f64(projection_override["conics"])
+        if straight_through:
+            own = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas)
+            live = (radii > 0)[..., None]
+            m2d = torch.where(live, own["means2d"] + (m2d - own["means2d"]).detach(), m2d)
+            con = torch.where(live, own["conics"] + (con - own["conics"]).detach(), con)
         proj = {"means2d": m2d, "conics": con, "depths": _f64(dep_f32), "radii": radii}
     if binning_override is not None:
         m2d_f32 = binning_override["means2d"].to(torch.float32)

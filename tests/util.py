@@ -13,7 +13,7 @@ def rel(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).norm() / b.norm().clamp(min=1e-30))
 
 
-def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, binning_override=None, **kw):
+def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, binning_override=None, straight_through=False, **kw):
     """float64 oracle on the scene's fp32 inputs (upcast). Returns (ldr, alpha, meta, grads dict)."""
     leaves = {}
     for k in LEAF_NAMES:
@@ -25,7 +25,7 @@ def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, binni
     ldr, alpha, meta = oracle.rasterize(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"],
                                         None, sc.Ks.cpu(), sc.width, sc.height, leaves["exposure_times"], sc.n_virtual, sc.crf_kind,
                                         leaves.get("crf_params"), spline=sp, projection_override=projection_override,
-                                        binning_override=binning_override, **kw)
+                                        binning_override=binning_override, straight_through=straight_through, **kw)
     grads = {}
     if with_grad:
         loss = (ldr * sc.v_ldr.cpu().double()).sum()
