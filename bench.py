@@ -160,7 +160,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def result(self):
         s = sorted(self.samples)
@@ -189,6 +189,8 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         comm = TorchComm() if os.environ.get("CHS_COMM", "cabi") == "torch" else ChsComm(rank, world, dev)
     L = _lib.lib()
