@@ -276,8 +276,8 @@ extern "C" int chs_bin_count(const chs_config* cfg, const int32_t* tiles_touched
   if (n_isect_host) {
     CHS_CUDA(cudaMemcpyAsync(n_isect_host, n_isect_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CHS_CUDA(cudaStreamSynchronize(s));
-    if (*n_isect_host >= ((int64_t)1 << 31)) {
-      chs_set_error("chs_bin_count: %lld intersections exceed the 2^31 limit of one launch; split the frame batch",
+    if (*n_isect_host >= ((int64_t)1 << 32) - 1) {
+      chs_set_error("chs_bin_count: %lld intersections exceed the 2^32 limit of one launch; split the frame batch",
                     (long long)*n_isect_host);
       return CHS_ERR_UNSUPPORTED;
     }
@@ -307,7 +307,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
   int st = chs_make_dims(cfg, &d);
   if (st) return st;
   CHS_REQUIRE(geom && radii && depths && isect_offsets && tile_offsets, "chs_bin_sort: null pointer");
-  CHS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 31), "chs_bin_sort: n_isect out of range");
+  CHS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 32) - 1, "chs_bin_sort: n_isect out of range");
   CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || order, "chs_bin_sort: order required for CHS_SORT_DEPTH_PRESORT");
   cudaStream_t s = (cudaStream_t)stream;
   const int n_lin = d.C * d.tiles;

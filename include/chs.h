@@ -26,7 +26,7 @@
  *    entry point returns CHS_ERR_CUDA.
  *  - Shapes: N Gaussians, B frames, n virtual poses per frame, C = B*n cameras, camera c = i*n + k,
  *    P = width*height, tiles = ceil(W/16)*ceil(H/16), M = number of (camera, tile, Gaussian)
- *    intersections (data dependent, < 2^31).
+ *    intersections (data dependent, < 2^32 - 1 per call).
  */
 #ifndef CHS_H_
 #define CHS_H_

@@ -20,8 +20,12 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "c3"
     sort_mode = sys.argv[2] if len(sys.argv) > 2 else "presort"
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    over = {}
+    for a in sys.argv[4:]:  # e.g. n_frames=1 n_gauss=2000000
+        k, v = a.split("=")
+        over[k] = int(v)
     t0 = time.time()
-    sc = make_config(name).to("cuda:0")
+    sc = make_config(name, **over).to("cuda:0")
     print(f"scene {name} built in {time.time() - t0:.1f}s", flush=True)
     L = _lib.lib()
     records = {k: [] for k in STAGES}
