@@ -179,7 +179,7 @@ def main():
     import torch.distributed as dist
 
     from casualhdrsplat_b200 import _lib
-    from casualhdrsplat_b200.parallel import ChsComm, TorchComm, formation_step, shard_frames
+    from casualhdrsplat_b200.parallel import ChsComm, NvlsComm, TorchComm, formation_step, shard_frames
     from casualhdrsplat_b200.scene import make_config
 
     if not torch.cuda.is_available():
@@ -192,7 +192,21 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-        comm = TorchComm() if os.environ.get("CHS_COMM", "cabi") == "torch" else ChsComm(rank, world, dev)
+        # default: the hand-written NVLS (multimem) all-reduce kernel; NCCL through the C ABI if the fabric has no multicast
+        which = os.environ.get("CHS_COMM", "nvls")
+        if which == "nvls":
+            try:
+                comm = NvlsComm(rank, world, dev)
+                comm.flat_buffer(1024)
+                ok = torch.ones(1, device=dev)
+            except Exception as exc:  # noqa: BLE001
+                print(f"[bench] NVLS unavailable on rank {rank}: {exc}", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) == 0.0:
+                which = "cabi"
+        if which != "nvls":
+            comm = TorchComm() if which == "torch" else ChsComm(rank, world, dev)
     L = _lib.lib()
 
     sc = make_config(args.workload)
@@ -207,7 +221,7 @@ def main():
     def upstream_fixed(fids, ldr):
         return torch.stack([v_ldr_local[i] for i in fids])
 
-    stats = {"count_pairs": True}
+    stats = {"count_pairs": True, "events": []}
     flat = None
 
     def step(upstream, st=None):
@@ -263,8 +277,9 @@ def main():
     launches0 = L.chs_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    stats["events"].clear()
     for _ in range(args.steps):
-        step(upstream_fixed)
+        step(upstream_fixed, stats)
     e1.record()
     barrier()
     sampler.stop_flag = True
@@ -273,6 +288,7 @@ def main():
     ms_per_step = ms / args.steps
     value = B / (ms_per_step / 1e3)
     stage_ms = {k[4:]: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in stage_events.items()}
+    stage_ms["allreduce"] = sum(a.elapsed_time(b) for a, b in stats["events"]) / args.steps if stats["events"] else 0.0
     bwd_calls = stage_events["chs_blend_bwd"]
     bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_calls) / max(len(bwd_calls), 1)
     for k, f in orig.items():
@@ -360,7 +376,9 @@ def main():
                                        f"global batch {B} frames sharded by frame, fwd+bwd incl. pose/exposure/CRF grads",
                            "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode,
                            "isects_per_frame": M_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
-                           "collective": None if world == 1 else ("ncclAllReduce via libchs C ABI" if isinstance(comm, ChsComm) else "torch.distributed all_reduce"),
+                           "collective": None if world == 1 else ("ncclAllReduce via libchs C ABI" if isinstance(comm, ChsComm) else
+                                                                 "NVLS multimem one-shot all-reduce kernel (libchs)" if isinstance(comm, NvlsComm)
+                                                                 else "torch.distributed all_reduce"),
                            "parallelism": f"dp{world} over frames"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline,
                 "cpu_baseline": cpu_baseline,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "chs_comm_init": (ctypes.c_int, [P, c_int32, c_int32, POINTER(c_void_p)]),
     "chs_allreduce_grads": (ctypes.c_int, [P, P, c_uint64, P]),
     "chs_comm_destroy": (ctypes.c_int, [P]),
+    "chs_nvls_allreduce": (ctypes.c_int, [P, c_uint64, c_int32, c_int32, P]),
 }
 
 _LIB = None

@@ -112,7 +112,7 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     return st
 
 
-def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ldr, v_alpha, v_hdr_out=None):
+def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ldr, v_alpha, v_hdr_out=None, grads_out=None):
     """Run K7-K9 (+K0 bwd). Returns dict of gradients; ``grads_flat`` is the [14N] buffer that multi-GPU runs all-reduce."""
     L = _lib.lib()
     cfg = st.cfg
@@ -138,7 +138,7 @@ def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ld
                           ptr(st.final_T), ptr(st.last_id), ptr(v_hdr), ptr(v_alpha), ptr(v_geom), ptr(v_cogr), ptr(v_blue), s),
           "chs_blend_bwd")
     # K9
-    grads_flat = _empty((14 * N,), torch.float32, dev)
+    grads_flat = grads_out if grads_out is not None else _empty((14 * N,), torch.float32, dev)  # grads_out: caller's [14N] slice
     v_viewmats = _empty((C, 4, 4), torch.float32, dev)
     check(L.chs_project_bwd(byref(cfg), ptr(means), ptr(quats), ptr(scales), ptr(st.viewmats), ptr(st.Ks), ptr(st.radii), ptr(v_geom),
                             ptr(v_cogr), ptr(v_blue), ptr(grads_flat), ptr(v_viewmats), ptr(red), red.numel(), s), "chs_project_bwd")

@@ -167,3 +167,45 @@ extern "C" int chs_comm_destroy(chs_comm* comm) {
   delete comm;
   return CHS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// K10, NVLS variant: one-shot all-reduce over the NVSwitch multicast mapping (no NCCL involved).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) nvls_allreduce_kernel(float* mc, uint64_t begin4, uint64_t end4, uint64_t tail_begin,
+                                                             uint64_t tail_end) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = begin4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += stride) {
+    float* p = mc + i * 4;
+    float a, b, c, d;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  }
+  // scalar tail (count % 4 floats), owned by the last rank
+  for (uint64_t i = tail_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tail_end; i += stride) {
+    float v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc + i) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(v) : "memory");
+  }
+}
+}  // namespace
+
+extern "C" int chs_nvls_allreduce(float* mc_ptr, uint64_t count, int32_t rank, int32_t world, void* stream) {
+  CHS_REQUIRE(mc_ptr, "chs_nvls_allreduce: null multicast pointer (no NVLS multicast support?)");
+  CHS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "chs_nvls_allreduce: bad rank %d / world %d", rank, world);
+  CHS_REQUIRE(((uintptr_t)mc_ptr) % 16 == 0, "chs_nvls_allreduce: pointer must be 16-byte aligned");
+  if (count == 0) return CHS_OK;
+  const uint64_t n4 = count / 4;
+  const uint64_t per = (n4 + world - 1) / world;
+  const uint64_t b4 = (uint64_t)rank * per < n4 ? (uint64_t)rank * per : n4;
+  const uint64_t e4 = b4 + per < n4 ? b4 + per : n4;
+  const uint64_t tb = rank == world - 1 ? n4 * 4 : count, te = count;
+  uint64_t work = (e4 - b4) > (te - tb) ? (e4 - b4) : (te - tb);
+  int blocks = (int)((work + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  nvls_allreduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mc_ptr, b4, e4, tb, te);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}

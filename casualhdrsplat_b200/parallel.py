@@ -83,6 +83,47 @@ class ChsComm:
             self._handle = ctypes.c_void_p()
 
 
+class NvlsComm:
+    """Hand-written one-shot all-reduce through the NVSwitch multicast mapping (NVLS), no NCCL in the data path.
+
+    The flat gradient buffer itself lives in symmetric memory (torch.distributed._symmetric_memory owns the allocation
+    and the rendezvous — plumbing), so K9 / the accumulations write straight into it; ``allreduce_`` is then
+    barrier -> ``chs_nvls_allreduce`` (multimem.ld_reduce + multimem.st on this rank's slice) -> barrier.
+    Every rank ends with bit-identical sums.  Raises if the fabric has no multicast support.
+    """
+
+    def __init__(self, rank: int, world: int, device: torch.device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self._symm, self._dist = symm, dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world, self.device = rank, world, device
+        self._buf = None
+        self._hdl = None
+
+    def flat_buffer(self, n_floats: int) -> torch.Tensor:
+        """The symmetric [n_floats] fp32 buffer (allocated and rendezvoused once, reused every step)."""
+        if self._buf is None or self._buf.numel() < n_floats:
+            padded = (n_floats + 1023) // 1024 * 1024
+            self._buf = self._symm.empty(padded, dtype=torch.float32, device=self.device)
+            self._hdl = self._symm.rendezvous(self._buf, self.group.group_name)
+            if not self._hdl.multicast_ptr:
+                raise RuntimeError("NvlsComm: this fabric/driver exposes no multicast (NVLS) mapping; use ChsComm (NCCL)")
+        return self._buf[:n_floats]
+
+    def allreduce_(self, buf: torch.Tensor) -> None:
+        if self._buf is None or buf.data_ptr() != self._buf.data_ptr():
+            raise RuntimeError("NvlsComm.allreduce_: the buffer must be the one returned by flat_buffer()")
+        self._hdl.barrier(channel=0)  # every rank's partial sums are in its symmetric buffer
+        _lib.check(_lib.lib().chs_nvls_allreduce(ctypes.c_void_p(self._hdl.multicast_ptr), buf.numel(), self.rank, self.world,
+                                                 _stream()), "chs_nvls_allreduce")
+        self._hdl.barrier(channel=1)  # every slice has been broadcast
+
+    def close(self) -> None:
+        self._buf, self._hdl = None, None
+
+
 class TorchComm:
     """Collective through torch.distributed (NCCL on GPUs; gloo in the CPU tests of the sharding logic)."""
 
@@ -120,6 +161,8 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
     n_crf = crf_params.numel() if crf_params is not None else 0
     layout = GradLayout(N, K, n_crf, B_total)
     dev = means.device
+    if out is None and hasattr(comm, "flat_buffer"):
+        out = comm.flat_buffer(layout.total)
     flat = out if out is not None else torch.empty(layout.total, dtype=torch.float32, device=dev)
     flat[layout.off_knots:].zero_()
     v = layout.views(flat)
@@ -136,9 +179,9 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
         st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline)
         v_ldr = upstream(ids, st.ldr).contiguous()
-        g = backward_stages(st, means, quats, scales, ex, crf_params, v_ldr, None)
+        # the first micro-batch writes K9's output straight into the flat buffer (which may be symmetric memory)
+        g = backward_stages(st, means, quats, scales, ex, crf_params, v_ldr, None, grads_out=flat[:14 * N] if first else None)
         if first:
-            flat[:14 * N].copy_(g["grads_flat"])
             first = False
         else:
             flat[:14 * N].add_(g["grads_flat"])
@@ -153,8 +196,16 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
     if first:
         flat[:14 * N].zero_()
     if comm is not None and comm.world > 1:
-        comm.allreduce_(flat)
+        if stats is not None and "events" in stats:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            comm.allreduce_(flat)
+            e1.record()
+            stats["events"].append((e0, e1))
+        else:
+            comm.allreduce_(flat)
     if stats is not None:
         stats["n_isect"] = n_isect_total
-        stats["m_g"] = m_g_total
+        if stats.get("count_pairs"):
+            stats["m_g"] = m_g_total
     return layout, flat

@@ -190,6 +190,14 @@ CHS_API int chs_comm_init(const void* unique_id_host_128, int32_t rank, int32_t 
 CHS_API int chs_allreduce_grads(chs_comm* comm, float* buf, uint64_t count, void* stream);
 CHS_API int chs_comm_destroy(chs_comm* comm);
 
+/* ---- K10 (NVLS variant): hand-written one-shot all-reduce through the NVSwitch multicast address ----
+ * mc_ptr is the MULTICAST device pointer of a symmetric buffer (same offset on every rank, e.g. from
+ * torch.distributed._symmetric_memory) that already holds each rank's partial sums.  Rank r reduces its
+ * slice in the switch (multimem.ld_reduce.add.v4.f32) and broadcasts the sum to every rank
+ * (multimem.st), so all ranks end with bit-identical buffers.  The caller must place a cross-rank
+ * barrier before (all partials written) and after (all slices broadcast) this call. count in floats. */
+CHS_API int chs_nvls_allreduce(float* mc_ptr, uint64_t count, int32_t rank, int32_t world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

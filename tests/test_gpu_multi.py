@@ -41,9 +41,9 @@ def _worker(rank, world, port, mode, out_dir):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        from casualhdrsplat_b200.parallel import ChsComm, TorchComm, shard_frames
+        from casualhdrsplat_b200.parallel import ChsComm, NvlsComm, TorchComm, shard_frames
 
-        comm = ChsComm(rank, world, dev) if mode == "cabi" else TorchComm()
+        comm = ChsComm(rank, world, dev) if mode == "cabi" else NvlsComm(rank, world, dev) if mode == "nvls" else TorchComm()
         sc = _scene()
         lay, flat = _step(sc, dev, shard_frames(sc.n_frames, rank, world), comm)
         torch.save(flat.cpu(), os.path.join(out_dir, f"flat_{rank}.pt"))
@@ -52,7 +52,7 @@ def _worker(rank, world, port, mode, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["cabi", "torch"])
+@pytest.mark.parametrize("mode", ["cabi", "torch", "nvls"])
 def test_sharded_step_matches_single_gpu(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
