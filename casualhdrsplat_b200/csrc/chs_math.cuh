@@ -57,6 +57,17 @@ CHS_HD float chs_exp2_fast(float x) {
 }
 CHS_HD double chs_exp2_fast(double x) { return exp2(x); }
 
+CHS_HD float chs_log2_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return log2f(x);
+#endif
+}
+CHS_HD double chs_log2_fast(double x) { return log2(x); }
+
 CHS_HD float chs_fma(float a, float b, float c) { return fmaf(a, b, c); }
 CHS_HD double chs_fma(double a, double b, double c) { return fma(a, b, c); }
 
@@ -359,11 +370,13 @@ CHS_HD void chs_make_splat(T mx, T my, T ca, T cb, T cc, T opac, T r, T g, T b, 
   s.qa = T(-0.5) * ChsK<T>::log2e * ca;
   s.qb = -ChsK<T>::log2e * cb;
   s.qc = T(-0.5) * ChsK<T>::log2e * cc;
-  s.lo = log2(opac);
+  // staged once per (tile, Gaussian) and shared by forward and backward: approximate log2 / reciprocal
+  // (2^-22 relative) are ample; rbc / rba only steer the conservative culling bound
+  s.lo = chs_log2_fast(opac);
   s.r = r; s.g = g; s.b = b;
-  s.inv_opac = T(1) / opac;
-  s.rbc = cc > T(0) ? -cb / cc : T(0);
-  s.rba = ca > T(0) ? -cb / ca : T(0);
+  s.inv_opac = chs_rcp_fast(opac);
+  s.rbc = cc > T(0) ? -cb * chs_rcp_fast(cc) : T(0);
+  s.rba = ca > T(0) ? -cb * chs_rcp_fast(ca) : T(0);
 }
 
 // Sub-tile culling.  Upper bound of log2(alpha) over the axis-aligned rectangle of pixel centres
