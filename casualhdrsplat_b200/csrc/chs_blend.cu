@@ -1,357 +1,42 @@
 // chs_blend.cu — K6 blend_fwd (+ fused formation epilogue) and K8 blend_bwd
 // (SURVEY.md section 2.4, Appendix A.5 / A.6 / A.7).
 //
-// Layout of one CTA: 256 threads = one 16x16 pixel tile; warp w owns the 8x4 pixel block at
-// ((w & 1) * 8, (w >> 1) * 4), lane l the pixel (l & 7, l >> 3) inside it.
+// Layout of one CTA: 128 threads = one 16x16 pixel tile; warp w owns the 8x8 pixel block at
+// ((w & 1) * 8, (w >> 1) * 8); lane l owns the TWO pixels (l & 7, l >> 3) and (l & 7, (l >> 3) + 4)
+// of that block.  Every per-pixel quantity is a register pair (pixel A, pixel B) and every
+// multiply/add on it is ONE packed fp32x2 instruction (Blackwell FFMA2 / FMUL2 / FADD2);
+// per-Gaussian scalars enter as broadcast operands (the .F32 operand mode), so no splat moves are
+// needed.  Compared with one pixel per thread (rounds r1a-c, see git history) this halves the
+// per-pixel cost of the arithmetic and amortises the per-(warp, Gaussian) fixed cost — bit scan,
+// shared-memory loads, the 14-shuffle butterfly and the RED — over 64 pixels instead of 32.
 //
 // Per batch of up to 256 tile-list entries the CTA gathers the per-(camera, Gaussian) records
-// (three 128-bit loads each) into shared memory, pre-scaling the conic for exp2.  Each warp then
-// *culls the batch against its own 8x4 block* with an exact ellipse-vs-rectangle bound
-// (chs_block_max_power): 32 lanes test 32 Gaussians, a ballot yields the survivors, and only those
-// are evaluated for the warp's 32 pixels.  Skipped pairs are exactly pairs with alpha < 1/255, so results are
-// unchanged, but most of the 256 pair evaluations per intersection of a naive tile kernel vanish.
-// Early termination is warp-granular (ballot of per-pixel "done") and CTA-granular
-// (__syncthreads_and) per batch.
+// (three 128-bit loads each) into shared memory, with the conic in completed-square form pre-scaled
+// for exp2 (chs_make_splat).  Each warp then *culls the batch against its own 8x8 block* with an
+// exact ellipse-vs-rectangle bound (chs_block_max_power): 32 lanes test 32 Gaussians, a ballot
+// yields the survivors, and only those are evaluated for the warp's 64 pixels.  Skipped pairs are
+// exactly pairs with alpha < 1/255, so results are unchanged, but most of the 256 pair evaluations
+// per intersection of a naive tile kernel vanish.  Early termination is warp-granular (ballot of the
+// per-pixel "done" state) and CTA-granular (__syncthreads_and) per batch.
 //
 // Forward fuses the whole formation epilogue: the CTA loops over the n virtual poses of its frame,
 // accumulates sum_k H_k in registers, and writes B = F(dt/n * sum_k H_k) once (decision D0 order).
 //
-// Backward walks each pixel's list back to front from last_id; the nine per-Gaussian partials are
-// reduced across the warp with a transposing butterfly (14 shuffles instead of 45) that leaves
-// value j on lane j, so a single RED instruction with nine active lanes adds all nine numbers
-// into the three [C,N] gradient planes.
+// Backward walks each pixel's list back to front from last_id; the nine per-Gaussian partials of
+// the thread's two pixels are added, then reduced across the warp with a transposing butterfly
+// (14 shuffles instead of 45) that leaves value j on lane j, so a single RED instruction with nine
+// active lanes adds all nine numbers into the three [C,N] gradient planes.
 #include <stdlib.h>
 
 #include "chs_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
+constexpr int kBatch = 256;
 #define CHS_LOG2_ALPHA_MIN (-7.994353436858858f) /* log2(1/255) */
 
-template <int kBatch> struct SplatSmemT {
-  float4 a[kBatch];  // mx, my, qa, qb
-  float4 b[kBatch];  // qc, lo, val (int bits; c * N + g), unused
-  float4 c[kBatch];  // r, g, b, 1/opacity
-  float2 r[kBatch];  // rbc, rba (culling test only)
-};
-
-template <class SplatSmem>
-__device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
-                                            const float* __restrict__ conic_c, const float4* __restrict__ rgbo) {
-  const float4 gm = __ldg(geom + val);
-  const float cc = __ldg(conic_c + val);
-  const float4 col = __ldg(rgbo + (val - cam_base));
-  ChsSplat<float> s;
-  chs_make_splat(gm.x, gm.y, gm.z, gm.w, cc, col.w, col.x, col.y, col.z, s);
-  sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.qb);
-  sm.b[slot] = make_float4(s.qc, s.lo, __int_as_float(val), 0.f);
-  sm.c[slot] = make_float4(s.r, s.g, s.b, s.inv_opac);
-  sm.r[slot] = make_float2(s.rbc, s.rba);
-}
-
-template <class SplatSmem>
-__device__ __forceinline__ ChsSplat<float> read_splat_ab(const SplatSmem& sm, int slot) {
-  const float4 a = sm.a[slot];
-  const float4 b = sm.b[slot];
-  ChsSplat<float> s;
-  s.mx = a.x; s.my = a.y; s.qa = a.z; s.qb = a.w;
-  s.qc = b.x; s.lo = b.y;
-  return s;
-}
-
-// can staged splat `slot` reach alpha >= 1/255 anywhere in the warp's rectangle of pixel centres?
-template <class SplatSmem>
-__device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
-  ChsSplat<float> s = read_splat_ab(sm, slot);
-  const float2 r = sm.r[slot];
-  s.rbc = r.x; s.rba = r.y;
-  return chs_block_max_power(s, bx0, bx1, by0, by1) >= CHS_LOG2_ALPHA_MIN - 1e-3f;
-}
-
-struct BlendFwdArgs {
-  int N, n_virtual, W, H, tile_w, tiles;
-  int crf_kind, crf_hidden;
-  float bg[3];
-  const float4* geom;
-  const float* conic_c;
-  const float4* rgbo;
-  const int32_t* vals;
-  const uint32_t* tile_offsets;
-  const float* exposure;
-  const float* crf_params;
-  float *ldr, *alpha, *hdr_mean, *final_T;
-  int32_t* last_id;
-};
-
-template <int kBatch, int kMinBlocks>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFwdArgs a) {
-  __shared__ SplatSmemT<kBatch> sm;
-  extern __shared__ float s_crf[];  // 3 * (3 Hd + 1) floats when the CRF is the MLP
-
-  const int tile = blockIdx.x, frame = blockIdx.y;
-  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 4;
-  const int ix = bx + (lane & 7), iy = by + (lane >> 3);
-  const bool inside = ix < a.W && iy < a.H;
-  const float px = ix + 0.5f, py = iy + 0.5f;
-  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 3.5f;
-  const int64_t P = (int64_t)a.W * a.H;
-  const int64_t pix = (int64_t)iy * a.W + ix;
-
-  if (a.crf_kind == CHS_CRF_MLP)
-    for (int i = tid; i < 3 * (3 * a.crf_hidden + 1); i += kThreads) s_crf[i] = a.crf_params[i];
-
-  float sum_r = 0.f, sum_g = 0.f, sum_b = 0.f, sum_alpha = 0.f;
-  for (int k = 0; k < a.n_virtual; ++k) {
-    const int c = frame * a.n_virtual + k;
-    const int cam_base = c * a.N;
-    const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
-    const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
-    float T = 1.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
-    int last = 0;
-    bool done = !inside;
-    bool warp_done = __all_sync(CHS_FULL_MASK, done);
-    for (uint32_t base = start; base < end; base += kBatch) {
-      // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
-      if (__syncthreads_and(done)) break;
-      const int cnt = min((uint32_t)kBatch, end - base);
-      if (tid < cnt) stage_splat(sm, tid, a.vals[base + tid], cam_base, a.geom, a.conic_c, a.rgbo);
-      __syncthreads();
-      if (warp_done) continue;
-      for (int sub = 0; sub < cnt; sub += 32) {
-        const int j = sub + lane;
-        const bool hit = (j < cnt) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
-        unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
-        while (mask) {
-          const int jj = sub + __ffs(mask) - 1;
-          mask &= mask - 1;
-          const ChsSplat<float> s = read_splat_ab(sm, jj);
-          float dx, dy;
-          const float power = chs_pair_power(s, px, py, dx, dy);
-          if (!done && power >= CHS_LOG2_ALPHA_MIN) {
-            const float alpha = fminf(CHS_ALPHA_MAX, chs_exp2_fast(power));
-            const float Tn = T * (1.f - alpha);
-            if (Tn <= CHS_T_STOP) {
-              done = true;
-            } else {
-              const float4 col = sm.c[jj];
-              const float w = alpha * T;
-              acc_r += w * col.x;
-              acc_g += w * col.y;
-              acc_b += w * col.z;
-              T = Tn;
-              last = (int)(base - start) + jj + 1;
-            }
-          }
-        }
-        if (__all_sync(CHS_FULL_MASK, done)) {
-          warp_done = true;
-          break;
-        }
-      }
-    }
-    __syncthreads();  // the next pose restages shared memory
-    if (inside) {
-      a.final_T[(int64_t)c * P + pix] = T;
-      a.last_id[(int64_t)c * P + pix] = last;
-      sum_r += acc_r + T * a.bg[0];
-      sum_g += acc_g + T * a.bg[1];
-      sum_b += acc_b + T * a.bg[2];
-      sum_alpha += 1.f - T;
-    }
-  }
-  if (!inside) return;
-  // formation epilogue (A.7, decision D0): mean over poses, x exposure, CRF
-  const float inv_n = 1.f / (float)a.n_virtual;
-  const float hr = sum_r * inv_n, hg = sum_g * inv_n, hb = sum_b * inv_n;
-  const float dt = a.exposure[frame];
-  float o0 = dt * hr, o1 = dt * hg, o2 = dt * hb;
-  if (a.crf_kind == CHS_CRF_MLP) {
-    const int stride = 3 * a.crf_hidden + 1;
-    o0 = chs_crf_mlp_fwd(o0, s_crf, a.crf_hidden);
-    o1 = chs_crf_mlp_fwd(o1, s_crf + stride, a.crf_hidden);
-    o2 = chs_crf_mlp_fwd(o2, s_crf + 2 * stride, a.crf_hidden);
-  }
-  const int64_t o = ((int64_t)frame * P + pix) * 3;
-  a.ldr[o] = o0; a.ldr[o + 1] = o1; a.ldr[o + 2] = o2;
-  a.hdr_mean[o] = hr; a.hdr_mean[o + 1] = hg; a.hdr_mean[o + 2] = hb;
-  a.alpha[(int64_t)frame * P + pix] = sum_alpha * inv_n;
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward
-// ---------------------------------------------------------------------------------------------
-struct BlendBwdArgs {
-  int N, n_virtual, W, H, tile_w, tiles;
-  float bg[3];
-  const float4* geom;
-  const float* conic_c;
-  const float4* rgbo;
-  const int32_t* vals;
-  const uint32_t* tile_offsets;
-  const float* final_T;
-  const int32_t* last_id;
-  const float* v_hdr;    // [B,H,W,3] gradient w.r.t. each pose's HDR image
-  const float* v_alpha;  // [B,H,W] or null (gradient w.r.t. the pose-averaged alpha)
-  float4* v_geom;        // [C,N] (v_mx, v_my, v_A, v_B)
-  float4* v_cogr;        // [C,N] (v_C, v_opacity, v_r, v_g)
-  float* v_blue;         // [C,N]  v_b
-};
-
-// Transposing butterfly: on entry every lane holds its pixel's 8 partials v[0..7]; on exit every
-// lane l holds the warp total of v[l & 7].  9 shuffles instead of 40.
-__device__ __forceinline__ float warp_transpose_reduce8(float v[8], int lane) {
-  {
-    const bool odd = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = odd ? v[2 * i] : v[2 * i + 1];
-      const float keep = odd ? v[2 * i + 1] : v[2 * i];
-      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 1);  // v[i] = value 2i + bit0
-    }
-  }
-  {
-    const bool odd = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = odd ? v[2 * i] : v[2 * i + 1];
-      const float keep = odd ? v[2 * i + 1] : v[2 * i];
-      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 2);  // v[i] = value 4i + 2 bit1 + bit0
-    }
-  }
-  {
-    const bool odd = lane & 4;
-    const float send = odd ? v[0] : v[1];
-    const float keep = odd ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 4);  // value lane & 7
-  }
-  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 8);
-  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 16);
-  return v[0];
-}
-
-template <int kBatch, int kMinBlocks>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd_kernel(BlendBwdArgs a) {
-  __shared__ SplatSmemT<kBatch> sm;
-  __shared__ int s_max_last;
-
-  const int tile = blockIdx.x, c = blockIdx.y;
-  const int frame = c / a.n_virtual;
-  const int cam_base = c * a.N;
-  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 4;
-  const int ix = bx + (lane & 7), iy = by + (lane >> 3);
-  const bool inside = ix < a.W && iy < a.H;
-  const float px = ix + 0.5f, py = iy + 0.5f;
-  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 3.5f;
-  const int64_t P = (int64_t)a.W * a.H;
-  const int64_t pix = (int64_t)iy * a.W + ix;
-  const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
-  const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
-  if (end <= start) return;
-
-  float Tr = 1.f, vh[3] = {0.f, 0.f, 0.f}, va_t = 0.f;
-  int my_last = 0;
-  if (inside) {
-    const float T_final = a.final_T[(int64_t)c * P + pix];
-    my_last = a.last_id[(int64_t)c * P + pix];
-    const int64_t o = ((int64_t)frame * P + pix) * 3;
-    vh[0] = a.v_hdr[o]; vh[1] = a.v_hdr[o + 1]; vh[2] = a.v_hdr[o + 2];
-    const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] / (float)a.n_virtual : 0.f;
-    va_t = T_final * (v_al - (a.bg[0] * vh[0] + a.bg[1] * vh[1] + a.bg[2] * vh[2]));
-    Tr = T_final;
-  }
-  if (tid == 0) s_max_last = 0;
-  __syncthreads();
-  {
-    int m = my_last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(CHS_FULL_MASK, m, o));
-    if (lane == 0 && m > 0) atomicMax(&s_max_last, m);
-  }
-  __syncthreads();
-  const int n_walk = s_max_last;  // entries [0, n_walk) of the tile list can matter
-  int warp_last = my_last;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(CHS_FULL_MASK, warp_last, o));
-
-  // lanes 0..7 own the eight totals of the butterfly, lane 8 the ninth (blue): one RED instruction
-  // with nine active lanes adds a Gaussian's whole gradient record
-  char* lane_base = nullptr;
-  uint32_t lane_stride = 0;
-  if (lane < 4) {
-    lane_base = reinterpret_cast<char*>(a.v_geom) + lane * 4;
-    lane_stride = 16;
-  } else if (lane < 8) {
-    lane_base = reinterpret_cast<char*>(a.v_cogr) + (lane - 4) * 4;
-    lane_stride = 16;
-  } else if (lane == 8) {
-    lane_base = reinterpret_cast<char*>(a.v_blue);
-    lane_stride = 4;
-  }
-
-  float buf[3] = {0.f, 0.f, 0.f};
-  for (int hi = n_walk; hi > 0; hi -= kBatch) {
-    const int lo = max(0, hi - kBatch);
-    const int cnt = hi - lo;
-    __syncthreads();
-    if (tid < cnt) {
-      stage_splat(sm, tid, a.vals[start + lo + tid], cam_base, a.geom, a.conic_c, a.rgbo);
-    }
-    __syncthreads();
-    if (warp_last <= lo) continue;  // none of this warp's pixels reaches into this batch
-    for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
-      const int sub_lo = max(0, sub_hi - 32);
-      if (warp_last <= lo + sub_lo) continue;
-      const int j = sub_lo + lane;
-      const bool hit = (j < sub_hi) && (lo + j < warp_last) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
-      unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
-      while (mask) {
-        const int bit = 31 - __clz(mask);
-        mask &= ~(1u << bit);
-        const int jj = sub_lo + bit;
-        const int rel = lo + jj + 1;  // 1-based index in the tile list
-        const float4 sa = sm.a[jj];
-        const float4 sb = sm.b[jj];
-        ChsSplat<float> s;
-        s.mx = sa.x; s.my = sa.y; s.qa = sa.z; s.qb = sa.w;
-        s.qc = sb.x; s.lo = sb.y;
-        const uint32_t val = (uint32_t)__float_as_int(sb.z);
-        float dx, dy;
-        const float power = chs_pair_power(s, px, py, dx, dy);
-        const bool valid = (rel <= my_last) && power >= CHS_LOG2_ALPHA_MIN;
-        if (!__any_sync(CHS_FULL_MASK, valid)) continue;
-        const float4 col = sm.c[jj];
-        s.r = col.x; s.g = col.y; s.b = col.z; s.inv_opac = col.w;
-        const float au = valid ? chs_exp2_fast(power) : 0.f;
-        float g[9];
-        chs_pair_bwd(s, dx, dy, au, fminf(CHS_ALPHA_MAX, au), Tr, buf, vh, va_t, g);
-        const float blue = chs_warp_sum(g[8]);
-        const float r8 = warp_transpose_reduce8(g, lane);
-        const float add = lane == 8 ? blue : r8;
-        if (lane < 9 && add != 0.f) atomicAdd(reinterpret_cast<float*>(lane_base + (uint64_t)val * (uint32_t)lane_stride), add);
-      }
-    }
-  }
-}
-
-
-// =============================================================================================
-// Two pixels per thread + packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2).
-//
-// CTA = 128 threads = one 16x16 tile; warp w owns the 8x8 block at ((w & 1) * 8, (w >> 1) * 8);
-// lane l owns the two pixels (l & 7, l >> 3) and (l & 7, (l >> 3) + 4) of that block.  Every
-// per-pixel quantity is a register pair (pixel A, pixel B) and every multiply/add on it is ONE
-// packed instruction; per-Gaussian scalars enter as free broadcast operands (the .F32 operand mode
-// of FFMA2), so no splat moves are needed.  Compared with one pixel per thread this halves the
-// per-pixel cost of the arithmetic and, more importantly, amortises the per-(warp, Gaussian) fixed
-// cost — bit scan, shared-memory loads, the 14-shuffle butterfly and the RED — over 64 pixels
-// instead of 32, while the exact ellipse-vs-block culling now works on 8x8 blocks (measured on c3:
-// 0.55x the warp-iterations for 1.1x the pixel evaluations).
-// =============================================================================================
+// ---- packed fp32x2 helpers ----
 struct P2 {
   unsigned long long v;
 };
@@ -394,27 +79,67 @@ __device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {
   return r;
 }
 __device__ __forceinline__ P2 neg2(P2 a) { return p2(-p2lo(a), -p2hi(a)); }
+__device__ __forceinline__ float p2sum(P2 a) { return p2lo(a) + p2hi(a); }
 
-constexpr int kThreads2 = 128;
+// ---- staged batch of tile-list entries ----
+struct SplatSmem {
+  float4 a[kBatch];  // mx, my, qa, r
+  float4 b[kBatch];  // kc, lo, val (int bits; c * N + g), rbc
+  float4 c[kBatch];  // r, g, b, 1/opacity
+};
 
-// log2(alpha) (before the 0.999 clamp) of one staged splat at this thread's two pixels; identical
-// operation order in forward and backward so both take the same skip decisions.
-__device__ __forceinline__ void pair_power2(const float4 sa, float qc, float lo, float px, P2 py2, float& dx, P2& dy2, float& s0,
-                                            float& s1, float& pA, float& pB) {
-  dx = sa.x - px;
-  dy2 = p2s(sa.y) - py2;
-  s0 = sa.z * dx;  // qa dx
-  s1 = sa.w * dx;  // qb dx
-  const P2 u2 = fma2(p2s(qc), dy2, p2s(s1));          // qb dx + qc dy
-  const P2 quad2 = fma2(u2, dy2, p2s(s0 * dx));       // qa dx^2 + qb dx dy + qc dy^2
-  pA = fminf(p2lo(quad2), 0.f) + lo;
-  pB = fminf(p2hi(quad2), 0.f) + lo;
+__device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
+                                            const float* __restrict__ conic_c, const float4* __restrict__ rgbo) {
+  const float4 gm = __ldg(geom + val);
+  const float cc = __ldg(conic_c + val);
+  const float4 col = __ldg(rgbo + (val - cam_base));
+  ChsSplat<float> s;
+  chs_make_splat(gm.x, gm.y, gm.z, gm.w, cc, col.w, col.x, col.y, col.z, s);
+  sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.r);
+  sm.b[slot] = make_float4(s.kc, s.lo, __int_as_float(val), s.rbc);
+  sm.c[slot] = make_float4(s.cr, s.cg, s.cb, s.inv_opac);
 }
 
-template <int kBatch>
-__global__ void __launch_bounds__(kThreads2) blend_fwd2_kernel(BlendFwdArgs a) {
-  __shared__ SplatSmemT<kBatch> sm;
-  extern __shared__ float s_crf[];
+// can staged splat `slot` reach alpha >= 1/255 anywhere in the warp's rectangle of pixel centres?
+__device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
+  const float4 a = sm.a[slot];
+  const float4 b = sm.b[slot];
+  ChsSplat<float> s;
+  s.mx = a.x; s.my = a.y; s.qa = a.z; s.r = a.w;
+  s.kc = b.x; s.lo = b.y; s.rbc = b.w;
+  return chs_block_max_power(s, bx0, bx1, by0, by1) >= CHS_LOG2_ALPHA_MIN - 1e-3f;
+}
+
+// log2(alpha) (before the 0.999 clamp) of a staged splat at this thread's two pixels (same column,
+// rows y and y + 4).  Identical operation order in forward and backward, so both take the same skip
+// decisions.  power = qa u^2 + kc dy^2 + lo with u = dx + r dy.
+__device__ __forceinline__ P2 pair_power2(const float4 sa, float kc, float lo, float px, P2 py2, float& dx, P2& dy2, P2& u2) {
+  dx = sa.x - px;
+  dy2 = p2s(sa.y) - py2;
+  u2 = fma2(p2s(sa.w), dy2, p2s(dx));
+  const P2 t2 = (p2s(kc) * dy2) * dy2;
+  return fma2(p2s(sa.z) * u2, u2, t2) + p2s(lo);
+}
+
+struct BlendFwdArgs {
+  int N, n_virtual, W, H, tile_w, tiles;
+  int crf_kind, crf_hidden;
+  float bg[3];
+  const float4* geom;
+  const float* conic_c;
+  const float4* rgbo;
+  const int32_t* vals;
+  const uint32_t* tile_offsets;
+  const float* exposure;
+  const float* crf_params;
+  float *ldr, *alpha, *hdr_mean, *final_T;
+  int32_t* last_id;
+};
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFwdArgs a) {
+  __shared__ SplatSmem sm;
+  extern __shared__ float s_crf[];  // 3 * (3 Hd + 1) floats when the CRF is the MLP
 
   const int tile = blockIdx.x, frame = blockIdx.y;
   const int tx = tile % a.tile_w, ty = tile / a.tile_w;
@@ -427,9 +152,10 @@ __global__ void __launch_bounds__(kThreads2) blend_fwd2_kernel(BlendFwdArgs a) {
   const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 7.5f;
   const int64_t P = (int64_t)a.W * a.H;
   const int64_t pixA = (int64_t)iyA * a.W + ix, pixB = (int64_t)iyB * a.W + ix;
+  const float kInf = __int_as_float(0x7f800000);
 
   if (a.crf_kind == CHS_CRF_MLP)
-    for (int i = tid; i < 3 * (3 * a.crf_hidden + 1); i += kThreads2) s_crf[i] = a.crf_params[i];
+    for (int i = tid; i < 3 * (3 * a.crf_hidden + 1); i += kThreads) s_crf[i] = a.crf_params[i];
 
   P2 sum_r2 = p2s(0.f), sum_g2 = p2s(0.f), sum_b2 = p2s(0.f), sum_al2 = p2s(0.f);
   for (int k = 0; k < a.n_virtual; ++k) {
@@ -439,14 +165,17 @@ __global__ void __launch_bounds__(kThreads2) blend_fwd2_kernel(BlendFwdArgs a) {
     const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
     P2 T2 = p2s(1.f), acc_r2 = p2s(0.f), acc_g2 = p2s(0.f), acc_b2 = p2s(0.f);
     int lastA = 0, lastB = 0;
-    bool doneA = !insideA, doneB = !insideB;
-    bool warp_done = __all_sync(CHS_FULL_MASK, doneA && doneB);
+    // "done" is folded into the pixel's alpha threshold: a finished pixel has threshold +inf
+    float thrA = insideA ? CHS_LOG2_ALPHA_MIN : kInf, thrB = insideB ? CHS_LOG2_ALPHA_MIN : kInf;
+    bool warp_done = __all_sync(CHS_FULL_MASK, thrA == kInf && thrB == kInf);
     for (uint32_t base = start; base < end; base += kBatch) {
-      if (__syncthreads_and(doneA && doneB)) break;
+      // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
+      if (__syncthreads_and(thrA == kInf && thrB == kInf)) break;
       const int cnt = min((uint32_t)kBatch, end - base);
-      for (int i = tid; i < cnt; i += kThreads2) stage_splat(sm, i, a.vals[base + i], cam_base, a.geom, a.conic_c, a.rgbo);
+      for (int i = tid; i < cnt; i += kThreads) stage_splat(sm, i, a.vals[base + i], cam_base, a.geom, a.conic_c, a.rgbo);
       __syncthreads();
       if (warp_done) continue;
+      const int idx0 = (int)(base - start) + 1;
       for (int sub = 0; sub < cnt; sub += 32) {
         const int j = sub + lane;
         const bool hit = (j < cnt) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
@@ -455,40 +184,38 @@ __global__ void __launch_bounds__(kThreads2) blend_fwd2_kernel(BlendFwdArgs a) {
           const int jj = sub + __ffs(mask) - 1;
           mask &= mask - 1;
           const float4 sa = sm.a[jj];
-          const float2 sb = *reinterpret_cast<const float2*>(&sm.b[jj]);  // qc, log2(opacity)
-          float dx, s0, s1, pA, pB;
-          P2 dy2;
-          pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, s0, s1, pA, pB);
-          const bool actA = !doneA && pA >= CHS_LOG2_ALPHA_MIN, actB = !doneB && pB >= CHS_LOG2_ALPHA_MIN;
+          const float2 sb = *reinterpret_cast<const float2*>(&sm.b[jj]);  // kc, log2(opacity)
+          float dx;
+          P2 dy2, u2;
+          const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+          const float pA = p2lo(pw2), pB = p2hi(pw2);
+          const bool actA = pA >= thrA, actB = pB >= thrB;
           if (actA || actB) {
             const float alA = actA ? fminf(CHS_ALPHA_MAX, chs_exp2_fast(pA)) : 0.f;
             const float alB = actB ? fminf(CHS_ALPHA_MAX, chs_exp2_fast(pB)) : 0.f;
             const P2 al2 = p2(alA, alB);
             const P2 Tn2 = T2 * (p2s(1.f) - al2);
-            const bool stopA = actA && p2lo(Tn2) <= CHS_T_STOP, stopB = actB && p2hi(Tn2) <= CHS_T_STOP;
-            const bool accA = actA && !stopA, accB = actB && !stopB;
-            doneA |= stopA;
-            doneB |= stopB;
-            P2 w2 = al2 * T2;
-            w2 = p2(accA ? p2lo(w2) : 0.f, accB ? p2hi(w2) : 0.f);
+            // stop (this Gaussian is not accumulated) when the transmittance would drop to <= 1e-4
+            const bool accA = actA && p2lo(Tn2) > CHS_T_STOP, accB = actB && p2hi(Tn2) > CHS_T_STOP;
+            thrA = (actA && !accA) ? kInf : thrA;
+            thrB = (actB && !accB) ? kInf : thrB;
+            const P2 w2 = p2(accA ? alA : 0.f, accB ? alB : 0.f) * T2;
             const float4 col = sm.c[jj];
             acc_r2 = fma2(p2s(col.x), w2, acc_r2);
             acc_g2 = fma2(p2s(col.y), w2, acc_g2);
             acc_b2 = fma2(p2s(col.z), w2, acc_b2);
             T2 = p2(accA ? p2lo(Tn2) : p2lo(T2), accB ? p2hi(Tn2) : p2hi(T2));
-            const int idx = (int)(base - start) + jj + 1;
-            lastA = accA ? idx : lastA;
-            lastB = accB ? idx : lastB;
+            lastA = accA ? idx0 + jj : lastA;
+            lastB = accB ? idx0 + jj : lastB;
           }
         }
-        if (__all_sync(CHS_FULL_MASK, doneA && doneB)) {
+        if (__all_sync(CHS_FULL_MASK, thrA == kInf && thrB == kInf)) {
           warp_done = true;
           break;
         }
       }
     }
-    __syncthreads();
-    const P2 bg_r = p2s(a.bg[0]), bg_g = p2s(a.bg[1]), bg_b = p2s(a.bg[2]);
+    __syncthreads();  // the next pose restages shared memory
     if (insideA) {
       a.final_T[(int64_t)c * P + pixA] = p2lo(T2);
       a.last_id[(int64_t)c * P + pixA] = lastA;
@@ -497,9 +224,9 @@ __global__ void __launch_bounds__(kThreads2) blend_fwd2_kernel(BlendFwdArgs a) {
       a.final_T[(int64_t)c * P + pixB] = p2hi(T2);
       a.last_id[(int64_t)c * P + pixB] = lastB;
     }
-    sum_r2 = sum_r2 + fma2(T2, bg_r, acc_r2);
-    sum_g2 = sum_g2 + fma2(T2, bg_g, acc_g2);
-    sum_b2 = sum_b2 + fma2(T2, bg_b, acc_b2);
+    sum_r2 = sum_r2 + fma2(T2, p2s(a.bg[0]), acc_r2);
+    sum_g2 = sum_g2 + fma2(T2, p2s(a.bg[1]), acc_g2);
+    sum_b2 = sum_b2 + fma2(T2, p2s(a.bg[2]), acc_b2);
     sum_al2 = sum_al2 + (p2s(1.f) - T2);
   }
   // formation epilogue (A.7, decision D0): mean over poses, x exposure, CRF
@@ -527,9 +254,61 @@ __global__ void __launch_bounds__(kThreads2) blend_fwd2_kernel(BlendFwdArgs a) {
   }
 }
 
-template <int kBatch>
-__global__ void __launch_bounds__(kThreads2) blend_bwd2_kernel(BlendBwdArgs a) {
-  __shared__ SplatSmemT<kBatch> sm;
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct BlendBwdArgs {
+  int N, n_virtual, W, H, tile_w, tiles;
+  float bg[3];
+  const float4* geom;
+  const float* conic_c;
+  const float4* rgbo;
+  const int32_t* vals;
+  const uint32_t* tile_offsets;
+  const float* final_T;
+  const int32_t* last_id;
+  const float* v_hdr;    // [B,H,W,3] gradient w.r.t. each pose's HDR image
+  const float* v_alpha;  // [B,H,W] or null (gradient w.r.t. the pose-averaged alpha)
+  float4* v_geom;        // [C,N] (v_mx, v_my, v_A, v_B)
+  float4* v_cogr;        // [C,N] (v_C, v_opacity, v_r, v_g)
+  float* v_blue;         // [C,N]  v_b
+};
+
+// Transposing butterfly: on entry every lane holds 8 partials v[0..7]; on exit every lane l holds
+// the warp total of v[l & 7].  9 shuffles instead of 40.
+__device__ __forceinline__ float warp_transpose_reduce8(float v[8], int lane) {
+  {
+    const bool odd = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = odd ? v[2 * i] : v[2 * i + 1];
+      const float keep = odd ? v[2 * i + 1] : v[2 * i];
+      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 1);  // v[i] = value 2i + bit0
+    }
+  }
+  {
+    const bool odd = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = odd ? v[2 * i] : v[2 * i + 1];
+      const float keep = odd ? v[2 * i + 1] : v[2 * i];
+      v[i] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 2);  // v[i] = value 4i + 2 bit1 + bit0
+    }
+  }
+  {
+    const bool odd = lane & 4;
+    const float send = odd ? v[0] : v[1];
+    const float keep = odd ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(CHS_FULL_MASK, send, 4);  // value lane & 7
+  }
+  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 8);
+  v[0] += __shfl_xor_sync(CHS_FULL_MASK, v[0], 16);
+  return v[0];
+}
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd_kernel(BlendBwdArgs a) {
+  __shared__ SplatSmem sm;
   __shared__ int s_max_last;
 
   const int tile = blockIdx.x, c = blockIdx.y;
@@ -578,8 +357,10 @@ __global__ void __launch_bounds__(kThreads2) blend_bwd2_kernel(BlendBwdArgs a) {
   for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(CHS_FULL_MASK, warp_last, o));
   if (lane == 0 && warp_last > 0) atomicMax(&s_max_last, warp_last);
   __syncthreads();
-  const int n_walk = s_max_last;
+  const int n_walk = s_max_last;  // entries [0, n_walk) of the tile list can matter
 
+  // lanes 0..7 own the eight totals of the butterfly, lane 8 the ninth (blue): one RED instruction
+  // with nine active lanes adds a Gaussian's whole gradient record
   char* lane_base = nullptr;
   uint32_t lane_stride = 0;
   if (lane < 4) {
@@ -594,14 +375,14 @@ __global__ void __launch_bounds__(kThreads2) blend_bwd2_kernel(BlendBwdArgs a) {
   }
 
   P2 buf_r2 = p2s(0.f), buf_g2 = p2s(0.f), buf_b2 = p2s(0.f);
-  const float kk = -1.0f / CHS_LOG2E;
+  const float k2 = -2.0f / CHS_LOG2E;
   for (int hi = n_walk; hi > 0; hi -= kBatch) {
     const int lo = max(0, hi - kBatch);
     const int cnt = hi - lo;
     __syncthreads();
-    for (int i = tid; i < cnt; i += kThreads2) stage_splat(sm, i, a.vals[start + lo + i], cam_base, a.geom, a.conic_c, a.rgbo);
+    for (int i = tid; i < cnt; i += kThreads) stage_splat(sm, i, a.vals[start + lo + i], cam_base, a.geom, a.conic_c, a.rgbo);
     __syncthreads();
-    if (warp_last <= lo) continue;
+    if (warp_last <= lo) continue;  // none of this warp's pixels reaches into this batch
     for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
       const int sub_lo = max(0, sub_hi - 32);
       if (warp_last <= lo + sub_lo) continue;
@@ -612,17 +393,19 @@ __global__ void __launch_bounds__(kThreads2) blend_bwd2_kernel(BlendBwdArgs a) {
         const int bit = 31 - __clz(mask);
         mask &= ~(1u << bit);
         const int jj = sub_lo + bit;
-        const int rel = lo + jj + 1;
-        const float4 sa = sm.a[jj];
-        const float4 sb = sm.b[jj];  // qc, log2(opacity), val
-        float dx, s0, s1, pA, pB;
-        P2 dy2;
-        pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, s0, s1, pA, pB);
+        const int rel = lo + jj + 1;  // 1-based index in the tile list
+        const float4 sa = sm.a[jj];   // mx, my, qa, r
+        const float4 sb = sm.b[jj];   // kc, log2(opacity), val, rbc
+        float dx;
+        P2 dy2, u2;
+        const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+        const float pA = p2lo(pw2), pB = p2hi(pw2);
         const bool validA = (rel <= lastA) && pA >= CHS_LOG2_ALPHA_MIN, validB = (rel <= lastB) && pB >= CHS_LOG2_ALPHA_MIN;
         if (!__any_sync(CHS_FULL_MASK, validA || validB)) continue;
         const float4 col = sm.c[jj];  // r, g, b, 1/opacity
+        // packed, branch-free chs_pair_bwd (csrc/chs_math.cuh) for the two pixels; a pixel that does not
+        // contribute runs with alpha = 0, which leaves its T / buf untouched and yields zero partials
         const float auA = validA ? chs_exp2_fast(pA) : 0.f, auB = validB ? chs_exp2_fast(pB) : 0.f;
-        const P2 au2 = p2(auA, auB);
         const P2 al2 = p2(fminf(CHS_ALPHA_MAX, auA), fminf(CHS_ALPHA_MAX, auB));
         const P2 om2 = p2s(1.f) - al2;
         const P2 ra2 = p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));
@@ -637,22 +420,18 @@ __global__ void __launch_bounds__(kThreads2) blend_bwd2_kernel(BlendBwdArgs a) {
         buf_r2 = fma2(p2s(col.x), f2, buf_r2);
         buf_g2 = fma2(p2s(col.y), f2, buf_g2);
         buf_b2 = fma2(p2s(col.z), f2, buf_b2);
-        // no gradient through the 0.999 clamp
-        const P2 vs_raw = neg2(au2) * v_al2;
-        const P2 vs2 = p2(auA <= CHS_ALPHA_MAX ? p2lo(vs_raw) : 0.f, auB <= CHS_ALPHA_MAX ? p2hi(vs_raw) : 0.f);
-        const P2 vk2 = vs2 * p2s(kk);
+        // v_sigma = -alpha_unclamped * v_alpha, and no gradient through the 0.999 clamp
+        const P2 vs2 = p2(auA <= CHS_ALPHA_MAX ? -auA : 0.f, auB <= CHS_ALPHA_MAX ? -auB : 0.f) * v_al2;
+        const P2 vk2 = vs2 * p2s(k2);
+        const P2 g0 = (vk2 * p2s(sa.z)) * u2;                        // v_sigma A u
+        const P2 g1 = fma2(p2s(sa.w), g0, (vk2 * p2s(sb.x)) * dy2);  // v_sigma (B dx + C dy)
         const P2 hs2 = vs2 * p2s(0.5f);
-        const P2 hx2 = hs2 * p2s(dx), hy2 = hs2 * dy2;
-        const P2 g0 = vk2 * fma2(p2s(sa.w), dy2, p2s(s0 + s0));      // 2 qa dx + qb dy
-        const P2 g1 = vk2 * fma2(p2s(sb.x + sb.x), dy2, p2s(s1));    // qb dx + 2 qc dy
+        const P2 hx2 = hs2 * p2s(dx);
         const P2 g2 = hx2 * p2s(dx);
         const P2 g3 = (hx2 + hx2) * dy2;
-        const P2 g4 = hy2 * dy2;
+        const P2 g4 = (hs2 * dy2) * dy2;
         const P2 g5 = neg2(vs2) * p2s(col.w);
-        float g[9];
-        g[0] = p2lo(g0) + p2hi(g0); g[1] = p2lo(g1) + p2hi(g1); g[2] = p2lo(g2) + p2hi(g2);
-        g[3] = p2lo(g3) + p2hi(g3); g[4] = p2lo(g4) + p2hi(g4); g[5] = p2lo(g5) + p2hi(g5);
-        g[6] = p2lo(g6) + p2hi(g6); g[7] = p2lo(g7) + p2hi(g7); g[8] = p2lo(g8) + p2hi(g8);
+        float g[9] = {p2sum(g0), p2sum(g1), p2sum(g2), p2sum(g3), p2sum(g4), p2sum(g5), p2sum(g6), p2sum(g7), p2sum(g8)};
         const uint32_t val = (uint32_t)__float_as_int(sb.z);
         const float blue = chs_warp_sum(g[8]);
         const float r8 = warp_transpose_reduce8(g, lane);
@@ -665,7 +444,7 @@ __global__ void __launch_bounds__(kThreads2) blend_bwd2_kernel(BlendBwdArgs a) {
 
 }  // namespace
 
-// tuning knob (development): selects a (batch size, min blocks/SM) instantiation of the blend kernels
+// tuning knob (development): selects the min-blocks-per-SM instantiation of the blend kernels
 static int blend_variant(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
@@ -701,10 +480,10 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   const size_t dyn = crf_smem_bytes(cfg);
   cudaStream_t s = (cudaStream_t)stream;
   switch (blend_variant("CHS_BLEND_FWD_VARIANT")) {
-    case 1: blend_fwd_kernel<256, 5><<<grid, kThreads, dyn, s>>>(a); break;   // one pixel per thread (r1a-c)
-    case 2: blend_fwd_kernel<128, 6><<<grid, kThreads, dyn, s>>>(a); break;
-    case 11: blend_fwd2_kernel<128><<<grid, kThreads2, dyn, s>>>(a); break;
-    default: blend_fwd2_kernel<256><<<grid, kThreads2, dyn, s>>>(a); break;   // two pixels per thread, packed fp32x2
+    case 1: blend_fwd_kernel<6><<<grid, kThreads, dyn, s>>>(a); break;
+    case 3: blend_fwd_kernel<10><<<grid, kThreads, dyn, s>>>(a); break;
+    case 4: blend_fwd_kernel<12><<<grid, kThreads, dyn, s>>>(a); break;
+    default: blend_fwd_kernel<8><<<grid, kThreads, dyn, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
   }
   CHS_LAUNCH_CHECK();
   return CHS_OK;
@@ -731,10 +510,10 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
   switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {
-    case 1: blend_bwd_kernel<256, 1><<<grid, kThreads, 0, s>>>(a); break;     // one pixel per thread (r1a-c)
-    case 2: blend_bwd_kernel<128, 5><<<grid, kThreads, 0, s>>>(a); break;
-    case 11: blend_bwd2_kernel<128><<<grid, kThreads2, 0, s>>>(a); break;
-    default: blend_bwd2_kernel<256><<<grid, kThreads2, 0, s>>>(a); break;     // two pixels per thread, packed fp32x2
+    case 1: blend_bwd_kernel<6><<<grid, kThreads, 0, s>>>(a); break;
+    case 3: blend_bwd_kernel<10><<<grid, kThreads, 0, s>>>(a); break;
+    case 4: blend_bwd_kernel<12><<<grid, kThreads, 0, s>>>(a); break;
+    default: blend_bwd_kernel<8><<<grid, kThreads, 0, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
   }
   CHS_LAUNCH_CHECK();
   return CHS_OK;

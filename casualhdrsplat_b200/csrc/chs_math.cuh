@@ -352,31 +352,41 @@ CHS_HD ChsTileRect chs_tile_bounds(float mx, float my, int radius, int tile_w, i
 
 // ---------------------------------------------------------------------------------------------
 // A.5 / A.6 blend arithmetic of one (pixel, Gaussian) pair.
-// A staged Gaussian carries a pre-scaled conic so that alpha = 2^(qa dx^2 + qb dx dy + qc dy^2 + lo):
-//   qa = -0.5 log2(e) A, qb = -log2(e) B, qc = -0.5 log2(e) C, lo = log2(opacity).
-// The exponent's quadratic part is clamped to <= 0 (sigma >= 0 for every positive-definite conic;
-// the clamp only guards fp32 rounding at delta ~ 0, where A.5's "skip if sigma < 0" would wrongly
-// drop a full-strength Gaussian).
+// A staged Gaussian carries its conic in completed-square form, pre-scaled for exp2:
+//   log2(alpha) = qa u^2 + kc dy^2 + lo,   u = dx + r dy,   (dx, dy) = mean2d - pixel
+//   qa = -0.5 log2(e) A (< 0),  r = B / A,  kc = -0.5 log2(e) (C - B^2 / A) (< 0),  lo = log2(opacity)
+// which equals -log2(e) sigma + log2(o) with sigma = 0.5 (A dx^2 + C dy^2) + B dx dy.  Both squared
+// terms have non-positive coefficients for every positive-definite conic, so the exponent can never
+// round to a positive number and A.5's "skip if sigma < 0" needs no code.
 // ---------------------------------------------------------------------------------------------
 template <class T> struct ChsSplat {
-  T mx, my, qa, qb;
-  T qc, lo, rbc, rba;  // rbc = -B/C, rba = -B/A: minimisers of the exponent along a vertical / horizontal line
-  T r, g, b, inv_opac;
+  T mx, my, qa, r;
+  T kc, lo, rbc;  // rbc = -B/C (culling only); -B/A = -r
+  T cr, cg, cb, inv_opac;
 };
 
 template <class T>
 CHS_HD void chs_make_splat(T mx, T my, T ca, T cb, T cc, T opac, T r, T g, T b, ChsSplat<T>& s) {
+  // staged once per (tile, Gaussian) and shared by forward and backward: approximate log2 / reciprocal
+  // (2^-22 relative) are ample; rbc only steers the conservative culling bound
+  const T rca = ca > T(0) ? chs_rcp_fast(ca) : T(0);
   s.mx = mx; s.my = my;
   s.qa = T(-0.5) * ChsK<T>::log2e * ca;
-  s.qb = -ChsK<T>::log2e * cb;
-  s.qc = T(-0.5) * ChsK<T>::log2e * cc;
-  // staged once per (tile, Gaussian) and shared by forward and backward: approximate log2 / reciprocal
-  // (2^-22 relative) are ample; rbc / rba only steer the conservative culling bound
+  s.r = cb * rca;
+  s.kc = T(-0.5) * ChsK<T>::log2e * (cc - cb * s.r);
+  s.kc = chs_min(s.kc, T(0));
   s.lo = chs_log2_fast(opac);
-  s.r = r; s.g = g; s.b = b;
-  s.inv_opac = chs_rcp_fast(opac);
   s.rbc = cc > T(0) ? -cb * chs_rcp_fast(cc) : T(0);
-  s.rba = ca > T(0) ? -cb * chs_rcp_fast(ca) : T(0);
+  s.cr = r; s.cg = g; s.cb = b;
+  s.inv_opac = chs_rcp_fast(opac);
+}
+
+// log2(alpha) before the 0.999 clamp; also returns dx, dy and u = dx + r dy
+template <class T> CHS_HD T chs_pair_power(const ChsSplat<T>& s, T px, T py, T& dx, T& dy, T& u) {
+  dx = s.mx - px;
+  dy = s.my - py;
+  u = chs_fma(s.r, dy, dx);
+  return chs_fma(s.qa * u, u, (s.kc * dy) * dy) + s.lo;
 }
 
 // Sub-tile culling.  Upper bound of log2(alpha) over the axis-aligned rectangle of pixel centres
@@ -389,20 +399,12 @@ template <class T> CHS_HD T chs_block_max_power(const ChsSplat<T>& s, T x0, T x1
   T ax0 = x0 - s.mx, ax1 = x1 - s.mx, ay0 = y0 - s.my, ay1 = y1 - s.my;
   T cx = chs_min(chs_max(T(0), ax0), ax1);
   T cy = chs_min(chs_max(T(0), ay0), ay1);
-  T dy1 = chs_min(chs_max(s.rbc * cx, ay0), ay1);
-  T dx2 = chs_min(chs_max(s.rba * cy, ax0), ax1);
-  T p1 = (s.qa * cx + s.qb * dy1) * cx + s.qc * dy1 * dy1;
-  T p2 = (s.qa * dx2 + s.qb * cy) * dx2 + s.qc * cy * cy;
-  return chs_min(chs_max(p1, p2), T(0)) + s.lo;
-}
-
-// log2(alpha) before the 0.999 clamp
-template <class T> CHS_HD T chs_pair_power(const ChsSplat<T>& s, T px, T py, T& dx, T& dy) {
-  dx = s.mx - px;
-  dy = s.my - py;
-  // explicit fma chain: forward and backward kernels must take identical skip decisions
-  T quad = chs_fma(chs_fma(s.qa, dx, s.qb * dy), dx, (s.qc * dy) * dy);
-  return chs_min(quad, T(0)) + s.lo;
+  T dy1 = chs_min(chs_max(s.rbc * cx, ay0), ay1);   // maximiser along the vertical line x = cx
+  T dx2 = chs_min(chs_max(-s.r * cy, ax0), ax1);    // maximiser along the horizontal line y = cy
+  T u1 = cx + s.r * dy1, u2 = dx2 + s.r * cy;
+  T p1 = s.qa * u1 * u1 + s.kc * dy1 * dy1;
+  T p2 = s.qa * u2 * u2 + s.kc * cy * cy;
+  return chs_max(p1, p2) + s.lo;
 }
 
 // Backward of one pair, walking back to front (A.6). On entry T = transmittance *after* this
@@ -412,7 +414,7 @@ template <class T> CHS_HD T chs_pair_power(const ChsSplat<T>& s, T px, T py, T& 
 // Branch-free: a pair that does not contribute is passed with alpha_unclamped = alpha = 0, which
 // leaves T and buf untouched and yields g = 0.
 template <class T>
-CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T alpha_unclamped, T alpha, T& Tr, T buf[3],
+CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T u, T alpha_unclamped, T alpha, T& Tr, T buf[3],
                          const T vh[3], T va_t, T g[9]) {
   T ra = chs_rcp_fast(T(1) - alpha);
   Tr = Tr * ra;  // transmittance before this Gaussian
@@ -420,21 +422,21 @@ CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T alpha_unclamped, T 
   g[6] = f * vh[0];
   g[7] = f * vh[1];
   g[8] = f * vh[2];
-  T v_alpha = (s.r * Tr - buf[0] * ra) * vh[0] + (s.g * Tr - buf[1] * ra) * vh[1] + (s.b * Tr - buf[2] * ra) * vh[2] + va_t * ra;
-  buf[0] += s.r * f;
-  buf[1] += s.g * f;
-  buf[2] += s.b * f;
+  T v_alpha = (s.cr * Tr - buf[0] * ra) * vh[0] + (s.cg * Tr - buf[1] * ra) * vh[1] + (s.cb * Tr - buf[2] * ra) * vh[2] + va_t * ra;
+  buf[0] += s.cr * f;
+  buf[1] += s.cg * f;
+  buf[2] += s.cb * f;
   // no gradient through the 0.999 clamp
   T v_sigma = alpha_unclamped <= ChsK<T>::alpha_max ? -alpha_unclamped * v_alpha : T(0);
-  // A dx + B dy = -(2 qa dx + qb dy) / log2e ;  B dx + C dy = -(qb dx + 2 qc dy) / log2e
-  const T k = T(-1) / ChsK<T>::log2e;
-  T vk = v_sigma * k;
-  T hx = T(0.5) * v_sigma * dx, hy = T(0.5) * v_sigma * dy;
-  g[0] = vk * (T(2) * s.qa * dx + s.qb * dy);
-  g[1] = vk * (s.qb * dx + T(2) * s.qc * dy);
+  // d sigma / d mean = (A dx + B dy, B dx + C dy) = (A u, r A u - (2 / log2e) kc dy),  A = -(2 / log2e) qa
+  const T k2 = T(-2) / ChsK<T>::log2e;
+  T vk = v_sigma * k2;
+  g[0] = vk * s.qa * u;
+  g[1] = s.r * g[0] + vk * s.kc * dy;
+  T hx = T(0.5) * v_sigma * dx;
   g[2] = hx * dx;
   g[3] = T(2) * hx * dy;
-  g[4] = hy * dy;
+  g[4] = T(0.5) * v_sigma * dy * dy;
   g[5] = -v_sigma * s.inv_opac;
 }
 

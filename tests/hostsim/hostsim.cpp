@@ -91,17 +91,17 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
     for (int j = 0; j < n_list; ++j) {
       // sub-tile cull exactly as the kernels apply it (8x4 pixel block of this pixel's warp): must never
       // drop a contributing pair
-      T bx0 = floor((px - T(0.5)) / 8) * 8 + T(0.5), by0 = floor((py - T(0.5)) / 4) * 4 + T(0.5);
-      bool reach = chs_block_max_power(sp[j], bx0, bx0 + 7, by0, by0 + 3) >= thr - T(1e-3);
-      T dx, dy;
-      T power = chs_pair_power(sp[j], px, py, dx, dy);
+      T bx0 = floor((px - T(0.5)) / 8) * 8 + T(0.5), by0 = floor((py - T(0.5)) / 8) * 8 + T(0.5);
+      bool reach = chs_block_max_power(sp[j], bx0, bx0 + 7, by0, by0 + 7) >= thr - T(1e-3);
+      T dx, dy, u;
+      T power = chs_pair_power(sp[j], px, py, dx, dy, u);
       if (!(power >= thr)) continue;
       if (!reach) { out_last[p] = -1000000; }  // flag: the cull would have dropped a live pair
       T alpha = chs_min(ChsK<T>::alpha_max, chs_exp2_fast(power));
       T Tn = Tr * (1 - alpha);
       if (Tn <= ChsK<T>::t_stop) break;
       T w = alpha * Tr;
-      acc[0] += w * sp[j].r; acc[1] += w * sp[j].g; acc[2] += w * sp[j].b;
+      acc[0] += w * sp[j].cr; acc[1] += w * sp[j].cg; acc[2] += w * sp[j].cb;
       Tr = Tn;
       last = j + 1;
     }
@@ -113,12 +113,12 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
     T va_t = Tr * (v_alpha[p] - (bg[0] * vh[0] + bg[1] * vh[1] + bg[2] * vh[2]));
     T buf[3] = {0, 0, 0};
     for (int j = last - 1; j >= 0; --j) {
-      T dx, dy;
-      T power = chs_pair_power(sp[j], px, py, dx, dy);
+      T dx, dy, u;
+      T power = chs_pair_power(sp[j], px, py, dx, dy, u);
       if (!(power >= thr)) continue;
       T au = chs_exp2_fast(power);
       T g[9];
-      chs_pair_bwd(sp[j], dx, dy, au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, g);
+      chs_pair_bwd(sp[j], dx, dy, u, au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, g);
       // g = [v_mx, v_my, v_A, v_B, v_C, v_o, v_r, v_g, v_b] -> params order (mx,my,A,B,C,o,r,g,b)
       for (int k = 0; k < 9; ++k) v_params[j * 9 + k] += g[k];
     }
@@ -168,8 +168,8 @@ void hs_block_bound_f32(int n, const float* params /* mx,my,A,B,C,o */, const fl
     float best = -1e30f;
     for (float y = r[2]; y <= r[3] + 1e-3f; y += 1.f)
       for (float x = r[0]; x <= r[1] + 1e-3f; x += 1.f) {
-        float dx, dy;
-        best = fmaxf(best, chs_pair_power(s, x, y, dx, dy));
+        float dx, dy, u;
+        best = fmaxf(best, chs_pair_power(s, x, y, dx, dy, u));
       }
     brute[i] = best;
   }

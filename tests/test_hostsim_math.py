@@ -200,12 +200,12 @@ def test_block_cull_bound_is_conservative_and_tight():
     B = (l1 - l2) * c * s_
     C = l1 * s_ * s_ + l2 * c * c
     bx = torch.randint(0, 8, (n,), generator=g).double() * 8 + 0.5
-    by = torch.randint(0, 8, (n,), generator=g).double() * 4 + 0.5
+    by = torch.randint(0, 8, (n,), generator=g).double() * 8 + 0.5
     mx = bx + torch.rand(n, generator=g) * 40 - 16
     my = by + torch.rand(n, generator=g) * 30 - 13
     o = torch.rand(n, generator=g) * 0.98 + 0.01
     params = np.ascontiguousarray(torch.stack([mx, my, A, B, C, o], 1).numpy().astype(np.float32))
-    rect = np.ascontiguousarray(torch.stack([bx, bx + 7, by, by + 3], 1).numpy().astype(np.float32))
+    rect = np.ascontiguousarray(torch.stack([bx, bx + 7, by, by + 7], 1).numpy().astype(np.float32))
     bound = np.zeros(n, np.float32); brute = np.zeros(n, np.float32)
     HS.hs_block_bound_f32(n, _p(params), _p(rect), _p(bound), _p(brute))
     thr = math.log2(1 / 255)
