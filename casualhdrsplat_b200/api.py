@@ -103,7 +103,8 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     # K6
     st.ldr = _empty((B, H, W, 3), torch.float32, dev)
     st.alpha = _empty((B, H, W), torch.float32, dev)
-    st.hdr_mean = _empty((B, H, W, 3), torch.float32, dev)
+    # default order: pose-averaged HDR per frame; crf_before_average (figure order): one HDR image per virtual pose
+    st.hdr_mean = _empty((C if cfg.crf_before_average else B, H, W, 3), torch.float32, dev)
     st.final_T = _empty((C, H, W), torch.float32, dev)
     st.last_id = _empty((C, H, W), torch.int32, dev)
     check(L.chs_blend_fwd(byref(cfg), ptr(st.geom), ptr(st.conic_c), ptr(st.rgbo), ptr(st.vals_sorted), ptr(st.tile_offsets),
@@ -123,13 +124,14 @@ def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ld
     ws = _lib.workspace_sizes(cfg, 0, st.n_knots)
     red = _empty((int(ws.reduce_bytes),), torch.uint8, dev)
     # K7
-    v_hdr = _empty((B, cfg.height, cfg.width, 3), torch.float32, dev)
+    v_hdr = _empty((C if cfg.crf_before_average else B, cfg.height, cfg.width, 3), torch.float32, dev)
     v_crf = torch.zeros_like(crf_params) if crf_params is not None else None
     v_exposure = _empty((B,), torch.float32, dev)
     check(L.chs_crf_bwd(byref(cfg), ptr(st.hdr_mean), ptr(exposure), ptr(crf_params), ptr(v_ldr), ptr(v_hdr), ptr(v_crf),
                         ptr(v_exposure), ptr(red), red.numel(), s), "chs_crf_bwd")
     if v_hdr_out is not None:  # gradient arriving at the returned pose-averaged HDR image (return_hdr=True)
-        v_hdr = v_hdr + v_hdr_out / float(n)
+        extra = v_hdr_out / float(n)
+        v_hdr = v_hdr + (extra.repeat_interleave(n, dim=0) if cfg.crf_before_average else extra)
     # K8
     v_geom = _empty((C, N, 4), torch.float32, dev)
     v_cogr = _empty((C, N, 4), torch.float32, dev)
@@ -180,7 +182,10 @@ class _Rasterize(torch.autograd.Function):
         ctx.has_crf = crf_params is not None
         opts["state_out"].append(st)
         ctx.set_materialize_grads(False)
-        return st.ldr, st.alpha.unsqueeze(-1), st.hdr_mean
+        hdr = st.hdr_mean
+        if cfg.crf_before_average:
+            hdr = hdr.view(cfg.n_frames, cfg.n_virtual, cfg.height, cfg.width, 3).mean(dim=1)
+        return st.ldr, st.alpha.unsqueeze(-1), hdr
 
     @staticmethod
     def backward(ctx, v_ldr, v_alpha, v_hdr_out):

@@ -123,7 +123,7 @@ __device__ __forceinline__ P2 pair_power2(const float4 sa, float kc, float lo, f
 
 struct BlendFwdArgs {
   int N, n_virtual, W, H, tile_w, tiles;
-  int crf_kind, crf_hidden;
+  int crf_kind, crf_hidden, crf_before_average;
   float bg[3];
   const float4* geom;
   const float* conic_c;
@@ -136,7 +136,7 @@ struct BlendFwdArgs {
   int32_t* last_id;
 };
 
-template <int kMinBlocks>
+template <int kMinBlocks, bool kPerPoseCrf>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFwdArgs a) {
   __shared__ SplatSmem sm;
   extern __shared__ float s_crf[];  // 3 * (3 Hd + 1) floats when the CRF is the MLP
@@ -157,6 +157,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
   if (a.crf_kind == CHS_CRF_MLP)
     for (int i = tid; i < 3 * (3 * a.crf_hidden + 1); i += kThreads) s_crf[i] = a.crf_params[i];
 
+  // crf_before_average (figure order): sum_* accumulate F(dt * H_k) instead of H_k, and the per-pose
+  // HDR images are written to hdr_mean, which is then [C,H,W,3] (the backward needs every H_k)
+  constexpr bool per_pose_crf = kPerPoseCrf;
+  const float dt = a.exposure[frame];
+  if (per_pose_crf) __syncthreads();  // s_crf is read inside the pose loop
   P2 sum_r2 = p2s(0.f), sum_g2 = p2s(0.f), sum_b2 = p2s(0.f), sum_al2 = p2s(0.f);
   for (int k = 0; k < a.n_virtual; ++k) {
     const int c = frame * a.n_virtual + k;
@@ -224,14 +229,36 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
       a.final_T[(int64_t)c * P + pixB] = p2hi(T2);
       a.last_id[(int64_t)c * P + pixB] = lastB;
     }
-    sum_r2 = sum_r2 + fma2(T2, p2s(a.bg[0]), acc_r2);
-    sum_g2 = sum_g2 + fma2(T2, p2s(a.bg[1]), acc_g2);
-    sum_b2 = sum_b2 + fma2(T2, p2s(a.bg[2]), acc_b2);
+    const P2 h_r2 = fma2(T2, p2s(a.bg[0]), acc_r2), h_g2 = fma2(T2, p2s(a.bg[1]), acc_g2), h_b2 = fma2(T2, p2s(a.bg[2]), acc_b2);
     sum_al2 = sum_al2 + (p2s(1.f) - T2);
+    if (!per_pose_crf) {
+      sum_r2 = sum_r2 + h_r2;
+      sum_g2 = sum_g2 + h_g2;
+      sum_b2 = sum_b2 + h_b2;
+    } else {
+      float y[2][3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float hr = h == 0 ? p2lo(h_r2) : p2hi(h_r2), hg = h == 0 ? p2lo(h_g2) : p2hi(h_g2), hb = h == 0 ? p2lo(h_b2) : p2hi(h_b2);
+        y[h][0] = dt * hr; y[h][1] = dt * hg; y[h][2] = dt * hb;
+        if (a.crf_kind == CHS_CRF_MLP) {
+          const int stride = 3 * a.crf_hidden + 1;
+          y[h][0] = chs_crf_mlp_fwd(y[h][0], s_crf, a.crf_hidden);
+          y[h][1] = chs_crf_mlp_fwd(y[h][1], s_crf + stride, a.crf_hidden);
+          y[h][2] = chs_crf_mlp_fwd(y[h][2], s_crf + 2 * stride, a.crf_hidden);
+        }
+        if (h == 0 ? insideA : insideB) {
+          const int64_t o = ((int64_t)c * P + (h == 0 ? pixA : pixB)) * 3;
+          a.hdr_mean[o] = hr; a.hdr_mean[o + 1] = hg; a.hdr_mean[o + 2] = hb;
+        }
+      }
+      sum_r2 = sum_r2 + p2(y[0][0], y[1][0]);
+      sum_g2 = sum_g2 + p2(y[0][1], y[1][1]);
+      sum_b2 = sum_b2 + p2(y[0][2], y[1][2]);
+    }
   }
   // formation epilogue (A.7, decision D0): mean over poses, x exposure, CRF
   const float inv_n = 1.f / (float)a.n_virtual;
-  const float dt = a.exposure[frame];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     if (!(h == 0 ? insideA : insideB)) continue;
@@ -239,6 +266,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
     const float hg = (h == 0 ? p2lo(sum_g2) : p2hi(sum_g2)) * inv_n;
     const float hb = (h == 0 ? p2lo(sum_b2) : p2hi(sum_b2)) * inv_n;
     const float al = (h == 0 ? p2lo(sum_al2) : p2hi(sum_al2)) * inv_n;
+    const int64_t pix = h == 0 ? pixA : pixB;
+    if (per_pose_crf) {  // the sums already hold F(dt * H_k)
+      const int64_t o = ((int64_t)frame * P + pix) * 3;
+      a.ldr[o] = hr; a.ldr[o + 1] = hg; a.ldr[o + 2] = hb;
+      a.alpha[(int64_t)frame * P + pix] = al;
+      continue;
+    }
     float o0 = dt * hr, o1 = dt * hg, o2 = dt * hb;
     if (a.crf_kind == CHS_CRF_MLP) {
       const int stride = 3 * a.crf_hidden + 1;
@@ -246,7 +280,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
       o1 = chs_crf_mlp_fwd(o1, s_crf + stride, a.crf_hidden);
       o2 = chs_crf_mlp_fwd(o2, s_crf + 2 * stride, a.crf_hidden);
     }
-    const int64_t pix = h == 0 ? pixA : pixB;
     const int64_t o = ((int64_t)frame * P + pix) * 3;
     a.ldr[o] = o0; a.ldr[o + 1] = o1; a.ldr[o + 2] = o2;
     a.hdr_mean[o] = hr; a.hdr_mean[o + 1] = hg; a.hdr_mean[o + 2] = hb;
@@ -258,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
 // backward
 // ---------------------------------------------------------------------------------------------
 struct BlendBwdArgs {
-  int N, n_virtual, W, H, tile_w, tiles;
+  int N, n_virtual, W, H, tile_w, tiles, v_hdr_per_camera;
   float bg[3];
   const float4* geom;
   const float* conic_c;
@@ -330,11 +363,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd_kernel(BlendBw
   float TfA = 1.f, TfB = 1.f, vA[3] = {0.f, 0.f, 0.f}, vB[3] = {0.f, 0.f, 0.f}, vatA = 0.f, vatB = 0.f;
   int lastA = 0, lastB = 0;
   const float inv_nv = 1.f / (float)a.n_virtual;
+  const int vimg = a.v_hdr_per_camera ? c : frame;  // figure-order CRF: every pose has its own HDR gradient
   if (insideA) {
     const int64_t pix = (int64_t)iyA * a.W + ix;
     TfA = a.final_T[(int64_t)c * P + pix];
     lastA = a.last_id[(int64_t)c * P + pix];
-    const int64_t o = ((int64_t)frame * P + pix) * 3;
+    const int64_t o = ((int64_t)vimg * P + pix) * 3;
     vA[0] = a.v_hdr[o]; vA[1] = a.v_hdr[o + 1]; vA[2] = a.v_hdr[o + 2];
     const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] * inv_nv : 0.f;
     vatA = TfA * (v_al - (a.bg[0] * vA[0] + a.bg[1] * vA[1] + a.bg[2] * vA[2]));
@@ -343,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd_kernel(BlendBw
     const int64_t pix = (int64_t)iyB * a.W + ix;
     TfB = a.final_T[(int64_t)c * P + pix];
     lastB = a.last_id[(int64_t)c * P + pix];
-    const int64_t o = ((int64_t)frame * P + pix) * 3;
+    const int64_t o = ((int64_t)vimg * P + pix) * 3;
     vB[0] = a.v_hdr[o]; vB[1] = a.v_hdr[o + 1]; vB[2] = a.v_hdr[o + 2];
     const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] * inv_nv : 0.f;
     vatB = TfB * (v_al - (a.bg[0] * vB[0] + a.bg[1] * vB[1] + a.bg[2] * vB[2]));
@@ -464,14 +498,10 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   CHS_REQUIRE(geom && conic_c && rgbo && tile_offsets && exposure, "chs_blend_fwd: null input");
   CHS_REQUIRE(ldr && alpha && hdr_mean && final_T && last_id, "chs_blend_fwd: null output");
   CHS_REQUIRE(cfg->crf_kind == CHS_CRF_IDENTITY || crf_params, "chs_blend_fwd: crf_params required for the MLP CRF");
-  if (cfg->crf_before_average) {
-    chs_set_error("chs_blend_fwd: crf_before_average=1 (figure order) is not implemented in CUDA yet (SURVEY.md section 8(f) row f3)");
-    return CHS_ERR_UNSUPPORTED;
-  }
   if (d.B == 0 || d.P == 0) return CHS_OK;
   BlendFwdArgs a;
   a.N = d.N; a.n_virtual = d.n; a.W = d.W; a.H = d.H; a.tile_w = d.tile_w; a.tiles = d.tiles;
-  a.crf_kind = cfg->crf_kind; a.crf_hidden = cfg->crf_hidden;
+  a.crf_kind = cfg->crf_kind; a.crf_hidden = cfg->crf_hidden; a.crf_before_average = cfg->crf_before_average;
   a.bg[0] = cfg->background[0]; a.bg[1] = cfg->background[1]; a.bg[2] = cfg->background[2];
   a.geom = (const float4*)geom; a.conic_c = conic_c; a.rgbo = (const float4*)rgbo; a.vals = vals_sorted; a.tile_offsets = tile_offsets;
   a.exposure = exposure; a.crf_params = crf_params;
@@ -479,11 +509,14 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   dim3 grid(d.tiles, d.B);
   const size_t dyn = crf_smem_bytes(cfg);
   cudaStream_t s = (cudaStream_t)stream;
-  switch (blend_variant("CHS_BLEND_FWD_VARIANT")) {
-    case 1: blend_fwd_kernel<6><<<grid, kThreads, dyn, s>>>(a); break;
-    case 3: blend_fwd_kernel<10><<<grid, kThreads, dyn, s>>>(a); break;
-    case 4: blend_fwd_kernel<12><<<grid, kThreads, dyn, s>>>(a); break;
-    default: blend_fwd_kernel<8><<<grid, kThreads, dyn, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
+  if (cfg->crf_before_average) {
+    blend_fwd_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
+  } else {
+    switch (blend_variant("CHS_BLEND_FWD_VARIANT")) {
+      case 1: blend_fwd_kernel<6, false><<<grid, kThreads, dyn, s>>>(a); break;
+      case 3: blend_fwd_kernel<10, false><<<grid, kThreads, dyn, s>>>(a); break;
+      default: blend_fwd_kernel<8, false><<<grid, kThreads, dyn, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
+    }
   }
   CHS_LAUNCH_CHECK();
   return CHS_OK;
@@ -507,12 +540,12 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.bg[0] = cfg->background[0]; a.bg[1] = cfg->background[1]; a.bg[2] = cfg->background[2];
   a.geom = (const float4*)geom; a.conic_c = conic_c; a.rgbo = (const float4*)rgbo; a.vals = vals_sorted; a.tile_offsets = tile_offsets;
   a.final_T = final_T; a.last_id = last_id; a.v_hdr = v_hdr; a.v_alpha = v_alpha;
+  a.v_hdr_per_camera = cfg->crf_before_average != 0;
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
   switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {
     case 1: blend_bwd_kernel<6><<<grid, kThreads, 0, s>>>(a); break;
     case 3: blend_bwd_kernel<10><<<grid, kThreads, 0, s>>>(a); break;
-    case 4: blend_bwd_kernel<12><<<grid, kThreads, 0, s>>>(a); break;
     default: blend_bwd_kernel<8><<<grid, kThreads, 0, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
   }
   CHS_LAUNCH_CHECK();

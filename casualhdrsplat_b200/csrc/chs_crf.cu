@@ -11,6 +11,9 @@ constexpr int kPix = 4;  // pixels per thread
 struct CrfBwdArgs {
   int64_t P;
   int n_virtual, crf_kind, hd;
+  int imgs_per_frame;  // 1: one HDR image per frame (default order); n: one per virtual pose (crf_before_average)
+  float vy_scale;      // gradient reaching each image's CRF output: 1 (default) or 1/n
+  float vh_div;        // v_hdr = dt * v_X / vh_div: n (default: mean over poses follows) or 1
   const float *hdr_mean, *exposure, *crf_params, *v_ldr;
   float* v_hdr;
   double* acc_crf;       // [3 * (3 hd + 1)]
@@ -31,7 +34,8 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
   float* s_g = s_p + 3 * stride;             // block-partial parameter gradients [3, stride]
   float* s_z = s_g + 3 * stride;             // [3][kThreads * kPix]
   float* s_gy = s_z + 3 * kThreads * kPix;   // [3][kThreads * kPix]
-  const int frame = blockIdx.y;
+  const int img = blockIdx.y;
+  const int frame = img / a.imgs_per_frame;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool mlp = a.crf_kind == CHS_CRF_MLP;
   if (mlp)
@@ -41,20 +45,21 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
     }
   __syncthreads();
   const float dt = a.exposure[frame];
-  const float scale = dt / (float)a.n_virtual;
+  const float scale = dt / a.vh_div;
   float v_dt = 0.f;
 #pragma unroll
   for (int q = 0; q < kPix; ++q) {
     const int slot = q * kThreads + tid;
     const int64_t pix = (int64_t)blockIdx.x * (kPix * kThreads) + slot;
     const bool live = pix < a.P;
-    const int64_t o = ((int64_t)frame * a.P + (live ? pix : 0)) * 3;
+    const int64_t o = ((int64_t)img * a.P + (live ? pix : 0)) * 3;
+    const int64_t of = ((int64_t)frame * a.P + (live ? pix : 0)) * 3;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       float zz = 0.f, g = 0.f;
       if (live) {
         const float h = a.hdr_mean[o + ch];
-        const float vy = a.v_ldr[o + ch];
+        const float vy = a.v_ldr[of + ch] * a.vy_scale;
         float vx;
         if (mlp) {
           const float* p = s_p + ch * stride;
@@ -161,10 +166,6 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
   CHS_REQUIRE(hdr_mean && exposure && v_ldr && v_hdr && v_exposure && workspace, "chs_crf_bwd: null pointer");
   const bool mlp = cfg->crf_kind == CHS_CRF_MLP;
   CHS_REQUIRE(!mlp || (crf_params && v_crf_params), "chs_crf_bwd: crf_params / v_crf_params required for the MLP CRF");
-  if (cfg->crf_before_average) {
-    chs_set_error("chs_crf_bwd: crf_before_average=1 is not implemented in CUDA yet");
-    return CHS_ERR_UNSUPPORTED;
-  }
   const int n_par = mlp ? 3 * (3 * cfg->crf_hidden + 1) : 0;
   const uint64_t need = (uint64_t)(n_par + d.B) * sizeof(double);
   if (workspace_bytes < need) {
@@ -176,10 +177,14 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
   CHS_CUDA(cudaMemsetAsync(acc, 0, need, s));
   if (d.B > 0 && d.P > 0) {
     CrfBwdArgs a;
+    const bool per_pose = cfg->crf_before_average != 0;
     a.P = d.P; a.n_virtual = d.n; a.crf_kind = cfg->crf_kind; a.hd = mlp ? cfg->crf_hidden : 0;
+    a.imgs_per_frame = per_pose ? d.n : 1;
+    a.vy_scale = per_pose ? 1.f / (float)d.n : 1.f;
+    a.vh_div = per_pose ? 1.f : (float)d.n;
     a.hdr_mean = hdr_mean; a.exposure = exposure; a.crf_params = crf_params; a.v_ldr = v_ldr; a.v_hdr = v_hdr;
     a.acc_crf = acc; a.acc_exposure = acc + n_par;
-    dim3 grid((unsigned)((d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix)), d.B);
+    dim3 grid((unsigned)((d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix)), per_pose ? d.C : d.B);
     size_t smem = mlp ? ((size_t)2 * n_par + (size_t)6 * kThreads * kPix) * sizeof(float) : 16;
     crf_bwd_kernel<<<grid, kThreads, smem, s>>>(a);
     CHS_LAUNCH_CHECK();

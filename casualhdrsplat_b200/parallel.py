@@ -143,7 +143,7 @@ class TorchComm:
 def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: int, height: int, n_virtual: int, crf_kind: int,
                    frame_ids: Sequence[int], upstream: Callable[[Sequence[int], torch.Tensor], torch.Tensor], *,
                    micro_batch: int = 1, sort_mode: str = "presort", comm=None, background=None, out: Optional[torch.Tensor] = None,
-                   stats: Optional[dict] = None):
+                   stats: Optional[dict] = None, crf_before_average: bool = False):
     """One fwd+bwd training step over this rank's frames, then the gradient all-reduce.
 
     params: CUDA fp32 tensors means [N,3], quats [N,4], scales [N,3], opacities [N], colors [N,3], knots [K,7],
@@ -175,7 +175,7 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
         ft, ex, Ks = params["frame_times"][idx].contiguous(), params["exposure_times"][idx].contiguous(), params["Ks"][idx].contiguous()
         cfg = _lib.make_config(N, len(ids), n_virtual, width, height, crf_kind=crf_kind,
                                crf_hidden=(crf_params.shape[1] - 1) // 3 if crf_params is not None else 0,
-                               sort_mode=_SORT[sort_mode], background=background)
+                               sort_mode=_SORT[sort_mode], background=background, crf_before_average=crf_before_average)
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
         st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline)
         v_ldr = upstream(ids, st.ldr).contiguous()

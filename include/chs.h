@@ -153,7 +153,10 @@ CHS_API int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float* ge
  * Per (frame, tile): for each virtual pose, front-to-back alpha blending in linear HDR; then
  * mean over poses, x exposure, CRF.  Outputs: ldr [B,H,W,3], alpha [B,H,W], hdr_mean [B,H,W,3]
  * (saved for the backward / return_hdr), final_T [C,H,W], last_id [C,H,W] int32 (1-based index
- * into the pixel's tile list of the last accumulated Gaussian, 0 = none). */
+ * into the pixel's tile list of the last accumulated Gaussian, 0 = none).
+ * With cfg->crf_before_average = 1 (the order assets/pipeline.png draws: B = mean_k F(dt H_k)) the
+ * `hdr_mean` buffer instead receives every pose's HDR image and must be [C,H,W,3]; chs_crf_bwd then
+ * reads it per pose and writes v_hdr [C,H,W,3], which chs_blend_bwd reads per camera. */
 CHS_API int chs_blend_fwd(const chs_config* cfg, const float* geom, const float* conic_c, const float* rgbo,
                   const int32_t* vals_sorted, const uint32_t* tile_offsets, const float* exposure,
                   const float* crf_params, float* ldr, float* alpha, float* hdr_mean, float* final_T,

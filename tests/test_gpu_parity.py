@@ -253,10 +253,21 @@ def test_ragged_image_and_single_pose():
     assert float(o_grads["exposure_times"].norm()) > 0
 
 
-def test_unsupported_crf_order_raises():
-    sc = make_config("tiny")
-    with pytest.raises(RuntimeError, match="crf_before_average"):
-        cuda_run(sc, with_grad=False, crf_before_average=True)
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_figure_order_crf_before_average(name):
+    """B = mean_k F(dt * H_k), the order assets/pipeline.png draws."""
+    sc = make_config(name)
+    g = torch.Generator().manual_seed(12)
+    v_alpha = torch.randn(sc.n_frames, sc.height, sc.width, 1, generator=g, dtype=torch.float32)
+    ldr, alpha, meta, grads = cuda_run(sc, v_alpha=v_alpha, crf_before_average=True, return_hdr=True)
+    o_ldr, o_alpha, o_meta, o_grads = oracle_run(sc, v_alpha=v_alpha, crf_before_average=True,
+                                                 projection_override=cuda_projection(meta), straight_through=True)
+    d_ldr, _, _, _ = oracle_run(sc, with_grad=False)
+    assert rel(o_ldr, d_ldr) > 1e-5, "the two orders must differ for a non-linear CRF"
+    assert rel(ldr, o_ldr) <= FWD_TOL and rel(alpha, o_alpha) <= FWD_TOL
+    assert rel(meta["hdr"], o_meta["hdr_mean"]) <= FWD_TOL
+    errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
+    assert all(e <= GRAD_TOL for e in errs.values()), errs
 
 
 def test_golden_config1_forward():
