@@ -26,6 +26,20 @@ class ChsConfig(ctypes.Structure):
     ]
 
 
+class ChsTensors(ctypes.Structure):
+    """chs_tensors of include/chs.h (one-shot entry points)."""
+    _fields_ = ([(n, c_void_p) for n in ["means", "quats", "scales", "opacities", "colors", "Ks", "exposure", "crf_params", "viewmats"]]
+                + [("spline_kind", c_int32), ("n_knots", c_int32), ("knots", c_void_p), ("frame_times", c_void_p),
+                   ("knot_t0", c_double), ("knot_dt", c_double)]
+                + [(n, c_void_p) for n in ["geom", "conic_c", "depths", "rgbo", "radii", "tiles_touched", "order", "vals_sorted", "last_id",
+                                           "isect_offsets", "tile_offsets", "n_isect_dev"]]
+                + [("isect_capacity", c_int64)]
+                + [(n, c_void_p) for n in ["ldr", "alpha", "hdr_mean", "final_T", "v_ldr", "v_alpha", "v_hdr", "v_geom", "v_cogr", "v_blue",
+                                           "grads_flat", "v_viewmats", "v_crf_params", "v_exposure", "v_knots", "v_frame_times",
+                                           "v_exposure_window", "workspace"]]
+                + [("workspace_bytes", c_uint64)])
+
+
 class ChsWorkspaceSizes(ctypes.Structure):
     _fields_ = [("bin_count_bytes", c_uint64), ("bin_sort_bytes", c_uint64), ("reduce_bytes", c_uint64)]
 
@@ -33,6 +47,7 @@ class ChsWorkspaceSizes(ctypes.Structure):
 # name -> (restype, argtypes); every symbol include/chs.h declares
 P = c_void_p
 CFG = POINTER(ChsConfig)
+
 SIGNATURES = {
     "chs_version": (ctypes.c_int, []),
     "chs_last_error": (c_char_p, []),
@@ -53,6 +68,8 @@ SIGNATURES = {
     "chs_allreduce_grads": (ctypes.c_int, [P, P, c_uint64, P]),
     "chs_comm_destroy": (ctypes.c_int, [P]),
     "chs_nvls_allreduce": (ctypes.c_int, [P, c_uint64, c_int32, c_int32, P]),
+    "chs_rasterize_fwd": (ctypes.c_int, [CFG, POINTER(ChsTensors), POINTER(c_int64), P]),
+    "chs_rasterize_bwd": (ctypes.c_int, [CFG, POINTER(ChsTensors), c_int64, P]),
 }
 
 _LIB = None

@@ -209,3 +209,71 @@ extern "C" int chs_nvls_allreduce(float* mc_ptr, uint64_t count, int32_t rank, i
   CHS_LAUNCH_CHECK();
   return CHS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// one-shot entry points
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void add_inplace_kernel(float* dst, const float* src, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+}  // namespace
+
+extern "C" int chs_rasterize_fwd(const chs_config* cfg, const chs_tensors* t, int64_t* n_isect_out, void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(t && n_isect_out, "chs_rasterize_fwd: null argument");
+  CHS_REQUIRE(t->viewmats && t->workspace, "chs_rasterize_fwd: viewmats / workspace required");
+  if (t->spline_kind >= 0) {
+    st = chs_spline_fwd(t->spline_kind, t->knots, t->n_knots, t->knot_t0, t->knot_dt, t->frame_times, t->exposure, d.B, d.n,
+                        t->viewmats, stream);
+    if (st) return st;
+  }
+  st = chs_project_fwd(cfg, t->means, t->quats, t->scales, t->opacities, t->colors, t->viewmats, t->Ks, t->geom, t->conic_c, t->depths,
+                       t->radii, t->tiles_touched, t->rgbo, stream);
+  if (st) return st;
+  int64_t M = 0;
+  st = chs_bin_count(cfg, t->tiles_touched, t->depths, t->isect_offsets, t->order, t->n_isect_dev, &M, t->workspace, t->workspace_bytes,
+                     stream);
+  *n_isect_out = M;
+  if (st) return st;
+  if (M > t->isect_capacity) {
+    chs_set_error("chs_rasterize_fwd: %lld intersections exceed isect_capacity %lld", (long long)M, (long long)t->isect_capacity);
+    return CHS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  st = chs_bin_sort(cfg, M, t->geom, t->radii, t->depths, t->isect_offsets, t->order, nullptr, t->vals_sorted, t->tile_offsets,
+                    t->workspace, t->workspace_bytes, stream);
+  if (st) return st;
+  return chs_blend_fwd(cfg, t->geom, t->conic_c, t->rgbo, t->vals_sorted, t->tile_offsets, t->exposure, t->crf_params, t->ldr, t->alpha,
+                       t->hdr_mean, t->final_T, t->last_id, stream);
+}
+
+extern "C" int chs_rasterize_bwd(const chs_config* cfg, const chs_tensors* t, int64_t n_isect, void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(t && t->workspace && t->v_ldr, "chs_rasterize_bwd: null argument");
+  (void)n_isect;
+  st = chs_crf_bwd(cfg, t->hdr_mean, t->exposure, t->crf_params, t->v_ldr, t->v_hdr, t->v_crf_params, t->v_exposure, t->workspace,
+                   t->workspace_bytes, stream);
+  if (st) return st;
+  st = chs_blend_bwd(cfg, t->geom, t->conic_c, t->rgbo, t->vals_sorted, t->tile_offsets, t->final_T, t->last_id, t->v_hdr, t->v_alpha,
+                     t->v_geom, t->v_cogr, t->v_blue, stream);
+  if (st) return st;
+  st = chs_project_bwd(cfg, t->means, t->quats, t->scales, t->viewmats, t->Ks, t->radii, t->v_geom, t->v_cogr, t->v_blue, t->grads_flat,
+                       t->v_viewmats, t->workspace, t->workspace_bytes, stream);
+  if (st) return st;
+  if (t->spline_kind >= 0) {
+    CHS_REQUIRE(t->v_knots && t->v_frame_times && t->v_exposure_window, "chs_rasterize_bwd: spline gradient outputs required");
+    st = chs_spline_bwd(t->spline_kind, t->knots, t->n_knots, t->knot_t0, t->knot_dt, t->frame_times, t->exposure, d.B, d.n, t->v_viewmats,
+                        t->v_knots, t->v_frame_times, t->v_exposure_window, t->workspace, t->workspace_bytes, stream);
+    if (st) return st;
+    if (d.B > 0) {
+      add_inplace_kernel<<<(d.B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t->v_exposure, t->v_exposure_window, d.B);
+      CHS_LAUNCH_CHECK();
+    }
+  }
+  return CHS_OK;
+}

@@ -193,6 +193,39 @@ CHS_API int chs_comm_init(const void* unique_id_host_128, int32_t rank, int32_t 
 CHS_API int chs_allreduce_grads(chs_comm* comm, float* buf, uint64_t count, void* stream);
 CHS_API int chs_comm_destroy(chs_comm* comm);
 
+/* ---- one-shot entry points: chain K0..K6 / K7..K9(+K0 bwd) over caller-owned buffers --------------------
+ * Every pointer is a device pointer with the shape documented at the staged entry point of the same
+ * name.  `viewmats` is an input when spline_kind < 0 and is written by K0 otherwise.  The intersection
+ * buffers (vals_sorted and the bin_sort part of `workspace`) must hold `isect_capacity` entries; if the
+ * frame needs more, chs_rasterize_fwd returns CHS_ERR_WORKSPACE_TOO_SMALL with *n_isect_out set to the
+ * required count (the call synchronises the stream once to learn M, exactly like chs_bin_count).
+ * workspace_bytes >= max(bin_count_bytes, bin_sort_bytes(isect_capacity), reduce_bytes). */
+typedef struct chs_tensors {
+  /* Gaussians, cameras, formation parameters (inputs) */
+  const float *means, *quats, *scales, *opacities, *colors, *Ks, *exposure, *crf_params;
+  float* viewmats;            /* [C,4,4] */
+  int32_t spline_kind;        /* < 0: explicit viewmats; else CHS_SPLINE_* */
+  int32_t n_knots;
+  const float *knots, *frame_times;
+  double knot_t0, knot_dt;
+  /* forward stage buffers */
+  float *geom, *conic_c, *depths, *rgbo;
+  int32_t *radii, *tiles_touched, *order, *vals_sorted, *last_id;
+  uint32_t *isect_offsets, *tile_offsets;
+  int64_t* n_isect_dev;
+  int64_t isect_capacity;
+  float *ldr, *alpha, *hdr_mean, *final_T;
+  /* backward: upstream gradients in, parameter gradients out */
+  const float *v_ldr, *v_alpha;
+  float *v_hdr, *v_geom, *v_cogr, *v_blue, *grads_flat, *v_viewmats, *v_crf_params, *v_exposure;
+  float *v_knots, *v_frame_times, *v_exposure_window; /* spline only */
+  void* workspace;
+  uint64_t workspace_bytes;
+} chs_tensors;
+CHS_API int chs_rasterize_fwd(const chs_config* cfg, const chs_tensors* t, int64_t* n_isect_out, void* stream);
+/* n_isect: the count chs_rasterize_fwd reported.  v_exposure receives brightness + window paths. */
+CHS_API int chs_rasterize_bwd(const chs_config* cfg, const chs_tensors* t, int64_t n_isect, void* stream);
+
 /* ---- K10 (NVLS variant): hand-written one-shot all-reduce through the NVSwitch multicast address ----
  * mc_ptr is the MULTICAST device pointer of a symmetric buffer (same offset on every rank, e.g. from
  * torch.distributed._symmetric_memory) that already holds each rank's partial sums.  Rank r reduces its

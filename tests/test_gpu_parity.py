@@ -380,3 +380,65 @@ def test_config3_forward_is_deterministic_and_linear(c3_scene):
     lhs = ((ldr4 - ldr.detach()).double() * v.double()).sum()
     rhs = (g_col.double() * d.double()).sum()
     assert abs(float(lhs - rhs)) <= 2e-3 * abs(float(rhs))
+
+
+def test_one_shot_c_abi_matches_staged_path():
+    """chs_rasterize_fwd / chs_rasterize_bwd (caller-owned buffers, capacity-checked M) against rasterize()."""
+    import ctypes
+    from ctypes import byref, c_int64
+
+    from casualhdrsplat_b200 import _lib, api
+
+    sc = make_config("small")
+    ldr, alpha, meta, grads = cuda_run(sc)
+    st = meta["state"]
+    dev = torch.device("cuda:0")
+    f32, i32 = torch.float32, torch.int32
+    B, n, N, W, H = sc.n_frames, sc.n_virtual, sc.means.shape[0], sc.width, sc.height
+    C, tiles, K = B * n, ((W + 15) // 16) * ((H + 15) // 16), sc.knots.shape[0]
+    cfg = st.cfg
+    cap = st.n_isect + 1000
+    ws0, ws1 = _lib.workspace_sizes(cfg, 0, K), _lib.workspace_sizes(cfg, cap, K)
+    wbytes = max(int(ws0.bin_count_bytes), int(ws1.bin_sort_bytes), int(ws0.reduce_bytes))
+    bufs = {}
+
+    def mk(name, shape, dtype=f32):
+        bufs[name] = torch.empty(shape, dtype=dtype, device=dev)
+        return ctypes.c_void_p(bufs[name].data_ptr())
+
+    inp = {k: getattr(sc, k).to(dev).contiguous() for k in ["means", "quats", "scales", "opacities", "colors", "Ks", "exposure_times",
+                                                              "crf_params", "knots", "frame_times", "v_ldr"]}
+    t = _lib.ChsTensors()
+    for k in ["means", "quats", "scales", "opacities", "colors", "Ks", "crf_params", "knots", "frame_times", "v_ldr"]:
+        setattr(t, k, inp[k].data_ptr())
+    t.exposure = inp["exposure_times"].data_ptr()
+    t.spline_kind, t.n_knots, t.knot_t0, t.knot_dt = sc.spline_kind, K, sc.knot_t0, sc.knot_dt
+    t.viewmats = mk("viewmats", (C, 4, 4))
+    t.geom, t.conic_c, t.depths, t.rgbo = mk("geom", (C, N, 4)), mk("conic_c", (C, N)), mk("depths", (C, N)), mk("rgbo", (N, 4))
+    t.radii, t.tiles_touched, t.order = mk("radii", (C, N), i32), mk("tiles", (C, N), i32), mk("order", (C * N,), i32)
+    t.vals_sorted, t.last_id = mk("vals", (cap,), i32), mk("last_id", (C, H, W), i32)
+    t.isect_offsets, t.tile_offsets = mk("offs", (C * N,), i32), mk("to", (C * tiles + 1,), i32)
+    t.n_isect_dev, t.isect_capacity = mk("nd", (1,), torch.int64), cap
+    t.ldr, t.alpha, t.hdr_mean, t.final_T = mk("ldr", (B, H, W, 3)), mk("alpha", (B, H, W)), mk("hdr", (B, H, W, 3)), mk("T", (C, H, W))
+    t.v_alpha = None
+    t.v_hdr, t.v_geom, t.v_cogr, t.v_blue = mk("v_hdr", (B, H, W, 3)), mk("v_geom", (C, N, 4)), mk("v_cogr", (C, N, 4)), mk("v_blue", (C, N))
+    t.grads_flat, t.v_viewmats = mk("flat", (14 * N,)), mk("v_vm", (C, 4, 4))
+    t.v_crf_params, t.v_exposure = mk("v_crf", tuple(sc.crf_params.shape)), mk("v_ex", (B,))
+    t.v_knots, t.v_frame_times, t.v_exposure_window = mk("v_knots", (K, 7)), mk("v_ft", (B,)), mk("v_exw", (B,))
+    t.workspace, t.workspace_bytes = mk("work", (wbytes,), torch.uint8), wbytes
+    M = c_int64(0)
+    L = _lib.lib()
+    _lib.check(L.chs_rasterize_fwd(byref(cfg), byref(t), byref(M), api._stream()), "chs_rasterize_fwd")
+    _lib.check(L.chs_rasterize_bwd(byref(cfg), byref(t), M.value, api._stream()), "chs_rasterize_bwd")
+    torch.cuda.synchronize()
+    assert M.value == st.n_isect
+    assert torch.equal(bufs["ldr"], ldr) and torch.equal(bufs["alpha"], alpha[..., 0])
+    vm, vq, vs, vo, vc = api.split_flat_grads(bufs["flat"], N)
+    for got, name in [(vm, "means"), (vq, "quats"), (vs, "scales"), (vo, "opacities"), (vc, "colors"), (bufs["v_knots"], "knots"),
+                      (bufs["v_ex"], "exposure_times"), (bufs["v_ft"], "frame_times"), (bufs["v_crf"], "crf_params")]:
+        assert rel(got, grads[name]) < 1e-5, name
+    # capacity check: too small a buffer is reported, with the required count
+    t.isect_capacity = 10
+    M2 = c_int64(0)
+    assert L.chs_rasterize_fwd(byref(cfg), byref(t), byref(M2), api._stream()) == -4
+    assert M2.value == st.n_isect and b"isect_capacity" in L.chs_last_error()
