@@ -442,3 +442,38 @@ def test_one_shot_c_abi_matches_staged_path():
     M2 = c_int64(0)
     assert L.chs_rasterize_fwd(byref(cfg), byref(t), byref(M2), api._stream()) == -4
     assert M2.value == st.n_isect and b"isect_capacity" in L.chs_last_error()
+
+
+def _stress_scene(n, w, h, frames, n_virtual, seed):
+    """Odd sizes, screen-filling and sub-pixel Gaussians, opacities below 1/255 and above the 0.999 clamp,
+    exact duplicates (position and depth ties), Gaussians behind / beside the camera."""
+    sc = make_scene(n, w, h, n_frames=frames, n_virtual=n_virtual, spline_kind=SPLINE_CUBIC, crf_hidden=16, scale_mult=10.0,
+                    scene_seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    k = n // 8
+    sc.scales[:k] *= 40.0                      # screen-filling
+    sc.scales[k:2 * k] *= 0.02                 # far below one pixel
+    sc.opacities[2 * k:2 * k + k // 2] = 0.003  # < 1/255: can never contribute
+    sc.opacities[2 * k + k // 2:3 * k] = 0.9996  # above the clamp
+    sc.means[3 * k:4 * k] = sc.means[3 * k:3 * k + 1]  # exact duplicates -> equal depths in every camera
+    sc.means[4 * k:4 * k + k // 2, 2] -= 40.0   # behind the camera
+    sc.means[4 * k + k // 2:5 * k, 0] += 500.0  # far off to the side
+    sc.quats[5 * k:6 * k] *= 7.5               # un-normalised quaternions are allowed
+    return sc
+
+
+@pytest.mark.parametrize("n,w,h,frames,n_virtual", [(1237, 33, 17, 1, 2), (801, 5, 3, 2, 1), (2049, 130, 70, 1, 3)])
+def test_stress_edge_cases(n, w, h, frames, n_virtual):
+    sc = _stress_scene(n, w, h, frames, n_virtual, seed=n)
+    for mode in ["presort", "key64"]:
+        ldr, alpha, meta, grads = cuda_run(sc, sort_mode=mode, debug_keys=True, background=[0.2, 0.1, 0.05])
+        st = meta["state"]
+        proj = cuda_projection(meta)
+        b = oracle.bin_tiles(proj["means2d"], proj["radii"], proj["depths"], w, h)
+        assert st.n_isect == b["n_isect"]
+        assert torch.equal(st.keys_sorted.cpu(), b["keys_sorted"]) and torch.equal(st.vals_sorted.cpu()[: st.n_isect], b["vals_sorted"])
+        assert torch.equal(_u32(st.tile_offsets), b["tile_offsets"])
+        o_ldr, o_alpha, o_meta, o_grads = oracle_run(sc, projection_override=proj, straight_through=True, background=[0.2, 0.1, 0.05])
+        assert rel(ldr, o_ldr) <= FWD_TOL and rel(alpha, o_alpha) <= FWD_TOL
+        errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
+        assert all(e <= GRAD_TOL for e in errs.values()), (mode, errs)
