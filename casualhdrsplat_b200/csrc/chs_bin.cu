@@ -49,12 +49,12 @@ __global__ void depth_keys_kernel(const int32_t* __restrict__ touched, const flo
 // the same order), which the 32 lanes write fully coalesced.  The owner of each output slot is found
 // by a 5-step binary search over the lanes' start offsets (shuffles), its tile rectangle fetched by
 // shuffle.  MODE 0: 64-bit cam|tile|depth keys; MODE 1: 32-bit linear (cam * tiles + tile) keys.
-template <int MODE>
+template <int MODE, class LinT>
 __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits,
                                                         const float4* __restrict__ geom, const int32_t* __restrict__ radii,
                                                         const float* __restrict__ depths, const uint32_t* __restrict__ offsets,
                                                         const int32_t* __restrict__ order, uint64_t* __restrict__ keys64,
-                                                        uint32_t* __restrict__ keys32, int32_t* __restrict__ vals) {
+                                                        LinT* __restrict__ keys32, int32_t* __restrict__ vals) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int32_t id = 0;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
       if (MODE == 0)
         keys64[o] = ((uint64_t)c << (32 + tile_bits)) | ((uint64_t)(ty * tile_w + tx) << 32) | (uint64_t)o_d;
       else
-        keys32[o] = c * (uint32_t)tiles + (uint32_t)(ty * tile_w + tx);
+        keys32[o] = (LinT)(c * (uint32_t)tiles + (uint32_t)(ty * tile_w + tx));
       vals[o] = o_id;
     }
   }
@@ -118,9 +118,9 @@ __device__ __forceinline__ uint32_t lin_of_key64(uint64_t key, int tile_bits, in
 
 // K5: tile_offsets[lin] = first sorted index whose (cam, tile) >= lin; tile_offsets[C*tiles] = M.
 // Four sorted entries per thread.
-template <int MODE>
+template <int MODE, class LinT>
 __global__ void __launch_bounds__(kThreads) tile_offsets_kernel(int64_t M, int n_lin, int tile_bits, int tiles,
-                                                                const uint64_t* __restrict__ keys64, const uint32_t* __restrict__ keys32,
+                                                                const uint64_t* __restrict__ keys64, const LinT* __restrict__ keys32,
                                                                 uint32_t* __restrict__ tile_offsets) {
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= M) return;
@@ -128,9 +128,12 @@ __global__ void __launch_bounds__(kThreads) tile_offsets_kernel(int64_t M, int n
   const int nv = (int)min((int64_t)4, M - i0);
   if (MODE == 0) {
     for (int k = 0; k < nv; ++k) lin[k] = lin_of_key64(keys64[i0 + k], tile_bits, tiles);
-  } else if (nv == 4) {
+  } else if (nv == 4 && sizeof(LinT) == 4) {
     const uint4 v = *reinterpret_cast<const uint4*>(keys32 + i0);
     lin[0] = v.x; lin[1] = v.y; lin[2] = v.z; lin[3] = v.w;
+  } else if (nv == 4) {
+    const uint2 v = *reinterpret_cast<const uint2*>(keys32 + i0);  // four 16-bit keys
+    lin[0] = v.x & 0xffffu; lin[1] = v.x >> 16; lin[2] = v.y & 0xffffu; lin[3] = v.y >> 16;
   } else {
     for (int k = 0; k < nv; ++k) lin[k] = keys32[i0 + k];
   }
@@ -149,7 +152,8 @@ __global__ void __launch_bounds__(kThreads) tile_offsets_kernel(int64_t M, int n
     for (uint32_t b = prev + 1; b <= (uint32_t)n_lin; ++b) tile_offsets[b] = (uint32_t)M;
 }
 
-__global__ void rebuild_keys_kernel(int64_t M, int tiles, int tile_bits, const uint32_t* __restrict__ lin_sorted,
+template <class LinT>
+__global__ void rebuild_keys_kernel(int64_t M, int tiles, int tile_bits, const LinT* __restrict__ lin_sorted,
                                     const int32_t* __restrict__ vals_sorted, const float* __restrict__ depths,
                                     uint64_t* __restrict__ keys_sorted) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,9 +191,14 @@ int sort_temp_size(const ChsDims& d, int sort_mode, int64_t M, size_t* bytes) {
   if (sort_mode == CHS_SORT_KEY64)
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
                                              (int32_t*)nullptr, M, 0, 32 + d.tile_bits + d.cam_bits));
-  else
+  else {
+    size_t b16 = 0;
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
                                              (int32_t*)nullptr, M, 0, chs_bit_length((uint64_t)d.C * d.tiles)));
+    CHS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b16, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const int32_t*)nullptr,
+                                             (int32_t*)nullptr, M, 0, 16));
+    if (b16 > *bytes) *bytes = b16;
+  }
   return CHS_OK;
 }
 
@@ -293,7 +302,7 @@ extern "C" int chs_bin_emit_keys(const chs_config* cfg, int64_t n_isect, const f
   CHS_REQUIRE(geom && radii && depths && isect_offsets, "chs_bin_emit_keys: null input");
   if (n_isect == 0 || d.CN == 0) return CHS_OK;
   CHS_REQUIRE(keys && vals, "chs_bin_emit_keys: null output");
-  emit_kernel<0><<<grid_for(d.CN), kThreads, 0, (cudaStream_t)stream>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits,
+  emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, (cudaStream_t)stream>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits,
                                                                          (const float4*)geom, radii, depths, isect_offsets, order, keys,
                                                                          nullptr, vals);
   CHS_LAUNCH_CHECK();
@@ -330,30 +339,53 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
       chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
       return CHS_ERR_WORKSPACE_TOO_SMALL;
     }
-    emit_kernel<0><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom, radii,
+    emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom, radii,
                                                        depths, isect_offsets, nullptr, k_in, nullptr, v_in);
     CHS_LAUNCH_CHECK();
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_in, k_out, (const int32_t*)v_in, vals_sorted, M, 0,
                                              32 + d.tile_bits + d.cam_bits, s));
-    tile_offsets_kernel<0><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, k_out, nullptr, tile_offsets);
+    tile_offsets_kernel<0, uint32_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, k_out, nullptr, tile_offsets);
     CHS_LAUNCH_CHECK();
   } else {
-    uint32_t* l_in = ar.take<uint32_t>(M);
-    uint32_t* l_out = ar.take<uint32_t>(M);
+    // linear (cam * tiles + tile) keys: 16 bits suffice for one 1080p frame of 8 poses (65280 buckets), which cuts
+    // the bytes every radix pass moves from 8 to 6 per intersection
+    const bool k16 = n_lin <= 65536;
+    void* l_in = k16 ? (void*)ar.take<uint16_t>(M) : (void*)ar.take<uint32_t>(M);
+    void* l_out = k16 ? (void*)ar.take<uint16_t>(M) : (void*)ar.take<uint32_t>(M);
     if (!ar.ok) {
       chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
       return CHS_ERR_WORKSPACE_TOO_SMALL;
     }
-    emit_kernel<1><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom, radii,
-                                                       depths, isect_offsets, order, nullptr, l_in, v_in);
-    CHS_LAUNCH_CHECK();
-    CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)l_in, l_out, (const int32_t*)v_in, vals_sorted, M, 0,
-                                             chs_bit_length((uint64_t)n_lin), s));
-    tile_offsets_kernel<1><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr, l_out, tile_offsets);
-    CHS_LAUNCH_CHECK();
-    if (keys_sorted) {
-      rebuild_keys_kernel<<<grid_for(M), kThreads, 0, s>>>(M, d.tiles, d.tile_bits, l_out, vals_sorted, depths, keys_sorted);
+    const int bits = n_lin > 1 ? chs_bit_length((uint64_t)n_lin - 1) : 1;
+    if (k16) {
+      emit_kernel<1, uint16_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom,
+                                                                   radii, depths, isect_offsets, order, nullptr, (uint16_t*)l_in, v_in);
       CHS_LAUNCH_CHECK();
+      size_t tb16 = tb;
+      CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb16, (const uint16_t*)l_in, (uint16_t*)l_out, (const int32_t*)v_in, vals_sorted, M, 0,
+                                               bits, s));
+      tile_offsets_kernel<1, uint16_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr,
+                                                                                   (const uint16_t*)l_out, tile_offsets);
+      CHS_LAUNCH_CHECK();
+      if (keys_sorted) {
+        rebuild_keys_kernel<uint16_t><<<grid_for(M), kThreads, 0, s>>>(M, d.tiles, d.tile_bits, (const uint16_t*)l_out, vals_sorted, depths,
+                                                                       keys_sorted);
+        CHS_LAUNCH_CHECK();
+      }
+    } else {
+      emit_kernel<1, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom,
+                                                                   radii, depths, isect_offsets, order, nullptr, (uint32_t*)l_in, v_in);
+      CHS_LAUNCH_CHECK();
+      CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)l_in, (uint32_t*)l_out, (const int32_t*)v_in, vals_sorted, M, 0,
+                                               bits, s));
+      tile_offsets_kernel<1, uint32_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr,
+                                                                                   (const uint32_t*)l_out, tile_offsets);
+      CHS_LAUNCH_CHECK();
+      if (keys_sorted) {
+        rebuild_keys_kernel<uint32_t><<<grid_for(M), kThreads, 0, s>>>(M, d.tiles, d.tile_bits, (const uint32_t*)l_out, vals_sorted, depths,
+                                                                       keys_sorted);
+        CHS_LAUNCH_CHECK();
+      }
     }
   }
   return CHS_OK;
