@@ -189,8 +189,7 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL prints its version banner to stdout otherwise; keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         # default: the hand-written NVLS (multimem) all-reduce kernel; NCCL through the C ABI if the fabric has no multicast
         which = os.environ.get("CHS_COMM", "nvls")
