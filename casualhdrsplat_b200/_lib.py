@@ -68,6 +68,8 @@ SIGNATURES = {
     "chs_allreduce_grads": (ctypes.c_int, [P, P, c_uint64, P]),
     "chs_comm_destroy": (ctypes.c_int, [P]),
     "chs_nvls_allreduce": (ctypes.c_int, [P, c_uint64, c_int32, c_int32, P]),
+    "chs_loss": (ctypes.c_int, [c_int32, P, P, c_uint64, c_float, P, P, P]),
+    "chs_adam_step": (ctypes.c_int, [P, P, P, P, c_uint64, c_float, c_float, c_float, c_float, c_int32, c_float, P]),
     "chs_rasterize_fwd": (ctypes.c_int, [CFG, POINTER(ChsTensors), POINTER(c_int64), P]),
     "chs_rasterize_bwd": (ctypes.c_int, [CFG, POINTER(ChsTensors), c_int64, P]),
 }

@@ -226,6 +226,17 @@ CHS_API int chs_rasterize_fwd(const chs_config* cfg, const chs_tensors* t, int64
 /* n_isect: the count chs_rasterize_fwd reported.  v_exposure receives brightness + window paths. */
 CHS_API int chs_rasterize_bwd(const chs_config* cfg, const chs_tensors* t, int64_t n_isect, void* stream);
 
+/* ---- the steps either side of the path in a trainer ----------------------
+ * chs_loss: photometric loss between the blurred LDR frames and the captured frames, emitting dL/dB in
+ * the same pass.  kind 0: L = 0.5 * scale * sum d^2, v = scale * d;  kind 1: L = scale * sum |d|,
+ * v = scale * sign(d);  d = ldr - target.  *loss_acc (device fp64) is ADDED to (zero it first). */
+CHS_API int chs_loss(int32_t kind, const float* ldr, const float* target, uint64_t count, float scale, float* v_ldr,
+             double* loss_acc, void* stream);
+/* Adam (bias-corrected) on `count` parameters given their section of the flat gradient buffer.
+ * step is 1-based; grad_scale multiplies the gradient first (e.g. 1 / global batch). */
+CHS_API int chs_adam_step(float* param, const float* grad, float* m, float* v, uint64_t count, float lr, float beta1,
+                  float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
 /* ---- K10 (NVLS variant): hand-written one-shot all-reduce through the NVSwitch multicast address ----
  * mc_ptr is the MULTICAST device pointer of a symmetric buffer (same offset on every rank, e.g. from
  * torch.distributed._symmetric_memory) that already holds each rank's partial sums.  Rank r reduces its

@@ -477,3 +477,57 @@ def test_stress_edge_cases(n, w, h, frames, n_virtual):
         assert rel(ldr, o_ldr) <= FWD_TOL and rel(alpha, o_alpha) <= FWD_TOL
         errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
         assert all(e <= GRAD_TOL for e in errs.values()), (mode, errs)
+
+
+def test_fused_loss_and_adam_match_torch():
+    """chs_loss (+ dL/dB in the same pass) and chs_adam_step against torch."""
+    from casualhdrsplat_b200.train import LOSS_L1, LOSS_L2, FlatAdam, photometric_loss
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    ldr = torch.rand(2, 37, 53, 3, generator=g, dtype=torch.float32).to(dev)
+    tgt = torch.rand(2, 37, 53, 3, generator=g, dtype=torch.float32).to(dev)
+    for kind, fn in [(LOSS_L2, lambda d: 0.5 * 0.25 * (d * d).sum()), (LOSS_L1, lambda d: 0.25 * d.abs().sum())]:
+        x = ldr.clone().double().requires_grad_(True)
+        want = fn(x - tgt.double())
+        (gx,) = torch.autograd.grad(want, x)
+        v, acc = photometric_loss(ldr, tgt, kind, scale=0.25)
+        assert abs(float(acc) - float(want)) <= 1e-6 * abs(float(want))
+        assert rel(v, gx) < 1e-6
+    p0 = torch.randn(1001, 3, generator=g, dtype=torch.float32).to(dev)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=3e-3, betas=(0.9, 0.99), eps=1e-8)
+    mine = {"w": p0.clone()}
+    fa = FlatAdam(mine, lr=3e-3, betas=(0.9, 0.99), eps=1e-8)
+    for it in range(5):
+        gr = torch.randn(1001, 3, generator=g, dtype=torch.float32).to(dev)
+        p_ref.grad = gr.clone() * 0.5
+        opt.step()
+        fa.step({"w": gr}, grad_scale=0.5)
+    assert rel(mine["w"], p_ref.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("figure_order", [False, True])
+def test_gradient_through_returned_hdr(figure_order):
+    """return_hdr=True (README R9: 'render HDR and LDR images'): a loss on the pose-averaged HDR image back-propagates too."""
+    from casualhdrsplat_b200 import rasterize
+
+    sc = make_config("tiny")
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(31)
+    w_h = torch.randn(sc.n_frames, sc.height, sc.width, 3, generator=g, dtype=torch.float32)
+    col = sc.colors.to(dev).requires_grad_(True)
+    op = sc.opacities.to(dev).requires_grad_(True)
+    sp = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in sc.spline().items()}
+    ldr, alpha, meta = rasterize(sc.means.to(dev), sc.quats.to(dev), sc.scales.to(dev), op, col, None, sc.Ks.to(dev), sc.width, sc.height,
+                                 sc.exposure_times.to(dev), sc.n_virtual, sc.crf_kind, sc.crf_params.to(dev), spline=sp,
+                                 return_hdr=True, crf_before_average=figure_order)
+    gc, go = torch.autograd.grad((meta["hdr"] * w_h.to(dev)).sum() + (ldr * sc.v_ldr.to(dev)).sum(), [col, op])
+    oc = sc.colors.double().requires_grad_(True)
+    oo = sc.opacities.double().requires_grad_(True)
+    o_ldr, _, o_meta = oracle.rasterize(sc.means, sc.quats, sc.scales, oo, oc, None, sc.Ks, sc.width, sc.height, sc.exposure_times,
+                                        sc.n_virtual, sc.crf_kind, sc.crf_params, spline=sc.spline(), crf_before_average=figure_order,
+                                        projection_override=cuda_projection(meta))
+    ogc, ogo = torch.autograd.grad((o_meta["hdr_mean"] * w_h.double()).sum() + (o_ldr * sc.v_ldr.double()).sum(), [oc, oo])
+    assert rel(meta["hdr"], o_meta["hdr_mean"]) <= FWD_TOL
+    assert rel(gc, ogc) <= GRAD_TOL and rel(go, ogo) <= GRAD_TOL
