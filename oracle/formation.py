@@ -188,7 +188,7 @@ def blend(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss
           background=None, tile=TILE, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP):
     """Front-to-back alpha blending of every camera's sorted tile lists in linear HDR radiance.
 
-    means2d [C,N,2], conics [C,N,3], opacities [N], colors [N,3] float64.
+    means2d [C,N,2], conics [C,N,3], opacities [N], colors [N,3] (or per camera [C,N,3], e.g. from SH) float64.
     Returns hdr [C,H,W,3], alpha [C,H,W], last_id [C,H,W] (sorted index of the last accumulated
     Gaussian, -1 if none).  ``tile_subset``: optional iterable of (c, tile_id) to restrict work
     (used for the bounded CPU-baseline timing); other pixels stay at background.
@@ -221,7 +221,7 @@ def blend(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss
         m = means2d[c, g]
         q = conics[c, g]
         o = opacities[g]
-        col = colors[g]
+        col = colors[c, g] if colors.dim() == 3 else colors[g]
         dx = m[:, 0, None] - PX[None, :]
         dy = m[:, 1, None] - PY[None, :]
         sigma = 0.5 * (q[:, 0, None] * dx * dx + q[:, 2, None] * dy * dy) + q[:, 1, None] * dx * dy
@@ -327,7 +327,8 @@ def formation(hdr_cams, alpha_cams, exposure, n_virtual, crf_kind, crf_params=No
 def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, width=0, height=0,
               exposure_times=None, n_virtual=1, crf_kind=CRF_IDENTITY, crf_params=None, *, spline=None,
               background=None, near=0.01, far=1e10, eps2d=0.3, tile_size=TILE, crf_before_average=False,
-              projection_override=None, binning_override=None, straight_through=False, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP,
+              projection_override=None, binning_override=None, straight_through=False, tile_subset=None,
+              sh_coeffs=None, sh_degree=0, alpha_min=ALPHA_MIN, t_stop=T_STOP,
               radius_sigmas=3.0):
     """Oracle of ``casualhdrsplat_b200.rasterize`` (same arguments and meaning; float64 CPU).
 
@@ -349,6 +350,8 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     otherwise dominate the error norm (discrete decisions carry no gradient, A.6).
     ``alpha_min`` / ``t_stop`` / ``radius_sigmas`` default to the model's constants (1/255, 1e-4, 3);
     tests override them only to obtain a discontinuity-free variant for finite-difference checks.
+    ``sh_coeffs`` [N,K,3] + ``sh_degree``: view-dependent colours, evaluated per virtual camera
+    (oracle/sh.py); ``colors`` is then ignored.
     Returns (ldr [B,H,W,3], alpha [B,H,W,1], meta dict).
     """
     means, quats, scales, opacities, colors = map(_f64, (means, quats, scales, opacities, colors))
@@ -368,6 +371,10 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     if Ks.shape[0] == B and C != B:
         Ks = Ks.repeat_interleave(n_virtual, dim=0)
     N = means.shape[0]
+    if sh_coeffs is not None:
+        from .sh import sh_colors
+
+        colors = sh_colors(_f64(sh_coeffs), means, viewmats, int(sh_degree))
     if projection_override is None:
         proj = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas)
         m2d_f32 = proj["means2d"].detach().to(torch.float32)

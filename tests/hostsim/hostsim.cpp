@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../casualhdrsplat_b200/csrc/chs_math.cuh"
+#include "../../casualhdrsplat_b200/csrc/chs_sh.cuh"
 #include "../../casualhdrsplat_b200/csrc/chs_spline.cuh"
 
 template <class T> static void load_cam(const T* viewmats, const T* Ks, int c, ChsCam<T>& cam) {
@@ -172,6 +173,25 @@ void hs_block_bound_f32(int n, const float* params /* mx,my,A,B,C,o */, const fl
         best = fmaxf(best, chs_pair_power(s, x, y, dx, dy, u));
       }
     brute[i] = best;
+  }
+}
+// SH colours for [C] cameras x [N] Gaussians and their backward (chs_sh.cuh), fp64
+void hs_sh_fwd_bwd(int N, int C, int deg, const double* sh, const double* means, const double* viewmats, const double* v_rgb,
+                   double* rgb, double* v_sh, double* v_means, double* v_viewmats /* [C,12] R|t */) {
+  const int K = (deg + 1) * (deg + 1);
+  std::memset(v_sh, 0, sizeof(double) * N * K * 3);
+  std::memset(v_means, 0, sizeof(double) * N * 3);
+  std::memset(v_viewmats, 0, sizeof(double) * C * 12);
+  for (int c = 0; c < C; ++c) {
+    double R[9], t[3], cp[3], v_cp[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = viewmats[c * 16 + i * 4 + j]; t[i] = viewmats[c * 16 + i * 4 + 3]; }
+    chs_campos(R, t, cp);
+    for (int g = 0; g < N; ++g) {
+      size_t o = ((size_t)c * N + g) * 3;
+      chs_sh_color(deg, sh + (size_t)g * K * 3, means + g * 3, cp, rgb + o);
+      chs_sh_color_bwd(deg, sh + (size_t)g * K * 3, means + g * 3, cp, v_rgb + o, v_sh + (size_t)g * K * 3, v_means + g * 3, v_cp);
+    }
+    chs_campos_bwd(R, t, v_cp, v_viewmats + c * 12, v_viewmats + c * 12 + 9);
   }
 }
 void hs_tile_bounds(int n, const float* mx, const float* my, const int32_t* radius, int tile_w, int tile_h, int32_t* rect) {

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "..", "..", "casualhdrsplat_b200", "csrc")
 
 
 def load():
-    deps = [SRC, os.path.join(CSRC, "chs_math.cuh"), os.path.join(CSRC, "chs_spline.cuh")]
+    deps = [SRC, os.path.join(CSRC, "chs_math.cuh"), os.path.join(CSRC, "chs_spline.cuh"), os.path.join(CSRC, "chs_sh.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", SO, SRC])
     return ctypes.CDLL(SO)

@@ -259,3 +259,33 @@ def test_spline_fwd_bwd_matches_oracle(kind, name):
     assert np.allclose(o_k, gk.numpy(), rtol=1e-8, atol=1e-9 * np.abs(gk.numpy()).max())
     assert np.allclose(o_f, gf.numpy(), rtol=1e-8, atol=1e-12)
     assert np.allclose(o_e, ge.numpy(), rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_sh_colour_fwd_bwd_matches_oracle(deg):
+    from oracle.sh import sh_colors
+
+    g = torch.Generator().manual_seed(40 + deg)
+    N, C, K = 300, 3, (deg + 1) ** 2
+    sh = (torch.randn(N, K, 3, generator=g) * 0.6).requires_grad_(True)
+    means = (torch.randn(N, 3, generator=g) * 2 + torch.tensor([0.0, 0.0, 6.0])).requires_grad_(True)
+    q = torch.randn(C, 4, generator=g)
+    R = se3.quat_to_rotmat(q)
+    vm = torch.eye(4).repeat(C, 1, 1)
+    vm[:, :3, :3] = R
+    vm[:, :3, 3] = torch.randn(C, 3, generator=g)
+    vm = vm.requires_grad_(True)
+    col = sh_colors(sh, means, vm, deg)
+    assert (col > 0).any() and (deg == 0 or (col == 0).any()), "both sides of the relu should be exercised"
+    v = torch.randn(C, N, 3, generator=g)
+    gs, gm, gv = torch.autograd.grad((col * v).sum(), [sh, means, vm], allow_unused=True)
+    gm = gm if gm is not None else torch.zeros_like(means)
+    gv = gv if gv is not None else torch.zeros_like(vm)
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np.float64))
+    rgb = np.zeros((C, N, 3)); o_sh = np.zeros((N, K, 3)); o_m = np.zeros((N, 3)); o_v = np.zeros((C, 12))
+    HS.hs_sh_fwd_bwd(N, C, deg, _p(arr(sh)), _p(arr(means)), _p(arr(vm)), _p(arr(v)), _p(rgb), _p(o_sh), _p(o_m), _p(o_v))
+    assert np.allclose(rgb, col.detach().numpy(), rtol=1e-12, atol=1e-13)
+    assert np.allclose(o_sh, gs.numpy(), rtol=1e-10, atol=1e-13)
+    assert np.allclose(o_m, gm.numpy(), rtol=1e-9, atol=1e-12)
+    assert np.allclose(o_v[:, :9], gv[:, :3, :3].reshape(C, 9).numpy(), rtol=1e-9, atol=1e-11)
+    assert np.allclose(o_v[:, 9:], gv[:, :3, 3].numpy(), rtol=1e-9, atol=1e-11)
