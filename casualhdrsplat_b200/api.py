@@ -47,12 +47,13 @@ class _State:
     """Everything one forward produced that the backward (and tests) need."""
     __slots__ = ("cfg", "spline", "viewmats", "Ks", "geom", "conic_c", "depths", "radii", "tiles_touched", "rgbo",
                  "isect_offsets", "order", "n_isect", "keys_sorted", "vals_sorted", "tile_offsets", "ldr", "alpha", "hdr_mean",
-                 "final_T", "last_id", "n_knots")
+                 "final_T", "last_id", "n_knots", "sh", "sh_degree", "rgbo_c")
 
 
 def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposure, crf_params, cfg, spline=None,
-                   want_keys=False) -> _State:
-    """Run K0-K6 through the C ABI. All tensors CUDA fp32 contiguous. Returns the stage buffers."""
+                   want_keys=False, sh=None, sh_degree=0) -> _State:
+    """Run K0-K6 through the C ABI. All tensors CUDA fp32 contiguous. Returns the stage buffers.
+    With ``sh`` [N,K,3] the colours are view dependent (chs_sh_fwd, per-camera records) and ``colors`` is ignored."""
     L = _lib.lib()
     dev = means.device
     st = _State()
@@ -70,6 +71,13 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
         check(L.chs_spline_fwd(kind, ptr(knots), knots.shape[0], c_double(knot_t0), c_double(knot_dt), ptr(frame_times),
                                ptr(exposure), B, n, ptr(viewmats), s), "chs_spline_fwd")
     st.viewmats = viewmats
+    st.sh, st.sh_degree, st.rgbo_c = sh, int(sh_degree), None
+    if sh is not None:
+        cfg.rgbo_per_camera = 1
+        st.rgbo_c = _empty((C, N, 4), torch.float32, dev)
+        check(L.chs_sh_fwd(byref(cfg), st.sh_degree, ptr(sh), ptr(means), ptr(opacities), ptr(viewmats), ptr(st.rgbo_c), s), "chs_sh_fwd")
+        if colors is None:
+            colors = torch.zeros((N, 3), dtype=torch.float32, device=dev)
     # K1
     st.geom = _empty((C, N, 4), torch.float32, dev)
     st.conic_c = _empty((C, N), torch.float32, dev)
@@ -107,7 +115,8 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     st.hdr_mean = _empty((C if cfg.crf_before_average else B, H, W, 3), torch.float32, dev)
     st.final_T = _empty((C, H, W), torch.float32, dev)
     st.last_id = _empty((C, H, W), torch.int32, dev)
-    check(L.chs_blend_fwd(byref(cfg), ptr(st.geom), ptr(st.conic_c), ptr(st.rgbo), ptr(st.vals_sorted), ptr(st.tile_offsets),
+    check(L.chs_blend_fwd(byref(cfg), ptr(st.geom), ptr(st.conic_c), ptr(st.rgbo_c if st.rgbo_c is not None else st.rgbo),
+                          ptr(st.vals_sorted), ptr(st.tile_offsets),
                           ptr(exposure), ptr(crf_params), ptr(st.ldr), ptr(st.alpha), ptr(st.hdr_mean), ptr(st.final_T),
                           ptr(st.last_id), s), "chs_blend_fwd")
     return st
@@ -136,7 +145,8 @@ def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ld
     v_geom = _empty((C, N, 4), torch.float32, dev)
     v_cogr = _empty((C, N, 4), torch.float32, dev)
     v_blue = _empty((C, N), torch.float32, dev)
-    check(L.chs_blend_bwd(byref(cfg), ptr(st.geom), ptr(st.conic_c), ptr(st.rgbo), ptr(st.vals_sorted), ptr(st.tile_offsets),
+    check(L.chs_blend_bwd(byref(cfg), ptr(st.geom), ptr(st.conic_c), ptr(st.rgbo_c if st.rgbo_c is not None else st.rgbo),
+                          ptr(st.vals_sorted), ptr(st.tile_offsets),
                           ptr(st.final_T), ptr(st.last_id), ptr(v_hdr), ptr(v_alpha), ptr(v_geom), ptr(v_cogr), ptr(v_blue), s),
           "chs_blend_bwd")
     # K9
@@ -144,7 +154,16 @@ def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ld
     v_viewmats = _empty((C, 4, 4), torch.float32, dev)
     check(L.chs_project_bwd(byref(cfg), ptr(means), ptr(quats), ptr(scales), ptr(st.viewmats), ptr(st.Ks), ptr(st.radii), ptr(v_geom),
                             ptr(v_cogr), ptr(v_blue), ptr(grads_flat), ptr(v_viewmats), ptr(red), red.numel(), s), "chs_project_bwd")
-    out = {"grads_flat": grads_flat, "v_viewmats": v_viewmats, "v_crf": v_crf, "v_exposure": v_exposure,
+    v_sh = None
+    if st.sh is not None:  # view-dependent colour: coefficient gradients + the view-direction path to means / poses
+        v_sh = _empty(tuple(st.sh.shape), torch.float32, dev)
+        v_means_sh = _empty((N, 3), torch.float32, dev)
+        v_vm_sh = _empty((C, 4, 4), torch.float32, dev)
+        check(L.chs_sh_bwd(byref(cfg), st.sh_degree, ptr(st.sh), ptr(means), ptr(st.viewmats), ptr(st.radii), ptr(v_cogr), ptr(v_blue),
+                           ptr(v_sh), ptr(v_means_sh), ptr(v_vm_sh), ptr(red), red.numel(), s), "chs_sh_bwd")
+        grads_flat[:3 * N].add_(v_means_sh.view(-1))
+        v_viewmats.add_(v_vm_sh)
+    out = {"grads_flat": grads_flat, "v_viewmats": v_viewmats, "v_crf": v_crf, "v_exposure": v_exposure, "v_sh": v_sh,
            "v_knots": None, "v_frame_times": None, "v_geom": v_geom, "v_cogr": v_cogr, "v_blue": v_blue, "v_hdr": v_hdr}
     if st.spline is not None:
         knots, knot_t0, knot_dt, frame_times, kind = st.spline
@@ -167,7 +186,7 @@ def split_flat_grads(grads_flat: torch.Tensor, N: int):
 
 class _Rasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means, quats, scales, opacities, colors, pose, frame_times, Ks, exposure, crf_params, opts):
+    def forward(ctx, means, quats, scales, opacities, colors, pose, frame_times, Ks, exposure, crf_params, sh, opts):
         cfg = opts["cfg"]
         spline = None
         viewmats = pose
@@ -175,7 +194,7 @@ class _Rasterize(torch.autograd.Function):
             spline = (pose, opts["knot_t0"], opts["knot_dt"], frame_times, opts["spline_kind"])
             viewmats = None
         st = forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposure, crf_params, cfg, spline,
-                            want_keys=opts["want_keys"])
+                            want_keys=opts["want_keys"], sh=sh, sh_degree=opts["sh_degree"])
         ctx.st = st
         ctx.opts = opts
         ctx.save_for_backward(means, quats, scales, exposure, crf_params if crf_params is not None else torch.empty(0))
@@ -205,13 +224,15 @@ class _Rasterize(torch.autograd.Function):
             v_pose, v_ft = g["v_knots"], g["v_frame_times"]
         else:
             v_pose, v_ft = g["v_viewmats"], None
-        return vm, vq, vs, vo, vc, v_pose, v_ft, None, g["v_exposure"], g["v_crf"], None
+        if st.sh is not None:
+            vc = None  # the per-Gaussian colour input is unused with SH
+        return vm, vq, vs, vo, vc, v_pose, v_ft, None, g["v_exposure"], g["v_crf"], g["v_sh"], None
 
 
 def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, width=0, height=0, exposure_times=None,
               n_virtual=1, crf_kind=_lib.CHS_CRF_IDENTITY, crf_params=None, *, spline=None, background=None, near=0.01,
               far=1e10, eps2d=0.3, tile_size=16, crf_before_average=False, return_hdr=False, sort_mode="presort",
-              debug_keys=False, grad_hook=None):
+              debug_keys=False, grad_hook=None, sh_coeffs=None, sh_degree=None):
     """Render the blurred LDR frames ``B_i = F_theta(dt_i * mean_k H_{i,k})`` and make them differentiable.
 
     Args (all tensors CUDA float32):
@@ -222,13 +243,24 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         the virtual poses are then sampled at t_i + (k/(n-1) - 1/2) * exposure_times[i].
         Ks [B,3,3] or [C,3,3]; width, height; exposure_times [B]; n_virtual;
         crf_kind 0 = identity, 1 = MLP with crf_params [3, 3*Hd+1] = [w1|b1|w2|b2] per channel.
+        sh_coeffs [N,K,3] (+ sh_degree <= 3, K >= (deg+1)^2 read as the first coefficients): view-dependent HDR colour
+        max(0, 0.5 + sum_k sh_k Y_k(view direction)) evaluated per virtual camera; `colors` may then be None.
     Returns:
         ldr [B,H,W,3], alpha [B,H,W,1], meta (dict: n_isect, viewmats, hdr (if return_hdr), state).
     """
     means = _f32(means, "means")
     dev = means.device
     quats, scales = _f32(quats, "quats"), _f32(scales, "scales")
-    opacities, colors = _f32(opacities, "opacities"), _f32(colors, "colors")
+    opacities = _f32(opacities, "opacities")
+    sh = None
+    if sh_coeffs is not None:
+        sh = _f32(sh_coeffs, "sh_coeffs")
+        deg = int(sh_degree) if sh_degree is not None else int(round(sh.shape[1] ** 0.5)) - 1
+        if sh.dim() != 3 or sh.shape[0] != means.shape[0] or sh.shape[2] != 3 or not (0 <= deg <= 3) or sh.shape[1] != (deg + 1) ** 2:
+            raise RuntimeError("rasterize: sh_coeffs must be [N, (sh_degree+1)^2, 3] with sh_degree in 0..3")
+        sh_degree = deg
+        colors = torch.zeros((means.shape[0], 3), dtype=torch.float32, device=dev)
+    colors = _f32(colors, "colors")
     exposure = _f32(exposure_times, "exposure_times")
     Ks = _f32(Ks, "Ks")
     B = exposure.shape[0]
@@ -253,7 +285,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
                            crf_kind=crf_kind, crf_hidden=crf_hidden, crf_before_average=crf_before_average,
                            ks_per_camera=ks_per_camera, sort_mode=_SORT_MODES[sort_mode], background=background)
     opts = {"cfg": cfg, "spline_kind": None, "knot_t0": 0.0, "knot_dt": 1.0, "want_keys": bool(debug_keys), "state_out": [],
-            "grad_hook": grad_hook}
+            "grad_hook": grad_hook, "sh_degree": int(sh_degree) if sh is not None else 0}
     if spline is not None:
         if viewmats is not None:
             raise RuntimeError("rasterize: pass either viewmats or spline, not both")
@@ -268,7 +300,8 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         if tuple(pose.shape) != (C, 4, 4):
             raise RuntimeError(f"rasterize: viewmats must be [B*n_virtual,4,4] = [{C},4,4], got {tuple(pose.shape)}")
         frame_times = None
-    ldr, alpha, hdr_mean = _Rasterize.apply(means, quats, scales, opacities, colors, pose, frame_times, Ks, exposure, crf_params, opts)
+    ldr, alpha, hdr_mean = _Rasterize.apply(means, quats, scales, opacities, colors, pose, frame_times, Ks, exposure, crf_params, sh,
+                                            opts)
     st = opts["state_out"][0]
     meta = {"n_isect": st.n_isect, "viewmats": st.viewmats, "state": st}
     if return_hdr:

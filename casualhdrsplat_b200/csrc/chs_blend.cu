@@ -123,7 +123,7 @@ __device__ __forceinline__ P2 pair_power2(const float4 sa, float kc, float lo, f
 
 struct BlendFwdArgs {
   int N, n_virtual, W, H, tile_w, tiles;
-  int crf_kind, crf_hidden, crf_before_average;
+  int crf_kind, crf_hidden, crf_before_average, rgbo_per_camera;
   float bg[3];
   const float4* geom;
   const float* conic_c;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
   P2 sum_r2 = p2s(0.f), sum_g2 = p2s(0.f), sum_b2 = p2s(0.f), sum_al2 = p2s(0.f);
   for (int k = 0; k < a.n_virtual; ++k) {
     const int c = frame * a.n_virtual + k;
-    const int cam_base = c * a.N;
+    const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;  // index of the camera's first record in rgbo
     const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
     const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
     P2 T2 = p2s(1.f), acc_r2 = p2s(0.f), acc_g2 = p2s(0.f), acc_b2 = p2s(0.f);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
 // backward
 // ---------------------------------------------------------------------------------------------
 struct BlendBwdArgs {
-  int N, n_virtual, W, H, tile_w, tiles, v_hdr_per_camera;
+  int N, n_virtual, W, H, tile_w, tiles, v_hdr_per_camera, rgbo_per_camera;
   float bg[3];
   const float4* geom;
   const float* conic_c;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kThreads / NP, kMinBlocks) blend_bwd_kernel(Bl
 
   const int tile = blockIdx.x, c = blockIdx.y;
   const int frame = c / a.n_virtual;
-  const int cam_base = c * a.N;
+  const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;  // index of the camera's first record in rgbo
   const int tx = tile % a.tile_w, ty = tile / a.tile_w;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (NP == 1 ? (warp >> 1) * 8 : 0);
@@ -526,6 +526,7 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   BlendFwdArgs a;
   a.N = d.N; a.n_virtual = d.n; a.W = d.W; a.H = d.H; a.tile_w = d.tile_w; a.tiles = d.tiles;
   a.crf_kind = cfg->crf_kind; a.crf_hidden = cfg->crf_hidden; a.crf_before_average = cfg->crf_before_average;
+  a.rgbo_per_camera = cfg->rgbo_per_camera;
   a.bg[0] = cfg->background[0]; a.bg[1] = cfg->background[1]; a.bg[2] = cfg->background[2];
   a.geom = (const float4*)geom; a.conic_c = conic_c; a.rgbo = (const float4*)rgbo; a.vals = vals_sorted; a.tile_offsets = tile_offsets;
   a.exposure = exposure; a.crf_params = crf_params;
@@ -565,6 +566,7 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.geom = (const float4*)geom; a.conic_c = conic_c; a.rgbo = (const float4*)rgbo; a.vals = vals_sorted; a.tile_offsets = tile_offsets;
   a.final_T = final_T; a.last_id = last_id; a.v_hdr = v_hdr; a.v_alpha = v_alpha;
   a.v_hdr_per_camera = cfg->crf_before_average != 0;
+  a.rgbo_per_camera = cfg->rgbo_per_camera;
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
   switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {

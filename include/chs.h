@@ -75,7 +75,8 @@ typedef struct chs_config {
   int32_t ks_per_camera;      /* 0: Ks is [B,3,3]; 1: Ks is [C,3,3] */
   int32_t sort_mode;          /* CHS_SORT_* */
   float background[3];
-  int32_t reserved[4];
+  int32_t rgbo_per_camera;    /* 0: rgbo is [N] (per Gaussian); 1: rgbo is [C,N] (per camera, e.g. from chs_sh_fwd) */
+  int32_t reserved[3];
 } chs_config;
 
 typedef struct chs_workspace_sizes {
@@ -225,6 +226,20 @@ typedef struct chs_tensors {
 CHS_API int chs_rasterize_fwd(const chs_config* cfg, const chs_tensors* t, int64_t* n_isect_out, void* stream);
 /* n_isect: the count chs_rasterize_fwd reported.  v_exposure receives brightness + window paths. */
 CHS_API int chs_rasterize_bwd(const chs_config* cfg, const chs_tensors* t, int64_t n_isect, void* stream);
+
+/* ---- view-dependent colour from spherical harmonics ----------------------
+ * colour_ch = max(0, 0.5 + sum_k sh[k][ch] Y_k(dir)), dir = normalize(mean - camera centre), degree 0..3,
+ * sh_coeffs [N, (deg+1)^2, 3].  chs_sh_fwd writes the per-camera records rgbo_c float4 [C,N] =
+ * (r, g, b, opacity); pass them as `rgbo` to chs_blend_fwd / chs_blend_bwd with cfg->rgbo_per_camera = 1.
+ * chs_sh_bwd turns the per-(camera, Gaussian) colour gradients chs_blend_bwd wrote (v_cogr.z/.w, v_blue)
+ * into v_sh [N,K,3], the extra mean gradient v_means [N,3] and the extra pose gradient v_viewmats [C,4,4]
+ * (view direction path); all three outputs are overwritten, the caller adds the latter two to the
+ * outputs of chs_project_bwd.  workspace: reduce_bytes. */
+CHS_API int chs_sh_fwd(const chs_config* cfg, int32_t sh_degree, const float* sh_coeffs, const float* means,
+               const float* opacities, const float* viewmats, float* rgbo_c, void* stream);
+CHS_API int chs_sh_bwd(const chs_config* cfg, int32_t sh_degree, const float* sh_coeffs, const float* means,
+               const float* viewmats, const int32_t* radii, const float* v_cogr, const float* v_blue, float* v_sh,
+               float* v_means, float* v_viewmats, void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* ---- the steps either side of the path in a trainer ----------------------
  * chs_loss: photometric loss between the blurred LDR frames and the captured frames, emitting dL/dB in

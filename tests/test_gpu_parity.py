@@ -531,3 +531,21 @@ def test_gradient_through_returned_hdr(figure_order):
     ogc, ogo = torch.autograd.grad((o_meta["hdr_mean"] * w_h.double()).sum() + (o_ldr * sc.v_ldr.double()).sum(), [oc, oo])
     assert rel(meta["hdr"], o_meta["hdr_mean"]) <= FWD_TOL
     assert rel(gc, ogc) <= GRAD_TOL and rel(go, ogo) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("deg,name", [(0, "tiny"), (2, "tiny"), (3, "small")])
+def test_sh_view_dependent_colour(deg, name):
+    """colours from spherical harmonics per virtual camera (chs_sh_fwd / chs_sh_bwd)."""
+    sc = make_config(name)
+    g = torch.Generator().manual_seed(50 + deg)
+    K = (deg + 1) ** 2
+    sh = torch.randn(sc.means.shape[0], K, 3, generator=g, dtype=torch.float32) * 0.5
+    sh[:, 0] += 1.5
+    ldr, alpha, meta, grads = cuda_run(sc, sh=sh)
+    o_ldr, o_alpha, o_meta, o_grads = oracle_run(sc, sh=sh, projection_override=cuda_projection(meta), straight_through=True)
+    assert rel(ldr, o_ldr) <= FWD_TOL and rel(alpha, o_alpha) <= FWD_TOL
+    assert float(o_grads["sh_coeffs"].norm()) > 0
+    skip = {"colors"}  # unused with SH
+    errs = {k: rel(grads[k], o_grads[k]) for k in grads if k not in skip and float(o_grads[k].norm()) > 0}
+    assert all(e <= GRAD_TOL for e in errs.values()), errs
+    assert float(grads["colors"].abs().max()) == 0.0

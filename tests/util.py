@@ -13,9 +13,15 @@ def rel(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).norm() / b.norm().clamp(min=1e-30))
 
 
-def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, binning_override=None, straight_through=False, **kw):
-    """float64 oracle on the scene's fp32 inputs (upcast). Returns (ldr, alpha, meta, grads dict)."""
+def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, binning_override=None, straight_through=False, sh=None,
+               **kw):
+    """float64 oracle on the scene's fp32 inputs (upcast). Returns (ldr, alpha, meta, grads dict).
+    ``sh`` [N,K,3]: view-dependent colours from spherical harmonics (the scene's ``colors`` are then unused)."""
     leaves = {}
+    if sh is not None:
+        leaves["sh_coeffs"] = sh.detach().cpu().double().requires_grad_(with_grad)
+        kw["sh_coeffs"] = leaves["sh_coeffs"]
+        kw["sh_degree"] = int(round(sh.shape[1] ** 0.5)) - 1
     for k in LEAF_NAMES:
         v = getattr(sc, k)
         if v is None:
@@ -37,12 +43,15 @@ def oracle_run(sc, with_grad=True, v_alpha=None, projection_override=None, binni
     return ldr.detach(), alpha.detach(), meta, grads
 
 
-def cuda_run(sc, with_grad=True, v_alpha=None, sort_mode="presort", debug_keys=False, **kw):
+def cuda_run(sc, with_grad=True, v_alpha=None, sort_mode="presort", debug_keys=False, sh=None, **kw):
     """The product path on cuda:0. Returns (ldr, alpha, meta, grads dict)."""
     from casualhdrsplat_b200 import rasterize
 
     dev = torch.device("cuda:0")
     leaves = {}
+    if sh is not None:
+        leaves["sh_coeffs"] = sh.detach().to(dev).requires_grad_(with_grad)
+        kw["sh_coeffs"] = leaves["sh_coeffs"]
     for k in LEAF_NAMES:
         v = getattr(sc, k)
         if v is None:
