@@ -301,9 +301,11 @@ def main():
     if not args.no_e2e:
         targets_host = {i: (sc.v_ldr[i] * 0.05 + 0.2).contiguous().pin_memory() for i in ids}  # synthetic "captured" frames
         grads_host = torch.empty(layout.total, dtype=torch.float32).pin_memory()
-        loss_dev = torch.zeros((), device=dev)
+        from casualhdrsplat_b200.train import LOSS_L2, photometric_loss
+
+        loss_dev = torch.zeros((), dtype=torch.float64, device=dev)
         h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(v.numel() * 4 for v in targets_host.values())
-        d2h = layout.total * 4 + 4
+        d2h = layout.total * 4 + 8
 
         def e2e_step():
             for k, v in host.items():
@@ -312,9 +314,10 @@ def main():
             loss_dev.zero_()
 
             def upstream_l2(fids, ldr):
-                d = ldr - torch.stack([tg[i] for i in fids])
-                loss_dev.add_(0.5 * (d * d).sum())
-                return d
+                # fused photometric loss (chs_loss): dL/dB and the loss in one pass over the frame
+                v, _ = photometric_loss(ldr, torch.stack([tg[i] for i in fids]) if len(fids) > 1 else tg[fids[0]][None], LOSS_L2,
+                                        scale=1.0, loss_acc=loss_dev)
+                return v
             step(upstream_l2)
             grads_host.copy_(flat, non_blocking=True)
             return loss_dev.item()  # D2H read of the step's loss (synchronises)

@@ -193,8 +193,9 @@ class _Rasterize(torch.autograd.Function):
         if opts["spline_kind"] is not None:
             spline = (pose, opts["knot_t0"], opts["knot_dt"], frame_times, opts["spline_kind"])
             viewmats = None
-        st = forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposure, crf_params, cfg, spline,
-                            want_keys=opts["want_keys"], sh=sh, sh_degree=opts["sh_degree"])
+        with torch.cuda.device(means.device):  # the C ABI launches on the current device
+            st = forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposure, crf_params, cfg, spline,
+                                want_keys=opts["want_keys"], sh=sh, sh_degree=opts["sh_degree"])
         ctx.st = st
         ctx.opts = opts
         ctx.save_for_backward(means, quats, scales, exposure, crf_params if crf_params is not None else torch.empty(0))
@@ -215,7 +216,8 @@ class _Rasterize(torch.autograd.Function):
         N = st.cfg.n_gauss
         v_ldr = v_ldr.contiguous() if v_ldr is not None else torch.zeros_like(st.ldr)
         v_alpha = v_alpha.contiguous().view(st.alpha.shape) if v_alpha is not None else None
-        g = backward_stages(st, means, quats, scales, exposure, crf_params, v_ldr, v_alpha, v_hdr_out)
+        with torch.cuda.device(means.device):
+            g = backward_stages(st, means, quats, scales, exposure, crf_params, v_ldr, v_alpha, v_hdr_out)
         hook = ctx.opts.get("grad_hook")
         if hook is not None:  # multi-GPU: all-reduce the flat Gaussian gradient buffer (+ small tails) in place
             hook(g)
