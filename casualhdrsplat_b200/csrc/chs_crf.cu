@@ -47,10 +47,14 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
   const float dt = a.exposure[frame];
   const float scale = dt / a.vh_div;
   float v_dt = 0.f;
+  // persistent over pixel chunks: the block-partial parameter gradients stay in shared memory across chunks, so the
+  // contended fp64 atomics happen once per block, not once per 1024 pixels
+  const int64_t n_chunks = (a.P + (int64_t)kPix * kThreads - 1) / ((int64_t)kPix * kThreads);
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
 #pragma unroll
   for (int q = 0; q < kPix; ++q) {
     const int slot = q * kThreads + tid;
-    const int64_t pix = (int64_t)blockIdx.x * (kPix * kThreads) + slot;
+    const int64_t pix = chunk * (kPix * kThreads) + slot;
     const bool live = pix < a.P;
     const int64_t o = ((int64_t)img * a.P + (live ? pix : 0)) * 3;
     const int64_t of = ((int64_t)frame * a.P + (live ? pix : 0)) * 3;
@@ -88,10 +92,6 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
       }
     }
   }
-  // exposure (brightness path): block reduce -> one fp64 atomic
-  v_dt = chs_warp_sum(v_dt);
-  __shared__ float s_dt[kThreads / 32];
-  if (lane == 0) s_dt[warp] = v_dt;
   __syncthreads();
   if (mlp) {
     const int upl = (a.hd + 31) / 32;  // units per lane
@@ -139,6 +139,12 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
       if (lane == 0) atomicAdd(&s_g[ch * stride + 3 * a.hd], g_b2);
     }
   }
+  __syncthreads();  // s_z / s_gy are rewritten by the next chunk
+  }
+  // exposure (brightness path): block reduce -> one fp64 atomic
+  v_dt = chs_warp_sum(v_dt);
+  __shared__ float s_dt[kThreads / 32];
+  if (lane == 0) s_dt[warp] = v_dt;
   __syncthreads();
   if (tid == 0) {
     float s = 0.f;
@@ -184,7 +190,11 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
     a.vh_div = per_pose ? 1.f : (float)d.n;
     a.hdr_mean = hdr_mean; a.exposure = exposure; a.crf_params = crf_params; a.v_ldr = v_ldr; a.v_hdr = v_hdr;
     a.acc_crf = acc; a.acc_exposure = acc + n_par;
-    dim3 grid((unsigned)((d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix)), per_pose ? d.C : d.B);
+    const int64_t n_chunks = (d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix);
+    const int n_img = per_pose ? d.C : d.B;
+    int gx = (148 * 4 + n_img - 1) / n_img;  // ~4 resident blocks per SM over all images
+    if (gx > n_chunks) gx = (int)n_chunks;
+    dim3 grid((unsigned)gx, n_img);
     size_t smem = mlp ? ((size_t)2 * n_par + (size_t)6 * kThreads * kPix) * sizeof(float) : 16;
     crf_bwd_kernel<<<grid, kThreads, smem, s>>>(a);
     CHS_LAUNCH_CHECK();
