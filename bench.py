@@ -125,7 +125,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                              "phase_seconds": {k: round(v, 3) for k, v in detail.items()}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -170,8 +170,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout to the one JSON line: NCCL prints its version banner with printf to fd 1 whenever NCCL_DEBUG=VERSION
+    (NCCL_DEBUG_FILE is ignored at that level), and other libraries may do the same.  Point fd 1 at stderr for the whole
+    run and keep a private handle on the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,7 +213,6 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL prints its version banner to stdout otherwise; keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         # default: the hand-written NVLS (multimem) all-reduce kernel; NCCL through the C ABI if the fabric has no multicast
         which = os.environ.get("CHS_COMM", "nvls")
@@ -390,7 +410,7 @@ def main():
                 "extra": {"stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
                           "step_algorithmic_bytes_per_frame": frame_bytes, "step_roofline_frac": step_frac,
                           "sort_passes_actual": key_passes, "mem_GB": torch.cuda.max_memory_allocated() / 1e9}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if comm is not None:
         comm.close()
     if world > 1:
