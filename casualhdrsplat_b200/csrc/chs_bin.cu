@@ -12,6 +12,24 @@
 //                           ties in Gaussian order — the same permutation as the 64-bit sort.
 // The radix passes themselves are cub::DeviceRadixSort (onesweep); everything around them
 // (key construction, ordering trick, offsets) is hand-written.
+//
+// CHS_SORT_DEPTH_PRESORT has a second, sort-free implementation (opt-in: CHS_BIN_VARIANT=2, see the
+// measurement note at the end of this comment): COUNTING PLACEMENT.  Once the (camera, Gaussian) pairs are in depth order, a tile list is simply
+// "the pairs that touch the tile, in the order they appear" — a stable multisplit into C*tiles
+// buckets, for which no keys ever need to exist.  The depth-ordered pairs of a camera are cut into
+// chunks; one warp per (camera, chunk, band of tile rows) walks its chunk IN ORDER and counts, in a
+// private shared-memory row, how many of its Gaussians touch each tile of the band (count_kernel);
+// a column scan over the chunks turns the [C, chunks, tiles] counts into start positions and the
+// per-(camera, tile) totals into tile_offsets; the same walk then places every Gaussian id at its
+// final position with one shared-memory atomic per intersection (place_kernel).  Traffic is
+// 4 B written per intersection plus the small count matrix, against 6 B written + 2 x 12 B moved
+// by the emit + two-pass radix route, and the result is the same permutation bit for bit.
+// Measured on B200 (c3, M = 94.1 M, chunk 4096; profiles/r1g_bin_variants.md): rects 0.08 ms, count
+// 0.55 ms, column scan 0.06 ms, place 2.7 ms — against 1.6 ms for emit + two onesweep passes.  The
+// count walk is issue-bound (~40 instructions per visited rectangle at 37 % lane use); the place walk
+// additionally thrashes L2 with long-lived partially written sectors (every resident warp keeps one
+// open 32 B sector per tile of its band: 3552 warps x 2040 tiles x 32 B = 232 MB > L2).  Kept as a
+// bit-exact, tested alternative; not the default.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
@@ -165,6 +183,189 @@ __global__ void rebuild_keys_kernel(int64_t M, int tiles, int tile_bits, const L
 
 __global__ void store_total_kernel(const int64_t* total, int64_t* n_isect_dev) { *n_isect_dev = *total; }
 
+
+// ---- counting placement -----------------------------------------------------------------------
+constexpr int kPlaceWarps = 8;        // warps per block, one private cursor row each
+constexpr int kBandTilesMax = 2048;   // tiles per band: 8 KB of u32 cursors per warp, 64 KB per block
+
+struct PlacePlan {
+  bool ok;
+  int chunk, n_chunks, band_rows, band_tiles, n_bands;
+  uint64_t matrix_elems;  // C * n_chunks * tiles
+};
+
+PlacePlan place_plan(const ChsDims& d) {
+  PlacePlan p;
+  memset(&p, 0, sizeof(p));
+  if (d.tile_w > kBandTilesMax || d.tile_w >= 65536 || d.tile_h >= 65536 || d.N <= 0 || d.C <= 0) return p;
+  p.band_rows = kBandTilesMax / d.tile_w;
+  if (p.band_rows > d.tile_h) p.band_rows = d.tile_h;
+  p.band_tiles = p.band_rows * d.tile_w;
+  p.n_bands = (d.tile_h + p.band_rows - 1) / p.band_rows;
+  int chunk = 4096;
+  if (const char* e = getenv("CHS_BIN_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+  const uint64_t budget = (uint64_t)256 << 20;  // bytes of count matrix
+  for (;;) {
+    p.chunk = chunk;
+    p.n_chunks = (d.N + chunk - 1) / chunk;
+    p.matrix_elems = (uint64_t)d.C * p.n_chunks * d.tiles;
+    if (p.matrix_elems * 4 <= budget || chunk >= (1 << 20)) break;
+    chunk *= 2;
+  }
+  p.ok = p.matrix_elems * 4 <= 2 * budget;
+  return p;
+}
+
+// tile rectangle of every (camera, Gaussian) pair, in depth order; empty for culled pairs
+__global__ void rects_kernel(int64_t CN, int tile_w, int tile_h, const float4* __restrict__ geom, const int32_t* __restrict__ radii,
+                             const int32_t* __restrict__ order, ushort4* __restrict__ rects) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CN) return;
+  const int32_t id = order[i];
+  const int radius = radii[id];
+  ushort4 r = make_ushort4(0, 0, 0, 0);
+  if (radius > 0) {
+    const float4 gm = geom[id];
+    const ChsTileRect t = chs_tile_bounds(gm.x, gm.y, radius, tile_w, tile_h);
+    r = make_ushort4((unsigned short)t.x0, (unsigned short)t.y0, (unsigned short)t.x1, (unsigned short)t.y1);
+  }
+  rects[i] = r;
+}
+
+struct PlaceArgs {
+  int N, tile_w, tile_h, tiles;
+  int chunk, n_chunks, band_rows, band_tiles, n_bands;
+  int64_t n_warps;
+  const ushort4* rects;         // [C, N] depth order
+  const int32_t* order;         // [C, N] flat ids c * N + g in depth order
+  uint32_t* matrix;             // [C, n_chunks, tiles] counts, then exclusive prefixes over chunks
+  const uint32_t* tile_offsets; // [C * tiles + 1]
+  int32_t* vals;                // [M]
+};
+
+// One warp = one (camera, chunk, band).  The warp walks the chunk's Gaussians strictly in order — 32 rectangles are
+// loaded at once, then visited one by one (ballot + find-first-set), the lanes spreading over the tiles of the
+// current rectangle — so the order in which a tile's cursor is bumped IS the depth order.  kPlace = false counts
+// (cursor rows start at 0 and are written to the matrix); kPlace = true starts every cursor at the tile's final
+// start position and writes the Gaussian id there.
+template <bool kPlace>
+__global__ void __launch_bounds__(kPlaceWarps * 32) place_kernel(PlaceArgs a) {
+  extern __shared__ uint32_t s_rows[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* row = s_rows + warp * a.band_tiles;
+  const int64_t wid = (int64_t)blockIdx.x * kPlaceWarps + warp;
+  if (wid >= a.n_warps) return;  // whole warps leave together; the kernel has no block-wide barrier
+  const int band = (int)(wid % a.n_bands);
+  const int64_t rest = wid / a.n_bands;
+  const int chunk = (int)(rest % a.n_chunks);
+  const int c = (int)(rest / a.n_chunks);
+  const int by0 = band * a.band_rows, by1 = min(by0 + a.band_rows, a.tile_h);
+  const int n_row = (by1 - by0) * a.tile_w;
+  uint32_t* mrow = a.matrix + ((int64_t)c * a.n_chunks + chunk) * a.tiles + (int64_t)by0 * a.tile_w;
+  if (kPlace) {
+    const uint32_t* toff = a.tile_offsets + (int64_t)c * a.tiles + (int64_t)by0 * a.tile_w;
+    for (int i = lane; i < n_row; i += 32) row[i] = toff[i] + mrow[i];
+  } else {
+    for (int i = lane; i < n_row; i += 32) row[i] = 0u;
+  }
+  __syncwarp();
+  const int p0 = chunk * a.chunk, p1 = min(p0 + a.chunk, a.N);
+  const int64_t seg = (int64_t)c * a.N;
+  for (int base = p0; base < p1; base += 32) {
+    const int pos = base + lane;
+    uint32_t packx = 0, packy = 0, magic = 0;
+    int32_t id = 0;
+    bool hit = false;
+    if (pos < p1) {
+      const ushort4 rc = a.rects[seg + pos];
+      const int y0 = max((int)rc.y, by0), y1 = min((int)rc.w, by1);
+      const int w = (int)rc.z - (int)rc.x;
+      hit = w > 0 && y1 > y0;
+      if (hit) {
+        packx = (uint32_t)rc.x | ((uint32_t)w << 16);
+        packy = (uint32_t)(y0 - by0) | ((uint32_t)(y1 - y0) << 16);
+        magic = w > 1 ? 0xFFFFFFFFu / (uint32_t)w + 1u : 0u;  // ceil(2^32 / w): t / w == umulhi(t, magic) for t * w < 2^32
+        if (kPlace) id = a.order[seg + pos];
+      }
+    }
+    unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint32_t px = __shfl_sync(CHS_FULL_MASK, packx, src);
+      const uint32_t py = __shfl_sync(CHS_FULL_MASK, packy, src);
+      const uint32_t mg = __shfl_sync(CHS_FULL_MASK, magic, src);
+      const int32_t gid = kPlace ? __shfl_sync(CHS_FULL_MASK, id, src) : 0;
+      const int x0 = (int)(px & 0xffffu), w = (int)(px >> 16), ry0 = (int)(py & 0xffffu), h = (int)(py >> 16);
+      const int n = w * h;
+#pragma unroll 1
+      for (int t = lane; t < n; t += 32) {
+        const int ly = w > 1 ? (int)__umulhi((uint32_t)t, mg) : t;
+        const int lx = t - ly * w;
+        const int idx = (ry0 + ly) * a.tile_w + x0 + lx;
+        const uint32_t o = atomicAdd(&row[idx], 1u);  // the lanes of one rectangle hit distinct tiles
+        if (kPlace) a.vals[o] = gid;
+      }
+      __syncwarp();  // the next rectangle's bumps are ordered after this one's
+    }
+  }
+  if (!kPlace) {
+    __syncwarp();
+    for (int i = lane; i < n_row; i += 32) mrow[i] = row[i];
+  }
+}
+
+// counts [C, n_chunks, tiles] -> exclusive prefix over the chunk axis (in place) + per-(camera, tile) totals
+__global__ void __launch_bounds__(kThreads) column_scan_kernel(int64_t n_lin, int tiles, int n_chunks, uint32_t* __restrict__ matrix,
+                                                               uint32_t* __restrict__ totals) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col == 0) totals[n_lin] = 0u;
+  if (col >= n_lin) return;
+  const int64_t c = col / tiles, tile = col % tiles;
+  uint32_t* p = matrix + c * (int64_t)n_chunks * tiles + tile;
+  uint32_t run = 0;
+  for (int k0 = 0; k0 < n_chunks; k0 += 16) {
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (k0 + j < n_chunks) ? p[(int64_t)(k0 + j) * tiles] : 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (k0 + j < n_chunks) {
+        p[(int64_t)(k0 + j) * tiles] = run;
+        run += v[j];
+      }
+  }
+  totals[col] = run;
+}
+
+// keys of the sorted list from (tile_offsets, vals): one block per (camera, tile) bucket
+__global__ void __launch_bounds__(128) rebuild_keys_from_offsets_kernel(int tiles, int tile_bits, const uint32_t* __restrict__ tile_offsets,
+                                                                       const int32_t* __restrict__ vals_sorted,
+                                                                       const float* __restrict__ depths, uint64_t* __restrict__ keys_sorted) {
+  const uint32_t lin = blockIdx.x;
+  const uint64_t c = lin / (uint32_t)tiles, t = lin % (uint32_t)tiles;
+  const uint64_t hi = (c << (32 + tile_bits)) | (t << 32);
+  const uint32_t e = tile_offsets[lin + 1];
+  for (uint32_t i = tile_offsets[lin] + threadIdx.x; i < e; i += blockDim.x) keys_sorted[i] = hi | (uint64_t)__float_as_uint(depths[vals_sorted[i]]);
+}
+
+size_t place_scan_temp(int64_t n) {
+  size_t b = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+  return b;
+}
+
+uint64_t place_bytes(const ChsDims& d, const PlacePlan& p) {
+  const int64_t n_lin = (int64_t)d.C * d.tiles;
+  return chs_align_up(place_scan_temp(n_lin + 1), 256) + chs_align_up((uint64_t)d.CN * sizeof(ushort4), 256) +
+         chs_align_up(p.matrix_elems * 4, 256) + chs_align_up((uint64_t)(n_lin + 1) * 4, 256);
+}
+
+bool place_enabled() {
+  const char* e = getenv("CHS_BIN_VARIANT");  // 2 = counting placement instead of emit + radix sort
+  return e && atoi(e) == 2;
+}
+
 inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 
 // CUB temp-storage sizes (need a CUDA context).
@@ -226,6 +427,13 @@ int chs_bin_sort_bytes(const ChsDims& d, int sort_mode, int64_t M, uint64_t* byt
     b += 2 * chs_align_up(m * 8, 256);  // keys_in + keys_out (when the caller does not want the keys)
   else
     b += 2 * chs_align_up(m * 4, 256);  // lin_in + lin_out
+  if (sort_mode == CHS_SORT_DEPTH_PRESORT) {
+    const PlacePlan p = place_plan(d);
+    if (p.ok) {
+      const uint64_t pb = place_bytes(d, p);
+      if (pb > b) b = pb;
+    }
+  }
   *bytes = b;
   return CHS_OK;
 }
@@ -326,6 +534,48 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
     return CHS_OK;
   }
   CHS_REQUIRE(vals_sorted && workspace, "chs_bin_sort: null output/workspace");
+  if (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT && place_enabled()) {
+    const PlacePlan p = place_plan(d);
+    if (p.ok) {
+      ChsArena pa(workspace, workspace_bytes);
+      size_t scan_b = place_scan_temp((int64_t)n_lin + 1);
+      char* scan_tmp = pa.take<char>(scan_b);
+      ushort4* rects = pa.take<ushort4>(d.CN);
+      uint32_t* matrix = pa.take<uint32_t>(p.matrix_elems);
+      uint32_t* totals = pa.take<uint32_t>((uint64_t)n_lin + 1);
+      if (!pa.ok) {
+        chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+        return CHS_ERR_WORKSPACE_TOO_SMALL;
+      }
+      static bool attr_set = false;
+      const size_t smem = (size_t)kPlaceWarps * p.band_tiles * sizeof(uint32_t);
+      if (!attr_set) {
+        CHS_CUDA(cudaFuncSetAttribute(place_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlaceWarps * kBandTilesMax * 4));
+        CHS_CUDA(cudaFuncSetAttribute(place_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlaceWarps * kBandTilesMax * 4));
+        attr_set = true;
+      }
+      rects_kernel<<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.tile_w, d.tile_h, (const float4*)geom, radii, order, rects);
+      CHS_LAUNCH_CHECK();
+      PlaceArgs a;
+      a.N = d.N; a.tile_w = d.tile_w; a.tile_h = d.tile_h; a.tiles = d.tiles;
+      a.chunk = p.chunk; a.n_chunks = p.n_chunks; a.band_rows = p.band_rows; a.band_tiles = p.band_tiles; a.n_bands = p.n_bands;
+      a.n_warps = (int64_t)d.C * p.n_chunks * p.n_bands;
+      a.rects = rects; a.order = order; a.matrix = matrix; a.tile_offsets = tile_offsets; a.vals = vals_sorted;
+      const unsigned blocks = (unsigned)((a.n_warps + kPlaceWarps - 1) / kPlaceWarps);
+      place_kernel<false><<<blocks, kPlaceWarps * 32, smem, s>>>(a);
+      CHS_LAUNCH_CHECK();
+      column_scan_kernel<<<grid_for(n_lin), kThreads, 0, s>>>(n_lin, d.tiles, p.n_chunks, matrix, totals);
+      CHS_LAUNCH_CHECK();
+      CHS_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_b, (const uint32_t*)totals, tile_offsets, n_lin + 1, s));
+      place_kernel<true><<<blocks, kPlaceWarps * 32, smem, s>>>(a);
+      CHS_LAUNCH_CHECK();
+      if (keys_sorted) {
+        rebuild_keys_from_offsets_kernel<<<n_lin, 128, 0, s>>>(d.tiles, d.tile_bits, tile_offsets, vals_sorted, depths, keys_sorted);
+        CHS_LAUNCH_CHECK();
+      }
+      return CHS_OK;
+    }
+  }
   size_t tb;
   st = sort_temp_size(d, cfg->sort_mode, M, &tb);
   if (st) return st;
