@@ -7,6 +7,7 @@ Bars (BASELINE.json north_star):
     evaluated on the same fp32 inputs).
 """
 import math
+import os
 
 import pytest
 import torch
@@ -60,10 +61,14 @@ def test_projection_parity(name):
 # ------------------------------------------------------------------------------------------------
 # K2-K5 binning: bit exact, both sort strategies
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("sort_mode", ["key64", "presort"])
+@pytest.mark.parametrize("sort_mode", ["key64", "presort", "presort-place"])
 @pytest.mark.parametrize("name", ["tiny", "small", "c1"])
-def test_binning_bit_exact(name, sort_mode):
+def test_binning_bit_exact(name, sort_mode, monkeypatch):
     sc = make_config(name)
+    if sort_mode == "presort-place":  # the sort-free counting-placement route of the presort mode (csrc/chs_bin.cu)
+        monkeypatch.setenv("CHS_BIN_VARIANT", "2")
+        monkeypatch.setenv("CHS_BIN_CHUNK", "96")  # many chunks even for the small scenes
+        sort_mode = "presort"
     _, _, meta, _ = cuda_run(sc, with_grad=False, sort_mode=sort_mode, debug_keys=True)
     st = meta["state"]
     proj = cuda_projection(meta)
@@ -87,8 +92,12 @@ def test_binning_depth_ties_and_sort_modes_agree():
     p[:, 2] = torch.where(torch.arange(3000) % 3 == 0, torch.tensor(4.0, dtype=torch.float64), p[:, 2])
     sc.means = ((p - t) @ R).float()
     outs = {}
-    for mode in ["key64", "presort"]:
-        _, _, meta, _ = cuda_run(sc, with_grad=False, sort_mode=mode, debug_keys=True)
+    for mode in ["key64", "presort", "presort-place"]:
+        os.environ.pop("CHS_BIN_VARIANT", None)
+        if mode == "presort-place":
+            os.environ["CHS_BIN_VARIANT"] = "2"
+        _, _, meta, _ = cuda_run(sc, with_grad=False, sort_mode=mode.split("-")[0], debug_keys=True)
+        os.environ.pop("CHS_BIN_VARIANT", None)
         st = meta["state"]
         outs[mode] = (st.keys_sorted.cpu(), st.vals_sorted.cpu()[: st.n_isect], st.tile_offsets.cpu())
         proj = cuda_projection(meta)
@@ -96,8 +105,9 @@ def test_binning_depth_ties_and_sort_modes_agree():
         ks = b["keys_sorted"]
         assert int((ks[1:] == ks[:-1]).sum()) > 50, "test scene should contain depth ties inside tiles"
         assert torch.equal(outs[mode][0], ks) and torch.equal(outs[mode][1], b["vals_sorted"])
-    for a, bb in zip(outs["key64"], outs["presort"]):
-        assert torch.equal(a, bb)
+    for other in ["presort", "presort-place"]:
+        for a, bb in zip(outs["key64"], outs[other]):
+            assert torch.equal(a, bb)
 
 
 # ------------------------------------------------------------------------------------------------
