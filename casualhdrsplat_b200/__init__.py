@@ -5,7 +5,7 @@ and CRF parameters), backed by hand-written sm_100a CUDA kernels behind a C-ABI 
 (``include/chs.h``).  There is no CPU fallback: calling :func:`rasterize` without the built
 library or without a CUDA device raises.
 """
-from .scene import CRF_IDENTITY, CRF_MLP, SPLINE_CUBIC, SPLINE_LINEAR  # noqa: F401
+from .scene import CRF_IDENTITY, CRF_LUT, CRF_MLP, SPLINE_CUBIC, SPLINE_LINEAR  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -12,7 +12,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int32, c_int64
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libchs.so")
 
-CHS_CRF_IDENTITY, CHS_CRF_MLP = 0, 1
+CHS_CRF_IDENTITY, CHS_CRF_MLP, CHS_CRF_LUT = 0, 1, 2
 CHS_SPLINE_LINEAR, CHS_SPLINE_CUBIC = 0, 1
 CHS_SORT_KEY64, CHS_SORT_DEPTH_PRESORT = 0, 1
 
@@ -131,3 +131,20 @@ def workspace_sizes(cfg: ChsConfig, n_isect: int = 0, n_knots: int = 0) -> ChsWo
     out = ChsWorkspaceSizes()
     check(lib().chs_workspace_query(byref(cfg), int(n_isect), int(n_knots), byref(out)), "chs_workspace_query")
     return out
+
+
+def crf_size(crf_kind: int, crf_params) -> int:
+    """chs_config.crf_hidden for a parameter tensor: Hd of the MLP ([3, 3*Hd+1]) or the knot count of the LUT ([3, L+2])."""
+    if crf_kind == CHS_CRF_IDENTITY or crf_params is None:
+        return 0
+    if crf_params.dim() != 2 or crf_params.shape[0] != 3:
+        raise RuntimeError("crf_params must be [3, P]")
+    if crf_kind == CHS_CRF_MLP:
+        if (crf_params.shape[1] - 1) % 3 != 0 or crf_params.shape[1] < 4:
+            raise RuntimeError("crf_params must be [3, 3*Hd+1] for the MLP CRF")
+        return (crf_params.shape[1] - 1) // 3
+    if crf_kind == CHS_CRF_LUT:
+        if crf_params.shape[1] < 4:
+            raise RuntimeError("crf_params must be [3, L+2] with L >= 2 for the LUT CRF")
+        return crf_params.shape[1] - 2
+    raise RuntimeError(f"unknown crf_kind {crf_kind}")

@@ -273,14 +273,13 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     if Ks.shape[0] not in (B, C) or tuple(Ks.shape[1:]) != (3, 3):
         raise RuntimeError(f"rasterize: Ks must be [B,3,3] or [C,3,3], got {tuple(Ks.shape)}")
     ks_per_camera = Ks.shape[0] == C and C != B
-    crf_hidden = 0
-    if crf_kind == _lib.CHS_CRF_MLP:
+    if crf_kind in (_lib.CHS_CRF_MLP, _lib.CHS_CRF_LUT):
         crf_params = _f32(crf_params, "crf_params")
-        if crf_params.dim() != 2 or crf_params.shape[0] != 3 or (crf_params.shape[1] - 1) % 3 != 0:
-            raise RuntimeError("rasterize: crf_params must be [3, 3*Hd+1]")
-        crf_hidden = (crf_params.shape[1] - 1) // 3
-    else:
+    elif crf_kind == _lib.CHS_CRF_IDENTITY:
         crf_params = None
+    else:
+        raise RuntimeError(f"rasterize: unknown crf_kind {crf_kind}")
+    crf_hidden = _lib.crf_size(crf_kind, crf_params)
     if sort_mode not in _SORT_MODES:
         raise RuntimeError(f"rasterize: sort_mode must be one of {sorted(_SORT_MODES)}")
     cfg = _lib.make_config(N, B, n_virtual, width, height, near=near, far=far, eps2d=eps2d, tile_size=tile_size,

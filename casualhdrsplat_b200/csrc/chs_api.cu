@@ -28,8 +28,10 @@ int chs_make_dims(const chs_config* cfg, ChsDims* d) {
   CHS_REQUIRE(cfg->tile_size == CHS_TILE, "tile_size must be %d (got %d)", CHS_TILE, cfg->tile_size);
   CHS_REQUIRE(cfg->n_gauss >= 0 && cfg->n_frames >= 0 && cfg->n_virtual >= 1, "bad n_gauss / n_frames / n_virtual");
   CHS_REQUIRE(cfg->width >= 1 && cfg->height >= 1, "bad image size %d x %d", cfg->width, cfg->height);
-  CHS_REQUIRE(cfg->crf_kind == CHS_CRF_IDENTITY || cfg->crf_kind == CHS_CRF_MLP, "unknown crf_kind %d", cfg->crf_kind);
+  CHS_REQUIRE(cfg->crf_kind == CHS_CRF_IDENTITY || cfg->crf_kind == CHS_CRF_MLP || cfg->crf_kind == CHS_CRF_LUT, "unknown crf_kind %d",
+              cfg->crf_kind);
   CHS_REQUIRE(cfg->crf_kind != CHS_CRF_MLP || (cfg->crf_hidden >= 1 && cfg->crf_hidden <= 128), "crf_hidden must be in [1,128]");
+  CHS_REQUIRE(cfg->crf_kind != CHS_CRF_LUT || (cfg->crf_hidden >= 2 && cfg->crf_hidden <= 1024), "LUT CRF needs 2..1024 knots");
   CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || cfg->sort_mode == CHS_SORT_DEPTH_PRESORT, "unknown sort_mode %d", cfg->sort_mode);
   d->N = cfg->n_gauss; d->B = cfg->n_frames; d->n = cfg->n_virtual;
   d->C = d->B * d->n;
@@ -67,7 +69,7 @@ extern "C" int chs_workspace_query(const chs_config* cfg, int64_t n_isect, int32
     if (st) return st;
   }
   out->bin_sort_bytes += 256;
-  uint64_t crf = cfg->crf_kind == CHS_CRF_MLP ? (uint64_t)3 * (3 * cfg->crf_hidden + 1) : 0;
+  uint64_t crf = (uint64_t)3 * chs_crf_stride(cfg->crf_kind, cfg->crf_hidden);
   uint64_t a = crf + d.B, b = (uint64_t)d.C * 12, c = (uint64_t)(n_knots > 0 ? n_knots : 0) * 7 + 2 * (uint64_t)d.B;
   uint64_t m = a > b ? a : b;
   m = m > c ? m : c;

@@ -139,7 +139,7 @@ struct BlendFwdArgs {
 template <int kMinBlocks, bool kPerPoseCrf>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFwdArgs a) {
   __shared__ SplatSmem sm;
-  extern __shared__ float s_crf[];  // 3 * (3 Hd + 1) floats when the CRF is the MLP
+  extern __shared__ float s_crf[];  // the CRF parameters [3, stride] when the CRF is learned
 
   const int tile = blockIdx.x, frame = blockIdx.y;
   const int tx = tile % a.tile_w, ty = tile / a.tile_w;
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
   const int64_t pixA = (int64_t)iyA * a.W + ix, pixB = (int64_t)iyB * a.W + ix;
   const float kInf = __int_as_float(0x7f800000);
 
-  if (a.crf_kind == CHS_CRF_MLP)
-    for (int i = tid; i < 3 * (3 * a.crf_hidden + 1); i += kThreads) s_crf[i] = a.crf_params[i];
+  const int crf_stride = chs_crf_stride(a.crf_kind, a.crf_hidden);  // 0 for the identity CRF
+  for (int i = tid; i < 3 * crf_stride; i += kThreads) s_crf[i] = a.crf_params[i];
 
   // crf_before_average (figure order): sum_* accumulate F(dt * H_k) instead of H_k, and the per-pose
   // HDR images are written to hdr_mean, which is then [C,H,W,3] (the backward needs every H_k)
@@ -241,11 +241,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
       for (int h = 0; h < 2; ++h) {
         const float hr = h == 0 ? p2lo(h_r2) : p2hi(h_r2), hg = h == 0 ? p2lo(h_g2) : p2hi(h_g2), hb = h == 0 ? p2lo(h_b2) : p2hi(h_b2);
         y[h][0] = dt * hr; y[h][1] = dt * hg; y[h][2] = dt * hb;
-        if (a.crf_kind == CHS_CRF_MLP) {
-          const int stride = 3 * a.crf_hidden + 1;
-          y[h][0] = chs_crf_mlp_fwd(y[h][0], s_crf, a.crf_hidden);
-          y[h][1] = chs_crf_mlp_fwd(y[h][1], s_crf + stride, a.crf_hidden);
-          y[h][2] = chs_crf_mlp_fwd(y[h][2], s_crf + 2 * stride, a.crf_hidden);
+        if (a.crf_kind != CHS_CRF_IDENTITY) {
+          y[h][0] = chs_crf_fwd(a.crf_kind, y[h][0], s_crf, a.crf_hidden);
+          y[h][1] = chs_crf_fwd(a.crf_kind, y[h][1], s_crf + crf_stride, a.crf_hidden);
+          y[h][2] = chs_crf_fwd(a.crf_kind, y[h][2], s_crf + 2 * crf_stride, a.crf_hidden);
         }
         if (h == 0 ? insideA : insideB) {
           const int64_t o = ((int64_t)c * P + (h == 0 ? pixA : pixB)) * 3;
@@ -274,11 +273,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
       continue;
     }
     float o0 = dt * hr, o1 = dt * hg, o2 = dt * hb;
-    if (a.crf_kind == CHS_CRF_MLP) {
-      const int stride = 3 * a.crf_hidden + 1;
-      o0 = chs_crf_mlp_fwd(o0, s_crf, a.crf_hidden);
-      o1 = chs_crf_mlp_fwd(o1, s_crf + stride, a.crf_hidden);
-      o2 = chs_crf_mlp_fwd(o2, s_crf + 2 * stride, a.crf_hidden);
+    if (a.crf_kind != CHS_CRF_IDENTITY) {
+      o0 = chs_crf_fwd(a.crf_kind, o0, s_crf, a.crf_hidden);
+      o1 = chs_crf_fwd(a.crf_kind, o1, s_crf + crf_stride, a.crf_hidden);
+      o2 = chs_crf_fwd(a.crf_kind, o2, s_crf + 2 * crf_stride, a.crf_hidden);
     }
     const int64_t o = ((int64_t)frame * P + pix) * 3;
     a.ldr[o] = o0; a.ldr[o + 1] = o1; a.ldr[o + 2] = o2;
@@ -509,7 +507,7 @@ static int blend_variant(const char* name) {
 }
 
 static size_t crf_smem_bytes(const chs_config* cfg) {
-  return cfg->crf_kind == CHS_CRF_MLP ? (size_t)3 * (3 * cfg->crf_hidden + 1) * sizeof(float) : 0;
+  return (size_t)3 * chs_crf_stride(cfg->crf_kind, cfg->crf_hidden) * sizeof(float);
 }
 
 extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const float* conic_c, const float* rgbo,
@@ -521,7 +519,7 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   if (st) return st;
   CHS_REQUIRE(geom && conic_c && rgbo && tile_offsets && exposure, "chs_blend_fwd: null input");
   CHS_REQUIRE(ldr && alpha && hdr_mean && final_T && last_id, "chs_blend_fwd: null output");
-  CHS_REQUIRE(cfg->crf_kind == CHS_CRF_IDENTITY || crf_params, "chs_blend_fwd: crf_params required for the MLP CRF");
+  CHS_REQUIRE(cfg->crf_kind == CHS_CRF_IDENTITY || crf_params, "chs_blend_fwd: crf_params required for a learned CRF");
   if (d.B == 0 || d.P == 0) return CHS_OK;
   BlendFwdArgs a;
   a.N = d.N; a.n_virtual = d.n; a.W = d.W; a.H = d.H; a.tile_w = d.tile_w; a.tiles = d.tiles;

@@ -29,7 +29,7 @@ constexpr int kMaxUnitsPerLane = 4;  // crf_hidden <= 128
 
 __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
   extern __shared__ float smem[];
-  const int stride = 3 * a.hd + 1;
+  const int stride = chs_crf_stride(a.crf_kind, a.hd);
   float* s_p = smem;                         // parameters [3, stride]
   float* s_g = s_p + 3 * stride;             // block-partial parameter gradients [3, stride]
   float* s_z = s_g + 3 * stride;             // [3][kThreads * kPix]
@@ -37,12 +37,11 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
   const int img = blockIdx.y;
   const int frame = img / a.imgs_per_frame;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool mlp = a.crf_kind == CHS_CRF_MLP;
-  if (mlp)
-    for (int i = tid; i < 3 * stride; i += kThreads) {
-      s_p[i] = a.crf_params[i];
-      s_g[i] = 0.f;
-    }
+  const bool mlp = a.crf_kind == CHS_CRF_MLP, lut = a.crf_kind == CHS_CRF_LUT;
+  for (int i = tid; i < 3 * stride; i += kThreads) {  // stride = 0 for the identity CRF
+    s_p[i] = a.crf_params[i];
+    s_g[i] = 0.f;
+  }
   __syncthreads();
   const float dt = a.exposure[frame];
   const float scale = dt / a.vh_div;
@@ -80,6 +79,13 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
           const float y = 1.f / (1.f + expf(-acc));
           g = vy * y * (1.f - y);
           vx = g * dz / xe;
+        } else if (lut) {
+          // piecewise-linear table: the two knot gradients go straight to the block's shared accumulators
+          const float* p = s_p + ch * stride;
+          const ChsLutPos<float> q = chs_crf_lut_pos(dt * h, p, a.hd);
+          atomicAdd(&s_g[ch * stride + 2 + q.i], vy * (1.f - q.f));
+          atomicAdd(&s_g[ch * stride + 3 + q.i], vy * q.f);
+          vx = vy * (p[3 + q.i] - p[2 + q.i]) * q.du_dz / q.xe;
         } else {
           vx = vy;
         }
@@ -151,9 +157,8 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
     for (int w = 0; w < kThreads / 32; ++w) s += s_dt[w];
     atomicAdd(&a.acc_exposure[frame], (double)s);
   }
-  if (mlp)
-    for (int i = tid; i < 3 * stride; i += kThreads)
-      if (s_g[i] != 0.f) atomicAdd(&a.acc_crf[i], (double)s_g[i]);
+  for (int i = tid; i < 3 * stride; i += kThreads)
+    if (s_g[i] != 0.f) atomicAdd(&a.acc_crf[i], (double)s_g[i]);
 }
 
 __global__ void finalize_f64_to_f32(const double* src, float* dst, int n) {
@@ -171,8 +176,9 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
   if (st) return st;
   CHS_REQUIRE(hdr_mean && exposure && v_ldr && v_hdr && v_exposure && workspace, "chs_crf_bwd: null pointer");
   const bool mlp = cfg->crf_kind == CHS_CRF_MLP;
-  CHS_REQUIRE(!mlp || (crf_params && v_crf_params), "chs_crf_bwd: crf_params / v_crf_params required for the MLP CRF");
-  const int n_par = mlp ? 3 * (3 * cfg->crf_hidden + 1) : 0;
+  const bool learned = cfg->crf_kind != CHS_CRF_IDENTITY;
+  CHS_REQUIRE(!learned || (crf_params && v_crf_params), "chs_crf_bwd: crf_params / v_crf_params required for a learned CRF");
+  const int n_par = 3 * chs_crf_stride(cfg->crf_kind, cfg->crf_hidden);
   const uint64_t need = (uint64_t)(n_par + d.B) * sizeof(double);
   if (workspace_bytes < need) {
     chs_set_error("chs_crf_bwd: workspace too small (%llu < %llu)", (unsigned long long)workspace_bytes, (unsigned long long)need);
@@ -184,7 +190,7 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
   if (d.B > 0 && d.P > 0) {
     CrfBwdArgs a;
     const bool per_pose = cfg->crf_before_average != 0;
-    a.P = d.P; a.n_virtual = d.n; a.crf_kind = cfg->crf_kind; a.hd = mlp ? cfg->crf_hidden : 0;
+    a.P = d.P; a.n_virtual = d.n; a.crf_kind = cfg->crf_kind; a.hd = learned ? cfg->crf_hidden : 0;
     a.imgs_per_frame = per_pose ? d.n : 1;
     a.vy_scale = per_pose ? 1.f / (float)d.n : 1.f;
     a.vh_div = per_pose ? 1.f : (float)d.n;
@@ -195,7 +201,7 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
     int gx = (148 * 4 + n_img - 1) / n_img;  // ~4 resident blocks per SM over all images
     if (gx > n_chunks) gx = (int)n_chunks;
     dim3 grid((unsigned)gx, n_img);
-    size_t smem = mlp ? ((size_t)2 * n_par + (size_t)6 * kThreads * kPix) * sizeof(float) : 16;
+    size_t smem = mlp ? ((size_t)2 * n_par + (size_t)6 * kThreads * kPix) * sizeof(float) : (size_t)2 * n_par * sizeof(float) + 16;
     crf_bwd_kernel<<<grid, kThreads, smem, s>>>(a);
     CHS_LAUNCH_CHECK();
   }

@@ -11,7 +11,7 @@
 //   A.4  tile bounds (bit-exact integer contract)  -> chs_tile_bounds
 //   A.5  alpha of one (pixel, Gaussian) pair       -> chs_pair_power / chs_pair_alpha
 //   A.6  blend backward of one pair                -> chs_pair_bwd
-//   A.7  camera response curve F_theta             -> chs_crf_mlp_fwd / chs_crf_mlp_bwd
+//   A.7  camera response curve F_theta             -> chs_crf_mlp_fwd / chs_crf_mlp_bwd, chs_crf_lut_fwd / chs_crf_lut_bwd
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -479,4 +479,58 @@ template <class T> CHS_HD T chs_crf_mlp_bwd(T X, const T* p, int hd, T v_y, T* v
     v_p[3 * hd] += gy;
   }
   return y * (T(1) - y) * dz / xe;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A.7 camera response curve, LUT kind: per channel a piecewise-linear
+// curve over log exposure, the classical Debevec-style response table.
+//   z = ln(X + 1e-5),  u = clamp((z - z_min) / (z_max - z_min), 0, 1) (L - 1),
+//   i = min(floor(u), L - 2),  f = u - i,  y = v_i + f (v_{i+1} - v_i)
+// params = [z_min | z_max | v_0 .. v_{L-1}] (L >= 2 knots).  The range (z_min, z_max) is a fixed
+// calibration of the table and receives no gradient; outside it the curve is constant.
+// ---------------------------------------------------------------------------------------------
+template <class T> struct ChsLutPos {
+  int i;      // left knot
+  T f;        // position inside the segment, in [0, 1]
+  T du_dz;    // (L - 1) / (z_max - z_min), or 0 where the clamp is active
+  T xe;       // X + eps
+};
+
+template <class T> CHS_HD ChsLutPos<T> chs_crf_lut_pos(T X, const T* p, int L) {
+  ChsLutPos<T> r;
+  r.xe = X + ChsK<T>::crf_eps;
+  const T z = log(r.xe);
+  const T scale = T(L - 1) / (p[1] - p[0]);
+  T u = (z - p[0]) * scale;
+  r.du_dz = (u > T(0) && u < T(L - 1)) ? scale : T(0);
+  u = chs_min(chs_max(u, T(0)), T(L - 1));
+  int i = (int)u;
+  if (i > L - 2) i = L - 2;
+  r.i = i;
+  r.f = u - T(i);
+  return r;
+}
+
+template <class T> CHS_HD T chs_crf_lut_fwd(T X, const T* p, int L) {
+  const ChsLutPos<T> q = chs_crf_lut_pos(X, p, L);
+  const T a = p[2 + q.i], b = p[3 + q.i];
+  return a + q.f * (b - a);
+}
+
+// Returns dy/dX and, if v_p != nullptr, accumulates v_y * dy/dparams into v_p (knot values only).
+template <class T> CHS_HD T chs_crf_lut_bwd(T X, const T* p, int L, T v_y, T* v_p) {
+  const ChsLutPos<T> q = chs_crf_lut_pos(X, p, L);
+  if (v_p) {
+    v_p[2 + q.i] += v_y * (T(1) - q.f);
+    v_p[3 + q.i] += v_y * q.f;
+  }
+  return (p[3 + q.i] - p[2 + q.i]) * q.du_dz / q.xe;
+}
+
+// number of CRF parameters per channel for a (kind, size) pair; kinds as in chs.h
+CHS_HD int chs_crf_stride(int crf_kind, int crf_size) { return crf_kind == 1 ? 3 * crf_size + 1 : crf_kind == 2 ? crf_size + 2 : 0; }
+
+// F_theta of either learned kind
+template <class T> CHS_HD T chs_crf_fwd(int crf_kind, T X, const T* p, int crf_size) {
+  return crf_kind == 1 ? chs_crf_mlp_fwd(X, p, crf_size) : chs_crf_lut_fwd(X, p, crf_size);
 }

@@ -155,7 +155,7 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
     """
     means, quats, scales = params["means"], params["quats"], params["scales"]
     opacities, colors, knots = params["opacities"], params["colors"], params["knots"]
-    crf_params = params.get("crf_params") if crf_kind == _lib.CHS_CRF_MLP else None
+    crf_params = params.get("crf_params") if crf_kind != _lib.CHS_CRF_IDENTITY else None
     N, K = means.shape[0], knots.shape[0]
     B_total = params["frame_times"].shape[0]
     n_crf = crf_params.numel() if crf_params is not None else 0
@@ -174,7 +174,7 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
         idx = torch.as_tensor(ids, device=dev)
         ft, ex, Ks = params["frame_times"][idx].contiguous(), params["exposure_times"][idx].contiguous(), params["Ks"][idx].contiguous()
         cfg = _lib.make_config(N, len(ids), n_virtual, width, height, crf_kind=crf_kind,
-                               crf_hidden=(crf_params.shape[1] - 1) // 3 if crf_params is not None else 0,
+                               crf_hidden=_lib.crf_size(crf_kind, crf_params),
                                sort_mode=_SORT[sort_mode], background=background, crf_before_average=crf_before_average)
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
         st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline)

@@ -18,6 +18,7 @@ SPLINE_LINEAR = 0
 SPLINE_CUBIC = 1
 CRF_IDENTITY = 0
 CRF_MLP = 1
+CRF_LUT = 2
 
 
 @dataclasses.dataclass
@@ -84,6 +85,19 @@ def _se3_exp_qt(xi):
     K = torch.tensor([[0, -phi[2], phi[1]], [phi[2], 0, -phi[0]], [-phi[1], phi[0], 0]], dtype=torch.float64)
     V = torch.eye(3, dtype=torch.float64) + (1 - math.cos(th)) / th**2 * K + (th - math.sin(th)) / th**3 * (K @ K)
     return q, V @ rho
+
+
+def gamma_lut_params(knots: int = 256, seed: int = 3, gamma: float = 2.2, z_min: float = -10.0, z_max: float = 1.5) -> torch.Tensor:
+    """LUT-CRF parameters [3, L+2] = [z_min | z_max | v_0..v_{L-1}] sampling X**(1/gamma) (clamped to [0, 1]) at L log-exposure
+    knots, with a small seeded per-channel gain so the channels differ as a calibrated table's do."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    zk = torch.linspace(z_min, z_max, knots, dtype=torch.float64)
+    out = []
+    for ch in range(3):
+        gain = 1.0 + 0.1 * (torch.rand((), generator=g, dtype=torch.float64) - 0.5)
+        v = (gain * torch.exp(zk / gamma)).clamp(0.0, 1.0)
+        out.append(torch.cat([torch.tensor([z_min, z_max], dtype=torch.float64), v]))
+    return torch.stack(out).to(torch.float32)
 
 
 def gamma_crf_params(hidden: int = 64, seed: int = 3, gamma: float = 2.2) -> torch.Tensor:
@@ -188,7 +202,7 @@ def make_scene(n_gauss: int, width: int, height: int, n_frames: int = 1, n_virtu
     opacities = 0.05 + 0.65 * torch.rand(n_gauss, generator=g0, dtype=f64)
     colors = torch.exp(1.5 * torch.randn(n_gauss, 3, generator=g0, dtype=f64))
 
-    crf_params = gamma_crf_params(crf_hidden, crf_seed) if crf_kind == CRF_MLP else None
+    crf_params = gamma_crf_params(crf_hidden, crf_seed) if crf_kind == CRF_MLP else gamma_lut_params(crf_hidden, crf_seed) if crf_kind == CRF_LUT else None
     v_ldr = torch.randn(B, height, width, 3, generator=g2, dtype=f64)
     f32 = torch.float32
     return Scene(means=means.to(f32), quats=quats.to(f32), scales=scales.to(f32), opacities=opacities.to(f32),

@@ -55,7 +55,12 @@ typedef enum chs_status {
   CHS_ERR_UNSUPPORTED = -5
 } chs_status;
 
-enum { CHS_CRF_IDENTITY = 0, CHS_CRF_MLP = 1 };
+/* Camera response F_theta, per channel, shared by all cameras.
+ *   CHS_CRF_IDENTITY  F(X) = X
+ *   CHS_CRF_MLP       z = ln(X + 1e-5), h = relu(w1 z + b1), y = sigmoid(w2 . h + b2)
+ *   CHS_CRF_LUT       piecewise-linear table over log exposure: u = clamp((z - z_min) / (z_max - z_min), 0, 1) (L - 1),
+ *                     y = lerp(v_floor(u), v_floor(u)+1, frac(u)); z_min / z_max are fixed (zero gradient) */
+enum { CHS_CRF_IDENTITY = 0, CHS_CRF_MLP = 1, CHS_CRF_LUT = 2 };
 enum { CHS_SPLINE_LINEAR = 0, CHS_SPLINE_CUBIC = 1 };
 /* CHS_SORT_KEY64: emit 64-bit cam|tile|depth keys and radix-sort them (the literal A.4 algorithm).
  * CHS_SORT_DEPTH_PRESORT: sort the C*N Gaussians by (cam, depth) once, emit intersections in that
@@ -70,7 +75,8 @@ typedef struct chs_config {
   int32_t tile_size;          /* must be 16 */
   float near_plane, far_plane, eps2d;
   int32_t crf_kind;           /* CHS_CRF_* */
-  int32_t crf_hidden;         /* Hd of the MLP CRF (params are [3, 3*Hd+1]); <= 128 */
+  int32_t crf_hidden;         /* size of the learned CRF: Hd of the MLP (params [3, 3*Hd+1], Hd <= 128) or the number of
+                               * knots L of the LUT (params [3, L+2] = [z_min | z_max | v_0..v_{L-1}], 2 <= L <= 1024) */
   int32_t crf_before_average; /* 0 = F(dt * mean_k H_k) (default, D0); 1 = mean_k F(dt * H_k) */
   int32_t ks_per_camera;      /* 0: Ks is [B,3,3]; 1: Ks is [C,3,3] */
   int32_t sort_mode;          /* CHS_SORT_* */
@@ -165,7 +171,7 @@ CHS_API int chs_blend_fwd(const chs_config* cfg, const float* geom, const float*
 
 /* ---- K7: CRF / exposure backward -----------------------------------------------------------------
  * v_ldr [B,H,W,3] -> v_hdr [B,H,W,3] (gradient w.r.t. each pose's HDR image, = dt_i/n * v_X),
- * v_crf_params [3, 3*Hd+1], v_exposure [B] (brightness path).  Outputs overwritten.
+ * v_crf_params (same shape as crf_params), v_exposure [B] (brightness path).  Outputs overwritten.
  * workspace: reduce_bytes. */
 CHS_API int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const float* exposure, const float* crf_params,
                 const float* v_ldr, float* v_hdr, float* v_crf_params, float* v_exposure, void* workspace,

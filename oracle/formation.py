@@ -33,6 +33,7 @@ ALPHA_MAX = 0.999
 T_STOP = 1e-4
 CRF_IDENTITY = 0
 CRF_MLP = 1
+CRF_LUT = 2
 CRF_EPS = 1e-5
 
 
@@ -293,9 +294,23 @@ def blend_pixel_loop(means2d, conics, opacities, colors, vals_sorted, tile_offse
 # ----------------------------------------------------------------------------------------------
 def crf_apply(X, crf_kind, crf_params=None):
     """Camera response F_theta, shared by all cameras. IDENTITY: F(X)=X. MLP [D6]: per channel
-    z=ln(X+1e-5), h=relu(w1 z + b1), y=sigmoid(w2.h + b2); params [3, 3*Hd+1] = [w1|b1|w2|b2]."""
+    z=ln(X+1e-5), h=relu(w1 z + b1), y=sigmoid(w2.h + b2); params [3, 3*Hd+1] = [w1|b1|w2|b2].
+    LUT: per channel piecewise-linear table over z (see below)."""
     if crf_kind == CRF_IDENTITY:
         return X
+    if crf_kind == CRF_LUT:
+        # piecewise-linear table over log exposure (SURVEY.md section 8 f3): params [3, L+2] = [z_min | z_max | v_0..v_{L-1}];
+        # the range is a fixed calibration (no gradient), the curve is constant outside it
+        P = _f64(crf_params)
+        L = P.shape[1] - 2
+        z_min, z_max, v = P[:, 0].detach(), P[:, 1].detach(), P[:, 2:]
+        z = torch.log(X + CRF_EPS)
+        u = torch.clamp((z - z_min) * ((L - 1) / (z_max - z_min)), 0.0, float(L - 1))
+        i = torch.clamp(torch.floor(u.detach()).to(torch.int64), max=L - 2)
+        f = u - i.to(u.dtype)
+        ch = torch.arange(3).expand(i.shape)
+        a, b = v[ch, i], v[ch, i + 1]
+        return a + f * (b - a)
     if crf_kind != CRF_MLP:
         raise ValueError(f"unknown crf_kind {crf_kind}")
     P = _f64(crf_params)

@@ -208,6 +208,17 @@ void hs_crf_f64(int n, const double* X, const double* params, int hd, const doub
     dydx[i] = chs_crf_mlp_bwd(X[i], params, hd, v_y[i], v_params);
   }
 }
+// CRF LUT: same contract; v_params has L + 2 entries (the two range entries stay 0)
+void hs_crf_lut_f64(int n, const double* X, const double* params, int L, const double* v_y, double* y, double* dydx, double* v_params) {
+  std::memset(v_params, 0, sizeof(double) * (L + 2));
+  for (int i = 0; i < n; ++i) {
+    y[i] = chs_crf_lut_fwd(X[i], params, L);
+    dydx[i] = chs_crf_lut_bwd(X[i], params, L, v_y[i], v_params);
+  }
+}
+void hs_crf_lut_f32(int n, const float* X, const float* params, int L, float* y) {
+  for (int i = 0; i < n; ++i) y[i] = chs_crf_fwd(2, X[i], params, L);
+}
 // spline: viewmats [C,16] fp64 and the backward contraction, mirroring chs_spline.cu
 void hs_spline_fwd(int kind, const float* knots, int n_knots, double t0, double dt, const float* frame_times, const float* exposure,
                    int B, int n, double* viewmats) {

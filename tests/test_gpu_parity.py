@@ -280,6 +280,25 @@ def test_figure_order_crf_before_average(name):
     assert all(e <= GRAD_TOL for e in errs.values()), errs
 
 
+@pytest.mark.parametrize("figure_order", [False, True])
+@pytest.mark.parametrize("name,knots", [("tiny", 24), ("small", 256)])
+def test_lut_crf_parity(name, knots, figure_order):
+    """the piecewise-linear log-exposure table as the learned CRF (crf_kind = CHS_CRF_LUT)."""
+    from casualhdrsplat_b200.scene import CRF_LUT
+
+    sc = make_config(name, crf_kind=CRF_LUT, crf_hidden=knots)
+    assert sc.crf_params.shape == (3, knots + 2)
+    ldr, alpha, meta, grads = cuda_run(sc, crf_before_average=figure_order)
+    o_ldr, o_alpha, o_meta, o_grads = oracle_run(sc, crf_before_average=figure_order, projection_override=cuda_projection(meta),
+                                                 straight_through=True)
+    assert 0.02 < float(o_ldr.mean()) < 0.98, "the table should be exercised in its sloped part"
+    assert rel(ldr, o_ldr) <= FWD_TOL and rel(alpha, o_alpha) <= FWD_TOL
+    errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
+    assert all(e <= GRAD_TOL for e in errs.values()), errs
+    assert float(o_grads["crf_params"][:, 2:].norm()) > 0
+    assert float(grads["crf_params"][:, :2].abs().max()) == 0.0  # the table range is a fixed calibration
+
+
 def test_golden_config1_forward():
     """Committed golden of BASELINE.json configs[0] (oracle-generated, tests/golden/make_golden.py)."""
     import os

@@ -237,6 +237,35 @@ def test_crf_mlp_fwd_bwd():
         assert np.allclose(o_p, gp.numpy(), rtol=1e-10, atol=1e-12)
 
 
+def test_crf_lut_fwd_bwd():
+    from casualhdrsplat_b200.scene import gamma_lut_params
+    L = 48
+    P = gamma_lut_params(L).double()
+    g = torch.Generator().manual_seed(5)
+    # exposures on both sides of the table range (z in [-10, 1.5]) as well as inside it
+    X = torch.exp(torch.randn(800, generator=g) * 4 - 4)
+    for ch in range(3):
+        p = P[ch].clone().requires_grad_(True)
+        Xl = X.clone().requires_grad_(True)
+        y = oracle.crf_apply(Xl[:, None].expand(-1, 3), oracle.CRF_LUT, torch.stack([p, p, p]))[:, 0]
+        vy = torch.randn(800, generator=g)
+        gx, gp = torch.autograd.grad((y * vy).sum(), [Xl, p])
+        assert float(gp[:2].abs().max()) == 0.0  # the range entries are a fixed calibration
+        o_y = np.zeros(800); o_d = np.zeros(800); o_p = np.zeros(L + 2)
+        HS.hs_crf_lut_f64(800, _p(X.numpy()), _p(np.ascontiguousarray(p.detach().numpy())), L, _p(vy.numpy()), _p(o_y), _p(o_d), _p(o_p))
+        assert np.allclose(o_y, y.detach().numpy(), rtol=1e-12, atol=1e-15)
+        assert np.allclose(o_d * vy.numpy(), gx.numpy(), rtol=1e-10, atol=1e-14)
+        assert np.allclose(o_p, gp.numpy(), rtol=1e-10, atol=1e-12)
+        # the fp32 instantiation the kernels use: the curve is continuous, so a knot decided differently costs nothing
+        o32 = np.zeros(800, np.float32)
+        HS.hs_crf_lut_f32(800, _p(X.numpy().astype(np.float32)), _p(np.ascontiguousarray(P[ch].numpy().astype(np.float32))), L, _p(o32))
+        assert np.abs(o32 - y.detach().numpy()).max() < 2e-5
+    # outside the table the response is constant
+    lo = oracle.crf_apply(torch.full((1, 3), 1e-9, dtype=torch.float64), oracle.CRF_LUT, P)
+    hi = oracle.crf_apply(torch.full((1, 3), 1e3, dtype=torch.float64), oracle.CRF_LUT, P)
+    assert torch.allclose(lo[0], P[:, 2]) and torch.allclose(hi[0], P[:, -1])
+
+
 @pytest.mark.parametrize("kind,name", [(se3.SPLINE_LINEAR, "c2"), (se3.SPLINE_CUBIC, "tiny")])
 def test_spline_fwd_bwd_matches_oracle(kind, name):
     sc = make_config(name, n_gauss=4) if name == "c2" else make_config(name)
