@@ -71,6 +71,7 @@ SIGNATURES = {
     "chs_sh_fwd": (ctypes.c_int, [CFG, c_int32, P, P, P, P, P, P]),
     "chs_sh_bwd": (ctypes.c_int, [CFG, c_int32] + [P] * 10 + [c_uint64, P]),
     "chs_loss": (ctypes.c_int, [c_int32, P, P, c_uint64, c_float, P, P, P]),
+    "chs_ssim_loss": (ctypes.c_int, [P, P, c_int32, c_int32, c_int32, c_float, c_float, P, P, P, c_uint64, P]),
     "chs_adam_step": (ctypes.c_int, [P, P, P, P, c_uint64, c_float, c_float, c_float, c_float, c_int32, c_float, P]),
     "chs_rasterize_fwd": (ctypes.c_int, [CFG, POINTER(ChsTensors), POINTER(c_int64), P]),
     "chs_rasterize_bwd": (ctypes.c_int, [CFG, POINTER(ChsTensors), c_int64, P]),

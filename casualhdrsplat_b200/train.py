@@ -23,6 +23,24 @@ def photometric_loss(ldr: torch.Tensor, target: torch.Tensor, kind: int = LOSS_L
     return v, loss_acc
 
 
+def ssim_loss(ldr: torch.Tensor, target: torch.Tensor, l1_weight: float = 0.8, ssim_weight: float = 0.2, loss_acc: torch.Tensor = None):
+    """The 3DGS photometric loss l1_weight * mean|d| + ssim_weight * (1 - mean SSIM) on frames [n, H, W, 3] (11x11 Gaussian
+    window, zero padding).  Returns (v_ldr, loss_acc) like ``photometric_loss``."""
+    if not (ldr.is_cuda and target.is_cuda and ldr.dtype == torch.float32 and target.dtype == torch.float32):
+        raise RuntimeError("ssim_loss: CUDA float32 tensors required (no CPU path)")
+    if ldr.dim() != 4 or ldr.shape[-1] != 3 or ldr.shape != target.shape:
+        raise RuntimeError("ssim_loss: ldr and target must both be [n, H, W, 3]")
+    ldr, target = ldr.contiguous(), target.contiguous()
+    v = torch.empty_like(ldr)
+    if loss_acc is None:
+        loss_acc = torch.zeros((), dtype=torch.float64, device=ldr.device)
+    work = torch.empty(3 * ldr.numel(), dtype=torch.float32, device=ldr.device)
+    n, h, w, _ = ldr.shape
+    _lib.check(_lib.lib().chs_ssim_loss(_lib.ptr(ldr), _lib.ptr(target), n, h, w, float(l1_weight), float(ssim_weight), _lib.ptr(v),
+                                        _lib.ptr(loss_acc), _lib.ptr(work), work.numel() * 4, _stream()), "chs_ssim_loss")
+    return v, loss_acc
+
+
 class FlatAdam:
     """Adam over named parameter tensors whose gradients are views of the flat gradient buffer (GradLayout.views)."""
 

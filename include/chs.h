@@ -253,6 +253,14 @@ CHS_API int chs_sh_bwd(const chs_config* cfg, int32_t sh_degree, const float* sh
  * v = scale * sign(d);  d = ldr - target.  *loss_acc (device fp64) is ADDED to (zero it first). */
 CHS_API int chs_loss(int32_t kind, const float* ldr, const float* target, uint64_t count, float scale, float* v_ldr,
              double* loss_acc, void* stream);
+/* chs_ssim_loss: the D-SSIM loss of 3DGS trainers with its gradient, for frames laid out [n_img, H, W, 3]:
+ *   L = l1_weight * mean|d| + ssim_weight * (1 - mean SSIM(ldr, target)),   v_ldr = dL/d ldr
+ * SSIM per channel with the 11x11 Gaussian window (sigma 1.5), zero padding, C1 = 0.01^2, C2 = 0.03^2; means over
+ * all n_img*H*W*3 values.  (l1_weight, ssim_weight) = (0.8, 0.2) is the usual 3DGS setting.  *loss_acc (device fp64)
+ * is ADDED to.  workspace: 3 * n_img*H*W*3 floats (the three derivative maps kept between the two kernels). */
+CHS_API int chs_ssim_loss(const float* ldr, const float* target, int32_t n_img, int32_t height, int32_t width,
+                  float l1_weight, float ssim_weight, float* v_ldr, double* loss_acc, void* workspace,
+                  uint64_t workspace_bytes, void* stream);
 /* Adam (bias-corrected) on `count` parameters given their section of the flat gradient buffer.
  * step is 1-based; grad_scale multiplies the gradient first (e.g. 1 / global batch). */
 CHS_API int chs_adam_step(float* param, const float* grad, float* m, float* v, uint64_t count, float lr, float beta1,
