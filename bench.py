@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=WORKLOAD, help="scene config name (casualhdrsplat_b200.scene.CONFIGS)")
     ap.add_argument("--sort-mode", default="presort", choices=["presort", "key64"])
+    ap.add_argument("--bounds", default="tight", choices=["tight", "square"],
+                    help="tile bounds used for binning: classic 3-sigma square, or the opacity-aware per-axis box (same images and "
+                         "gradients, fewer intersections)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-tiles", type=int, default=48, help="tiles in the CPU-oracle sample")
@@ -246,10 +249,12 @@ def main():
     stats = {"count_pairs": True, "events": []}
     flat = None
 
-    def step(upstream, st=None, params=None):
+    tight = args.bounds == "tight"
+
+    def step(upstream, st=None, params=None, tight_bounds=None):
         nonlocal flat
         layout, flat = formation_step(P if params is None else params, spline_meta, W, H, n, sc.crf_kind, ids, upstream, micro_batch=1, sort_mode=args.sort_mode,
-                                      comm=comm, out=flat, stats=st)
+                                      comm=comm, out=flat, stats=st, tight_bounds=tight if tight_bounds is None else tight_bounds)
         return layout
 
     def barrier():
@@ -266,9 +271,19 @@ def main():
         return float(t.item())
 
     # ---- warm-up (also collects M and M_g) ----
+    # The algorithmic unit count M is the number of intersections of the reference binning (3-sigma square bounds); with
+    # --bounds tight fewer are emitted, so one extra untimed step in square mode measures M itself.
+    m_ref = None
+    if tight:
+        ref_stats = {"count_pairs": False}
+        step(upstream_fixed, ref_stats, tight_bounds=False)
+        m_ref = ref_stats["n_isect"]
     for _ in range(max(args.warmup, 3)):
         layout = step(upstream_fixed, stats)
     stats["count_pairs"] = False
+    m_emitted = stats["n_isect"]
+    if m_ref is None:
+        m_ref = m_emitted
 
     # ---- per-kernel events for the dominant kernel (K8 blend_bwd), recorded on the launching stream ----
     bwd_events = []
@@ -424,7 +439,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     n_local = max(len(ids), 1)
-    M_f = stats["n_isect"] / n_local
+    M_f = m_ref / n_local
     Mg_f = stats["m_g"] / n_local
     Ppix = W * H
     bwd_bytes = 40 * M_f + 36 * Mg_f + 8 * n * Ppix + 12 * 1 * Ppix
@@ -461,7 +476,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload}: BASELINE.json configs[3] — {N} Gaussians, {W}x{H}, {n} virtual poses/frame, "
                                        f"global batch {B} frames sharded by frame, fwd+bwd incl. pose/exposure/CRF grads",
-                           "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode,
+                           "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode, "tile_bounds": args.bounds,
+                           "isects_emitted_per_frame": m_emitted / n_local,
                            "isects_per_frame": M_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
                            "collective": None if world == 1 else ("ncclAllReduce via libchs C ABI" if isinstance(comm, ChsComm) else
                                                                  "NVLS multimem one-shot all-reduce kernel (libchs)" if isinstance(comm, NvlsComm)

@@ -22,7 +22,7 @@ class ChsConfig(ctypes.Structure):
         ("n_gauss", c_int32), ("n_frames", c_int32), ("n_virtual", c_int32), ("width", c_int32), ("height", c_int32),
         ("tile_size", c_int32), ("near_plane", c_float), ("far_plane", c_float), ("eps2d", c_float),
         ("crf_kind", c_int32), ("crf_hidden", c_int32), ("crf_before_average", c_int32), ("ks_per_camera", c_int32),
-        ("sort_mode", c_int32), ("background", c_float * 3), ("rgbo_per_camera", c_int32), ("reserved", c_int32 * 3),
+        ("sort_mode", c_int32), ("background", c_float * 3), ("rgbo_per_camera", c_int32), ("tight_bounds", c_int32), ("reserved", c_int32 * 2),
     ]
 
 
@@ -113,7 +113,7 @@ def ptr(t):
 
 def make_config(n_gauss, n_frames, n_virtual, width, height, *, near=0.01, far=1e10, eps2d=0.3, tile_size=16,
                 crf_kind=CHS_CRF_IDENTITY, crf_hidden=0, crf_before_average=False, ks_per_camera=False,
-                sort_mode=CHS_SORT_DEPTH_PRESORT, background=None, rgbo_per_camera=False) -> ChsConfig:
+                sort_mode=CHS_SORT_DEPTH_PRESORT, background=None, rgbo_per_camera=False, tight_bounds=False) -> ChsConfig:
     cfg = ChsConfig()
     cfg.n_gauss, cfg.n_frames, cfg.n_virtual = int(n_gauss), int(n_frames), int(n_virtual)
     cfg.width, cfg.height, cfg.tile_size = int(width), int(height), int(tile_size)
@@ -123,6 +123,7 @@ def make_config(n_gauss, n_frames, n_virtual, width, height, *, near=0.01, far=1
     cfg.ks_per_camera = int(bool(ks_per_camera))
     cfg.sort_mode = int(sort_mode)
     cfg.rgbo_per_camera = int(bool(rgbo_per_camera))
+    cfg.tight_bounds = int(bool(tight_bounds))
     bg = (0.0, 0.0, 0.0) if background is None else tuple(float(v) for v in background)
     cfg.background[0], cfg.background[1], cfg.background[2] = bg
     return cfg

@@ -68,7 +68,7 @@ __global__ void depth_keys_kernel(const int32_t* __restrict__ touched, const flo
 // by a 5-step binary search over the lanes' start offsets (shuffles), its tile rectangle fetched by
 // shuffle.  MODE 0: 64-bit cam|tile|depth keys; MODE 1: 32-bit linear (cam * tiles + tile) keys.
 template <int MODE, class LinT>
-__global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits,
+__global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits, int tight,
                                                         const float4* __restrict__ geom, const int32_t* __restrict__ radii,
                                                         const float* __restrict__ depths, const uint32_t* __restrict__ offsets,
                                                         const int32_t* __restrict__ order, uint64_t* __restrict__ keys64,
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
     const int radius = radii[id];
     if (radius > 0) {
       const float4 gm = geom[id];
-      const ChsTileRect r = chs_tile_bounds(gm.x, gm.y, radius, tile_w, tile_h);
+      const ChsTileRect r = chs_tile_bounds_of(gm.x, gm.y, radius, tight, tile_w, tile_h);
       x0 = r.x0; y0 = r.y0;
       w = max(r.x1 - r.x0, 1);
       cnt = (r.x1 - r.x0) * (r.y1 - r.y0);
@@ -217,7 +217,7 @@ PlacePlan place_plan(const ChsDims& d) {
 }
 
 // tile rectangle of every (camera, Gaussian) pair, in depth order; empty for culled pairs
-__global__ void rects_kernel(int64_t CN, int tile_w, int tile_h, const float4* __restrict__ geom, const int32_t* __restrict__ radii,
+__global__ void rects_kernel(int64_t CN, int tile_w, int tile_h, int tight, const float4* __restrict__ geom, const int32_t* __restrict__ radii,
                              const int32_t* __restrict__ order, ushort4* __restrict__ rects) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= CN) return;
@@ -226,7 +226,7 @@ __global__ void rects_kernel(int64_t CN, int tile_w, int tile_h, const float4* _
   ushort4 r = make_ushort4(0, 0, 0, 0);
   if (radius > 0) {
     const float4 gm = geom[id];
-    const ChsTileRect t = chs_tile_bounds(gm.x, gm.y, radius, tile_w, tile_h);
+    const ChsTileRect t = chs_tile_bounds_of(gm.x, gm.y, radius, tight, tile_w, tile_h);
     r = make_ushort4((unsigned short)t.x0, (unsigned short)t.y0, (unsigned short)t.x1, (unsigned short)t.y1);
   }
   rects[i] = r;
@@ -510,7 +510,7 @@ extern "C" int chs_bin_emit_keys(const chs_config* cfg, int64_t n_isect, const f
   CHS_REQUIRE(geom && radii && depths && isect_offsets, "chs_bin_emit_keys: null input");
   if (n_isect == 0 || d.CN == 0) return CHS_OK;
   CHS_REQUIRE(keys && vals, "chs_bin_emit_keys: null output");
-  emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, (cudaStream_t)stream>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits,
+  emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, (cudaStream_t)stream>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0,
                                                                          (const float4*)geom, radii, depths, isect_offsets, order, keys,
                                                                          nullptr, vals);
   CHS_LAUNCH_CHECK();
@@ -554,7 +554,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
         CHS_CUDA(cudaFuncSetAttribute(place_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlaceWarps * kBandTilesMax * 4));
         attr_set = true;
       }
-      rects_kernel<<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.tile_w, d.tile_h, (const float4*)geom, radii, order, rects);
+      rects_kernel<<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.tile_w, d.tile_h, cfg->tight_bounds != 0, (const float4*)geom, radii, order, rects);
       CHS_LAUNCH_CHECK();
       PlaceArgs a;
       a.N = d.N; a.tile_w = d.tile_w; a.tile_h = d.tile_h; a.tiles = d.tiles;
@@ -589,7 +589,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
       chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
       return CHS_ERR_WORKSPACE_TOO_SMALL;
     }
-    emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom, radii,
+    emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, (const float4*)geom, radii,
                                                        depths, isect_offsets, nullptr, k_in, nullptr, v_in);
     CHS_LAUNCH_CHECK();
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_in, k_out, (const int32_t*)v_in, vals_sorted, M, 0,
@@ -608,7 +608,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
     }
     const int bits = n_lin > 1 ? chs_bit_length((uint64_t)n_lin - 1) : 1;
     if (k16) {
-      emit_kernel<1, uint16_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom,
+      emit_kernel<1, uint16_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, (const float4*)geom,
                                                                    radii, depths, isect_offsets, order, nullptr, (uint16_t*)l_in, v_in);
       CHS_LAUNCH_CHECK();
       size_t tb16 = tb;
@@ -623,7 +623,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
         CHS_LAUNCH_CHECK();
       }
     } else {
-      emit_kernel<1, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, (const float4*)geom,
+      emit_kernel<1, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, (const float4*)geom,
                                                                    radii, depths, isect_offsets, order, nullptr, (uint32_t*)l_in, v_in);
       CHS_LAUNCH_CHECK();
       CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)l_in, (uint32_t*)l_out, (const int32_t*)v_in, vals_sorted, M, 0,

@@ -156,6 +156,7 @@ template <class T> struct ChsProj {
   T mx, my;      // mean2d
   T depth;       // z in camera frame
   T ca, cb, cc;  // conic = inverse 2D covariance (A, B, C)
+  T sxx, syy;    // diagonal of the 2D covariance (after the eps2d blur)
   int radius;    // ceil(3 sqrt(lambda_max)), 0 when culled
 };
 
@@ -167,7 +168,7 @@ CHS_HD int chs_project_fwd(const T mu[3], const T S[6], const ChsCam<T>& cam, T 
   T x = R[0] * mu[0] + R[1] * mu[1] + R[2] * mu[2] + cam.t[0];
   T y = R[3] * mu[0] + R[4] * mu[1] + R[5] * mu[2] + cam.t[1];
   T z = R[6] * mu[0] + R[7] * mu[1] + R[8] * mu[2] + cam.t[2];
-  out.mx = out.my = out.ca = out.cb = out.cc = T(0);
+  out.mx = out.my = out.ca = out.cb = out.cc = out.sxx = out.syy = T(0);
   out.depth = z;
   out.radius = 0;
   if (!(z >= near_plane) || !(z <= far_plane)) return 0;
@@ -210,8 +211,25 @@ CHS_HD int chs_project_fwd(const T mu[3], const T S[6], const ChsCam<T>& cam, T 
   out.ca = c * rdet;
   out.cb = -b * rdet;
   out.cc = a * rdet;
+  out.sxx = a;
+  out.syy = c;
   out.radius = (int)rad;
   return out.radius;
+}
+
+// Opacity-aware per-axis bounds (chs_config.tight_bounds).  alpha >= 1/255 only inside the ellipse
+// sigma(d) <= ln(255 o); its axis-aligned bounding box has half extents sqrt(tau Sxx), sqrt(tau Syy)
+// with tau = 2 (ln(255 o) + margin).  Returns rx | ry << 16 with rx = min(radius, ceil(sqrt(tau Sxx)))
+// (likewise ry), each in [1, 65535], or 0 when tau <= 0 (the Gaussian can never reach 1/255).  The
+// tight rectangle only drops tiles whose every pixel fails the alpha test, so images are unchanged.
+#define CHS_TIGHT_MARGIN 2e-3
+template <class T> CHS_HD int chs_tight_radii(T sxx, T syy, T opacity, int radius) {
+  const T tau = T(2) * (log(T(255) * opacity) + T(CHS_TIGHT_MARGIN));
+  if (!(tau > T(0))) return 0;
+  const T cap = T(radius < 65535 ? radius : 65535);
+  const T rx = chs_max(T(1), chs_min(cap, ceil(sqrt(tau * sxx))));
+  const T ry = chs_max(T(1), chs_min(cap, ceil(sqrt(tau * syy))));
+  return (int)rx | ((int)ry << 16);
 }
 
 // A.3 backward for one (camera, Gaussian): given v_mean2d and v_conic, accumulate
@@ -338,16 +356,24 @@ struct ChsTileRect {
   int x0, y0, x1, y1;  // [x0, x1) x [y0, y1) in tile units
 };
 
-CHS_HD ChsTileRect chs_tile_bounds(float mx, float my, int radius, int tile_w, int tile_h) {
+CHS_HD ChsTileRect chs_tile_bounds2(float mx, float my, int radius_x, int radius_y, int tile_w, int tile_h) {
   const float inv = 1.0f / CHS_TILE;
-  float tr = chs_mul_rn((float)radius, inv);
+  float trx = chs_mul_rn((float)radius_x, inv), try_ = chs_mul_rn((float)radius_y, inv);
   float tx = chs_mul_rn(mx, inv), ty = chs_mul_rn(my, inv);
   ChsTileRect r;
-  r.x0 = (int)fminf(fmaxf(floorf(chs_sub_rn(tx, tr)), 0.0f), (float)tile_w);
-  r.x1 = (int)fminf(fmaxf(ceilf(chs_add_rn(tx, tr)), 0.0f), (float)tile_w);
-  r.y0 = (int)fminf(fmaxf(floorf(chs_sub_rn(ty, tr)), 0.0f), (float)tile_h);
-  r.y1 = (int)fminf(fmaxf(ceilf(chs_add_rn(ty, tr)), 0.0f), (float)tile_h);
+  r.x0 = (int)fminf(fmaxf(floorf(chs_sub_rn(tx, trx)), 0.0f), (float)tile_w);
+  r.x1 = (int)fminf(fmaxf(ceilf(chs_add_rn(tx, trx)), 0.0f), (float)tile_w);
+  r.y0 = (int)fminf(fmaxf(floorf(chs_sub_rn(ty, try_)), 0.0f), (float)tile_h);
+  r.y1 = (int)fminf(fmaxf(ceilf(chs_add_rn(ty, try_)), 0.0f), (float)tile_h);
   return r;
+}
+CHS_HD ChsTileRect chs_tile_bounds(float mx, float my, int radius, int tile_w, int tile_h) {
+  return chs_tile_bounds2(mx, my, radius, radius, tile_w, tile_h);
+}
+// `radii` entry -> tile rectangle: a plain radius, or the packed per-axis radii of chs_config.tight_bounds
+CHS_HD ChsTileRect chs_tile_bounds_of(float mx, float my, int radii_entry, int tight, int tile_w, int tile_h) {
+  return tight ? chs_tile_bounds2(mx, my, radii_entry & 0xffff, (radii_entry >> 16) & 0xffff, tile_w, tile_h)
+               : chs_tile_bounds2(mx, my, radii_entry, radii_entry, tile_w, tile_h);
 }
 
 // ---------------------------------------------------------------------------------------------

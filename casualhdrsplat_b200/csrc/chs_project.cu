@@ -40,7 +40,7 @@ __device__ __forceinline__ void read_camera(const float* s_cam, int c, ChsCam<fl
 }
 
 struct ProjectFwdArgs {
-  int N, C, n_virtual, ks_per_camera, tile_w, tile_h;
+  int N, C, n_virtual, ks_per_camera, tile_w, tile_h, tight_bounds;
   float width, height, near_plane, far_plane, eps2d;
   const float *means, *quats, *scales, *opacities, *colors, *viewmats, *Ks;
   float4* geom;
@@ -75,16 +75,18 @@ __global__ void __launch_bounds__(kThreads) project_fwd_kernel(ProjectFwdArgs a)
   const float mu[3] = {s_means[t * 3], s_means[t * 3 + 1], s_means[t * 3 + 2]};
   float S[6];
   chs_cov3d(q, s, S);
-  a.rgbo[g] = make_float4(s_colors[t * 3], s_colors[t * 3 + 1], s_colors[t * 3 + 2], a.opacities[g]);
+  const float opac = a.opacities[g];
+  a.rgbo[g] = make_float4(s_colors[t * 3], s_colors[t * 3 + 1], s_colors[t * 3 + 2], opac);
 
   for (int c = 0; c < a.C; ++c) {
     ChsCam<float> cam;
     read_camera(s_cam, c, cam);
     ChsProj<float> pr;
     int radius = chs_project_fwd(mu, S, cam, a.width, a.height, a.near_plane, a.far_plane, a.eps2d, pr);
+    if (radius > 0 && a.tight_bounds) radius = chs_tight_radii(pr.sxx, pr.syy, opac, radius);  // packed rx | ry << 16, or 0
     int touched = 0;
     if (radius > 0) {
-      ChsTileRect r = chs_tile_bounds(pr.mx, pr.my, radius, a.tile_w, a.tile_h);
+      ChsTileRect r = chs_tile_bounds_of(pr.mx, pr.my, radius, a.tight_bounds, a.tile_w, a.tile_h);
       touched = (r.x1 - r.x0) * (r.y1 - r.y0);
     }
     const int64_t o = (int64_t)c * a.N + g;
@@ -224,6 +226,7 @@ extern "C" int chs_project_fwd(const chs_config* cfg, const float* means, const 
   if (d.N == 0) return CHS_OK;
   ProjectFwdArgs a;
   a.N = d.N; a.C = d.C; a.n_virtual = d.n; a.ks_per_camera = cfg->ks_per_camera; a.tile_w = d.tile_w; a.tile_h = d.tile_h;
+  a.tight_bounds = cfg->tight_bounds != 0;
   a.width = (float)d.W; a.height = (float)d.H; a.near_plane = cfg->near_plane; a.far_plane = cfg->far_plane; a.eps2d = cfg->eps2d;
   a.means = means; a.quats = quats; a.scales = scales; a.opacities = opacities; a.colors = colors; a.viewmats = viewmats; a.Ks = Ks;
   a.geom = (float4*)geom; a.conic_c = conic_c; a.depths = depths; a.radii = radii; a.tiles_touched = tiles_touched; a.rgbo = (float4*)rgbo;

@@ -143,12 +143,13 @@ class TorchComm:
 def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: int, height: int, n_virtual: int, crf_kind: int,
                    frame_ids: Sequence[int], upstream: Callable[[Sequence[int], torch.Tensor], torch.Tensor], *,
                    micro_batch: int = 1, sort_mode: str = "presort", comm=None, background=None, out: Optional[torch.Tensor] = None,
-                   stats: Optional[dict] = None, crf_before_average: bool = False):
+                   stats: Optional[dict] = None, crf_before_average: bool = False, tight_bounds: bool = False):
     """One fwd+bwd training step over this rank's frames, then the gradient all-reduce.
 
     params: CUDA fp32 tensors means [N,3], quats [N,4], scales [N,3], opacities [N], colors [N,3], knots [K,7],
             frame_times [B], exposure_times [B], Ks [B,3,3], crf_params [3,3Hd+1] (or absent for the identity CRF);
             B is the GLOBAL batch.  spline_meta: knot_t0, knot_dt, kind.
+    tight_bounds: opacity-aware tile bounds (``rasterize``): same gradients, shorter tile lists.
     frame_ids: the frames this rank renders (``shard_frames``).  ``upstream(ids, ldr[len(ids),H,W,3])`` returns the
             gradient of the loss w.r.t. those LDR frames (same shape).
     Returns (GradLayout, flat gradient buffer summed over all ranks).
@@ -175,7 +176,8 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
         ft, ex, Ks = params["frame_times"][idx].contiguous(), params["exposure_times"][idx].contiguous(), params["Ks"][idx].contiguous()
         cfg = _lib.make_config(N, len(ids), n_virtual, width, height, crf_kind=crf_kind,
                                crf_hidden=_lib.crf_size(crf_kind, crf_params),
-                               sort_mode=_SORT[sort_mode], background=background, crf_before_average=crf_before_average)
+                               sort_mode=_SORT[sort_mode], background=background, crf_before_average=crf_before_average,
+                               tight_bounds=tight_bounds)
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
         st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline)
         v_ldr = upstream(ids, st.ldr).contiguous()

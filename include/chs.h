@@ -82,7 +82,10 @@ typedef struct chs_config {
   int32_t sort_mode;          /* CHS_SORT_* */
   float background[3];
   int32_t rgbo_per_camera;    /* 0: rgbo is [N] (per Gaussian); 1: rgbo is [C,N] (per camera, e.g. from chs_sh_fwd) */
-  int32_t reserved[3];
+  int32_t tight_bounds;       /* 0: classic square 3-sigma tile bounds (radii = r); 1: opacity-aware per-axis bounds — the
+                               * axis-aligned box of the alpha >= 1/255 ellipse, intersected with the 3-sigma square; radii
+                               * entries are then PACKED rx | ry << 16.  Same images and gradients, ~1/3 fewer intersections */
+  int32_t reserved[2];
 } chs_config;
 
 typedef struct chs_workspace_sizes {

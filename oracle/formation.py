@@ -44,12 +44,22 @@ def _f64(x):
 # ----------------------------------------------------------------------------------------------
 # A.3 projection + EWA
 # ----------------------------------------------------------------------------------------------
+TIGHT_MARGIN = 2e-3  # slack (natural-log units) on ln(255 o) in the opacity-aware bounds
+
+
 def project(means, quats, scales, viewmats, Ks, width, height, near=0.01, far=1e10, eps2d=0.3,
-            radius_sigmas=3.0):
+            radius_sigmas=3.0, opacities=None, tight_bounds=False):
     """Per (camera, Gaussian) projection. Returns dict of [C,N,...] float64 tensors + int32 radii.
 
     Follows SURVEY.md A.3 [D5]: pinhole, EWA Jacobian with the frustum clamp, +eps2d*I blur,
     conic = inverse 2D covariance, radius = ceil(3 sqrt(lambda_max)), off-screen cull.
+
+    ``tight_bounds`` (needs ``opacities``): opacity-aware per-axis bounds.  alpha >= 1/255 only inside the ellipse
+    sigma(d) <= ln(255 o), whose axis-aligned bounding box has half extents sqrt(tau Sxx), sqrt(tau Syy) with
+    tau = 2 (ln(255 o) + TIGHT_MARGIN) and S the 2D covariance (after the eps2d blur).  The radii become
+    rx = min(r, ceil(sqrt(tau Sxx))), ry = min(r, ceil(sqrt(tau Syy))) (r the classic 3-sigma radius), returned PACKED as
+    rx | ry << 16; a Gaussian with tau <= 0 can never reach 1/255 and is culled.  Because the tight rectangle only
+    drops tiles in which every pixel fails the alpha >= 1/255 test, rendered images and gradients are unchanged.
     """
     means, quats, scales, viewmats, Ks = map(_f64, (means, quats, scales, viewmats, Ks))
     C, N = viewmats.shape[0], means.shape[0]
@@ -93,7 +103,17 @@ def project(means, quats, scales, viewmats, Ks, width, height, near=0.01, far=1e
     r = radius.detach()
     mx, my = means2d[..., 0].detach(), means2d[..., 1].detach()
     valid = valid & ~((mx + r <= 0) | (mx - r >= W) | (my + r <= 0) | (my - r >= H))
-    radii = torch.where(valid, r, torch.zeros_like(r)).to(torch.int32)
+    if tight_bounds:
+        tau = 2.0 * (torch.log(255.0 * _f64(opacities).detach()) + TIGHT_MARGIN)[None, :]
+        valid = valid & (tau > 0)
+        taus = torch.clamp(tau, min=0.0)
+        cap = torch.clamp(r, max=65535.0)
+        rx = torch.clamp(torch.minimum(torch.ceil(torch.sqrt(taus * a.detach())), cap), min=1.0)
+        ry = torch.clamp(torch.minimum(torch.ceil(torch.sqrt(taus * c.detach())), cap), min=1.0)
+        packed = rx.to(torch.int64) | (ry.to(torch.int64) << 16)
+        radii = torch.where(valid, packed, torch.zeros_like(packed)).to(torch.int32)
+    else:
+        radii = torch.where(valid, r, torch.zeros_like(r)).to(torch.int32)
     return {"means2d": means2d, "depths": z, "conics": conics, "radii": radii, "valid": valid}
 
 
@@ -113,30 +133,35 @@ def key_bits(n_cams, width, height, tile=TILE):
     return tile_bits, cam_bits
 
 
-def tile_bounds(means2d_f32, radii_i32, width, height, tile=TILE):
-    """fp32, round-to-nearest, no FMA: lo = mx/16 - r/16, hi = mx/16 + r/16 (the /16 scalings are exact)."""
+def tile_bounds(means2d_f32, radii_i32, width, height, tile=TILE, tight=False):
+    """fp32, round-to-nearest, no FMA: lo = mx/16 - r/16, hi = mx/16 + r/16 (the /16 scalings are exact).
+    ``tight``: radii are the packed per-axis radii rx | ry << 16 of ``project(tight_bounds=True)``."""
     assert means2d_f32.dtype == torch.float32 and radii_i32.dtype == torch.int32
     tile_w, tile_h = tile_grid(width, height, tile)
     inv = torch.tensor(1.0 / tile, dtype=torch.float32)
-    tr = radii_i32.to(torch.float32) * inv
+    if tight:
+        trx = (radii_i32 & 0xFFFF).to(torch.float32) * inv
+        try_ = ((radii_i32 >> 16) & 0xFFFF).to(torch.float32) * inv
+    else:
+        trx = try_ = radii_i32.to(torch.float32) * inv
     tx = means2d_f32[..., 0] * inv
     ty = means2d_f32[..., 1] * inv
     zero = torch.tensor(0.0, dtype=torch.float32)
 
-    def lo(v, n):
+    def lo(v, tr, n):
         return torch.minimum(torch.maximum(torch.floor(v - tr), zero), torch.tensor(float(n))).to(torch.int32)
 
-    def hi(v, n):
+    def hi(v, tr, n):
         return torch.minimum(torch.maximum(torch.ceil(v + tr), zero), torch.tensor(float(n))).to(torch.int32)
 
-    min_x, max_x = lo(tx, tile_w), hi(tx, tile_w)
-    min_y, max_y = lo(ty, tile_h), hi(ty, tile_h)
+    min_x, max_x = lo(tx, trx, tile_w), hi(tx, trx, tile_w)
+    min_y, max_y = lo(ty, try_, tile_h), hi(ty, try_, tile_h)
     touched = (max_x - min_x) * (max_y - min_y)
     touched = torch.where(radii_i32 > 0, touched, torch.zeros_like(touched))
     return min_x, min_y, max_x, max_y, touched
 
 
-def bin_tiles(means2d_f32, radii_i32, depths_f32, width, height, tile=TILE):
+def bin_tiles(means2d_f32, radii_i32, depths_f32, width, height, tile=TILE, tight=False):
     """Tile binning, 64-bit key generation, stable sort, per-(camera, tile) offsets.
 
     key = cam << (32 + tile_bits) | tile << 32 | float_as_uint(depth);  val = c * N + g.
@@ -147,7 +172,7 @@ def bin_tiles(means2d_f32, radii_i32, depths_f32, width, height, tile=TILE):
     tile_w, tile_h = tile_grid(width, height, tile)
     tiles = tile_w * tile_h
     tile_bits, cam_bits = key_bits(C, width, height, tile)
-    min_x, min_y, max_x, max_y, touched = tile_bounds(means2d_f32, radii_i32, width, height, tile)
+    min_x, min_y, max_x, max_y, touched = tile_bounds(means2d_f32, radii_i32, width, height, tile, tight)
     counts = touched.reshape(-1).to(torch.int64)
     offsets = torch.cumsum(counts, 0) - counts
     M = int(counts.sum())
@@ -344,7 +369,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
               background=None, near=0.01, far=1e10, eps2d=0.3, tile_size=TILE, crf_before_average=False,
               projection_override=None, binning_override=None, straight_through=False, tile_subset=None,
               sh_coeffs=None, sh_degree=0, alpha_min=ALPHA_MIN, t_stop=T_STOP,
-              radius_sigmas=3.0):
+              radius_sigmas=3.0, tight_bounds=False):
     """Oracle of ``casualhdrsplat_b200.rasterize`` (same arguments and meaning; float64 CPU).
 
     ``spline`` = dict(knots [K,7], knot_t0, knot_dt, frame_times [B], kind) or explicit
@@ -367,6 +392,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     tests override them only to obtain a discontinuity-free variant for finite-difference checks.
     ``sh_coeffs`` [N,K,3] + ``sh_degree``: view-dependent colours, evaluated per virtual camera
     (oracle/sh.py); ``colors`` is then ignored.
+    ``tight_bounds``: opacity-aware per-axis tile bounds (see ``project``); same images, shorter tile lists.
     Returns (ldr [B,H,W,3], alpha [B,H,W,1], meta dict).
     """
     means, quats, scales, opacities, colors = map(_f64, (means, quats, scales, opacities, colors))
@@ -391,7 +417,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
 
         colors = sh_colors(_f64(sh_coeffs), means, viewmats, int(sh_degree))
     if projection_override is None:
-        proj = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas)
+        proj = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas, opacities, tight_bounds)
         m2d_f32 = proj["means2d"].detach().to(torch.float32)
         dep_f32 = proj["depths"].detach().to(torch.float32)
         radii = proj["radii"]
@@ -402,7 +428,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         radii = projection_override["radii"].to(torch.int32)
         m2d, con = _f64(m2d_f32), _f64(projection_override["conics"])
         if straight_through:
-            own = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas)
+            own = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas, opacities, tight_bounds)
             live = (radii > 0)[..., None]
             m2d = torch.where(live, own["means2d"] + (m2d - own["means2d"]).detach(), m2d)
             con = torch.where(live, own["conics"] + (con - own["conics"]).detach(), con)
@@ -411,7 +437,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         m2d_f32 = binning_override["means2d"].to(torch.float32)
         dep_f32 = binning_override["depths"].to(torch.float32)
         radii = binning_override["radii"].to(torch.int32)
-    bins = bin_tiles(m2d_f32, radii, dep_f32, width, height, tile_size)
+    bins = bin_tiles(m2d_f32, radii, dep_f32, width, height, tile_size, tight_bounds)
     hdr, alpha_c, last_id = blend(m2d, con, opacities, colors, bins["vals_sorted"], bins["tile_offsets"], N,
                                   width, height, background, tile_size, tile_subset, alpha_min, t_stop)
     ldr, alpha, hdr_mean = formation(hdr, alpha_c, exposure, n_virtual, crf_kind, crf_params, crf_before_average)

@@ -200,6 +200,19 @@ void hs_tile_bounds(int n, const float* mx, const float* my, const int32_t* radi
     rect[i * 4] = r.x0; rect[i * 4 + 1] = r.y0; rect[i * 4 + 2] = r.x1; rect[i * 4 + 3] = r.y1;
   }
 }
+// tight bounds: packed per-axis radii and the rectangle they decode to
+void hs_tight_radii(int n, const double* sxx, const double* syy, const double* opacity, const int* radius, int* packed64, int* packed32) {
+  for (int i = 0; i < n; ++i) {
+    packed64[i] = chs_tight_radii(sxx[i], syy[i], opacity[i], radius[i]);
+    packed32[i] = chs_tight_radii((float)sxx[i], (float)syy[i], (float)opacity[i], radius[i]);
+  }
+}
+void hs_tile_bounds_packed(int n, const float* mx, const float* my, const int* packed, int tile_w, int tile_h, int* rect) {
+  for (int i = 0; i < n; ++i) {
+    ChsTileRect r = chs_tile_bounds_of(mx[i], my[i], packed[i], 1, tile_w, tile_h);
+    rect[i * 4] = r.x0; rect[i * 4 + 1] = r.y0; rect[i * 4 + 2] = r.x1; rect[i * 4 + 3] = r.y1;
+  }
+}
 // CRF MLP: y and dy/dX per value, parameter gradient accumulated with weights v_y
 void hs_crf_f64(int n, const double* X, const double* params, int hd, const double* v_y, double* y, double* dydx, double* v_params) {
   std::memset(v_params, 0, sizeof(double) * (3 * hd + 1));

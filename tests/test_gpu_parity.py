@@ -299,6 +299,40 @@ def test_lut_crf_parity(name, knots, figure_order):
     assert float(grads["crf_params"][:, :2].abs().max()) == 0.0  # the table range is a fixed calibration
 
 
+@pytest.mark.parametrize("name", ["tiny", "small", "c1"])
+def test_tight_bounds_same_images_shorter_lists(name):
+    """chs_config.tight_bounds (opacity-aware per-axis bounds): binning stays bit-exact against the oracle's definition,
+    the rendered frames are bit-identical to the classic square bounds, and gradients agree with the oracle."""
+    sc = make_config(name)
+    ldr_sq, alpha_sq, meta_sq, grads_sq = cuda_run(sc)
+    ldr, alpha, meta, grads = cuda_run(sc, tight_bounds=True, debug_keys=True)
+    st = meta["state"]
+    assert st.n_isect < 0.9 * meta_sq["n_isect"]
+    # (a) binning bit-exact on the kernel's own fp32 projection (packed radii)
+    proj = cuda_projection(meta)
+    b = oracle.bin_tiles(proj["means2d"], proj["radii"], proj["depths"], sc.width, sc.height, tight=True)
+    assert torch.equal(st.tiles_touched.cpu(), b["tiles_touched"]) and st.n_isect == b["n_isect"]
+    assert torch.equal(st.keys_sorted.cpu(), b["keys_sorted"])
+    assert torch.equal(st.vals_sorted.cpu()[: st.n_isect], b["vals_sorted"])
+    assert torch.equal(_u32(st.tile_offsets), b["tile_offsets"])
+    # (b) only dead entries were dropped: the frames are the same bits
+    assert torch.equal(ldr, ldr_sq) and torch.equal(alpha, alpha_sq)
+    for k in grads:
+        assert rel(grads[k], grads_sq[k]) <= 1e-5, k  # atomics order differs, nothing else
+    # (c) oracle parity in tight mode
+    o_ldr, o_alpha, o_meta, o_grads = oracle_run(sc, projection_override=proj, straight_through=True, tight_bounds=True)
+    assert rel(ldr, o_ldr) <= FWD_TOL and rel(alpha, o_alpha) <= FWD_TOL
+    errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
+    assert all(e <= GRAD_TOL for e in errs.values()), errs
+    # (d) the kernel's packed radii agree with the oracle's own float64 ones up to a pixel at ceil() boundaries
+    own = oracle_run(sc, with_grad=False, tight_bounds=True)[2]["proj"]["radii"]
+    mine = proj["radii"]
+    both = (own > 0) & (mine > 0)
+    assert int(((own > 0) != (mine > 0)).sum()) <= 2
+    assert int(((own & 0xFFFF) - (mine & 0xFFFF)).abs()[both].max()) <= 1 and int(((own >> 16) - (mine >> 16)).abs()[both].max()) <= 1
+    assert float(((own != mine) & both).float().mean()) < 1e-3
+
+
 def test_golden_config1_forward():
     """Committed golden of BASELINE.json configs[0] (oracle-generated, tests/golden/make_golden.py)."""
     import os

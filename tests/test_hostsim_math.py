@@ -92,6 +92,47 @@ def test_tile_bounds_bit_exact_random():
     assert np.array_equal(rect[:, 1], y0r.numpy()) and np.array_equal(rect[:, 3], y1r.numpy())
 
 
+def test_tight_bounds_radii_and_rectangles():
+    """chs_config.tight_bounds: packed per-axis radii (formula) and their tile rectangles (bit-exact vs the oracle)."""
+    import math
+    g = torch.Generator().manual_seed(6)
+    n = 4000
+    sxx = torch.exp(torch.randn(n, generator=g, dtype=torch.float64) * 1.5 + 2)
+    syy = torch.exp(torch.randn(n, generator=g, dtype=torch.float64) * 1.5 + 2)
+    op = torch.rand(n, generator=g, dtype=torch.float64) * 0.99 + 0.0005
+    op[:50] = 1.0 / 255.0 * torch.linspace(0.5, 1.5, 50, dtype=torch.float64)  # around the visibility limit
+    lam = torch.maximum(sxx, syy) * (1 + torch.rand(n, generator=g, dtype=torch.float64))
+    radius = torch.ceil(3 * torch.sqrt(lam)).to(torch.int32)
+    p64 = np.zeros(n, np.int32); p32 = np.zeros(n, np.int32)
+    HS.hs_tight_radii(n, _p(sxx.numpy()), _p(syy.numpy()), _p(op.numpy()), _p(radius.numpy()), _p(p64), _p(p32))
+    margin = oracle.TIGHT_MARGIN
+    n_cull = 0
+    for i in range(n):
+        tau = 2 * (math.log(255 * float(op[i])) + margin)
+        if tau <= 0:
+            assert p64[i] == 0
+            n_cull += 1
+            continue
+        cap = min(int(radius[i]), 65535)
+        rx = max(1, min(cap, math.ceil(math.sqrt(tau * float(sxx[i])))))
+        ry = max(1, min(cap, math.ceil(math.sqrt(tau * float(syy[i])))))
+        assert p64[i] == (rx | (ry << 16))
+        # the fp32 instantiation may differ by one pixel at a ceil() boundary, never more, and never exceeds the square radius
+        rx32, ry32 = int(p32[i]) & 0xFFFF, int(p32[i]) >> 16
+        assert abs(rx32 - rx) <= 1 and abs(ry32 - ry) <= 1 and rx32 <= cap and ry32 <= cap
+    assert n_cull > 10
+    # rectangles of the packed radii: bit-exact against the oracle's tile_bounds(tight=True)
+    live = p32 > 0
+    mx = (torch.rand(n, generator=g) * 2200 - 140).float()
+    my = (torch.rand(n, generator=g) * 1300 - 110).float()
+    rect = np.zeros((n, 4), np.int32)
+    HS.hs_tile_bounds_packed(n, _p(mx.numpy()), _p(my.numpy()), _p(p32), 120, 68, _p(rect))
+    x0, y0, x1, y1, touched = oracle.tile_bounds(torch.stack([mx, my], -1), torch.from_numpy(p32.copy()), 1920, 1080, tight=True)
+    for k, t in enumerate([x0, y0, x1, y1]):
+        assert np.array_equal(rect[live, k], t.numpy()[live])
+    assert int(touched[~torch.from_numpy(live)].sum()) == 0
+
+
 def test_project_bwd_f64_matches_autograd():
     sc, vm, Ks = _scene_cams("tiny")
     N, C = sc.means.shape[0], vm.shape[0]

@@ -150,3 +150,24 @@ def test_exposure_gradient_has_two_paths():
     g = torch.Generator().manual_seed(5)
     (gr2,) = torch.autograd.grad((alpha * torch.randn(alpha.shape, generator=g)).sum(), ex2)
     assert gr2.abs().min() > 0
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_tight_bounds_change_lists_but_not_images(name):
+    """Opacity-aware per-axis bounds only drop tiles in which every pixel fails alpha >= 1/255: images and gradients are
+    bit-identical to the classic square bounds, with fewer intersections."""
+    from tests.util import oracle_run
+
+    sc = make_config(name)
+    a = oracle_run(sc)
+    b = oracle_run(sc, tight_bounds=True)
+    assert b[2]["n_isect"] < 0.9 * a[2]["n_isect"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for k in a[3]:
+        assert torch.equal(a[3][k], b[3][k]), k
+    # every tight rectangle lies inside the square one
+    sq = oracle.tile_bounds(a[2]["proj"]["means2d"].detach().float(), a[2]["proj"]["radii"], sc.width, sc.height)
+    tg = oracle.tile_bounds(b[2]["proj"]["means2d"].detach().float(), b[2]["proj"]["radii"], sc.width, sc.height, tight=True)
+    live = tg[4] > 0
+    assert bool((tg[0][live] >= sq[0][live]).all() and (tg[2][live] <= sq[2][live]).all())
+    assert bool((tg[1][live] >= sq[1][live]).all() and (tg[3][live] <= sq[3][live]).all())

@@ -21,9 +21,13 @@ def main():
     sort_mode = sys.argv[2] if len(sys.argv) > 2 else "presort"
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     over = {}
-    for a in sys.argv[4:]:  # e.g. n_frames=1 n_gauss=2000000
+    tight = False
+    for a in sys.argv[4:]:  # e.g. n_frames=1 n_gauss=2000000 tight=1
         k, v = a.split("=")
-        over[k] = int(v)
+        if k == "tight":
+            tight = bool(int(v))
+        else:
+            over[k] = int(v)
     t0 = time.time()
     sc = make_config(name, **over).to("cuda:0")
     print(f"scene {name} built in {time.time() - t0:.1f}s", flush=True)
@@ -59,7 +63,7 @@ def main():
         e0.record()
         ldr, alpha, meta = rasterize(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"], None, sc.Ks,
                                      sc.width, sc.height, leaves["exposure_times"], sc.n_virtual, sc.crf_kind, crf, spline=sp,
-                                     sort_mode=sort_mode)
+                                     sort_mode=sort_mode, tight_bounds=tight)
         (ldr * sc.v_ldr).sum().backward()
         e1.record()
         torch.cuda.synchronize()
@@ -70,7 +74,7 @@ def main():
             print(json.dumps({"iter": it, "total_ms": round(total[-1], 3), **{k[4:]: round(v, 3) for k, v in row.items()}}), flush=True)
         del ldr, alpha, meta
     st = sorted(total)
-    tt = {"config": name, "sort_mode": sort_mode, "M": M, "median_ms": st[len(st) // 2], "min_ms": st[0],
+    tt = {"config": name, "sort_mode": sort_mode, "tight_bounds": tight, "M": M, "median_ms": st[len(st) // 2], "min_ms": st[0],
           "frames_per_s": sc.n_frames / (st[len(st) // 2] / 1e3), "mem_GB": torch.cuda.max_memory_allocated() / 1e9}
     print(json.dumps(tt), flush=True)
 
