@@ -82,13 +82,16 @@ __device__ __forceinline__ P2 neg2(P2 a) { return p2(-p2lo(a), -p2hi(a)); }
 __device__ __forceinline__ float p2sum(P2 a) { return p2lo(a) + p2hi(a); }
 
 // ---- staged batch of tile-list entries ----
-struct SplatSmem {
-  float4 a[kBatch];  // mx, my, qa, r
-  float4 b[kBatch];  // kc, lo, val (int bits; c * N + g), rbc
-  float4 c[kBatch];  // r, g, b, 1/opacity
+template <int kB>
+struct SplatSmemT {
+  float4 a[kB];  // mx, my, qa, r
+  float4 b[kB];  // kc, lo, val (int bits; c * N + g), rbc
+  float4 c[kB];  // r, g, b, 1/opacity
 };
+using SplatSmem = SplatSmemT<kBatch>;
 
-__device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
+template <class Smem>
+__device__ __forceinline__ void stage_splat(Smem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
                                             const float* __restrict__ conic_c, const float4* __restrict__ rgbo) {
   const float4 gm = __ldg(geom + val);
   const float cc = __ldg(conic_c + val);
@@ -101,7 +104,8 @@ __device__ __forceinline__ void stage_splat(SplatSmem& sm, int slot, int32_t val
 }
 
 // can staged splat `slot` reach alpha >= 1/255 anywhere in the warp's rectangle of pixel centres?
-__device__ __forceinline__ bool splat_hits_block(const SplatSmem& sm, int slot, float bx0, float bx1, float by0, float by1) {
+template <class Smem>
+__device__ __forceinline__ bool splat_hits_block(const Smem& sm, int slot, float bx0, float bx1, float by0, float by1) {
   const float4 a = sm.a[slot];
   const float4 b = sm.b[slot];
   ChsSplat<float> s;
@@ -498,6 +502,274 @@ __global__ void __launch_bounds__(kThreads / NP, kMinBlocks) blend_bwd_kernel(Bl
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// backward, tabled form (default).
+//
+// The per-(warp, Gaussian) cost of blend_bwd_kernel above is dominated not by the pair arithmetic
+// but by what surrounds it: 9 partials x 2 pixels per lane have to be folded across the warp
+// (~60 instructions of p2sum / select / shuffle / add) before one RED.  Here the roles are swapped
+// for that part of the work:
+//   phase A (lane = pixel pair, as before) walks the list back to front and computes, per
+//           contributing Gaussian, only what is inherently sequential per pixel — alpha, the
+//           transmittance before it, the colour behind it — and from those the two scalars every
+//           gradient of that (pixel, Gaussian) pair is a multiple of:  vs = dL/dsigma  and
+//           f = alpha T.  They go to a per-warp shared-memory table [slot][pixel].
+//   phase B (lane = Gaussian) runs when kSlots Gaussians are tabled: each lane owns one of them (and
+//           one part of the warp's 64 pixels), streams its table rows with 128-bit loads and
+//           accumulates the nine sums  sum vs u, sum vs dy, sum vs dx^2, ...  sum f v_rgb  privately in
+//           packed registers — no cross-lane reduction except one xor-shuffle per pixel part — then
+//           scales them by the Gaussian's constants and issues two float4 REDs (+ one scalar).
+// Issued instructions per (warp, Gaussian) drop from ~147 to ~87 at equal arithmetic (ncu: 5.39 G ->
+// 3.43 G warp instructions per frame of c3).  A three-phase variant that first tables the alphas and
+// then runs the sequential part as a separate branch-free loop was tried and lost (4.45 G
+// instructions: the extra table round trip and loop bookkeeping cost more than the ILP gained).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowPad = 68;  // 64 pixels + 4: rows stay 16-byte aligned and 128-bit loads of different slots hit different banks
+
+template <int kSlots>
+struct __align__(16) BwdWarpSmem {
+  float vs[kSlots][kRowPad];  // dL/dsigma of (slot, pixel)
+  float f[kSlots][kRowPad];   // alpha * T of (slot, pixel)
+  float vh[3][64];            // dL/dH of the warp's pixels (r, g, b planes)
+  int ent[kSlots];            // staged-batch index of the slot's Gaussian
+};
+
+// phase B for the n_slots tabled Gaussians of this warp
+template <int kSlots, class Smem>
+__device__ __forceinline__ void bwd_round(const Smem& sm, const BwdWarpSmem<kSlots>& ws, int n_slots, int lane, float bxc, float byc,
+                                          const BlendBwdArgs& a) {
+  __syncwarp();
+  constexpr int kParts = 32 / kSlots;  // lanes per Gaussian, each covering kRows rows of 8 pixels
+  constexpr int kRows = 8 / kParts;
+  static_assert(kParts >= 1 && kParts <= 4, "kSlots must be 8, 16 or 32");
+  const int k = lane % kSlots, part = lane / kSlots;
+  const bool active = k < n_slots;
+  P2 S_u = p2s(0.f), S_xx = p2s(0.f), S_dy = p2s(0.f), S_xy = p2s(0.f), S_yy = p2s(0.f), S_v = p2s(0.f);
+  P2 G6 = p2s(0.f), G7 = p2s(0.f), G8 = p2s(0.f);
+  float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+  float inv_opac = 0.f;
+  if (active) {
+    const int jj = ws.ent[k];
+    sa = sm.a[jj];  // mx, my, qa, r
+    sb = sm.b[jj];  // kc, log2(opacity), val, rbc
+    inv_opac = sm.c[jj].w;
+    const float dxb = sa.x - bxc;  // mean - centre of pixel column 0
+    P2 dx2[4];
+#pragma unroll
+    for (int xp = 0; xp < 4; ++xp) dx2[xp] = p2(dxb - (float)(2 * xp), dxb - (float)(2 * xp + 1));
+#pragma unroll
+    for (int yy = 0; yy < kRows; ++yy) {
+      const int y = part * kRows + yy;
+      const float dy = sa.y - (byc + (float)y);
+      const P2 rdy = p2s(sa.w * dy);
+      P2 rowvs = p2s(0.f), rowt = p2s(0.f);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int q = y * 8 + 4 * c;
+        const float4 vs4 = *reinterpret_cast<const float4*>(&ws.vs[k][q]);
+        const float4 f4 = *reinterpret_cast<const float4*>(&ws.f[k][q]);
+        const float4 r4 = *reinterpret_cast<const float4*>(&ws.vh[0][q]);
+        const float4 g4 = *reinterpret_cast<const float4*>(&ws.vh[1][q]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&ws.vh[2][q]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const P2 vs2 = h ? p2(vs4.z, vs4.w) : p2(vs4.x, vs4.y);
+          const P2 f2 = h ? p2(f4.z, f4.w) : p2(f4.x, f4.y);
+          const P2 dxp = dx2[2 * c + h];
+          const P2 u2 = dxp + rdy;
+          S_u = fma2(vs2, u2, S_u);
+          const P2 t2 = vs2 * dxp;
+          S_xx = fma2(t2, dxp, S_xx);
+          rowvs = rowvs + vs2;
+          rowt = rowt + t2;
+          G6 = fma2(f2, h ? p2(r4.z, r4.w) : p2(r4.x, r4.y), G6);
+          G7 = fma2(f2, h ? p2(g4.z, g4.w) : p2(g4.x, g4.y), G7);
+          G8 = fma2(f2, h ? p2(b4.z, b4.w) : p2(b4.x, b4.y), G8);
+        }
+      }
+      const P2 dy2 = p2s(dy);
+      S_dy = fma2(rowvs, dy2, S_dy);
+      S_xy = fma2(rowt, dy2, S_xy);
+      S_yy = fma2(rowvs * dy2, dy2, S_yy);
+      S_v = S_v + rowvs;
+    }
+  }
+  float t[9] = {p2sum(S_u), p2sum(S_dy), p2sum(S_xx), p2sum(S_xy), p2sum(S_yy), p2sum(S_v), p2sum(G6), p2sum(G7), p2sum(G8)};
+#pragma unroll
+  for (int o = kSlots; o < 32; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t[i] += __shfl_xor_sync(CHS_FULL_MASK, t[i], o);
+  if (active) {
+    const float k2 = -2.0f / CHS_LOG2E;
+    const float g0 = k2 * sa.z * t[0];                  // sum v_sigma A u
+    const float g1 = fmaf(sa.w, g0, k2 * sb.x * t[1]);  // sum v_sigma (B dx + C dy)
+    const uint32_t val = (uint32_t)__float_as_int(sb.z);
+    if (part == 0) {
+      atomicAdd(a.v_geom + val, make_float4(g0, g1, 0.5f * t[2], t[3]));
+      if (kParts < 3) atomicAdd(a.v_blue + val, t[8]);
+    }
+    if (part == (kParts > 1 ? 1 : 0)) atomicAdd(a.v_cogr + val, make_float4(0.5f * t[4], -t[5] * inv_opac, t[6], t[7]));
+    if (kParts >= 3 && part == 2) atomicAdd(a.v_blue + val, t[8]);
+  }
+  __syncwarp();  // the table is rewritten by the next round
+}
+
+template <int kSlots, int kB, int kMinBlocks, bool kPipe>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd2_kernel(BlendBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Smem = SplatSmemT<kB>;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  __shared__ int s_max_last;
+
+  const int tile = blockIdx.x, c = blockIdx.y;
+  const int frame = c / a.n_virtual;
+  const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;
+  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  BwdWarpSmem<kSlots>& ws = reinterpret_cast<BwdWarpSmem<kSlots>*>(smem_raw + sizeof(Smem))[warp];
+  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 8;
+  const int ix = bx + (lane & 7), iy0 = by + (lane >> 3);
+  const float px = ix + 0.5f;
+  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 7.5f;
+  const int64_t P = (int64_t)a.W * a.H;
+  const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
+  const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
+  if (end <= start) return;
+
+  const float inv_nv = 1.f / (float)a.n_virtual;
+  const int vimg = a.v_hdr_per_camera ? c : frame;
+  int last[2];
+  int warp_last = 0;
+  float Tf[2] = {1.f, 1.f}, v[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, vat[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int iy = iy0 + 4 * h;
+    last[h] = 0;
+    if (ix < a.W && iy < a.H) {
+      const int64_t pix = (int64_t)iy * a.W + ix;
+      Tf[h] = a.final_T[(int64_t)c * P + pix];
+      last[h] = a.last_id[(int64_t)c * P + pix];
+      const int64_t o = ((int64_t)vimg * P + pix) * 3;
+      v[h][0] = a.v_hdr[o]; v[h][1] = a.v_hdr[o + 1]; v[h][2] = a.v_hdr[o + 2];
+      const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] * inv_nv : 0.f;
+      vat[h] = Tf[h] * (v_al - (a.bg[0] * v[h][0] + a.bg[1] * v[h][1] + a.bg[2] * v[h][2]));
+    }
+    warp_last = max(warp_last, last[h]);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) ws.vh[ch][lane + 32 * h] = v[h][ch];  // pixel id = lane + 32 h  <->  (x, y) = (id & 7, id >> 3)
+  }
+  const P2 py2 = p2(iy0 + 0.5f, iy0 + 4.5f);
+  P2 Tr2 = p2(Tf[0], Tf[1]);
+  const P2 vh_r2 = p2(v[0][0], v[1][0]), vh_g2 = p2(v[0][1], v[1][1]), vh_b2 = p2(v[0][2], v[1][2]);
+  const P2 vat2 = p2(vat[0], vat[1]);
+  P2 buf_r2 = p2s(0.f), buf_g2 = p2s(0.f), buf_b2 = p2s(0.f);
+  if (tid == 0) s_max_last = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(CHS_FULL_MASK, warp_last, o));
+  if (lane == 0 && warp_last > 0) atomicMax(&s_max_last, warp_last);
+  __syncthreads();
+  const int n_walk = s_max_last;
+
+  int n_slots = 0;
+  for (int hi = n_walk; hi > 0; hi -= kB) {
+    const int lo = max(0, hi - kB);
+    const int cnt = hi - lo;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += kThreads) stage_splat(sm, i, a.vals[start + lo + i], cam_base, a.geom, a.conic_c, a.rgbo);
+    __syncthreads();
+    if (warp_last <= lo) continue;
+    for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
+      const int sub_lo = max(0, sub_hi - 32);
+      if (warp_last <= lo + sub_lo) continue;
+      const int j = sub_lo + lane;
+      const bool hit = (j < sub_hi) && (lo + j < warp_last) && splat_hits_block(sm, j, bx0, bx1, by0, by1);
+      unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+      // ---- phase A over the survivors, back to front.  kPipe: the record and exponent of the NEXT survivor are fetched
+      // before the current one's sequential chain (they do not depend on it), which roughly doubles the ILP of the loop ----
+      int jj = 0;
+      float4 sa = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 sb = make_float2(0.f, 0.f);
+      P2 pw2 = p2s(0.f);
+      float dx;
+      P2 dy2, u2;
+      bool have = mask != 0;
+      if (kPipe && have) {
+        const int bit = 31 - __clz(mask);
+        mask &= ~(1u << bit);
+        jj = sub_lo + bit;
+        sa = sm.a[jj];
+        sb = *reinterpret_cast<const float2*>(&sm.b[jj]);
+        pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+      }
+      while (kPipe ? have : mask != 0) {
+        int jn = 0;
+        P2 pwn = p2s(0.f);
+        if (kPipe) {
+          have = mask != 0;
+          if (have) {
+            const int bit = 31 - __clz(mask);
+            mask &= ~(1u << bit);
+            jn = sub_lo + bit;
+            const float4 san = sm.a[jn];
+            const float2 sbn = *reinterpret_cast<const float2*>(&sm.b[jn]);
+            pwn = pair_power2(san, sbn.x, sbn.y, px, py2, dx, dy2, u2);
+          }
+        } else {
+          const int bit = 31 - __clz(mask);
+          mask &= ~(1u << bit);
+          jj = sub_lo + bit;
+          sa = sm.a[jj];
+          sb = *reinterpret_cast<const float2*>(&sm.b[jj]);  // kc, log2(opacity)
+          pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+        }
+        const int rel = lo + jj + 1;
+        const float pA = p2lo(pw2), pB = p2hi(pw2);
+        const bool validA = (rel <= last[0]) && pA >= CHS_LOG2_ALPHA_MIN;
+        const bool validB = (rel <= last[1]) && pB >= CHS_LOG2_ALPHA_MIN;
+        const int jcur = jj;
+        if (kPipe) {
+          jj = jn;
+          pw2 = pwn;
+        }
+        if (!__any_sync(CHS_FULL_MASK, validA || validB)) continue;
+        const float4 col = sm.c[jcur];
+        const float auA = validA ? chs_exp2_fast(pA) : 0.f;
+        const float auB = validB ? chs_exp2_fast(pB) : 0.f;
+        const P2 al2 = p2(fminf(CHS_ALPHA_MAX, auA), fminf(CHS_ALPHA_MAX, auB));
+        const P2 om2 = p2s(1.f) - al2;
+        const P2 ra2 = p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));
+        Tr2 = Tr2 * ra2;  // transmittance before this Gaussian
+        const P2 f2 = al2 * Tr2;
+        const P2 nra2 = neg2(ra2);
+        const P2 c0 = fma2(p2s(col.x), Tr2, buf_r2 * nra2);
+        const P2 c1 = fma2(p2s(col.y), Tr2, buf_g2 * nra2);
+        const P2 c2 = fma2(p2s(col.z), Tr2, buf_b2 * nra2);
+        const P2 v_al2 = fma2(c0, vh_r2, fma2(c1, vh_g2, fma2(c2, vh_b2, vat2 * ra2)));
+        buf_r2 = fma2(p2s(col.x), f2, buf_r2);
+        buf_g2 = fma2(p2s(col.y), f2, buf_g2);
+        buf_b2 = fma2(p2s(col.z), f2, buf_b2);
+        // v_sigma = -alpha_unclamped * v_alpha, and no gradient through the 0.999 clamp
+        const P2 vs2 = p2(auA <= CHS_ALPHA_MAX ? -auA : 0.f, auB <= CHS_ALPHA_MAX ? -auB : 0.f) * v_al2;
+        ws.vs[n_slots][lane] = p2lo(vs2);
+        ws.vs[n_slots][lane + 32] = p2hi(vs2);
+        ws.f[n_slots][lane] = p2lo(f2);
+        ws.f[n_slots][lane + 32] = p2hi(f2);
+        if (lane == 0) ws.ent[n_slots] = jcur;
+        if (++n_slots == kSlots) {
+          bwd_round<kSlots>(sm, ws, n_slots, lane, bx0, by0, a);
+          n_slots = 0;
+        }
+      }
+    }
+    if (n_slots > 0) {  // the staged batch is about to be replaced
+      bwd_round<kSlots>(sm, ws, n_slots, lane, bx0, by0, a);
+      n_slots = 0;
+    }
+  }
+}
+
 }  // namespace
 
 // tuning knob (development): selects the min-blocks-per-SM instantiation of the blend kernels
@@ -567,11 +839,25 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.rgbo_per_camera = cfg->rgbo_per_camera;
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
+#define CHS_BWD2_SMEM(S, B) (sizeof(SplatSmemT<B>) + 4 * sizeof(BwdWarpSmem<S>))
+#define CHS_BWD2_LAUNCH(S, B, MB, PIPE) blend_bwd2_kernel<S, B, MB, PIPE><<<grid, kThreads, CHS_BWD2_SMEM(S, B), s>>>(a)
+#define CHS_BWD2_ATTR(S, B, MB, PIPE) \
+  CHS_CUDA(cudaFuncSetAttribute(blend_bwd2_kernel<S, B, MB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHS_BWD2_SMEM(S, B)))
+  static bool attr_set = false;
+  if (!attr_set) {
+    CHS_BWD2_ATTR(8, 128, 7, false); CHS_BWD2_ATTR(16, 128, 5, false); CHS_BWD2_ATTR(16, 256, 4, false); CHS_BWD2_ATTR(8, 128, 7, true);
+    attr_set = true;
+  }
+  // r1g sweep on c3 (ms per frame of 8 poses, tight bounds): direct kernel 6.07 | tabled 16 slots / batch 256 / 4 CTAs per SM 5.36 |
+  // 16 / 128 / 5: 5.21 | 8 / 128 / 7: 5.01 (default) | 8 / 128 / 8 (64 registers, spills) 5.18 | 8 / 64 / 8: 5.12 | 8 / 256 / 6: 5.51 |
+  // software-pipelined phase A (kPipe): +0.5 ms in every configuration
   switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {
-    case 1: blend_bwd_kernel<1, 6><<<grid, kThreads, 0, s>>>(a); break;
-    case 22: blend_bwd_kernel<2, 12><<<grid, kThreads / 2, 0, s>>>(a); break;   // four pixels per thread, 85 registers: ~3 % faster
-                                                                                   // on c3 (r1e sweep), not worth the coarser culling
-    default: blend_bwd_kernel<1, 8><<<grid, kThreads, 0, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
+    case 1: blend_bwd_kernel<1, 8><<<grid, kThreads, 0, s>>>(a); break;          // the direct (r1d-f) kernel, two pixels per thread
+    case 22: blend_bwd_kernel<2, 12><<<grid, kThreads / 2, 0, s>>>(a); break;    // direct, four pixels per thread
+    case 40: CHS_BWD2_LAUNCH(16, 256, 4, false); break;
+    case 41: CHS_BWD2_LAUNCH(16, 128, 5, false); break;
+    case 45: CHS_BWD2_LAUNCH(8, 128, 7, true); break;
+    default: CHS_BWD2_LAUNCH(8, 128, 7, false); break;  // tabled: 8 slots per round, 128-entry batches, 72 registers, 28 warps/SM
   }
   CHS_LAUNCH_CHECK();
   return CHS_OK;
