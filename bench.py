@@ -448,7 +448,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "blend_bwd_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "blend_bwd_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "blend_bwd2_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
                 "launch_ms": bwd_ms, "isects_per_launch": M_f}
     # whole-step algorithmic bytes, per frame
