@@ -547,13 +547,10 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
         chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
         return CHS_ERR_WORKSPACE_TOO_SMALL;
       }
-      static bool attr_set = false;
       const size_t smem = (size_t)kPlaceWarps * p.band_tiles * sizeof(uint32_t);
-      if (!attr_set) {
-        CHS_CUDA(cudaFuncSetAttribute(place_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlaceWarps * kBandTilesMax * 4));
-        CHS_CUDA(cudaFuncSetAttribute(place_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlaceWarps * kBandTilesMax * 4));
-        attr_set = true;
-      }
+      // up to 64 KB of dynamic shared memory: opt in (per device, so not cached in a static)
+      CHS_CUDA(cudaFuncSetAttribute(place_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlaceWarps * kBandTilesMax * 4));
+      CHS_CUDA(cudaFuncSetAttribute(place_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlaceWarps * kBandTilesMax * 4));
       rects_kernel<<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.tile_w, d.tile_h, cfg->tight_bounds != 0, (const float4*)geom, radii, order, rects);
       CHS_LAUNCH_CHECK();
       PlaceArgs a;

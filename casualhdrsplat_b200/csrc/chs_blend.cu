@@ -22,10 +22,17 @@
 // Forward fuses the whole formation epilogue: the CTA loops over the n virtual poses of its frame,
 // accumulates sum_k H_k in registers, and writes B = F(dt/n * sum_k H_k) once (decision D0 order).
 //
-// Backward walks each pixel's list back to front from last_id; the nine per-Gaussian partials of
-// the thread's two pixels are added, then reduced across the warp with a transposing butterfly
-// (14 shuffles instead of 45) that leaves value j on lane j, so a single RED instruction with nine
-// active lanes adds all nine numbers into the three [C,N] gradient planes.
+// Backward walks each pixel's list back to front from last_id.  Two implementations:
+//   blend_bwd2_kernel (default, "tabled"): the per-pixel sequential part runs pixel-parallel and leaves two
+//     scalars per (pixel, Gaussian) in a per-warp shared-memory table; every 8 Gaussians the lanes switch
+//     to one Gaussian each and sum their table rows privately (see the comment above the kernel).
+//   blend_bwd_kernel (CHS_BLEND_BWD_VARIANT=1, "direct"): the nine per-Gaussian partials of the thread's two
+//     pixels are added, then reduced across the warp with a transposing butterfly (14 shuffles instead of
+//     45) that leaves value j on lane j, so a single RED instruction with nine active lanes adds all nine
+//     numbers into the three [C,N] gradient planes.
+// Negative results kept out of the code (r1g, c3): prefetching the next survivor's staged record inside the
+// forward pair loop (to hide the bit-scan -> address -> LDS chain) made K6 2.55 -> 2.95 ms at 64 registers and
+// 3.00 ms at 72; software-pipelining phase A of the tabled backward cost +0.5 ms.
 #include <stdlib.h>
 
 #include "chs_common.cuh"
@@ -843,18 +850,13 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
 #define CHS_BWD2_LAUNCH(S, B, MB, PIPE) blend_bwd2_kernel<S, B, MB, PIPE><<<grid, kThreads, CHS_BWD2_SMEM(S, B), s>>>(a)
 #define CHS_BWD2_ATTR(S, B, MB, PIPE) \
   CHS_CUDA(cudaFuncSetAttribute(blend_bwd2_kernel<S, B, MB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHS_BWD2_SMEM(S, B)))
-  static bool attr_set = false;
-  if (!attr_set) {
-    CHS_BWD2_ATTR(8, 128, 7, false); CHS_BWD2_ATTR(16, 128, 5, false); CHS_BWD2_ATTR(16, 256, 4, false); CHS_BWD2_ATTR(8, 128, 7, true);
-    attr_set = true;
-  }
   // r1g sweep on c3 (ms per frame of 8 poses, tight bounds): direct kernel 6.07 | tabled 16 slots / batch 256 / 4 CTAs per SM 5.36 |
   // 16 / 128 / 5: 5.21 | 8 / 128 / 7: 5.01 (default) | 8 / 128 / 8 (64 registers, spills) 5.18 | 8 / 64 / 8: 5.12 | 8 / 256 / 6: 5.51 |
   // software-pipelined phase A (kPipe): +0.5 ms in every configuration
   switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {
     case 1: blend_bwd_kernel<1, 8><<<grid, kThreads, 0, s>>>(a); break;          // the direct (r1d-f) kernel, two pixels per thread
     case 22: blend_bwd_kernel<2, 12><<<grid, kThreads / 2, 0, s>>>(a); break;    // direct, four pixels per thread
-    case 40: CHS_BWD2_LAUNCH(16, 256, 4, false); break;
+    case 40: CHS_BWD2_ATTR(16, 256, 4, false); CHS_BWD2_LAUNCH(16, 256, 4, false); break;  // 50 KB of dynamic shared memory: opt in
     case 41: CHS_BWD2_LAUNCH(16, 128, 5, false); break;
     case 45: CHS_BWD2_LAUNCH(8, 128, 7, true); break;
     default: CHS_BWD2_LAUNCH(8, 128, 7, false); break;  // tabled: 8 slots per round, 128-entry batches, 72 registers, 28 warps/SM
