@@ -547,10 +547,11 @@ template <int kSlots, class Smem>
 __device__ __forceinline__ void bwd_round(const Smem& sm, const BwdWarpSmem<kSlots>& ws, int n_slots, int lane, float bxc, float byc,
                                           const BlendBwdArgs& a) {
   __syncwarp();
-  constexpr int kParts = 32 / kSlots;  // lanes per Gaussian, each covering kRows rows of 8 pixels
+  constexpr int kW = kSlots <= 8 ? 8 : (kSlots <= 16 ? 16 : 32);  // lanes per pixel part (slots padded to a power of two)
+  constexpr int kParts = 32 / kW;                                   // lanes per Gaussian, each covering kRows rows of 8 pixels
   constexpr int kRows = 8 / kParts;
-  static_assert(kParts >= 1 && kParts <= 4, "kSlots must be 8, 16 or 32");
-  const int k = lane % kSlots, part = lane / kSlots;
+  static_assert(kSlots >= 1 && kSlots <= 32, "at most one lane group per slot");
+  const int k = lane % kW, part = lane / kW;
   const bool active = k < n_slots;
   P2 S_u = p2s(0.f), S_xx = p2s(0.f), S_dy = p2s(0.f), S_xy = p2s(0.f), S_yy = p2s(0.f), S_v = p2s(0.f);
   P2 G6 = p2s(0.f), G7 = p2s(0.f), G8 = p2s(0.f);
@@ -604,7 +605,7 @@ __device__ __forceinline__ void bwd_round(const Smem& sm, const BwdWarpSmem<kSlo
   }
   float t[9] = {p2sum(S_u), p2sum(S_dy), p2sum(S_xx), p2sum(S_xy), p2sum(S_yy), p2sum(S_v), p2sum(G6), p2sum(G7), p2sum(G8)};
 #pragma unroll
-  for (int o = kSlots; o < 32; o <<= 1)
+  for (int o = kW; o < 32; o <<= 1)
 #pragma unroll
     for (int i = 0; i < 9; ++i) t[i] += __shfl_xor_sync(CHS_FULL_MASK, t[i], o);
   if (active) {
@@ -852,7 +853,7 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   CHS_CUDA(cudaFuncSetAttribute(blend_bwd2_kernel<S, B, MB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHS_BWD2_SMEM(S, B)))
   // r1g sweep on c3 (ms per frame of 8 poses, tight bounds): direct kernel 6.07 | tabled 16 slots / batch 256 / 4 CTAs per SM 5.36 |
   // 16 / 128 / 5: 5.21 | 8 / 128 / 7: 5.01 (default) | 8 / 128 / 8 (64 registers, spills) 5.18 | 8 / 64 / 8: 5.12 | 8 / 256 / 6: 5.51 |
-  // software-pipelined phase A (kPipe): +0.5 ms in every configuration
+  // 12 / 128 / 6: 5.64 | 10 / 128 / 6: 5.69 (idle lanes in phase B) | software-pipelined phase A (kPipe): +0.5 ms in every configuration
   switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {
     case 1: blend_bwd_kernel<1, 8><<<grid, kThreads, 0, s>>>(a); break;          // the direct (r1d-f) kernel, two pixels per thread
     case 22: blend_bwd_kernel<2, 12><<<grid, kThreads / 2, 0, s>>>(a); break;    // direct, four pixels per thread
