@@ -61,6 +61,39 @@ def test_no_cpu_fallback():
         rasterize(z(4, 3), z(4, 4), z(4, 3), z(4), z(4, 3), z(1, 4, 4), z(1, 3, 3), 16, 16, z(1), 1)
 
 
+def test_loss_entry_points_validate_and_refuse_cpu(L):
+    from casualhdrsplat_b200 import _lib
+    from casualhdrsplat_b200.train import photometric_loss, ssim_loss
+
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ssim_loss(z(1, 8, 8, 3), z(1, 8, 8, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        photometric_loss(z(1, 8, 8, 3), z(1, 8, 8, 3))
+    # argument validation happens before any device work
+    assert L.chs_ssim_loss(None, None, 1, 8, 8, 0.8, 0.2, None, None, None, 0, None) == -1 and b"null" in L.chs_last_error()
+    assert L.chs_ssim_loss(None, None, 1, 0, 8, 0.8, 0.2, None, None, None, 0, None) == -1 and b"shape" in L.chs_last_error()
+    assert L.chs_ssim_loss(None, None, 0, 8, 8, 0.8, 0.2, None, None, None, 0, None) == 0  # no images: nothing to do
+    assert L.chs_loss(2, None, None, 0, 1.0, None, None, None) == -1 and b"kind" in L.chs_last_error()
+
+
+def test_crf_kinds_and_sizes(L):
+    from casualhdrsplat_b200 import _lib
+
+    out = _lib.ChsWorkspaceSizes()
+    for kind, size, ok in [(_lib.CHS_CRF_MLP, 64, True), (_lib.CHS_CRF_MLP, 129, False), (_lib.CHS_CRF_LUT, 256, True),
+                           (_lib.CHS_CRF_LUT, 1, False), (_lib.CHS_CRF_LUT, 1025, False), (3, 8, False)]:
+        cfg = _lib.make_config(0, 1, 1, 32, 32, crf_kind=kind, crf_hidden=size)  # no Gaussians: no CUB size query, no device needed
+        assert (L.chs_workspace_query(ctypes.byref(cfg), 0, 4, ctypes.byref(out)) == 0) == ok, (kind, size)
+    # parameter-tensor shapes of the operator
+    assert _lib.crf_size(_lib.CHS_CRF_MLP, torch.zeros(3, 3 * 16 + 1)) == 16
+    assert _lib.crf_size(_lib.CHS_CRF_LUT, torch.zeros(3, 34)) == 32
+    assert _lib.crf_size(_lib.CHS_CRF_IDENTITY, None) == 0
+    for kind, shape in [(_lib.CHS_CRF_MLP, (3, 48)), (_lib.CHS_CRF_LUT, (3, 3)), (_lib.CHS_CRF_MLP, (2, 49)), (7, (3, 49))]:
+        with pytest.raises(RuntimeError):
+            _lib.crf_size(kind, torch.zeros(*shape))
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "casualhdrsplat_b200")
     for dirpath, _, files in os.walk(pkg):
