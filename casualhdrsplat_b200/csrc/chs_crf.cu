@@ -1,6 +1,8 @@
 // chs_crf.cu — K7 crf_bwd: gradient of the formation epilogue B = F_theta(dt * mean_k H_k)
 // (SURVEY.md Appendix A.7).  Streaming per-pixel kernel; the CRF parameter gradients are reduced
 // warp -> shared memory -> fp64 global accumulators.
+#include <stdlib.h>
+
 #include "chs_common.cuh"
 
 namespace {
@@ -27,7 +29,8 @@ struct CrfBwdArgs {
 // units in registers, so no cross-lane reduction is needed at all.
 constexpr int kMaxUnitsPerLane = 4;  // crf_hidden <= 128
 
-__global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_kernel(CrfBwdArgs a) {
   extern __shared__ float smem[];
   const int stride = chs_crf_stride(a.crf_kind, a.hd);
   float* s_p = smem;                         // parameters [3, stride]
@@ -50,51 +53,76 @@ __global__ void __launch_bounds__(kThreads) crf_bwd_kernel(CrfBwdArgs a) {
   // contended fp64 atomics happen once per block, not once per 1024 pixels
   const int64_t n_chunks = (a.P + (int64_t)kPix * kThreads - 1) / ((int64_t)kPix * kThreads);
   for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  int64_t o_img[kPix], o_frm[kPix];
+  bool live[kPix];
 #pragma unroll
   for (int q = 0; q < kPix; ++q) {
-    const int slot = q * kThreads + tid;
-    const int64_t pix = chunk * (kPix * kThreads) + slot;
-    const bool live = pix < a.P;
-    const int64_t o = ((int64_t)img * a.P + (live ? pix : 0)) * 3;
-    const int64_t of = ((int64_t)frame * a.P + (live ? pix : 0)) * 3;
+    const int64_t pix = chunk * (kPix * kThreads) + q * kThreads + tid;
+    live[q] = pix < a.P;
+    o_img[q] = ((int64_t)img * a.P + (live[q] ? pix : 0)) * 3;
+    o_frm[q] = ((int64_t)frame * a.P + (live[q] ? pix : 0)) * 3;
+  }
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      float zz = 0.f, g = 0.f;
-      if (live) {
-        const float h = a.hdr_mean[o + ch];
-        const float vy = a.v_ldr[of + ch] * a.vy_scale;
-        float vx;
-        if (mlp) {
-          const float* p = s_p + ch * stride;
-          const float xe = dt * h + CHS_CRF_EPS;
-          zz = logf(xe);
-          float acc = p[3 * a.hd], dz = 0.f;
-          for (int j = 0; j < a.hd; ++j) {
-            const float pre = fmaf(p[j], zz, p[a.hd + j]);
-            if (pre > 0.f) {
-              acc = fmaf(p[2 * a.hd + j], pre, acc);
-              dz = fmaf(p[2 * a.hd + j], p[j], dz);
-            }
-          }
-          const float y = 1.f / (1.f + expf(-acc));
-          g = vy * y * (1.f - y);
-          vx = g * dz / xe;
-        } else if (lut) {
-          // piecewise-linear table: the two knot gradients go straight to the block's shared accumulators
-          const float* p = s_p + ch * stride;
-          const ChsLutPos<float> q = chs_crf_lut_pos(dt * h, p, a.hd);
-          atomicAdd(&s_g[ch * stride + 2 + q.i], vy * (1.f - q.f));
-          atomicAdd(&s_g[ch * stride + 3 + q.i], vy * q.f);
-          vx = vy * (p[3 + q.i] - p[2 + q.i]) * q.du_dz / q.xe;
-        } else {
-          vx = vy;
-        }
-        v_dt = fmaf(vx, h, v_dt);
-        a.v_hdr[o + ch] = vx * scale;
+  for (int ch = 0; ch < 3; ++ch) {
+    float h[kPix], vy[kPix], vx[kPix];
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) {
+      h[q] = live[q] ? a.hdr_mean[o_img[q] + ch] : 0.f;
+      vy[q] = live[q] ? a.v_ldr[o_frm[q] + ch] * a.vy_scale : 0.f;
+    }
+    if (mlp) {
+      // the unit's three weights are fetched once for the thread's kPix pixels
+      const float* p = s_p + ch * stride;
+      float xe[kPix], zz[kPix], acc[kPix], dz[kPix];
+#pragma unroll
+      for (int q = 0; q < kPix; ++q) {
+        xe[q] = dt * h[q] + CHS_CRF_EPS;
+        zz[q] = logf(xe[q]);
+        acc[q] = p[3 * a.hd];
+        dz[q] = 0.f;
       }
-      if (mlp) {
-        s_z[ch * (kThreads * kPix) + slot] = zz;
-        s_gy[ch * (kThreads * kPix) + slot] = g;  // 0 for pixels past the end: they add nothing below
+      for (int j = 0; j < a.hd; ++j) {
+        const float w1 = p[j], b1 = p[a.hd + j], w2 = p[2 * a.hd + j];
+        const float w21 = w2 * w1;
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) {
+          const float pre = fmaf(w1, zz[q], b1);
+          if (pre > 0.f) {
+            acc[q] = fmaf(w2, pre, acc[q]);
+            dz[q] += w21;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kPix; ++q) {
+        const float y = 1.f / (1.f + expf(-acc[q]));
+        const float g = vy[q] * y * (1.f - y);  // 0 for pixels past the end: they add nothing below
+        vx[q] = g * dz[q] / xe[q];
+        s_z[ch * (kThreads * kPix) + q * kThreads + tid] = zz[q];
+        s_gy[ch * (kThreads * kPix) + q * kThreads + tid] = g;
+      }
+    } else if (lut) {
+      // piecewise-linear table: the two knot gradients go straight to the block's shared accumulators
+      const float* p = s_p + ch * stride;
+#pragma unroll
+      for (int q = 0; q < kPix; ++q) {
+        vx[q] = 0.f;
+        if (live[q]) {
+          const ChsLutPos<float> pos = chs_crf_lut_pos(dt * h[q], p, a.hd);
+          atomicAdd(&s_g[ch * stride + 2 + pos.i], vy[q] * (1.f - pos.f));
+          atomicAdd(&s_g[ch * stride + 3 + pos.i], vy[q] * pos.f);
+          vx[q] = vy[q] * (p[3 + pos.i] - p[2 + pos.i]) * pos.du_dz / pos.xe;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kPix; ++q) vx[q] = vy[q];
+    }
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) {
+      if (live[q]) {
+        v_dt = fmaf(vx[q], h[q], v_dt);
+        a.v_hdr[o_img[q] + ch] = vx[q] * scale;
       }
     }
   }
@@ -198,11 +226,18 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
     a.acc_crf = acc; a.acc_exposure = acc + n_par;
     const int64_t n_chunks = (d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix);
     const int n_img = per_pose ? d.C : d.B;
-    int gx = (148 * 4 + n_img - 1) / n_img;  // ~4 resident blocks per SM over all images
+    const char* ev = getenv("CHS_CRF_BWD_VARIANT");  // development knob: resident blocks per SM
+    const int mb = ev ? atoi(ev) : 4;  // r1g, c3: 2 -> 0.306 ms, 3 -> 0.296, 4 -> 0.280 (previous phase-1 loop order: 0.317)
+    int gx = (148 * mb + n_img - 1) / n_img;  // one wave of resident blocks over all images
     if (gx > n_chunks) gx = (int)n_chunks;
     dim3 grid((unsigned)gx, n_img);
     size_t smem = mlp ? ((size_t)2 * n_par + (size_t)6 * kThreads * kPix) * sizeof(float) : (size_t)2 * n_par * sizeof(float) + 16;
-    crf_bwd_kernel<<<grid, kThreads, smem, s>>>(a);
+    if (mb == 4)
+      crf_bwd_kernel<4><<<grid, kThreads, smem, s>>>(a);
+    else if (mb == 2)
+      crf_bwd_kernel<2><<<grid, kThreads, smem, s>>>(a);
+    else
+      crf_bwd_kernel<3><<<grid, kThreads, smem, s>>>(a);
     CHS_LAUNCH_CHECK();
   }
   if (n_par > 0) {
