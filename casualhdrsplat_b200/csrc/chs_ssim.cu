@@ -8,7 +8,8 @@
 // run over all n_img * H * W * 3 values.
 //
 // Two streaming kernels, one 16x16-pixel tile (all three channels) per CTA, separable 11-tap window in
-// shared memory:
+// shared memory, register blocked (4 outputs per work item in both passes, 128-bit shared-memory loads),
+// outputs staged through shared memory so that the channel-interleaved stores are coalesced:
 //   ssim_fwd_kernel  x, y (+5-pixel halo) -> window statistics -> SSIM; adds the loss terms to a device
 //                    fp64 scalar and stores the three partial-derivative maps dS/dmu1, dS/dE[x^2],
 //                    dS/dE[xy] (12 B per value) for the backward;
@@ -41,9 +42,11 @@ struct SsimArgs {
   SsimWindow win;
 };
 
+constexpr int kPW = 28;  // padded patch row: 26 used columns, rows stay 16-byte aligned for 128-bit loads
+
 // loads the (tile + halo) x 3-channel patch of `src` at the CTA's tile into dst[ch][row][col], zero outside the image
 __device__ __forceinline__ void load_patch(const float* __restrict__ src, int img, int H, int W, int y0, int x0,
-                                           float (*dst)[kExt][kExt + 1], int tid) {
+                                           float (*dst)[kExt][kPW], int tid) {
   const float* base = src + (int64_t)img * H * W * 3;
   for (int i = tid; i < kExt * kExt * 3; i += kThreads) {
     const int row = i / (kExt * 3), rem = i % (kExt * 3);
@@ -55,72 +58,115 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ src, int im
   }
 }
 
+// 16 consecutive patch values starting at a 16-byte aligned column
+__device__ __forceinline__ void load16(const float* p, float v[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+
+// Both kernels are register blocked: a horizontal work item is (channel, patch row, group of 4 output columns) — 14 inputs
+// fetched with four 128-bit loads feed 4 x 11 taps — and a vertical one is (channel, group of 4 output rows, column).
+constexpr int kHItems = 3 * kExt * (kTile / 4);  // 312
+constexpr int kVItems = 3 * (kTile / 4) * kTile; // 192 threads carry 4 outputs each
+
 __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(SsimArgs a) {
-  __shared__ float s_x[3][kExt][kExt + 1];
-  __shared__ float s_y[3][kExt][kExt + 1];
-  __shared__ float s_h[5][kExt][kTile + 1];  // horizontal pass of x, y, x^2, y^2, xy for one channel
+  __shared__ __align__(16) float s_xy[2][3][kExt][kPW];    // x and y patches; reused as the output staging area
+  __shared__ __align__(16) float s_h[5][3][kExt][kTile];   // horizontal pass of x, y, x^2, y^2, xy
   __shared__ float s_red[kThreads / 32];
-  const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
+  const int tid = threadIdx.x;
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile, img = blockIdx.z;
-  load_patch(a.x, img, a.H, a.W, y0, x0, s_x, tid);
-  load_patch(a.y, img, a.H, a.W, y0, x0, s_y, tid);
+  load_patch(a.x, img, a.H, a.W, y0, x0, s_xy[0], tid);
+  load_patch(a.y, img, a.H, a.W, y0, x0, s_xy[1], tid);
   __syncthreads();
-  const int px = x0 + tx, py = y0 + ty;
-  const bool inside = px < a.W && py < a.H;
-  float part = 0.f;  // this thread's contribution to the loss
-  float m_mu[3], m_e11[3], m_e12[3];
-  for (int ch = 0; ch < 3; ++ch) {
-    for (int i = tid; i < kExt * kTile; i += kThreads) {
-      const int row = i / kTile, col = i % kTile;
-      float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+  for (int item = tid; item < kHItems; item += kThreads) {
+    const int ch = item / (kExt * 4), rem = item % (kExt * 4);
+    const int row = rem / 4, c0 = (rem % 4) * 4;
+    float xv[16], yv[16];
+    load16(&s_xy[0][ch][row][c0], xv);
+    load16(&s_xy[1][ch][row][c0], yv);
+    float o[5][4];
 #pragma unroll
-      for (int k = 0; k < kWin; ++k) {
-        const float w = a.win.w[k], xv = s_x[ch][row][col + k], yv = s_y[ch][row][col + k];
-        sx = fmaf(w, xv, sx);
-        sy = fmaf(w, yv, sy);
-        sxx = fmaf(w * xv, xv, sxx);
-        syy = fmaf(w * yv, yv, syy);
-        sxy = fmaf(w * xv, yv, sxy);
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[q][j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {  // input i feeds output j through tap k = i - j
+      const float xx = xv[i] * xv[i], yy = yv[i] * yv[i], xy = xv[i] * yv[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = i - j;
+        if (k >= 0 && k < kWin) {
+          const float w = a.win.w[k];
+          o[0][j] = fmaf(w, xv[i], o[0][j]);
+          o[1][j] = fmaf(w, yv[i], o[1][j]);
+          o[2][j] = fmaf(w, xx, o[2][j]);
+          o[3][j] = fmaf(w, yy, o[3][j]);
+          o[4][j] = fmaf(w, xy, o[4][j]);
+        }
       }
-      s_h[0][row][col] = sx; s_h[1][row][col] = sy; s_h[2][row][col] = sxx; s_h[3][row][col] = syy; s_h[4][row][col] = sxy;
     }
-    __syncthreads();
-    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) {
-      const float w = a.win.w[k];
-      mu1 = fmaf(w, s_h[0][ty + k][tx], mu1);
-      mu2 = fmaf(w, s_h[1][ty + k][tx], mu2);
-      e11 = fmaf(w, s_h[2][ty + k][tx], e11);
-      e22 = fmaf(w, s_h[3][ty + k][tx], e22);
-      e12 = fmaf(w, s_h[4][ty + k][tx], e12);
+    for (int q = 0; q < 5; ++q) *reinterpret_cast<float4*>(&s_h[q][ch][row][c0]) = make_float4(o[q][0], o[q][1], o[q][2], o[q][3]);
+  }
+  __syncthreads();
+  float part = 0.f;  // this thread's contribution to the loss
+  float m_out[3][4];
+  const int tx = tid % kTile, grp = tid / kTile;  // grp = ch * 4 + row group
+  const int ch = grp / 4, r0 = (grp % 4) * 4;
+  const bool vwork = tid < kVItems;
+  if (vwork) {
+    float st[5][4];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float v[14];
+#pragma unroll
+      for (int i = 0; i < 14; ++i) v[i] = s_h[q][ch][r0 + i][tx];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) acc = fmaf(a.win.w[k], v[j + k], acc);
+        st[q][j] = acc;
+      }
     }
-    __syncthreads();  // s_h is rewritten for the next channel
-    const float s11 = e11 - mu1 * mu1, s22 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
-    const float A1 = 2.f * mu1 * mu2 + kC1, A2 = 2.f * s12 + kC2, B1 = mu1 * mu1 + mu2 * mu2 + kC1, B2 = s11 + s22 + kC2;
-    const float iB1 = 1.f / B1, iB2 = 1.f / B2;
-    const float S = A1 * A2 * iB1 * iB2;
-    // partial derivatives of S w.r.t. the x-side window statistics (mu1 total, through s11 and s12 as well)
-    const float d_e11 = -S * iB2;
-    const float d_e12 = 2.f * A1 * iB1 * iB2;
-    const float d_mu = 2.f * mu2 * A2 * iB1 * iB2 - 2.f * mu1 * S * iB1 - 2.f * mu1 * d_e11 - mu2 * d_e12;
-    m_mu[ch] = inside ? d_mu : 0.f;
-    m_e11[ch] = inside ? d_e11 : 0.f;
-    m_e12[ch] = inside ? d_e12 : 0.f;
-    if (inside) {
-      const float d = s_x[ch][ty + kHalo][tx + kHalo] - s_y[ch][ty + kHalo][tx + kHalo];
-      part += a.l1_scale * fabsf(d) + a.ssim_scale * (1.f - S);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mu1 = st[0][j], mu2 = st[1][j];
+      const float s11 = st[2][j] - mu1 * mu1, s22 = st[3][j] - mu2 * mu2, s12 = st[4][j] - mu1 * mu2;
+      const float A1 = 2.f * mu1 * mu2 + kC1, A2 = 2.f * s12 + kC2, B1 = mu1 * mu1 + mu2 * mu2 + kC1, B2 = s11 + s22 + kC2;
+      const float iB1 = 1.f / B1, iB2 = 1.f / B2;
+      const float S = A1 * A2 * iB1 * iB2;
+      // partial derivatives of S w.r.t. the x-side window statistics (mu1 total, through s11 and s12 as well)
+      const float d_e11 = -S * iB2;
+      const float d_e12 = 2.f * A1 * iB1 * iB2;
+      const float d_mu = 2.f * mu2 * A2 * iB1 * iB2 - 2.f * mu1 * S * iB1 - 2.f * mu1 * d_e11 - mu2 * d_e12;
+      const bool inside = x0 + tx < a.W && y0 + r0 + j < a.H;
+      m_out[0][j] = inside ? d_mu : 0.f;
+      m_out[1][j] = inside ? d_e11 : 0.f;
+      m_out[2][j] = inside ? d_e12 : 0.f;
+      if (inside) {
+        const float d = s_xy[0][ch][r0 + j + kHalo][tx + kHalo] - s_xy[1][ch][r0 + j + kHalo][tx + kHalo];
+        part += a.l1_scale * fabsf(d) + a.ssim_scale * (1.f - S);
+      }
     }
   }
-  if (inside) {
-    const int64_t plane = (int64_t)a.n_img * a.H * a.W * 3;
-    const int64_t o = (((int64_t)img * a.H + py) * a.W + px) * 3;
+  __syncthreads();  // the patches are dead: stage the three maps [map][pixel][channel] for coalesced stores
+  float* s_out = &s_xy[0][0][0][0];
+  if (vwork) {
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      a.maps[o + ch] = m_mu[ch];
-      a.maps[plane + o + ch] = m_e11[ch];
-      a.maps[2 * plane + o + ch] = m_e12[ch];
-    }
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_out[m * (kThreads * 3) + ((r0 + j) * kTile + tx) * 3 + ch] = m_out[m][j];
+  }
+  __syncthreads();
+  const int64_t plane = (int64_t)a.n_img * a.H * a.W * 3;
+  for (int i = tid; i < 3 * kThreads * 3; i += kThreads) {
+    const int m = i / (kThreads * 3), rem = i % (kThreads * 3);
+    const int py = y0 + rem / (kTile * 3), px = x0 + (rem % (kTile * 3)) / 3, c = rem % 3;
+    if (px < a.W && py < a.H) a.maps[m * plane + (((int64_t)img * a.H + py) * a.W + px) * 3 + c] = s_out[i];
   }
   part = chs_warp_sum(part);
   if ((tid & 31) == 0) s_red[tid >> 5] = part;
@@ -133,50 +179,70 @@ __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(SsimArgs a) {
 }
 
 __global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(SsimArgs a) {
-  __shared__ float s_m[3][kExt][kExt + 1];   // one derivative map, three channels, with halo
-  __shared__ float s_h[3][kExt][kTile + 1];  // its horizontal pass
-  const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
+  __shared__ __align__(16) float s_m[3][kExt][kPW];    // one derivative map, three channels, with halo; reused for the output
+  __shared__ __align__(16) float s_h[3][kExt][kTile];  // its horizontal pass
+  __shared__ float s_c[2][kThreads * 3];               // x and y of the tile's own pixels, [pixel][channel]
+  const int tid = threadIdx.x;
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile, img = blockIdx.z;
-  const int px = x0 + tx, py = y0 + ty;
-  const bool inside = px < a.W && py < a.H;
   const int64_t plane = (int64_t)a.n_img * a.H * a.W * 3;
-  const int64_t o = (((int64_t)img * a.H + py) * a.W + px) * 3;
-  float acc[3] = {0.f, 0.f, 0.f};
-  float xv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f};
-  if (inside) {
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      xv[ch] = a.x[o + ch];
-      yv[ch] = a.y[o + ch];
-    }
+  for (int i = tid; i < kThreads * 3; i += kThreads) {
+    const int py = y0 + i / (kTile * 3), px = x0 + (i % (kTile * 3)) / 3, c = i % 3;
+    const bool in = px < a.W && py < a.H;
+    const int64_t o = (((int64_t)img * a.H + py) * a.W + px) * 3 + c;
+    s_c[0][i] = in ? a.x[o] : 0.f;
+    s_c[1][i] = in ? a.y[o] : 0.f;
   }
+  const int tx = tid % kTile, grp = tid / kTile;
+  const int ch = grp / 4, r0 = (grp % 4) * 4;
+  const bool vwork = tid < kVItems;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int m = 0; m < 3; ++m) {  // dS/dmu1, dS/dE[x^2], dS/dE[xy]
     __syncthreads();
     load_patch(a.maps + m * plane, img, a.H, a.W, y0, x0, s_m, tid);
     __syncthreads();
-    for (int i = tid; i < 3 * kExt * kTile; i += kThreads) {
-      const int ch = i / (kExt * kTile), rem = i % (kExt * kTile);
-      const int row = rem / kTile, col = rem % kTile;
-      float s = 0.f;
+    for (int item = tid; item < kHItems; item += kThreads) {
+      const int hc = item / (kExt * 4), rem = item % (kExt * 4);
+      const int row = rem / 4, c0 = (rem % 4) * 4;
+      float v[16];
+      load16(&s_m[hc][row][c0], v);
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < kWin; ++k) s = fmaf(a.win.w[k], s_m[ch][row][col + k], s);
-      s_h[ch][row][col] = s;
+      for (int i = 0; i < 14; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = i - j;
+          if (k >= 0 && k < kWin) o[j] = fmaf(a.win.w[k], v[i], o[j]);
+        }
+      *reinterpret_cast<float4*>(&s_h[hc][row][c0]) = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
+    if (vwork) {
+      float v[14];
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      float s = 0.f;
+      for (int i = 0; i < 14; ++i) v[i] = s_h[ch][r0 + i][tx];
 #pragma unroll
-      for (int k = 0; k < kWin; ++k) s = fmaf(a.win.w[k], s_h[ch][ty + k][tx], s);
-      acc[ch] += m == 0 ? s : (m == 1 ? 2.f * xv[ch] * s : yv[ch] * s);
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) s = fmaf(a.win.w[k], v[j + k], s);
+        const int pi = ((r0 + j) * kTile + tx) * 3 + ch;
+        acc[j] += m == 0 ? s : (m == 1 ? 2.f * s_c[0][pi] * s : s_c[1][pi] * s);
+      }
     }
   }
-  if (inside) {
+  __syncthreads();
+  float* s_out = &s_m[0][0][0];
+  if (vwork) {
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const float d = xv[ch] - yv[ch];
+    for (int j = 0; j < 4; ++j) s_out[((r0 + j) * kTile + tx) * 3 + ch] = acc[j];
+  }
+  __syncthreads();
+  for (int i = tid; i < kThreads * 3; i += kThreads) {
+    const int py = y0 + i / (kTile * 3), px = x0 + (i % (kTile * 3)) / 3, c = i % 3;
+    if (px < a.W && py < a.H) {
+      const float d = s_c[0][i] - s_c[1][i];
       const float l1 = d > 0.f ? a.l1_scale : (d < 0.f ? -a.l1_scale : 0.f);
-      a.v_x[o + ch] = l1 - a.ssim_scale * acc[ch];
+      a.v_x[(((int64_t)img * a.H + py) * a.W + px) * 3 + c] = l1 - a.ssim_scale * s_out[i];
     }
   }
 }
