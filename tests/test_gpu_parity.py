@@ -578,7 +578,7 @@ def test_fused_loss_and_adam_match_torch():
         want = fn(x - tgt.double())
         (gx,) = torch.autograd.grad(want, x)
         v, acc = photometric_loss(ldr, tgt, kind, scale=0.25)
-        assert abs(float(acc) - float(want)) <= 1e-6 * abs(float(want))
+        assert abs(float(acc) - float(want.detach())) <= 1e-6 * abs(float(want.detach()))
         assert rel(v, gx) < 1e-6
     p0 = torch.randn(1001, 3, generator=g, dtype=torch.float32).to(dev)
     p_ref = p0.clone().requires_grad_(True)
