@@ -44,18 +44,42 @@ struct SsimArgs {
 
 constexpr int kPW = 28;  // padded patch row: 26 used columns, rows stay 16-byte aligned for 128-bit loads
 
-// loads the (tile + halo) x 3-channel patch of `src` at the CTA's tile into dst[ch][row][col], zero outside the image
+// loads the (tile + halo) x 3-channel patch of `src` at the CTA's tile into dst[ch][row][col], zero outside the image.
+// Three patch rows per sweep: a thread decodes its (row offset, column, channel) once, the loop only adds.
 __device__ __forceinline__ void load_patch(const float* __restrict__ src, int img, int H, int W, int y0, int x0,
                                            float (*dst)[kExt][kPW], int tid) {
-  const float* base = src + (int64_t)img * H * W * 3;
-  for (int i = tid; i < kExt * kExt * 3; i += kThreads) {
-    const int row = i / (kExt * 3), rem = i % (kExt * 3);
-    const int col = rem / 3, ch = rem % 3;
-    const int yy = y0 - kHalo + row, xx = x0 - kHalo + col;
+  constexpr int kRowF = kExt * 3;  // 78 consecutive floats per patch row
+  if (tid >= 3 * kRowF) return;    // 234 of the 256 threads carry the loads
+  const int r_off = tid / kRowF, cc = tid % kRowF;
+  const int col = cc / 3, ch = cc % 3;
+  const int xx = x0 - kHalo + col;
+  const bool x_in = xx >= 0 && xx < W;
+  const float* base = src + (int64_t)img * H * W * 3 + (int64_t)xx * 3 + ch;
+#pragma unroll
+  for (int row = r_off; row < kExt; row += 3) {
+    const int yy = y0 - kHalo + row;
     float v = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = base[((int64_t)yy * W + xx) * 3 + ch];
+    if (x_in && yy >= 0 && yy < H) v = base[(int64_t)yy * W * 3];
     dst[ch][row][col] = v;
   }
+}
+
+// the tile's own 256 x 3 values in [pixel][channel] order are covered by three sweeps of the CTA: element tid + 256 s
+struct TileElems {
+  int64_t off[3];  // offset of the element in a [n_img, H, W, 3] array
+  bool in[3];
+};
+__device__ __forceinline__ TileElems tile_elems(int img, int H, int W, int y0, int x0, int tid) {
+  TileElems e;
+#pragma unroll
+  for (int sw = 0; sw < 3; ++sw) {
+    const int i = tid + kThreads * sw;
+    const int p = i / 3, c = i % 3;
+    const int py = y0 + (p >> 4), px = x0 + (p & 15);
+    e.in[sw] = px < W && py < H;
+    e.off[sw] = (((int64_t)img * H + py) * W + px) * 3 + c;
+  }
+  return e;
 }
 
 // 16 consecutive patch values starting at a 16-byte aligned column
@@ -72,7 +96,7 @@ __device__ __forceinline__ void load16(const float* p, float v[16]) {
 constexpr int kHItems = 3 * kExt * (kTile / 4);  // 312
 constexpr int kVItems = 3 * (kTile / 4) * kTile; // 192 threads carry 4 outputs each
 
-__global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(SsimArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) ssim_fwd_kernel(SsimArgs a) {
   __shared__ __align__(16) float s_xy[2][3][kExt][kPW];    // x and y patches; reused as the output staging area
   __shared__ __align__(16) float s_h[5][3][kExt][kTile];   // horizontal pass of x, y, x^2, y^2, xy
   __shared__ float s_red[kThreads / 32];
@@ -163,11 +187,12 @@ __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(SsimArgs a) {
   }
   __syncthreads();
   const int64_t plane = (int64_t)a.n_img * a.H * a.W * 3;
-  for (int i = tid; i < 3 * kThreads * 3; i += kThreads) {
-    const int m = i / (kThreads * 3), rem = i % (kThreads * 3);
-    const int py = y0 + rem / (kTile * 3), px = x0 + (rem % (kTile * 3)) / 3, c = rem % 3;
-    if (px < a.W && py < a.H) a.maps[m * plane + (((int64_t)img * a.H + py) * a.W + px) * 3 + c] = s_out[i];
-  }
+  const TileElems te = tile_elems(img, a.H, a.W, y0, x0, tid);
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+#pragma unroll
+    for (int sw = 0; sw < 3; ++sw)
+      if (te.in[sw]) a.maps[m * plane + te.off[sw]] = s_out[m * (kThreads * 3) + tid + kThreads * sw];
   part = chs_warp_sum(part);
   if ((tid & 31) == 0) s_red[tid >> 5] = part;
   __syncthreads();
@@ -178,19 +203,18 @@ __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(SsimArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(SsimArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) ssim_bwd_kernel(SsimArgs a) {
   __shared__ __align__(16) float s_m[3][kExt][kPW];    // one derivative map, three channels, with halo; reused for the output
   __shared__ __align__(16) float s_h[3][kExt][kTile];  // its horizontal pass
   __shared__ float s_c[2][kThreads * 3];               // x and y of the tile's own pixels, [pixel][channel]
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile, img = blockIdx.z;
   const int64_t plane = (int64_t)a.n_img * a.H * a.W * 3;
-  for (int i = tid; i < kThreads * 3; i += kThreads) {
-    const int py = y0 + i / (kTile * 3), px = x0 + (i % (kTile * 3)) / 3, c = i % 3;
-    const bool in = px < a.W && py < a.H;
-    const int64_t o = (((int64_t)img * a.H + py) * a.W + px) * 3 + c;
-    s_c[0][i] = in ? a.x[o] : 0.f;
-    s_c[1][i] = in ? a.y[o] : 0.f;
+  const TileElems te = tile_elems(img, a.H, a.W, y0, x0, tid);
+#pragma unroll
+  for (int sw = 0; sw < 3; ++sw) {
+    s_c[0][tid + kThreads * sw] = te.in[sw] ? a.x[te.off[sw]] : 0.f;
+    s_c[1][tid + kThreads * sw] = te.in[sw] ? a.y[te.off[sw]] : 0.f;
   }
   const int tx = tid % kTile, grp = tid / kTile;
   const int ch = grp / 4, r0 = (grp % 4) * 4;
@@ -237,12 +261,13 @@ __global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(SsimArgs a) {
     for (int j = 0; j < 4; ++j) s_out[((r0 + j) * kTile + tx) * 3 + ch] = acc[j];
   }
   __syncthreads();
-  for (int i = tid; i < kThreads * 3; i += kThreads) {
-    const int py = y0 + i / (kTile * 3), px = x0 + (i % (kTile * 3)) / 3, c = i % 3;
-    if (px < a.W && py < a.H) {
+#pragma unroll
+  for (int sw = 0; sw < 3; ++sw) {
+    if (te.in[sw]) {
+      const int i = tid + kThreads * sw;
       const float d = s_c[0][i] - s_c[1][i];
       const float l1 = d > 0.f ? a.l1_scale : (d < 0.f ? -a.l1_scale : 0.f);
-      a.v_x[(((int64_t)img * a.H + py) * a.W + px) * 3 + c] = l1 - a.ssim_scale * s_out[i];
+      a.v_x[te.off[sw]] = l1 - a.ssim_scale * s_out[i];
     }
   }
 }
