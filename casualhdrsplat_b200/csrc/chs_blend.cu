@@ -609,16 +609,17 @@ __device__ __forceinline__ void bwd_round(const Smem& sm, const BwdWarpSmem<kSlo
 #pragma unroll
     for (int i = 0; i < 9; ++i) t[i] += __shfl_xor_sync(CHS_FULL_MASK, t[i], o);
   if (active) {
-    const float k2 = -2.0f / CHS_LOG2E;
-    const float g0 = k2 * sa.z * t[0];                  // sum v_sigma A u
-    const float g1 = fmaf(sa.w, g0, k2 * sb.x * t[1]);  // sum v_sigma (B dx + C dy)
+    ChsSplat<float> sp;
+    sp.qa = sa.z; sp.r = sa.w; sp.kc = sb.x; sp.inv_opac = inv_opac;
+    float g[9];
+    chs_moments_to_grads(sp, t, g);  // csrc/chs_math.cuh, checked on the host against chs_pair_bwd and the oracle
     const uint32_t val = (uint32_t)__float_as_int(sb.z);
     if (part == 0) {
-      atomicAdd(a.v_geom + val, make_float4(g0, g1, 0.5f * t[2], t[3]));
-      if (kParts < 3) atomicAdd(a.v_blue + val, t[8]);
+      atomicAdd(a.v_geom + val, make_float4(g[0], g[1], g[2], g[3]));
+      if (kParts < 3) atomicAdd(a.v_blue + val, g[8]);
     }
-    if (part == (kParts > 1 ? 1 : 0)) atomicAdd(a.v_cogr + val, make_float4(0.5f * t[4], -t[5] * inv_opac, t[6], t[7]));
-    if (kParts >= 3 && part == 2) atomicAdd(a.v_blue + val, t[8]);
+    if (part == (kParts > 1 ? 1 : 0)) atomicAdd(a.v_cogr + val, make_float4(g[4], g[5], g[6], g[7]));
+    if (kParts >= 3 && part == 2) atomicAdd(a.v_blue + val, g[8]);
   }
   __syncwarp();  // the table is rewritten by the next round
 }

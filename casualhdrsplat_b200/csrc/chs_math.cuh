@@ -466,6 +466,49 @@ CHS_HD void chs_pair_bwd(const ChsSplat<T>& s, T dx, T dy, T u, T alpha_unclampe
   g[5] = -v_sigma * s.inv_opac;
 }
 
+// Tabled form of the pair backward (blend_bwd2_kernel in chs_blend.cu evaluates exactly these three steps, packed two
+// pixels per lane).  All nine partials of a (pixel, Gaussian) pair are multiples of two scalars, vs = dL/dsigma and
+// f = alpha * T_before:
+//   phase A  chs_pair_bwd_scalars: the state update of chs_pair_bwd (same operations, same order), returning (vs, f);
+//   phase B  chs_pair_moments:     m += (vs u, vs dy, vs dx^2, vs dx dy, vs dy^2, vs, f v_r, f v_g, f v_b), summed over pixels;
+//            chs_moments_to_grads: the Gaussian's constants applied once to the sums.
+template <class T>
+CHS_HD void chs_pair_bwd_scalars(const ChsSplat<T>& s, T alpha_unclamped, T alpha, T& Tr, T buf[3], const T vh[3], T va_t, T& vs,
+                                 T& f) {
+  T ra = chs_rcp_fast(T(1) - alpha);
+  Tr = Tr * ra;  // transmittance before this Gaussian
+  f = alpha * Tr;
+  T v_alpha = (s.cr * Tr - buf[0] * ra) * vh[0] + (s.cg * Tr - buf[1] * ra) * vh[1] + (s.cb * Tr - buf[2] * ra) * vh[2] + va_t * ra;
+  buf[0] += s.cr * f;
+  buf[1] += s.cg * f;
+  buf[2] += s.cb * f;
+  vs = alpha_unclamped <= ChsK<T>::alpha_max ? -alpha_unclamped * v_alpha : T(0);  // no gradient through the 0.999 clamp
+}
+template <class T> CHS_HD void chs_pair_moments(T vs, T f, T dx, T dy, T u, const T vh[3], T m[9]) {
+  m[0] += vs * u;
+  m[1] += vs * dy;
+  m[2] += vs * dx * dx;
+  m[3] += vs * dx * dy;
+  m[4] += vs * dy * dy;
+  m[5] += vs;
+  m[6] += f * vh[0];
+  m[7] += f * vh[1];
+  m[8] += f * vh[2];
+}
+// g = [v_mx, v_my, v_A, v_B, v_C, v_opacity, v_r, v_g, v_b] from the moment sums (uses s.qa, s.r, s.kc, s.inv_opac)
+template <class T> CHS_HD void chs_moments_to_grads(const ChsSplat<T>& s, const T m[9], T g[9]) {
+  const T k2 = T(-2) / ChsK<T>::log2e;
+  g[0] = k2 * s.qa * m[0];
+  g[1] = s.r * g[0] + k2 * s.kc * m[1];
+  g[2] = T(0.5) * m[2];
+  g[3] = m[3];
+  g[4] = T(0.5) * m[4];
+  g[5] = -m[5] * s.inv_opac;
+  g[6] = m[6];
+  g[7] = m[7];
+  g[8] = m[8];
+}
+
 // ---------------------------------------------------------------------------------------------
 // A.7 camera response curve, MLP kind [D6]: per channel z = ln(X + 1e-5), h = relu(w1 z + b1),
 // y = sigmoid(w2 . h + b2).  params = [w1 (Hd) | b1 (Hd) | w2 (Hd) | b2].

@@ -75,9 +75,11 @@ static void project_bwd_impl(int N, int C, int W, int H, T eps2d, const T* means
 
 // One tile list blended over a set of pixels, forward then backward, the way the kernels walk it.
 // splat params per list entry: mean2d (2), conic (3), opacity, rgb (3) = 9 numbers.
+// tabled != 0: the backward in the form blend_bwd2_kernel uses (per-pair scalars -> moment sums -> gradients)
 template <class T>
 static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, const T* bg, const T* v_hdr, const T* v_alpha,
-                       T* out_hdr, T* out_alpha, int32_t* out_last, T* v_params) {
+                       T* out_hdr, T* out_alpha, int32_t* out_last, T* v_params, int tabled = 0) {
+  std::vector<T> moments((size_t)n_list * 9, T(0));
   std::vector<ChsSplat<T>> sp(n_list);
   for (int j = 0; j < n_list; ++j) {
     const T* p = params + j * 9;
@@ -118,12 +120,20 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
       T power = chs_pair_power(sp[j], px, py, dx, dy, u);
       if (!(power >= thr)) continue;
       T au = chs_exp2_fast(power);
+      if (tabled) {
+        T vs, f;
+        chs_pair_bwd_scalars(sp[j], au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, vs, f);
+        chs_pair_moments(vs, f, dx, dy, u, vh, &moments[(size_t)j * 9]);
+        continue;
+      }
       T g[9];
       chs_pair_bwd(sp[j], dx, dy, u, au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, g);
       // g = [v_mx, v_my, v_A, v_B, v_C, v_o, v_r, v_g, v_b] -> params order (mx,my,A,B,C,o,r,g,b)
       for (int k = 0; k < 9; ++k) v_params[j * 9 + k] += g[k];
     }
   }
+  if (tabled)
+    for (int j = 0; j < n_list; ++j) chs_moments_to_grads(sp[j], &moments[(size_t)j * 9], v_params + (size_t)j * 9);
 }
 
 extern "C" {
@@ -157,6 +167,14 @@ void hs_blend_f64(int n_list, const double* params, int n_pix, const double* pix
 void hs_blend_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
                   const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
   blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params);
+}
+void hs_blend_tabled_f64(int n_list, const double* params, int n_pix, const double* pix_xy, const double* bg, const double* v_hdr,
+                         const double* v_alpha, double* out_hdr, double* out_alpha, int32_t* out_last, double* v_params) {
+  blend_impl<double>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 1);
+}
+void hs_blend_tabled_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
+                         const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
+  blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 1);
 }
 // brute-force check helper: the culling bound for a block vs the true maximum over its pixel centres
 void hs_block_bound_f32(int n, const float* params /* mx,my,A,B,C,o */, const float* rect /* x0,x1,y0,y1 */, float* bound, float* brute) {
