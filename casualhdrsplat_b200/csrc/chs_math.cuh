@@ -222,6 +222,8 @@ CHS_HD int chs_project_fwd(const T mu[3], const T S[6], const ChsCam<T>& cam, T 
 // with tau = 2 (ln(255 o) + margin).  Returns rx | ry << 16 with rx = min(radius, ceil(sqrt(tau Sxx)))
 // (likewise ry), each in [1, 65535], or 0 when tau <= 0 (the Gaussian can never reach 1/255).  The
 // tight rectangle only drops tiles whose every pixel fails the alpha test, so images are unchanged.
+// 65535 means "unbounded along this axis" (a splat wider than 65534 pixels): chs_tile_bounds_of then
+// takes every tile column / row, which is a superset of what the classic square would give.
 #define CHS_TIGHT_MARGIN 2e-3
 template <class T> CHS_HD int chs_tight_radii(T sxx, T syy, T opacity, int radius) {
   const T tau = T(2) * (log(T(255) * opacity) + T(CHS_TIGHT_MARGIN));
@@ -372,8 +374,12 @@ CHS_HD ChsTileRect chs_tile_bounds(float mx, float my, int radius, int tile_w, i
 }
 // `radii` entry -> tile rectangle: a plain radius, or the packed per-axis radii of chs_config.tight_bounds
 CHS_HD ChsTileRect chs_tile_bounds_of(float mx, float my, int radii_entry, int tight, int tile_w, int tile_h) {
-  return tight ? chs_tile_bounds2(mx, my, radii_entry & 0xffff, (radii_entry >> 16) & 0xffff, tile_w, tile_h)
-               : chs_tile_bounds2(mx, my, radii_entry, radii_entry, tile_w, tile_h);
+  if (!tight) return chs_tile_bounds2(mx, my, radii_entry, radii_entry, tile_w, tile_h);
+  const int rx = radii_entry & 0xffff, ry = (radii_entry >> 16) & 0xffff;
+  ChsTileRect r = chs_tile_bounds2(mx, my, rx, ry, tile_w, tile_h);
+  if (rx == 0xffff) { r.x0 = 0; r.x1 = tile_w; }  // unbounded axis (see chs_tight_radii)
+  if (ry == 0xffff) { r.y0 = 0; r.y1 = tile_h; }
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------

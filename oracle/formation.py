@@ -58,7 +58,8 @@ def project(means, quats, scales, viewmats, Ks, width, height, near=0.01, far=1e
     sigma(d) <= ln(255 o), whose axis-aligned bounding box has half extents sqrt(tau Sxx), sqrt(tau Syy) with
     tau = 2 (ln(255 o) + TIGHT_MARGIN) and S the 2D covariance (after the eps2d blur).  The radii become
     rx = min(r, ceil(sqrt(tau Sxx))), ry = min(r, ceil(sqrt(tau Syy))) (r the classic 3-sigma radius), returned PACKED as
-    rx | ry << 16; a Gaussian with tau <= 0 can never reach 1/255 and is culled.  Because the tight rectangle only
+    rx | ry << 16 (65535 = unbounded along that axis, for splats wider than 65534 pixels); a Gaussian with tau <= 0 can
+    never reach 1/255 and is culled.  Because the tight rectangle only
     drops tiles in which every pixel fails the alpha >= 1/255 test, rendered images and gradients are unchanged.
     """
     means, quats, scales, viewmats, Ks = map(_f64, (means, quats, scales, viewmats, Ks))
@@ -156,6 +157,12 @@ def tile_bounds(means2d_f32, radii_i32, width, height, tile=TILE, tight=False):
 
     min_x, max_x = lo(tx, trx, tile_w), hi(tx, trx, tile_w)
     min_y, max_y = lo(ty, try_, tile_h), hi(ty, try_, tile_h)
+    if tight:  # 65535 = unbounded axis: every tile column / row
+        ux, uy = (radii_i32 & 0xFFFF) == 0xFFFF, ((radii_i32 >> 16) & 0xFFFF) == 0xFFFF
+        min_x = torch.where(ux, torch.zeros_like(min_x), min_x)
+        max_x = torch.where(ux, torch.full_like(max_x, tile_w), max_x)
+        min_y = torch.where(uy, torch.zeros_like(min_y), min_y)
+        max_y = torch.where(uy, torch.full_like(max_y, tile_h), max_y)
     touched = (max_x - min_x) * (max_y - min_y)
     touched = torch.where(radii_i32 > 0, touched, torch.zeros_like(touched))
     return min_x, min_y, max_x, max_y, touched

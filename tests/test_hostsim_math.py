@@ -131,6 +131,21 @@ def test_tight_bounds_radii_and_rectangles():
     for k, t in enumerate([x0, y0, x1, y1]):
         assert np.array_equal(rect[live, k], t.numpy()[live])
     assert int(touched[~torch.from_numpy(live)].sum()) == 0
+    # a splat wider than 65534 pixels whose mean is far off screen: the packed radius saturates at 65535 = unbounded, and the
+    # rectangle must still cover the screen (the classic square of the true radius would)
+    big = np.zeros(2, np.int32)
+    b64 = np.zeros(2, np.int32)
+    HS.hs_tight_radii(2, _p(np.array([4e9, 100.0])), _p(np.array([50.0, 6e9])), _p(np.array([0.9, 0.9])),
+                      _p(np.array([200000, 250000], np.int32)), _p(b64), _p(big))
+    assert (big[0] & 0xFFFF) == 0xFFFF and (big[1] >> 16) & 0xFFFF == 0xFFFF and np.array_equal(big, b64)
+    rect2 = np.zeros((2, 4), np.int32)
+    far = np.array([-100000.0, 500.0], np.float32), np.array([300.0, 150000.0], np.float32)
+    HS.hs_tile_bounds_packed(2, _p(far[0]), _p(far[1]), _p(big), 120, 68, _p(rect2))
+    assert rect2[0, 0] == 0 and rect2[0, 2] == 120 and rect2[1, 1] == 0 and rect2[1, 3] == 68
+    o = oracle.tile_bounds(torch.stack([torch.from_numpy(far[0]), torch.from_numpy(far[1])], -1), torch.from_numpy(big.copy()), 1920, 1080,
+                           tight=True)
+    for k in range(4):
+        assert np.array_equal(rect2[:, k], o[k].numpy())
 
 
 def test_project_bwd_f64_matches_autograd():
