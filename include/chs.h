@@ -13,6 +13,14 @@
  *                   time", "implicit CRF"        /root/reference/assets/pipeline.png
  *   chs_crf_bwd     "joint estimation of camera motion, exposure time, and camera response curve"
  *                                                /root/reference/Readme.md:54
+ *   chs_sh_*        view-dependent HDR colour in front of the path; the reference's
+ *                   "3DGS" (Readme.md:54) evaluates spherical harmonics per camera
+ *   chs_loss, chs_ssim_loss, chs_adam_step
+ *                   "Jointly optimize" (assets/pipeline.png): the photometric loss on the blurred LDR frame B_i and
+ *                   the optimizer step behind the path
+ *   chs_rasterize_* the whole operator in two calls
+ *   chs_nvls_allreduce, chs_comm_*, chs_allreduce_grads
+ *                   gradient all-reduce of the frame-sharded step (BASELINE.json north_star)
  *
  * Conventions
  *  - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its name
