@@ -123,6 +123,22 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
       if (tabled) {
         T vs, f;
         chs_pair_bwd_scalars(sp[j], au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, vs, f);
+        if (tabled == 2) {  // what-if: the table held in IEEE half precision
+          vs = (T)(float)(_Float16)(float)vs;
+          f = (T)(float)(_Float16)(float)f;
+        } else if (tabled == 3) {  // what-if: bfloat16 (round to nearest even on the top 16 bits)
+          auto bf = [](T v) {
+            float x = (float)v;
+            uint32_t b;
+            std::memcpy(&b, &x, 4);
+            b += 0x7fffu + ((b >> 16) & 1u);
+            b &= 0xffff0000u;
+            std::memcpy(&x, &b, 4);
+            return (T)x;
+          };
+          vs = bf(vs);
+          f = bf(f);
+        }
         chs_pair_moments(vs, f, dx, dy, u, vh, &moments[(size_t)j * 9]);
         continue;
       }
@@ -175,6 +191,11 @@ void hs_blend_tabled_f64(int n_list, const double* params, int n_pix, const doub
 void hs_blend_tabled_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
                          const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
   blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 1);
+}
+// design study (DESIGN.md "next levers"): mode 2 = table in fp16, 3 = bf16
+void hs_blend_tabled_lowp_f32(int mode, int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
+                              const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
+  blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, mode);
 }
 // brute-force check helper: the culling bound for a block vs the true maximum over its pixel centres
 void hs_block_bound_f32(int n, const float* params /* mx,my,A,B,C,o */, const float* rect /* x0,x1,y0,y1 */, float* bound, float* brute) {

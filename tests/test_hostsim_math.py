@@ -247,6 +247,30 @@ def test_blend_pair_math_matches_oracle(dtype, form):
         assert rel(o_v[:, k], ref[:, k]) < gtol, (k, rel(o_v[:, k], ref[:, k]))
 
 
+def test_design_study_low_precision_table():
+    """DESIGN.md "next levers" 1: would a 16-bit table of (vs, f) keep the gradients inside the 1e-3 bar?  fp16 does, with
+    little margin (and needs range management for HDR magnitudes); bfloat16 does not.  Pins the numbers the decision rests on."""
+    m, conic, o, col, pix, bg = _tile_case()
+    n_list, n_pix = m.shape[0], pix.shape[0]
+    leaves = [t.clone().requires_grad_(True) for t in (m, conic, o, col)]
+    hdr, alpha, _ = oracle.blend(leaves[0][None], leaves[1][None], leaves[2], leaves[3], torch.arange(n_list, dtype=torch.int32),
+                                 torch.tensor([0, n_list]), n_list, 16, 16, background=bg)
+    g = torch.Generator().manual_seed(3)
+    vh, va = torch.randn(16, 16, 3, generator=g), torch.randn(16, 16, generator=g)
+    grads = torch.autograd.grad((hdr[0] * vh).sum() + (alpha[0] * va).sum(), leaves)
+    ref = torch.cat([grads[0], grads[1], grads[2][:, None], grads[3]], 1).numpy()
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np.float32))
+    params = arr(torch.cat([m, conic, o[:, None], col], 1))
+    worst = {}
+    for mode, name in [(1, "fp32"), (2, "fp16"), (3, "bf16")]:
+        o_h = np.zeros((n_pix, 3), np.float32); o_a = np.zeros(n_pix, np.float32); o_l = np.zeros(n_pix, np.int32)
+        o_v = np.zeros((n_list, 9), np.float32)
+        HS.hs_blend_tabled_lowp_f32(mode, n_list, _p(params), n_pix, _p(arr(pix)), _p(arr(bg)), _p(arr(vh.reshape(-1, 3))),
+                                    _p(arr(va.reshape(-1))), _p(o_h), _p(o_a), _p(o_l), _p(o_v))
+        worst[name] = max(np.linalg.norm(o_v[:, k] - ref[:, k]) / np.linalg.norm(ref[:, k]) for k in range(9))
+    assert worst["fp32"] < 5e-6 and 5e-5 < worst["fp16"] < 1e-3 and worst["bf16"] > 1e-3, worst
+
+
 def test_block_cull_bound_is_conservative_and_tight():
     """chs_block_max_power >= max over the block's pixel centres (never culls a live pair) and is tight."""
     g = torch.Generator().manual_seed(9)
