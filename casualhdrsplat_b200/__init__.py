@@ -7,11 +7,11 @@ library or without a CUDA device raises.
 """
 from .scene import CRF_IDENTITY, CRF_LUT, CRF_MLP, SPLINE_CUBIC, SPLINE_LINEAR  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 
 def __getattr__(name):
-    if name in ("rasterize", "rasterize_sharded", "RasterizeMeta"):
+    if name == "rasterize":
         from . import api
         return getattr(api, name)
     raise AttributeError(name)

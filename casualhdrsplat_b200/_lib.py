@@ -22,7 +22,9 @@ class ChsConfig(ctypes.Structure):
         ("n_gauss", c_int32), ("n_frames", c_int32), ("n_virtual", c_int32), ("width", c_int32), ("height", c_int32),
         ("tile_size", c_int32), ("near_plane", c_float), ("far_plane", c_float), ("eps2d", c_float),
         ("crf_kind", c_int32), ("crf_hidden", c_int32), ("crf_before_average", c_int32), ("ks_per_camera", c_int32),
-        ("sort_mode", c_int32), ("background", c_float * 3), ("rgbo_per_camera", c_int32), ("tight_bounds", c_int32), ("reserved", c_int32 * 2),
+        ("sort_mode", c_int32), ("background", c_float * 3), ("rgbo_per_camera", c_int32), ("tight_bounds", c_int32), ("pose_fused", c_int32),
+        ("tune_blend_fwd", c_int32), ("tune_blend_bwd", c_int32), ("tune_crf_bwd", c_int32), ("tune_bin", c_int32),
+        ("tune_bin_chunk", c_int32), ("reserved", c_int32 * 2),
     ]
 
 
@@ -52,6 +54,7 @@ SIGNATURES = {
     "chs_version": (ctypes.c_int, []),
     "chs_last_error": (c_char_p, []),
     "chs_launch_count": (c_uint64, []),
+    "chs_sizeof": (c_uint64, [c_int32]),
     "chs_workspace_query": (ctypes.c_int, [CFG, c_int64, c_int32, POINTER(ChsWorkspaceSizes)]),
     "chs_spline_fwd": (ctypes.c_int, [c_int32, P, c_int32, c_double, c_double, P, P, c_int32, c_int32, P, P]),
     "chs_spline_bwd": (ctypes.c_int, [c_int32, P, c_int32, c_double, c_double, P, P, c_int32, c_int32, P, P, P, P, P, c_uint64, P]),
@@ -93,6 +96,10 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        for which, struct in enumerate([ChsConfig, ChsWorkspaceSizes, ChsTensors]):
+            if l.chs_sizeof(which) != ctypes.sizeof(struct):
+                raise RuntimeError(f"{LIB_PATH}: stale build ({struct.__name__} is {l.chs_sizeof(which)} bytes in the library, "
+                                   f"{ctypes.sizeof(struct)} in the binding); rebuild with `make -C casualhdrsplat_b200/csrc`")
         _LIB = l
     return _LIB
 
@@ -113,7 +120,9 @@ def ptr(t):
 
 def make_config(n_gauss, n_frames, n_virtual, width, height, *, near=0.01, far=1e10, eps2d=0.3, tile_size=16,
                 crf_kind=CHS_CRF_IDENTITY, crf_hidden=0, crf_before_average=False, ks_per_camera=False,
-                sort_mode=CHS_SORT_DEPTH_PRESORT, background=None, rgbo_per_camera=False, tight_bounds=False) -> ChsConfig:
+                sort_mode=CHS_SORT_DEPTH_PRESORT, background=None, rgbo_per_camera=False, tight_bounds=False, pose_fused=False,
+                tuning=None) -> ChsConfig:
+    """``tuning``: optional dict of development knobs {blend_fwd, blend_bwd, crf_bwd, bin, bin_chunk} (chs_config.tune_*)."""
     cfg = ChsConfig()
     cfg.n_gauss, cfg.n_frames, cfg.n_virtual = int(n_gauss), int(n_frames), int(n_virtual)
     cfg.width, cfg.height, cfg.tile_size = int(width), int(height), int(tile_size)
@@ -124,6 +133,11 @@ def make_config(n_gauss, n_frames, n_virtual, width, height, *, near=0.01, far=1
     cfg.sort_mode = int(sort_mode)
     cfg.rgbo_per_camera = int(bool(rgbo_per_camera))
     cfg.tight_bounds = int(bool(tight_bounds))
+    cfg.pose_fused = int(bool(pose_fused))
+    for k, v in (tuning or {}).items():
+        if not hasattr(cfg, "tune_" + k):
+            raise RuntimeError(f"make_config: unknown tuning knob `{k}`")
+        setattr(cfg, "tune_" + k, int(v))
     bg = (0.0, 0.0, 0.0) if background is None else tuple(float(v) for v in background)
     cfg.background[0], cfg.background[1], cfg.background[2] = bg
     return cfg

@@ -234,7 +234,7 @@ class _Rasterize(torch.autograd.Function):
 def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, width=0, height=0, exposure_times=None,
               n_virtual=1, crf_kind=_lib.CHS_CRF_IDENTITY, crf_params=None, *, spline=None, background=None, near=0.01,
               far=1e10, eps2d=0.3, tile_size=16, crf_before_average=False, return_hdr=False, sort_mode="presort", tight_bounds=False,
-              debug_keys=False, grad_hook=None, sh_coeffs=None, sh_degree=None):
+              debug_keys=False, grad_hook=None, sh_coeffs=None, sh_degree=None, pose_fused=False, tuning=None):
     """Render the blurred LDR frames ``B_i = F_theta(dt_i * mean_k H_{i,k})`` and make them differentiable.
 
     Args (all tensors CUDA float32):
@@ -249,6 +249,9 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         tight_bounds: bin with opacity-aware per-axis bounds (the box of the alpha >= 1/255 ellipse inside the classic
         3-sigma square) — identical images and gradients, about a third fewer intersections; meta["state"].radii then
         holds packed rx | ry << 16.
+        pose_fused: the n virtual poses of a frame share one tile list per (frame, tile) (a flagged
+        variant of the model, see chs_config.pose_fused): n-fold less binning work, per-pose projection and alpha tests kept.
+        tuning: dict of development knobs (chs_config.tune_*: blend_fwd, blend_bwd, crf_bwd, bin, bin_chunk).
         sh_coeffs [N,K,3] (+ sh_degree <= 3, K >= (deg+1)^2 read as the first coefficients): view-dependent HDR colour
         max(0, 0.5 + sum_k sh_k Y_k(view direction)) evaluated per virtual camera; `colors` may then be None.
     Returns:
@@ -289,7 +292,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     cfg = _lib.make_config(N, B, n_virtual, width, height, near=near, far=far, eps2d=eps2d, tile_size=tile_size,
                            crf_kind=crf_kind, crf_hidden=crf_hidden, crf_before_average=crf_before_average,
                            ks_per_camera=ks_per_camera, sort_mode=_SORT_MODES[sort_mode], background=background,
-                           tight_bounds=tight_bounds)
+                           tight_bounds=tight_bounds, pose_fused=pose_fused, tuning=tuning)
     opts = {"cfg": cfg, "spline_kind": None, "knot_t0": 0.0, "knot_dt": 1.0, "want_keys": bool(debug_keys), "state_out": [],
             "grad_hook": grad_hook, "sh_degree": int(sh_degree) if sh is not None else 0}
     if spline is not None:

@@ -21,6 +21,9 @@ void chs_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" uint64_t chs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int chs_version(void) { return CHS_VERSION; }
+extern "C" uint64_t chs_sizeof(int32_t which) {
+  return which == 0 ? sizeof(chs_config) : which == 1 ? sizeof(chs_workspace_sizes) : which == 2 ? sizeof(chs_tensors) : 0;
+}
 extern "C" const char* chs_last_error(void) { return g_err; }
 
 int chs_make_dims(const chs_config* cfg, ChsDims* d) {
@@ -43,7 +46,8 @@ int chs_make_dims(const chs_config* cfg, ChsDims* d) {
   d->cam_bits = chs_bit_length((uint64_t)d->C);
   d->CN = (int64_t)d->C * d->N;
   d->P = (int64_t)d->W * d->H;
-  CHS_REQUIRE(d->C <= 4096, "too many cameras in one call (%d)", d->C);
+  // the projection kernels keep the whole camera table in shared memory (112 B per camera in the backward)
+  CHS_REQUIRE(d->C <= 1024, "too many cameras in one call (%d > 1024 = frames x virtual poses); split the frame batch", d->C);
   CHS_REQUIRE(d->CN < ((int64_t)1 << 31), "C*N = %lld exceeds int32 ids; split the frame batch", (long long)d->CN);
   CHS_REQUIRE((int64_t)d->C * d->tiles < ((int64_t)1 << 31), "C*tiles exceeds int32");
   CHS_REQUIRE(32 + d->tile_bits + d->cam_bits <= 64, "key does not fit 64 bits");
@@ -227,6 +231,7 @@ extern "C" int chs_rasterize_fwd(const chs_config* cfg, const chs_tensors* t, in
   int st = chs_make_dims(cfg, &d);
   if (st) return st;
   CHS_REQUIRE(t && n_isect_out, "chs_rasterize_fwd: null argument");
+  CHS_REQUIRE(!cfg->rgbo_per_camera, "chs_rasterize_fwd: per-camera colour records (SH) need the staged entry points (chs_sh_fwd + chs_blend_fwd)");
   CHS_REQUIRE(t->viewmats && t->workspace, "chs_rasterize_fwd: viewmats / workspace required");
   if (t->spline_kind >= 0) {
     st = chs_spline_fwd(t->spline_kind, t->knots, t->n_knots, t->knot_t0, t->knot_dt, t->frame_times, t->exposure, d.B, d.n,
@@ -257,6 +262,7 @@ extern "C" int chs_rasterize_bwd(const chs_config* cfg, const chs_tensors* t, in
   int st = chs_make_dims(cfg, &d);
   if (st) return st;
   CHS_REQUIRE(t && t->workspace && t->v_ldr, "chs_rasterize_bwd: null argument");
+  CHS_REQUIRE(!cfg->rgbo_per_camera, "chs_rasterize_bwd: per-camera colour records (SH) need the staged entry points");
   (void)n_isect;
   st = chs_crf_bwd(cfg, t->hdr_mean, t->exposure, t->crf_params, t->v_ldr, t->v_hdr, t->v_crf_params, t->v_exposure, t->workspace,
                    t->workspace_bytes, stream);

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
     id = order ? order[i] : (int32_t)i;
     off = offsets[i];
     const int radius = radii[id];
-    if (radius > 0) {
+    if (radius != 0) {
       const float4 gm = geom[id];
       const ChsTileRect r = chs_tile_bounds_of(gm.x, gm.y, radius, tight, tile_w, tile_h);
       x0 = r.x0; y0 = r.y0;
@@ -224,7 +224,7 @@ __global__ void rects_kernel(int64_t CN, int tile_w, int tile_h, int tight, cons
   const int32_t id = order[i];
   const int radius = radii[id];
   ushort4 r = make_ushort4(0, 0, 0, 0);
-  if (radius > 0) {
+  if (radius != 0) {
     const float4 gm = geom[id];
     const ChsTileRect t = chs_tile_bounds_of(gm.x, gm.y, radius, tight, tile_w, tile_h);
     r = make_ushort4((unsigned short)t.x0, (unsigned short)t.y0, (unsigned short)t.x1, (unsigned short)t.y1);

@@ -26,15 +26,13 @@
 //   blend_bwd2_kernel (default, "tabled"): the per-pixel sequential part runs pixel-parallel and leaves two
 //     scalars per (pixel, Gaussian) in a per-warp shared-memory table; every 8 Gaussians the lanes switch
 //     to one Gaussian each and sum their table rows privately (see the comment above the kernel).
-//   blend_bwd_kernel (CHS_BLEND_BWD_VARIANT=1, "direct"): the nine per-Gaussian partials of the thread's two
+//   blend_bwd_kernel (chs_config.tune_blend_bwd = 1, "direct"): the nine per-Gaussian partials of the thread's two
 //     pixels are added, then reduced across the warp with a transposing butterfly (14 shuffles instead of
 //     45) that leaves value j on lane j, so a single RED instruction with nine active lanes adds all nine
 //     numbers into the three [C,N] gradient planes.
 // Negative results kept out of the code (r1g, c3): prefetching the next survivor's staged record inside the
 // forward pair loop (to hide the bit-scan -> address -> LDS chain) made K6 2.55 -> 2.95 ms at 64 registers and
 // 3.00 ms at 72; software-pipelining phase A of the tabled backward cost +0.5 ms.
-#include <stdlib.h>
-
 #include "chs_common.cuh"
 
 namespace {
@@ -781,12 +779,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd2_kernel(BlendB
 
 }  // namespace
 
-// tuning knob (development): selects the min-blocks-per-SM instantiation of the blend kernels
-static int blend_variant(const char* name) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : 0;
-}
-
 static size_t crf_smem_bytes(const chs_config* cfg) {
   return (size_t)3 * chs_crf_stride(cfg->crf_kind, cfg->crf_hidden) * sizeof(float);
 }
@@ -816,7 +808,7 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   if (cfg->crf_before_average) {
     blend_fwd_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
   } else {
-    switch (blend_variant("CHS_BLEND_FWD_VARIANT")) {
+    switch (cfg->tune_blend_fwd) {  // development knob (chs_config)
       case 1: blend_fwd_kernel<6, false><<<grid, kThreads, dyn, s>>>(a); break;
       case 3: blend_fwd_kernel<10, false><<<grid, kThreads, dyn, s>>>(a); break;
       default: blend_fwd_kernel<8, false><<<grid, kThreads, dyn, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
@@ -855,7 +847,7 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   // r1g sweep on c3 (ms per frame of 8 poses, tight bounds): direct kernel 6.07 | tabled 16 slots / batch 256 / 4 CTAs per SM 5.36 |
   // 16 / 128 / 5: 5.21 | 8 / 128 / 7: 5.01 (default) | 8 / 128 / 8 (64 registers, spills) 5.18 | 8 / 64 / 8: 5.12 | 8 / 256 / 6: 5.51 |
   // 12 / 128 / 6: 5.64 | 10 / 128 / 6: 5.69 (idle lanes in phase B) | software-pipelined phase A (kPipe): +0.5 ms in every configuration
-  switch (blend_variant("CHS_BLEND_BWD_VARIANT")) {
+  switch (cfg->tune_blend_bwd) {  // development knob (chs_config)
     case 1: blend_bwd_kernel<1, 8><<<grid, kThreads, 0, s>>>(a); break;          // the direct (r1d-f) kernel, two pixels per thread
     case 22: blend_bwd_kernel<2, 12><<<grid, kThreads / 2, 0, s>>>(a); break;    // direct, four pixels per thread
     case 40: CHS_BWD2_ATTR(16, 256, 4, false); CHS_BWD2_LAUNCH(16, 256, 4, false); break;  // 50 KB of dynamic shared memory: opt in

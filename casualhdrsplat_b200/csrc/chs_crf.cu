@@ -1,8 +1,6 @@
 // chs_crf.cu — K7 crf_bwd: gradient of the formation epilogue B = F_theta(dt * mean_k H_k)
 // (SURVEY.md Appendix A.7).  Streaming per-pixel kernel; the CRF parameter gradients are reduced
 // warp -> shared memory -> fp64 global accumulators.
-#include <stdlib.h>
-
 #include "chs_common.cuh"
 
 namespace {
@@ -76,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_kernel(CrfBwdArg
       float xe[kPix], zz[kPix], acc[kPix], dz[kPix];
 #pragma unroll
       for (int q = 0; q < kPix; ++q) {
-        xe[q] = dt * h[q] + CHS_CRF_EPS;
+        xe[q] = fmaxf(dt * h[q], 0.f) + CHS_CRF_EPS;  // X clamped to >= 0 (chs_crf_mlp_fwd)
         zz[q] = logf(xe[q]);
         acc[q] = p[3 * a.hd];
         dz[q] = 0.f;
@@ -97,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_kernel(CrfBwdArg
       for (int q = 0; q < kPix; ++q) {
         const float y = 1.f / (1.f + expf(-acc[q]));
         const float g = vy[q] * y * (1.f - y);  // 0 for pixels past the end: they add nothing below
-        vx[q] = g * dz[q] / xe[q];
+        vx[q] = dt * h[q] >= 0.f ? g * dz[q] / xe[q] : 0.f;  // zero gradient below the clamp
         s_z[ch * (kThreads * kPix) + q * kThreads + tid] = zz[q];
         s_gy[ch * (kThreads * kPix) + q * kThreads + tid] = g;
       }
@@ -226,8 +224,7 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
     a.acc_crf = acc; a.acc_exposure = acc + n_par;
     const int64_t n_chunks = (d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix);
     const int n_img = per_pose ? d.C : d.B;
-    const char* ev = getenv("CHS_CRF_BWD_VARIANT");  // development knob: resident blocks per SM
-    const int mb = ev ? atoi(ev) : 4;  // r1g, c3: 2 -> 0.306 ms, 3 -> 0.296, 4 -> 0.280 (previous phase-1 loop order: 0.317)
+    const int mb = cfg->tune_crf_bwd ? cfg->tune_crf_bwd : 4;  // development knob (chs_config): resident blocks per SM  // r1g, c3: 2 -> 0.306 ms, 3 -> 0.296, 4 -> 0.280 (previous phase-1 loop order: 0.317)
     int gx = (148 * mb + n_img - 1) / n_img;  // one wave of resident blocks over all images
     if (gx > n_chunks) gx = (int)n_chunks;
     dim3 grid((unsigned)gx, n_img);

@@ -231,7 +231,7 @@ template <class T> CHS_HD int chs_tight_radii(T sxx, T syy, T opacity, int radiu
   const T cap = T(radius < 65535 ? radius : 65535);
   const T rx = chs_max(T(1), chs_min(cap, ceil(sqrt(tau * sxx))));
   const T ry = chs_max(T(1), chs_min(cap, ceil(sqrt(tau * syy))));
-  return (int)rx | ((int)ry << 16);
+  return (int)((uint32_t)rx | ((uint32_t)ry << 16));  // an unsigned pair: consumers gate on != 0, never on > 0
 }
 
 // A.3 backward for one (camera, Gaussian): given v_mean2d and v_conic, accumulate
@@ -519,8 +519,10 @@ template <class T> CHS_HD void chs_moments_to_grads(const ChsSplat<T>& s, const 
 // A.7 camera response curve, MLP kind [D6]: per channel z = ln(X + 1e-5), h = relu(w1 z + b1),
 // y = sigmoid(w2 . h + b2).  params = [w1 (Hd) | b1 (Hd) | w2 (Hd) | b2].
 // ---------------------------------------------------------------------------------------------
+// Exposure X = dt * H is clamped to >= 0 before the logarithm (zero gradient w.r.t. X below the clamp): an optimiser stepping
+// on unclamped per-Gaussian colours can drive H slightly negative, and ln(X + 1e-5) must not turn that into NaN.
 template <class T> CHS_HD T chs_crf_mlp_fwd(T X, const T* p, int hd) {
-  T z = log(X + ChsK<T>::crf_eps);
+  T z = log(chs_max(X, T(0)) + ChsK<T>::crf_eps);
   T acc = p[3 * hd];
   for (int j = 0; j < hd; ++j) acc += p[2 * hd + j] * chs_max(T(0), p[j] * z + p[hd + j]);
   return T(1) / (T(1) + exp(-acc));
@@ -528,7 +530,7 @@ template <class T> CHS_HD T chs_crf_mlp_fwd(T X, const T* p, int hd) {
 
 // Returns dy/dX (for v_X = v_y * dy/dX) and, if v_p != nullptr, accumulates v_y * dy/dparams into v_p.
 template <class T> CHS_HD T chs_crf_mlp_bwd(T X, const T* p, int hd, T v_y, T* v_p) {
-  T xe = X + ChsK<T>::crf_eps;
+  T xe = chs_max(X, T(0)) + ChsK<T>::crf_eps;
   T z = log(xe);
   T acc = p[3 * hd];
   T dz = T(0);
@@ -553,7 +555,7 @@ template <class T> CHS_HD T chs_crf_mlp_bwd(T X, const T* p, int hd, T v_y, T* v
     }
     v_p[3 * hd] += gy;
   }
-  return y * (T(1) - y) * dz / xe;
+  return X >= T(0) ? y * (T(1) - y) * dz / xe : T(0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -573,11 +575,11 @@ template <class T> struct ChsLutPos {
 
 template <class T> CHS_HD ChsLutPos<T> chs_crf_lut_pos(T X, const T* p, int L) {
   ChsLutPos<T> r;
-  r.xe = X + ChsK<T>::crf_eps;
+  r.xe = chs_max(X, T(0)) + ChsK<T>::crf_eps;  // X clamped to >= 0, zero gradient below (see chs_crf_mlp_fwd)
   const T z = log(r.xe);
   const T scale = T(L - 1) / (p[1] - p[0]);
   T u = (z - p[0]) * scale;
-  r.du_dz = (u > T(0) && u < T(L - 1)) ? scale : T(0);
+  r.du_dz = (u > T(0) && u < T(L - 1) && X >= T(0)) ? scale : T(0);
   u = chs_min(chs_max(u, T(0)), T(L - 1));
   int i = (int)u;
   if (i > L - 2) i = L - 2;

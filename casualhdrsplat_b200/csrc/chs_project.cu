@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) project_fwd_kernel(ProjectFwdArgs a)
     int radius = chs_project_fwd(mu, S, cam, a.width, a.height, a.near_plane, a.far_plane, a.eps2d, pr);
     if (radius > 0 && a.tight_bounds) radius = chs_tight_radii(pr.sxx, pr.syy, opac, radius);  // packed rx | ry << 16, or 0
     int touched = 0;
-    if (radius > 0) {
+    if (radius != 0) {  // packed tight radii are an unsigned pair: ry >= 32768 sets bit 31
       ChsTileRect r = chs_tile_bounds_of(pr.mx, pr.my, radius, a.tight_bounds, a.tile_w, a.tile_h);
       touched = (r.x1 - r.x0) * (r.y1 - r.y0);
     }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) project_bwd_kernel(ProjectBwdArgs a)
 
   for (int c = 0; c < a.C; ++c) {
     const int64_t o = (int64_t)c * a.N + g;
-    const bool hit = live && a.radii[o] > 0;
+    const bool hit = live && a.radii[o] != 0;
     float vcam[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) vcam[i] = 0.f;
@@ -232,6 +232,8 @@ extern "C" int chs_project_fwd(const chs_config* cfg, const float* means, const 
   a.geom = (float4*)geom; a.conic_c = conic_c; a.depths = depths; a.radii = radii; a.tiles_touched = tiles_touched; a.rgbo = (float4*)rgbo;
   size_t smem = (((size_t)d.C * kCamFloats + 3) & ~(size_t)3) * 4 + 3 * kThreads * 3 * 4;
   int blocks = (d.N + kThreads - 1) / kThreads;
+  // the camera table lives in dynamic shared memory (64 B per camera): above the 48 KB default the kernel must opt in
+  if (smem > 48 * 1024) CHS_CUDA(cudaFuncSetAttribute(project_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   project_fwd_kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(a);
   CHS_LAUNCH_CHECK();
   return CHS_OK;
@@ -265,6 +267,7 @@ extern "C" int chs_project_bwd(const chs_config* cfg, const float* means, const 
     a.quat_section_aligned = ((uintptr_t)(grads_flat + 3 * (size_t)d.N)) % 16 == 0;
     size_t smem = ((((size_t)d.C * kCamFloats + 3) & ~(size_t)3) + (((size_t)d.C * 12 + 3) & ~(size_t)3)) * 4 + 3 * kThreads * 3 * 4;
     int blocks = (d.N + kThreads - 1) / kThreads;
+    if (smem > 48 * 1024) CHS_CUDA(cudaFuncSetAttribute(project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     project_bwd_kernel<<<blocks, kThreads, smem, s>>>(a);
     CHS_LAUNCH_CHECK();
   }

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kThreads) sh_bwd_kernel(int N, int C, const fl
   float v_mu[3] = {0.f, 0.f, 0.f};
   for (int c = 0; c < C; ++c) {
     const int64_t o = (int64_t)c * N + g;
-    const bool hit = live && radii[o] > 0;
+    const bool hit = live && radii[o] != 0;  // packed tight radii may have bit 31 set
     float v_cp[3] = {0.f, 0.f, 0.f};
     if (hit) {
       const float4 vc = v_cogr[o];

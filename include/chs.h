@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CHS_VERSION 100 /* 0.1.0 */
+#define CHS_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define CHS_API __attribute__((visibility("default")))
@@ -93,6 +93,19 @@ typedef struct chs_config {
   int32_t tight_bounds;       /* 0: classic square 3-sigma tile bounds (radii = r); 1: opacity-aware per-axis bounds — the
                                * axis-aligned box of the alpha >= 1/255 ellipse, intersected with the 3-sigma square; radii
                                * entries are then PACKED rx | ry << 16.  Same images and gradients, ~1/3 fewer intersections */
+  int32_t pose_fused;         /* SURVEY.md 8(f) row f1.  0: one tile list per (camera, tile), the A.4 contract (default).
+                               * 1: the n virtual poses of a frame share ONE tile list per (frame, tile): a Gaussian is binned once
+                               * per frame into the union of its n per-pose tile rectangles and ordered by its depth at the frame's
+                               * middle pose (k = n / 2); every pose still evaluates its own projection (mean2d, conic) per pixel.
+                               * Binning work drops n-fold; images differ from pose_fused = 0 only where the depth order of two
+                               * overlapping Gaussians differs between the middle pose and pose k (oracle: pose_fused=True). */
+  /* Development knobs (0 = the measured-best default everywhere).  They select between bit-/tolerance-equivalent kernel
+   * instantiations and never change results beyond atomics order; see DESIGN.md section 7. */
+  int32_t tune_blend_fwd;     /* 1 / 3: 6 / 10 CTAs per SM */
+  int32_t tune_blend_bwd;     /* 1: direct kernel; 22: direct, four pixels per thread; 40 / 41: tabled, 16 slots */
+  int32_t tune_crf_bwd;       /* resident blocks per SM (2, 3, 4) */
+  int32_t tune_bin;           /* 1: CUB radix passes instead of the hand-written ones; 2: counting placement */
+  int32_t tune_bin_chunk;     /* counting placement: pairs per chunk */
   int32_t reserved[2];
 } chs_config;
 
@@ -104,6 +117,9 @@ typedef struct chs_workspace_sizes {
 
 CHS_API int chs_version(void);
 CHS_API const char* chs_last_error(void);
+/* sizeof() of the ABI structs as this library was compiled: 0 chs_config, 1 chs_workspace_sizes, 2 chs_tensors (0 for any
+ * other value).  A binding checks its own struct layout against these before the first call. */
+CHS_API uint64_t chs_sizeof(int32_t which);
 /* Number of hand-written kernels this process has launched so far (CUB passes and memsets excluded). */
 CHS_API uint64_t chs_launch_count(void);
 

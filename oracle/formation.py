@@ -164,7 +164,7 @@ def tile_bounds(means2d_f32, radii_i32, width, height, tile=TILE, tight=False):
         min_y = torch.where(uy, torch.zeros_like(min_y), min_y)
         max_y = torch.where(uy, torch.full_like(max_y, tile_h), max_y)
     touched = (max_x - min_x) * (max_y - min_y)
-    touched = torch.where(radii_i32 > 0, touched, torch.zeros_like(touched))
+    touched = torch.where(radii_i32 != 0, touched, torch.zeros_like(touched))  # packed tight radii may be negative as int32
     return min_x, min_y, max_x, max_y, touched
 
 
@@ -336,7 +336,7 @@ def crf_apply(X, crf_kind, crf_params=None):
         P = _f64(crf_params)
         L = P.shape[1] - 2
         z_min, z_max, v = P[:, 0].detach(), P[:, 1].detach(), P[:, 2:]
-        z = torch.log(X + CRF_EPS)
+        z = torch.log(torch.clamp(X, min=0.0) + CRF_EPS)  # X clamped to >= 0: no NaN from slightly negative radiance
         u = torch.clamp((z - z_min) * ((L - 1) / (z_max - z_min)), 0.0, float(L - 1))
         i = torch.clamp(torch.floor(u.detach()).to(torch.int64), max=L - 2)
         f = u - i.to(u.dtype)
@@ -348,7 +348,7 @@ def crf_apply(X, crf_kind, crf_params=None):
     P = _f64(crf_params)
     hd = (P.shape[1] - 1) // 3
     w1, b1, w2, b2 = P[:, :hd], P[:, hd:2 * hd], P[:, 2 * hd:3 * hd], P[:, 3 * hd]
-    z = torch.log(X + CRF_EPS)
+    z = torch.log(torch.clamp(X, min=0.0) + CRF_EPS)  # X clamped to >= 0: no NaN from slightly negative radiance
     h = torch.relu(z[..., None] * w1 + b1)
     return torch.sigmoid((h * w2).sum(-1) + b2)
 
@@ -436,7 +436,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         m2d, con = _f64(m2d_f32), _f64(projection_override["conics"])
         if straight_through:
             own = project(means, quats, scales, viewmats, Ks, width, height, near, far, eps2d, radius_sigmas, opacities, tight_bounds)
-            live = (radii > 0)[..., None]
+            live = (radii != 0)[..., None]
             m2d = torch.where(live, own["means2d"] + (m2d - own["means2d"]).detach(), m2d)
             con = torch.where(live, own["conics"] + (con - own["conics"]).detach(), con)
         proj = {"means2d": m2d, "conics": con, "depths": _f64(dep_f32), "radii": radii}

@@ -34,8 +34,10 @@ def test_exports_every_declared_symbol(L):
 def test_version_and_struct_layout(L):
     from casualhdrsplat_b200 import _lib
 
-    assert L.chs_version() == 100
-    assert ctypes.sizeof(_lib.ChsConfig) == 4 * (6 + 3 + 5 + 3 + 4)
+    assert L.chs_version() == 200
+    assert ctypes.sizeof(_lib.ChsConfig) == 4 * (6 + 3 + 5 + 3 + 2 + 8) == L.chs_sizeof(0)
+    assert ctypes.sizeof(_lib.ChsWorkspaceSizes) == L.chs_sizeof(1) and ctypes.sizeof(_lib.ChsTensors) == L.chs_sizeof(2)
+    assert L.chs_sizeof(3) == 0
 
 
 def test_argument_validation_sets_error_message(L):

@@ -61,15 +61,18 @@ def test_projection_parity(name):
 # ------------------------------------------------------------------------------------------------
 # K2-K5 binning: bit exact, both sort strategies
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("sort_mode", ["key64", "presort", "presort-place"])
+# sort routes: the literal 64-bit key sort; depth presort + hand-written multisplit (default); the same with CUB radix passes
+# (chs_config.tune_bin = 1); the sort-free counting placement (tune_bin = 2, small chunks so even tiny scenes have many)
+BIN_ROUTES = {"key64": ("key64", None), "presort": ("presort", None), "presort-cub": ("presort", {"bin": 1}),
+              "presort-place": ("presort", {"bin": 2, "bin_chunk": 96}), "key64-cub": ("key64", {"bin": 1})}
+
+
+@pytest.mark.parametrize("route", list(BIN_ROUTES))
 @pytest.mark.parametrize("name", ["tiny", "small", "c1"])
-def test_binning_bit_exact(name, sort_mode, monkeypatch):
+def test_binning_bit_exact(name, route):
     sc = make_config(name)
-    if sort_mode == "presort-place":  # the sort-free counting-placement route of the presort mode (csrc/chs_bin.cu)
-        monkeypatch.setenv("CHS_BIN_VARIANT", "2")
-        monkeypatch.setenv("CHS_BIN_CHUNK", "96")  # many chunks even for the small scenes
-        sort_mode = "presort"
-    _, _, meta, _ = cuda_run(sc, with_grad=False, sort_mode=sort_mode, debug_keys=True)
+    sort_mode, tuning = BIN_ROUTES[route]
+    _, _, meta, _ = cuda_run(sc, with_grad=False, sort_mode=sort_mode, debug_keys=True, tuning=tuning)
     st = meta["state"]
     proj = cuda_projection(meta)
     b = oracle.bin_tiles(proj["means2d"], proj["radii"], proj["depths"], sc.width, sc.height)
@@ -92,12 +95,9 @@ def test_binning_depth_ties_and_sort_modes_agree():
     p[:, 2] = torch.where(torch.arange(3000) % 3 == 0, torch.tensor(4.0, dtype=torch.float64), p[:, 2])
     sc.means = ((p - t) @ R).float()
     outs = {}
-    for mode in ["key64", "presort", "presort-place"]:
-        os.environ.pop("CHS_BIN_VARIANT", None)
-        if mode == "presort-place":
-            os.environ["CHS_BIN_VARIANT"] = "2"
-        _, _, meta, _ = cuda_run(sc, with_grad=False, sort_mode=mode.split("-")[0], debug_keys=True)
-        os.environ.pop("CHS_BIN_VARIANT", None)
+    for mode in BIN_ROUTES:
+        sort_mode, tuning = BIN_ROUTES[mode]
+        _, _, meta, _ = cuda_run(sc, with_grad=False, sort_mode=sort_mode, debug_keys=True, tuning=tuning)
         st = meta["state"]
         outs[mode] = (st.keys_sorted.cpu(), st.vals_sorted.cpu()[: st.n_isect], st.tile_offsets.cpu())
         proj = cuda_projection(meta)
@@ -105,7 +105,7 @@ def test_binning_depth_ties_and_sort_modes_agree():
         ks = b["keys_sorted"]
         assert int((ks[1:] == ks[:-1]).sum()) > 50, "test scene should contain depth ties inside tiles"
         assert torch.equal(outs[mode][0], ks) and torch.equal(outs[mode][1], b["vals_sorted"])
-    for other in ["presort", "presort-place"]:
+    for other in BIN_ROUTES:
         for a, bb in zip(outs["key64"], outs[other]):
             assert torch.equal(a, bb)
 
@@ -327,9 +327,9 @@ def test_tight_bounds_same_images_shorter_lists(name):
     # (d) the kernel's packed radii agree with the oracle's own float64 ones up to a pixel at ceil() boundaries
     own = oracle_run(sc, with_grad=False, tight_bounds=True)[2]["proj"]["radii"]
     mine = proj["radii"]
-    both = (own > 0) & (mine > 0)
-    assert int(((own > 0) != (mine > 0)).sum()) <= 2
-    assert int(((own & 0xFFFF) - (mine & 0xFFFF)).abs()[both].max()) <= 1 and int(((own >> 16) - (mine >> 16)).abs()[both].max()) <= 1
+    both = (own != 0) & (mine != 0)
+    assert int(((own != 0) != (mine != 0)).sum()) <= 2
+    assert int(((own & 0xFFFF) - (mine & 0xFFFF)).abs()[both].max()) <= 1 and int((((own >> 16) & 0xFFFF) - ((mine >> 16) & 0xFFFF)).abs()[both].max()) <= 1
     assert float(((own != mine) & both).float().mean()) < 1e-3
 
 
@@ -661,3 +661,41 @@ def test_sh_view_dependent_colour(deg, name):
     errs = {k: rel(grads[k], o_grads[k]) for k in grads if k not in skip and float(o_grads[k].norm()) > 0}
     assert all(e <= GRAD_TOL for e in errs.values()), errs
     assert float(grads["colors"].abs().max()) == 0.0
+
+
+def test_tight_bounds_keep_splats_with_half_extent_above_32767():
+    """a near-camera floater whose tight vertical half extent is >= 32768 px packs to an int32 with bit
+    31 set.  Every consumer gates on != 0, so tight and square bounds render the same frame and the same gradients, and the
+    binning stays bit-exact against the oracle."""
+    from casualhdrsplat_b200 import rasterize
+    from tests.util import huge_splat_scene
+
+    kw = huge_splat_scene()
+    dev = torch.device("cuda:0")
+    names = ["means", "quats", "scales", "opacities", "colors"]
+
+    def run(tight):
+        args = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+        for k in names:
+            args[k] = args[k].requires_grad_(True)
+        ldr, alpha, meta = rasterize(**args, tight_bounds=tight, debug_keys=True)
+        g = torch.autograd.grad((ldr * torch.linspace(0.5, 1.5, ldr.numel(), device=dev).view_as(ldr)).sum(), [args[k] for k in names])
+        return ldr.detach(), alpha.detach(), meta, g
+
+    ldr_sq, alpha_sq, meta_sq, g_sq = run(False)
+    ldr, alpha, meta, g = run(True)
+    st = meta["state"]
+    packed = int(st.radii[0, 0])
+    assert packed < 0 and (packed >> 16) & 0xFFFF >= 32768
+    tiles = ((kw["width"] + 15) // 16) * ((kw["height"] + 15) // 16)
+    assert int(st.tiles_touched[0, 0]) == tiles
+    assert torch.equal(ldr, ldr_sq) and torch.equal(alpha, alpha_sq)
+    for a, b in zip(g, g_sq):
+        assert rel(a, b) <= 1e-5
+    assert float(g[0][0].abs().sum()) > 0  # the floater receives a gradient in tight mode
+    proj = cuda_projection(meta)
+    b = oracle.bin_tiles(proj["means2d"], proj["radii"], proj["depths"], kw["width"], kw["height"], tight=True)
+    assert st.n_isect == b["n_isect"] and torch.equal(st.vals_sorted.cpu()[: st.n_isect], b["vals_sorted"])
+    assert torch.equal(_u32(st.tile_offsets), b["tile_offsets"])
+    o_ldr, _, _ = oracle.rasterize(**kw, tight_bounds=True, projection_override=proj)
+    assert rel(ldr, o_ldr) <= FWD_TOL

@@ -118,11 +118,11 @@ def test_tight_bounds_radii_and_rectangles():
         ry = max(1, min(cap, math.ceil(math.sqrt(tau * float(syy[i])))))
         assert p64[i] == (rx | (ry << 16))
         # the fp32 instantiation may differ by one pixel at a ceil() boundary, never more, and never exceeds the square radius
-        rx32, ry32 = int(p32[i]) & 0xFFFF, int(p32[i]) >> 16
+        rx32, ry32 = int(p32[i]) & 0xFFFF, (int(p32[i]) >> 16) & 0xFFFF
         assert abs(rx32 - rx) <= 1 and abs(ry32 - ry) <= 1 and rx32 <= cap and ry32 <= cap
     assert n_cull > 10
     # rectangles of the packed radii: bit-exact against the oracle's tile_bounds(tight=True)
-    live = p32 > 0
+    live = p32 != 0
     mx = (torch.rand(n, generator=g) * 2200 - 140).float()
     my = (torch.rand(n, generator=g) * 1300 - 110).float()
     rect = np.zeros((n, 4), np.int32)
@@ -146,6 +146,21 @@ def test_tight_bounds_radii_and_rectangles():
                            tight=True)
     for k in range(4):
         assert np.array_equal(rect2[:, k], o[k].numpy())
+    # a vertical half extent in [32768, 65534] sets bit 31 of the packed entry: it is an unsigned pair, still live (!= 0), and
+    # decodes to the same rectangle on both sides (gating on `> 0` silently culled such splats)
+    neg = np.zeros(2, np.int32)
+    n64 = np.zeros(2, np.int32)
+    HS.hs_tight_radii(2, _p(np.array([1.5e8, 2.0e8])), _p(np.array([2.0e8, 50.0])), _p(np.array([0.5, 0.5])),
+                      _p(np.array([46639, 60000], np.int32)), _p(n64), _p(neg))
+    assert neg[0] < 0 and (int(neg[0]) >> 16) & 0xFFFF >= 32768 and neg[1] > 0
+    rect3 = np.zeros((2, 4), np.int32)
+    ctr = np.array([900.0, 40.0], np.float32), np.array([500.0, 700.0], np.float32)
+    HS.hs_tile_bounds_packed(2, _p(ctr[0]), _p(ctr[1]), _p(neg), 120, 68, _p(rect3))
+    o3 = oracle.tile_bounds(torch.stack([torch.from_numpy(ctr[0]), torch.from_numpy(ctr[1])], -1), torch.from_numpy(neg.copy()), 1920, 1080,
+                            tight=True)
+    for k in range(4):
+        assert np.array_equal(rect3[:, k], o3[k].numpy())
+    assert int(o3[4][0]) == 120 * 68 and int(o3[4][1]) > 0
 
 
 def test_project_bwd_f64_matches_autograd():

@@ -171,3 +171,20 @@ def test_tight_bounds_change_lists_but_not_images(name):
     live = tg[4] > 0
     assert bool((tg[0][live] >= sq[0][live]).all() and (tg[2][live] <= sq[2][live]).all())
     assert bool((tg[1][live] >= sq[1][live]).all() and (tg[3][live] <= sq[3][live]).all())
+
+
+def test_tight_bounds_keep_splats_with_half_extent_above_32767():
+    """A near-camera floater whose opacity-aware vertical half extent is >= 32768 px packs to a NEGATIVE int32 entry; it must
+    stay live (gate on != 0) so that tight and square bounds render the same frame."""
+    from tests.util import huge_splat_scene
+
+    kw = huge_splat_scene()
+    a = oracle.rasterize(**kw)
+    b = oracle.rasterize(**kw, tight_bounds=True)
+    packed = b[2]["proj"]["radii"][0, 0]
+    assert int(packed) < 0 and (int(packed) >> 16) & 0xFFFF >= 32768
+    tiles = ((kw["width"] + 15) // 16) * ((kw["height"] + 15) // 16)
+    tb = oracle.tile_bounds(b[2]["proj"]["means2d"].detach().float(), b[2]["proj"]["radii"], kw["width"], kw["height"], tight=True)
+    assert int(tb[4][0, 0]) == tiles  # the floater covers every tile
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert float((a[0] - oracle.rasterize(**{**kw, "opacities": kw["opacities"] * torch.cat([torch.zeros(1), torch.ones(300)])})[0]).abs().max()) > 1e-3

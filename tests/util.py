@@ -88,3 +88,21 @@ def robust_grad_report(a: torch.Tensor, b: torch.Tensor):
     nz = b.norm(dim=1) > 0
     e = (a - b).norm(dim=1)[nz] / b.norm(dim=1)[nz]
     return float(e.median()), float((e > 1e-2).double().mean())
+
+
+def huge_splat_scene(n_back=300, width=64, height=48, seed=11):
+    """Explicit-camera scene with one near-camera Gaussian whose tight half extents exceed 32767 px (packed radii entry with
+    bit 31 set) in front of `n_back` ordinary ones.  Returns the keyword arguments of rasterize() as CPU fp32 tensors."""
+    g = torch.Generator().manual_seed(seed)
+    f = 50.0
+    z = 2.0 + 4.0 * torch.rand(n_back, generator=g)
+    xy = (torch.rand(n_back, 2, generator=g) - 0.5) * torch.tensor([width, height]) / f * z[:, None]
+    means = torch.cat([torch.tensor([[0.0, 0.0, 0.012]]), torch.cat([xy, z[:, None]], 1)])
+    scales = torch.cat([torch.full((1, 3), 3.0), 0.05 + 0.2 * torch.rand(n_back, 3, generator=g)])
+    quats = torch.randn(n_back + 1, 4, generator=g)
+    quats[0] = torch.tensor([1.0, 0.0, 0.0, 0.0])
+    opac = torch.cat([torch.tensor([0.5]), 0.1 + 0.8 * torch.rand(n_back, generator=g)])
+    colors = torch.rand(n_back + 1, 3, generator=g) * 2
+    K = torch.tensor([[[f, 0, width / 2], [0, f, height / 2], [0, 0, 1]]])
+    return dict(means=means, quats=quats, scales=scales, opacities=opac, colors=colors, viewmats=torch.eye(4)[None].clone(), Ks=K,
+                width=width, height=height, exposure_times=torch.ones(1), n_virtual=1)
