@@ -55,7 +55,7 @@ int chs_make_dims(const chs_config* cfg, ChsDims* d) {
 }
 
 int chs_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes);
-int chs_bin_sort_bytes(const ChsDims& d, int sort_mode, int64_t M, uint64_t* bytes);
+int chs_bin_sort_bytes(const ChsDims& d, const chs_config* cfg, int64_t M, uint64_t* bytes);
 
 extern "C" int chs_workspace_query(const chs_config* cfg, int64_t n_isect, int32_t n_knots, chs_workspace_sizes* out) {
   ChsDims d;
@@ -69,7 +69,7 @@ extern "C" int chs_workspace_query(const chs_config* cfg, int64_t n_isect, int32
   }
   out->bin_count_bytes += 256;
   if (n_isect > 0) {
-    st = chs_bin_sort_bytes(d, cfg->sort_mode, n_isect, &out->bin_sort_bytes);
+    st = chs_bin_sort_bytes(d, cfg, n_isect, &out->bin_sort_bytes);
     if (st) return st;
   }
   out->bin_sort_bytes += 256;

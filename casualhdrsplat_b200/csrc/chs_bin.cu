@@ -1,35 +1,38 @@
-// chs_bin.cu — K2 intersection count, K3 key generation, K4 radix sort, K5 tile offsets
+// chs_bin.cu — K2 intersection count, K3 key generation, K4 radix sort / tile multisplit, K5 tile offsets
 // (SURVEY.md section 2.4, Appendix A.4).  Integer work, bit-exact against the oracle.
 //
 // Two sort strategies with identical outputs:
-//   CHS_SORT_KEY64          the literal algorithm: one 64-bit key cam|tile|depth per intersection,
-//                           stable LSD radix sort of the low 32+tile_bits+cam_bits bits
-//                           (~7 passes x 24 B per intersection at 1080p).
-//   CHS_SORT_DEPTH_PRESORT  depth is a property of the (camera, Gaussian) pair, not of the
-//                           intersection: sort the C*N pairs by (cam, depth) once (C*N << M), emit
-//                           intersections in that order, then a *stable* sort on the cam|tile bits
-//                           alone (2-3 passes x 16 B) leaves every tile list depth-ordered with
-//                           ties in Gaussian order — the same permutation as the 64-bit sort.
-// The radix passes themselves are cub::DeviceRadixSort (onesweep); everything around them
-// (key construction, ordering trick, offsets) is hand-written.
+//   CHS_SORT_KEY64          the literal algorithm: one 64-bit key cam|tile|depth per intersection, stable LSD radix sort of
+//                           the low 32+tile_bits+cam_bits bits (7 passes of 12-byte pairs at 1080p).
+//   CHS_SORT_DEPTH_PRESORT  depth is a property of the (camera, Gaussian) pair, not of the intersection: sort the C*N pairs by
+//                           depth inside every camera once (C*N << M), emit intersections in that order, then a *stable*
+//                           multisplit on the tile id alone leaves every tile list depth-ordered with ties in Gaussian order
+//                           — the same permutation as the 64-bit sort.
+// Every pass is hand-written (chs_sort.cuh: count -> column scan -> rank / local reorder / run-wise scatter, MATCH.ANY
+// ranking, no look-back spinning).  The presort route never forms a cam|tile key at all: emission order is camera-major, so
+// cameras are SEGMENTS of the item array, and the 16-bit tile id is split most-significant digit first:
+//   pass 1  inside each camera, by tile >> 8   (a band of 256 consecutive tile ids, ~2 tile rows at 1080p): a tile of 4096
+//           consecutive items scatters into the ~32 bands of ONE camera -> ~128-item (512 B) runs, well coalesced;
+//   pass 2  inside each (camera, band) bucket, by tile & 255: the destination is the bucket's own ~1 MB region, which stays in L2
+//           while its source tiles are processed, so the 16-item runs merge into full lines before they reach HBM.  The pass
+//           reads a 1-byte digit + the value and writes the value only.
+// The column totals of pass 2 ARE the per-(camera, tile) counts, so tile_offsets is an exclusive scan of them (K5 needs no
+// pass over the sorted keys) and every list's final start is known before the last scatter.
+// cub::DeviceRadixSort / DeviceScan remain behind chs_config.tune_bin = 1 as the measured baseline (profiles/), never the default.
 //
-// CHS_SORT_DEPTH_PRESORT has a second, sort-free implementation (opt-in: CHS_BIN_VARIANT=2, see the
-// measurement note at the end of this comment): COUNTING PLACEMENT.  Once the (camera, Gaussian) pairs are in depth order, a tile list is simply
+// CHS_SORT_DEPTH_PRESORT has a third, sort-free implementation (opt-in: chs_config.tune_bin = 2): COUNTING PLACEMENT.  Once
+// the (camera, Gaussian) pairs are in depth order, a tile list is simply
 // "the pairs that touch the tile, in the order they appear" — a stable multisplit into C*tiles
 // buckets, for which no keys ever need to exist.  The depth-ordered pairs of a camera are cut into
 // chunks; one warp per (camera, chunk, band of tile rows) walks its chunk IN ORDER and counts, in a
 // private shared-memory row, how many of its Gaussians touch each tile of the band (count_kernel);
 // a column scan over the chunks turns the [C, chunks, tiles] counts into start positions and the
 // per-(camera, tile) totals into tile_offsets; the same walk then places every Gaussian id at its
-// final position with one shared-memory atomic per intersection (place_kernel).  Traffic is
-// 4 B written per intersection plus the small count matrix, against 6 B written + 2 x 12 B moved
-// by the emit + two-pass radix route, and the result is the same permutation bit for bit.
+// final position with one shared-memory atomic per intersection (place_kernel).
 // Measured on B200 (c3, M = 94.1 M, chunk 4096; profiles/r1g_bin_variants.md): rects 0.08 ms, count
-// 0.55 ms, column scan 0.06 ms, place 2.7 ms — against 1.6 ms for emit + two onesweep passes.  The
+// 0.55 ms, column scan 0.06 ms, place 2.7 ms — slower than either sort route.  The
 // count walk is issue-bound (~40 instructions per visited rectangle at 37 % lane use); the place walk
-// additionally thrashes L2 with long-lived partially written sectors (every resident warp keeps one
-// open 32 B sector per tile of its band: 3552 warps x 2040 tiles x 32 B = 232 MB > L2).  Kept as a
-// bit-exact, tested alternative; not the default.
+// additionally thrashes L2 with long-lived partially written sectors.  Kept as a bit-exact, tested alternative.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
@@ -37,6 +40,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include "chs_common.cuh"
+#include "chs_sort.cuh"
 
 namespace {
 
@@ -66,9 +70,11 @@ __global__ void depth_keys_kernel(const int32_t* __restrict__ touched, const flo
 // emission order; their intersections occupy one contiguous output range (the exclusive scan is in
 // the same order), which the 32 lanes write fully coalesced.  The owner of each output slot is found
 // by a 5-step binary search over the lanes' start offsets (shuffles), its tile rectangle fetched by
-// shuffle.  MODE 0: 64-bit cam|tile|depth keys; MODE 1: 32-bit linear (cam * tiles + tile) keys.
+// shuffle.  MODE 0: 64-bit cam|tile|depth keys; MODE 1: linear (cam * tiles + tile) keys; MODE 2: the tile id alone (the camera
+// is implied by the item's position: emission order is camera-major).  Slots at or past `cap` (the capacity of the
+// intersection buffers when the host sized them without knowing M) are not written.
 template <int MODE, class LinT>
-__global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits, int tight,
+__global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int tile_w, int tile_h, int tiles, int tile_bits, int tight, uint32_t cap,
                                                         const float4* __restrict__ geom, const int32_t* __restrict__ radii,
                                                         const float* __restrict__ depths, const uint32_t* __restrict__ offsets,
                                                         const int32_t* __restrict__ order, uint64_t* __restrict__ keys64,
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
     if (i >= CN && lane >= d) off = max(off, o2);
   }
   const uint32_t w_begin = __shfl_sync(CHS_FULL_MASK, off, 0);
-  const uint32_t w_end = __shfl_sync(CHS_FULL_MASK, off + (uint32_t)cnt, 31);
+  const uint32_t w_end = min(__shfl_sync(CHS_FULL_MASK, off + (uint32_t)cnt, 31), cap);
   for (uint32_t o = w_begin + lane; __any_sync(CHS_FULL_MASK, o < w_end); o += 32) {
     int lo_l = 0, hi_l = 31;
 #pragma unroll
@@ -122,8 +128,10 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
       const uint32_t c = (uint32_t)(o_id / N);
       if (MODE == 0)
         keys64[o] = ((uint64_t)c << (32 + tile_bits)) | ((uint64_t)(ty * tile_w + tx) << 32) | (uint64_t)o_d;
-      else
+      else if (MODE == 1)
         keys32[o] = (LinT)(c * (uint32_t)tiles + (uint32_t)(ty * tile_w + tx));
+      else
+        keys32[o] = (LinT)(ty * tile_w + tx);
       vals[o] = o_id;
     }
   }
@@ -194,7 +202,7 @@ struct PlacePlan {
   uint64_t matrix_elems;  // C * n_chunks * tiles
 };
 
-PlacePlan place_plan(const ChsDims& d) {
+PlacePlan place_plan(const ChsDims& d, int chunk_knob) {
   PlacePlan p;
   memset(&p, 0, sizeof(p));
   if (d.tile_w > kBandTilesMax || d.tile_w >= 65536 || d.tile_h >= 65536 || d.N <= 0 || d.C <= 0) return p;
@@ -202,8 +210,7 @@ PlacePlan place_plan(const ChsDims& d) {
   if (p.band_rows > d.tile_h) p.band_rows = d.tile_h;
   p.band_tiles = p.band_rows * d.tile_w;
   p.n_bands = (d.tile_h + p.band_rows - 1) / p.band_rows;
-  int chunk = 4096;
-  if (const char* e = getenv("CHS_BIN_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+  int chunk = chunk_knob > 0 ? chunk_knob : 4096;  // chs_config.tune_bin_chunk
   const uint64_t budget = (uint64_t)256 << 20;  // bytes of count matrix
   for (;;) {
     p.chunk = chunk;
@@ -361,11 +368,6 @@ uint64_t place_bytes(const ChsDims& d, const PlacePlan& p) {
          chs_align_up(p.matrix_elems * 4, 256) + chs_align_up((uint64_t)(n_lin + 1) * 4, 256);
 }
 
-bool place_enabled() {
-  const char* e = getenv("CHS_BIN_VARIANT");  // 2 = counting placement instead of emit + radix sort
-  return e && atoi(e) == 2;
-}
-
 inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 
 // CUB temp-storage sizes (need a CUDA context).
@@ -417,7 +419,8 @@ int chs_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes) {
   return CHS_OK;
 }
 
-int chs_bin_sort_bytes(const ChsDims& d, int sort_mode, int64_t M, uint64_t* bytes) {
+int chs_bin_sort_bytes(const ChsDims& d, const chs_config* cfg, int64_t M, uint64_t* bytes) {
+  const int sort_mode = cfg->sort_mode;
   size_t t;
   int st = sort_temp_size(d, sort_mode, M, &t);
   if (st) return st;
@@ -428,7 +431,7 @@ int chs_bin_sort_bytes(const ChsDims& d, int sort_mode, int64_t M, uint64_t* byt
   else
     b += 2 * chs_align_up(m * 4, 256);  // lin_in + lin_out
   if (sort_mode == CHS_SORT_DEPTH_PRESORT) {
-    const PlacePlan p = place_plan(d);
+    const PlacePlan p = place_plan(d, cfg->tune_bin_chunk);
     if (p.ok) {
       const uint64_t pb = place_bytes(d, p);
       if (pb > b) b = pb;
@@ -510,7 +513,7 @@ extern "C" int chs_bin_emit_keys(const chs_config* cfg, int64_t n_isect, const f
   CHS_REQUIRE(geom && radii && depths && isect_offsets, "chs_bin_emit_keys: null input");
   if (n_isect == 0 || d.CN == 0) return CHS_OK;
   CHS_REQUIRE(keys && vals, "chs_bin_emit_keys: null output");
-  emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, (cudaStream_t)stream>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0,
+  emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, (cudaStream_t)stream>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, 0xFFFFFFFFu,
                                                                          (const float4*)geom, radii, depths, isect_offsets, order, keys,
                                                                          nullptr, vals);
   CHS_LAUNCH_CHECK();
@@ -534,8 +537,8 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
     return CHS_OK;
   }
   CHS_REQUIRE(vals_sorted && workspace, "chs_bin_sort: null output/workspace");
-  if (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT && place_enabled()) {
-    const PlacePlan p = place_plan(d);
+  if (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT && cfg->tune_bin == 2) {  // counting placement instead of emit + sort
+    const PlacePlan p = place_plan(d, cfg->tune_bin_chunk);
     if (p.ok) {
       ChsArena pa(workspace, workspace_bytes);
       size_t scan_b = place_scan_temp((int64_t)n_lin + 1);
@@ -586,7 +589,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
       chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
       return CHS_ERR_WORKSPACE_TOO_SMALL;
     }
-    emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, (const float4*)geom, radii,
+    emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, 0xFFFFFFFFu, (const float4*)geom, radii,
                                                        depths, isect_offsets, nullptr, k_in, nullptr, v_in);
     CHS_LAUNCH_CHECK();
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_in, k_out, (const int32_t*)v_in, vals_sorted, M, 0,
@@ -605,7 +608,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
     }
     const int bits = n_lin > 1 ? chs_bit_length((uint64_t)n_lin - 1) : 1;
     if (k16) {
-      emit_kernel<1, uint16_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, (const float4*)geom,
+      emit_kernel<1, uint16_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, 0xFFFFFFFFu, (const float4*)geom,
                                                                    radii, depths, isect_offsets, order, nullptr, (uint16_t*)l_in, v_in);
       CHS_LAUNCH_CHECK();
       size_t tb16 = tb;
@@ -620,7 +623,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
         CHS_LAUNCH_CHECK();
       }
     } else {
-      emit_kernel<1, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, (const float4*)geom,
+      emit_kernel<1, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, cfg->tight_bounds != 0, 0xFFFFFFFFu, (const float4*)geom,
                                                                    radii, depths, isect_offsets, order, nullptr, (uint32_t*)l_in, v_in);
       CHS_LAUNCH_CHECK();
       CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)l_in, (uint32_t*)l_out, (const int32_t*)v_in, vals_sorted, M, 0,

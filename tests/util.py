@@ -106,3 +106,34 @@ def huge_splat_scene(n_back=300, width=64, height=48, seed=11):
     K = torch.tensor([[[f, 0, width / 2], [0, f, height / 2], [0, 0, 1]]])
     return dict(means=means, quats=quats, scales=scales, opacities=opac, colors=colors, viewmats=torch.eye(4)[None].clone(), Ks=K,
                 width=width, height=height, exposure_times=torch.ones(1), n_virtual=1)
+
+
+# ---- tile-subset parity at sizes the full oracle cannot finish (SURVEY.md A.8, VERDICT r1 item 1) --------------------------
+def tile_pixel_mask(width, height, tile_ids, tile=16):
+    """[H,W] bool mask of the pixels of the given tile ids (row-major tile numbering)."""
+    tile_w = (width + tile - 1) // tile
+    m = torch.zeros(height, width, dtype=torch.bool)
+    for tid in tile_ids:
+        ty, tx = divmod(int(tid), tile_w)
+        m[ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile] = True
+    return m
+
+
+def gaussians_of_tiles(vals_sorted, tile_offsets, n_gauss, n_cams, tiles, tile_ids):
+    """Sorted unique Gaussian ids appearing in the lists of (every camera, each chosen tile)."""
+    to = (tile_offsets.cpu().to(torch.int64) & 0xFFFFFFFF).tolist()
+    vals = vals_sorted.cpu().to(torch.int64)
+    parts = [vals[to[c * tiles + t]:to[c * tiles + t + 1]] - c * n_gauss for c in range(n_cams) for t in tile_ids]
+    return torch.unique(torch.cat(parts)) if parts else torch.zeros(0, dtype=torch.int64)
+
+
+def subset_scene(sc, g_idx):
+    """The scene restricted to Gaussians g_idx (ascending), everything else unchanged."""
+    import dataclasses
+
+    return dataclasses.replace(sc, means=sc.means[g_idx], quats=sc.quats[g_idx], scales=sc.scales[g_idx], opacities=sc.opacities[g_idx],
+                               colors=sc.colors[g_idx])
+
+
+def subset_projection(proj, g_idx):
+    return {k: v[:, g_idx].contiguous() for k, v in proj.items()}
