@@ -62,6 +62,8 @@ SIGNATURES = {
     "chs_project_bwd": (ctypes.c_int, [CFG] + [P] * 12 + [c_uint64, P]),
     "chs_bin_count": (ctypes.c_int, [CFG, P, P, P, P, P, POINTER(c_int64), P, c_uint64, P]),
     "chs_bin_sort": (ctypes.c_int, [CFG, c_int64] + [P] * 9 + [c_uint64, P]),
+    "chs_bin_sort_dev": (ctypes.c_int, [CFG, c_int64] + [P] * 10 + [c_uint64, P]),
+    "chs_radix_sort_pairs": (ctypes.c_int, [P, c_int32, ctypes.c_uint32, c_int32, P, P, P, c_uint64, P]),
     "chs_bin_emit_keys": (ctypes.c_int, [CFG, c_int64] + [P] * 8),
     "chs_blend_fwd": (ctypes.c_int, [CFG] + [P] * 13),
     "chs_crf_bwd": (ctypes.c_int, [CFG] + [P] * 8 + [c_uint64, P]),

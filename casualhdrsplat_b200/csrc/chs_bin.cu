@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int32_t id = 0;
-  int x0 = 0, y0 = 0, w = 1, cnt = 0;
-  uint32_t off = 0, dbits = 0;
+  int w = 1, cnt = 0;
+  uint32_t off = 0, dbits = 0, xy0 = 0, magic = 0;
   if (i < CN) {
     id = order ? order[i] : (int32_t)i;
     off = offsets[i];
@@ -91,9 +91,12 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
     if (radius != 0) {
       const float4 gm = geom[id];
       const ChsTileRect r = chs_tile_bounds_of(gm.x, gm.y, radius, tight, tile_w, tile_h);
-      x0 = r.x0; y0 = r.y0;
+      xy0 = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
       w = max(r.x1 - r.x0, 1);
       cnt = (r.x1 - r.x0) * (r.y1 - r.y0);
+      // ceil(2^32 / w): local / w == umulhi(local, magic) while local * w < 2^32 (local < tiles <= 2^16 here, w <= tile_w);
+      // one division per pair instead of one per intersection
+      magic = w > 1 ? 0xFFFFFFFFu / (uint32_t)w + 1u : 0u;
       if (MODE == 0) dbits = __float_as_uint(depths[id]);
     }
   }
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
   }
   const uint32_t w_begin = __shfl_sync(CHS_FULL_MASK, off, 0);
   const uint32_t w_end = min(__shfl_sync(CHS_FULL_MASK, off + (uint32_t)cnt, 31), cap);
+  const bool use_magic = (uint64_t)tiles * (uint64_t)tile_w < (1ull << 32);
   for (uint32_t o = w_begin + lane; __any_sync(CHS_FULL_MASK, o < w_end); o += 32) {
     int lo_l = 0, hi_l = 31;
 #pragma unroll
@@ -117,21 +121,25 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int64_t CN, int N, int t
       if (v <= o) lo_l = mid; else hi_l = mid - 1;
     }
     const uint32_t o_off = __shfl_sync(CHS_FULL_MASK, off, lo_l);
-    const int o_x0 = __shfl_sync(CHS_FULL_MASK, x0, lo_l);
-    const int o_y0 = __shfl_sync(CHS_FULL_MASK, y0, lo_l);
+    const uint32_t o_xy = __shfl_sync(CHS_FULL_MASK, xy0, lo_l);
     const int o_w = __shfl_sync(CHS_FULL_MASK, w, lo_l);
+    const uint32_t o_mg = __shfl_sync(CHS_FULL_MASK, magic, lo_l);
     const int32_t o_id = __shfl_sync(CHS_FULL_MASK, id, lo_l);
-    const uint32_t o_d = __shfl_sync(CHS_FULL_MASK, dbits, lo_l);
+    const uint32_t o_d = MODE == 0 ? __shfl_sync(CHS_FULL_MASK, dbits, lo_l) : 0u;
     if (o < w_end) {
-      const int local = (int)(o - o_off);
-      const int ty = o_y0 + local / o_w, tx = o_x0 + local % o_w;
-      const uint32_t c = (uint32_t)(o_id / N);
-      if (MODE == 0)
-        keys64[o] = ((uint64_t)c << (32 + tile_bits)) | ((uint64_t)(ty * tile_w + tx) << 32) | (uint64_t)o_d;
-      else if (MODE == 1)
-        keys32[o] = (LinT)(c * (uint32_t)tiles + (uint32_t)(ty * tile_w + tx));
-      else
-        keys32[o] = (LinT)(ty * tile_w + tx);
+      const uint32_t local = o - o_off;
+      const uint32_t ly = o_w > 1 ? (use_magic ? __umulhi(local, o_mg) : local / (uint32_t)o_w) : local;
+      const uint32_t lx = local - ly * (uint32_t)o_w;
+      const uint32_t tile = ((o_xy >> 16) + ly) * (uint32_t)tile_w + (o_xy & 0xffffu) + lx;
+      if (MODE == 0) {
+        const uint32_t c = (uint32_t)(o_id / N);
+        keys64[o] = ((uint64_t)c << (32 + tile_bits)) | ((uint64_t)tile << 32) | (uint64_t)o_d;
+      } else if (MODE == 1) {
+        const uint32_t c = (uint32_t)(o_id / N);
+        keys32[o] = (LinT)(c * (uint32_t)tiles + tile);
+      } else {
+        keys32[o] = (LinT)tile;
+      }
       vals[o] = o_id;
     }
   }
@@ -145,9 +153,17 @@ __device__ __forceinline__ uint32_t lin_of_key64(uint64_t key, int tile_bits, in
 // K5: tile_offsets[lin] = first sorted index whose (cam, tile) >= lin; tile_offsets[C*tiles] = M.
 // Four sorted entries per thread.
 template <int MODE, class LinT>
-__global__ void __launch_bounds__(kThreads) tile_offsets_kernel(int64_t M, int n_lin, int tile_bits, int tiles,
+__global__ void __launch_bounds__(kThreads) tile_offsets_kernel(int64_t M, const int64_t* __restrict__ m_dev, int n_lin, int tile_bits, int tiles,
                                                                 const uint64_t* __restrict__ keys64, const LinT* __restrict__ keys32,
                                                                 uint32_t* __restrict__ tile_offsets) {
+  if (m_dev) {  // M is then the capacity of the buffers; the live count only exists on the device
+    const int64_t live = *m_dev;
+    M = live < 0 ? 0 : (live < M ? live : M);
+    if (M == 0) {
+      for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_lin; b += (int64_t)gridDim.x * blockDim.x) tile_offsets[b] = 0u;
+      return;
+    }
+  }
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= M) return;
   uint32_t lin[4];
@@ -407,8 +423,8 @@ int sort_temp_size(const ChsDims& d, int sort_mode, int64_t M, size_t* bytes) {
 
 }  // namespace
 
-// exported to chs_api.cu
-int chs_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes) {
+// ---- baseline route (chs_config.tune_bin = 1): cub::DeviceRadixSort / DeviceScan; tune_bin = 2: counting placement ----
+static int cub_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes) {
   CountTemp t;
   int st = count_temp_sizes(d, sort_mode, &t);
   if (st) return st;
@@ -419,7 +435,7 @@ int chs_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes) {
   return CHS_OK;
 }
 
-int chs_bin_sort_bytes(const ChsDims& d, const chs_config* cfg, int64_t M, uint64_t* bytes) {
+static int legacy_bin_sort_bytes(const ChsDims& d, const chs_config* cfg, int64_t M, uint64_t* bytes) {
   const int sort_mode = cfg->sort_mode;
   size_t t;
   int st = sort_temp_size(d, sort_mode, M, &t);
@@ -441,9 +457,9 @@ int chs_bin_sort_bytes(const ChsDims& d, const chs_config* cfg, int64_t M, uint6
   return CHS_OK;
 }
 
-extern "C" int chs_bin_count(const chs_config* cfg, const int32_t* tiles_touched, const float* depths, uint32_t* isect_offsets,
-                             int32_t* order, int64_t* n_isect_dev, int64_t* n_isect_host, void* workspace,
-                             uint64_t workspace_bytes, void* stream) {
+static int cub_bin_count(const chs_config* cfg, const int32_t* tiles_touched, const float* depths, uint32_t* isect_offsets,
+                         int32_t* order, int64_t* n_isect_dev, int64_t* n_isect_host, void* workspace,
+                         uint64_t workspace_bytes, void* stream) {
   ChsDims d;
   int st = chs_make_dims(cfg, &d);
   if (st) return st;
@@ -520,9 +536,9 @@ extern "C" int chs_bin_emit_keys(const chs_config* cfg, int64_t n_isect, const f
   return CHS_OK;
 }
 
-extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii, const float* depths,
-                            const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted,
-                            uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, void* stream) {
+static int legacy_bin_sort(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii, const float* depths,
+                           const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted,
+                           uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, void* stream) {
   ChsDims d;
   int st = chs_make_dims(cfg, &d);
   if (st) return st;
@@ -594,7 +610,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
     CHS_LAUNCH_CHECK();
     CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_in, k_out, (const int32_t*)v_in, vals_sorted, M, 0,
                                              32 + d.tile_bits + d.cam_bits, s));
-    tile_offsets_kernel<0, uint32_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, k_out, nullptr, tile_offsets);
+    tile_offsets_kernel<0, uint32_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, nullptr, n_lin, d.tile_bits, d.tiles, k_out, nullptr, tile_offsets);
     CHS_LAUNCH_CHECK();
   } else {
     // linear (cam * tiles + tile) keys: 16 bits suffice for one 1080p frame of 8 poses (65280 buckets), which cuts
@@ -614,7 +630,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
       size_t tb16 = tb;
       CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb16, (const uint16_t*)l_in, (uint16_t*)l_out, (const int32_t*)v_in, vals_sorted, M, 0,
                                                bits, s));
-      tile_offsets_kernel<1, uint16_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr,
+      tile_offsets_kernel<1, uint16_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, nullptr, n_lin, d.tile_bits, d.tiles, nullptr,
                                                                                    (const uint16_t*)l_out, tile_offsets);
       CHS_LAUNCH_CHECK();
       if (keys_sorted) {
@@ -628,7 +644,7 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
       CHS_LAUNCH_CHECK();
       CHS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)l_in, (uint32_t*)l_out, (const int32_t*)v_in, vals_sorted, M, 0,
                                                bits, s));
-      tile_offsets_kernel<1, uint32_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, n_lin, d.tile_bits, d.tiles, nullptr,
+      tile_offsets_kernel<1, uint32_t><<<grid_for((M + 3) / 4), kThreads, 0, s>>>(M, nullptr, n_lin, d.tile_bits, d.tiles, nullptr,
                                                                                    (const uint32_t*)l_out, tile_offsets);
       CHS_LAUNCH_CHECK();
       if (keys_sorted) {
@@ -637,6 +653,531 @@ extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float*
         CHS_LAUNCH_CHECK();
       }
     }
+  }
+  return CHS_OK;
+}
+
+// =================================================================================================
+// hand-written route (default): segmented depth presort, gathered scan, tile multisplit — all from chs_sort.cuh
+// =================================================================================================
+namespace {
+
+namespace cs = chs_sort;
+
+struct TouchedIn {
+  const int32_t* touched;
+  const int32_t* order;
+  __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return (uint32_t)touched[order ? order[i] : (int64_t)i]; }
+};
+struct ArrayIn {
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return p[i]; }
+};
+struct StoreU32 {
+  uint32_t* out;
+  __device__ __forceinline__ void operator()(uint64_t i, uint32_t v) const { out[i] = v; }
+};
+
+// live item count: the device counter clamped to the capacity of the buffers (or the capacity itself when the host knows M)
+__device__ __forceinline__ uint32_t live_items(const int64_t* n_dev, uint32_t cap) {
+  if (!n_dev) return cap;
+  const int64_t m = *n_dev;
+  return m < 0 ? 0u : (m < (int64_t)cap ? (uint32_t)m : cap);
+}
+
+// segment lengths of pass 1: camera c owns the items [offsets[c * N], offsets[(c + 1) * N]) of the camera-major emission order
+struct CamLen {
+  const uint32_t* offsets;
+  int N, C;
+  const int64_t* n_dev;
+  uint32_t cap;
+  __device__ __forceinline__ uint32_t begin(int c) const {
+    const uint32_t live = live_items(n_dev, cap);
+    return c < C ? min(offsets[(int64_t)c * N], live) : live;
+  }
+  __device__ __forceinline__ uint32_t operator()(int c) const { return begin(c + 1) - begin(c); }
+};
+// segment lengths of pass 2: bucket (camera c, band b) holds what pass 1 counted for digit b of segment c
+struct BucketLen {
+  const uint32_t* totals1;
+  int nb;
+  __device__ __forceinline__ uint32_t operator()(int i) const { return totals1[(int64_t)(i / nb) * cs::kDigits + (i % nb)]; }
+};
+
+// single block: seg_begin = exclusive scan of the lengths, tile_first = exclusive scan of ceil(length / tile); entry n_seg = totals
+template <class LenFn>
+__global__ void __launch_bounds__(1024) segments_kernel(LenFn len_of, int n_seg, uint32_t* __restrict__ seg_begin,
+                                                        uint32_t* __restrict__ tile_first) {
+  __shared__ uint64_t s_warp[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t carry = 0;  // tiles << 40 | items  (items < 2^32, tiles < 2^21)
+  for (int b0 = 0; b0 < n_seg; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const uint32_t len = i < n_seg ? len_of(i) : 0u;
+    const uint64_t v = ((uint64_t)((len + cs::kTile - 1) / cs::kTile) << 40) | (uint64_t)len;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t u = __shfl_up_sync(CHS_FULL_MASK, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t run = 0;
+      for (int w = 0; w < 32; ++w) {
+        const uint64_t c = s_warp[w];
+        s_warp[w] = run;
+        run += c;
+      }
+      s_warp[32] = run;
+    }
+    __syncthreads();
+    if (i < n_seg) {
+      const uint64_t e = carry + s_warp[warp] + incl - v;
+      seg_begin[i] = (uint32_t)(e & 0xFFFFFFFFFFull);
+      tile_first[i] = (uint32_t)(e >> 40);
+    }
+    carry += s_warp[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    seg_begin[n_seg] = (uint32_t)(carry & 0xFFFFFFFFFFull);
+    tile_first[n_seg] = (uint32_t)(carry >> 40);
+  }
+}
+
+// K5 without a pass over sorted keys: list starts of every (camera, tile) from the scanned column totals of pass 2
+__global__ void __launch_bounds__(kThreads) tile_offsets_from_base_kernel(int64_t n_lin, int tiles, int nb, const uint32_t* __restrict__ base2,
+                                                                           const uint32_t* __restrict__ seg_begin2, int n_seg2,
+                                                                           uint32_t* __restrict__ tile_offsets) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lin) {
+    const int64_t c = i / tiles;
+    const int t = (int)(i - c * tiles);
+    tile_offsets[i] = base2[(c * nb + (t >> 8)) * cs::kDigits + (t & 255)];
+  } else if (i == n_lin) {
+    tile_offsets[n_lin] = seg_begin2[n_seg2];
+  }
+}
+
+// K5 of the LSD routes when M only exists on the device: a one-thread shim that forwards it to tile_offsets_kernel's argument
+// is not possible, so that kernel reads the live count itself (m_dev) and uses `M` as the capacity.
+
+template <class Keys>
+int launch_count(const cs::TileMap& map, Keys keys, int shift, uint32_t* counts, uint32_t t_cap, cudaStream_t s) {
+  cs::radix_count_kernel<Keys><<<t_cap, cs::kThreads, 0, s>>>(map, keys, shift, counts, t_cap);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}
+int launch_colscan(const cs::TileMap& map, uint32_t* counts, uint32_t t_cap, uint32_t* totals, cudaStream_t s) {
+  const int64_t cols = (int64_t)map.n_seg * cs::kDigits;
+  cs::radix_colscan_kernel<<<(unsigned)((cols + cs::kWarps - 1) / cs::kWarps), cs::kThreads, 0, s>>>(map, counts, t_cap, totals);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}
+// nbits <= 5 selects the instantiation with five ballots per round (digits < 32: the tile bands of one camera)
+template <class Keys, class KeyOutT>
+int launch_scatter(const cs::ScatterArgs<Keys, KeyOutT>& a, int nbits, cudaStream_t s) {
+  typedef typename Keys::key_type KeyT;
+  const size_t smem = cs::scatter_smem_bytes<KeyT>();
+  if (nbits <= 5) {
+    if (smem > 48 * 1024)
+      CHS_CUDA(cudaFuncSetAttribute(cs::radix_scatter_kernel<5, Keys, KeyOutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cs::radix_scatter_kernel<5, Keys, KeyOutT><<<a.t_cap, cs::kThreads, smem, s>>>(a);
+  } else {
+    if (smem > 48 * 1024)
+      CHS_CUDA(cudaFuncSetAttribute(cs::radix_scatter_kernel<8, Keys, KeyOutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cs::radix_scatter_kernel<8, Keys, KeyOutT><<<a.t_cap, cs::kThreads, smem, s>>>(a);
+  }
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}
+
+// one stable pass by the 8-bit digit at `shift`: count -> column scan -> scatter
+template <class Keys, class KeyOutT>
+int radix_pass(const cs::TileMap& map, Keys keys, const int32_t* vals_in, KeyOutT* keys_out, int32_t* vals_out, int shift, int nbits,
+               uint32_t* counts, uint32_t t_cap, uint32_t* totals, const uint32_t* digit_base, cudaStream_t s) {
+  int st = launch_count(map, keys, shift, counts, t_cap, s);
+  if (st) return st;
+  st = launch_colscan(map, counts, t_cap, totals, s);
+  if (st) return st;
+  cs::ScatterArgs<Keys, KeyOutT> a;
+  a.map = map; a.keys = keys; a.vals_in = vals_in; a.keys_out = keys_out; a.vals_out = vals_out; a.shift = shift;
+  a.prefix = counts; a.t_cap = t_cap; a.totals = totals; a.digit_base = digit_base;
+  return launch_scatter(a, nbits, s);
+}
+
+template <class In, class Out>
+int exclusive_scan(In in, uint64_t n, uint64_t* sums, Out out, int64_t* total_out, cudaStream_t s) {
+  const uint32_t blocks = (uint32_t)((n + cs::kScanTile - 1) / cs::kScanTile);
+  if (blocks == 0) {
+    if (total_out) CHS_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), s));
+    return CHS_OK;
+  }
+  cs::scan_sums_kernel<In><<<blocks, cs::kThreads, 0, s>>>(in, n, sums);
+  CHS_LAUNCH_CHECK();
+  cs::scan_of_sums_kernel<<<1, 1024, 0, s>>>(sums, blocks, total_out, nullptr);
+  CHS_LAUNCH_CHECK();
+  cs::scan_final_kernel<In, Out><<<blocks, cs::kThreads, 0, s>>>(in, n, sums, out);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}
+
+inline uint32_t tiles_of(uint64_t n) { return (uint32_t)((n + cs::kTile - 1) / cs::kTile); }
+
+// ---- workspace layouts (one definition for the size query and for the launch) ----
+struct CountPlan {
+  uint32_t tps, t_cap;
+  uint64_t sum_blocks;
+};
+CountPlan count_plan(const ChsDims& d) {
+  CountPlan p;
+  p.tps = tiles_of((uint64_t)d.N);
+  p.t_cap = p.tps * (uint32_t)d.C;
+  p.sum_blocks = ((uint64_t)d.CN + cs::kScanTile - 1) / cs::kScanTile;
+  return p;
+}
+uint64_t hw_count_bytes(const ChsDims& d, int sort_mode) {
+  const CountPlan p = count_plan(d);
+  uint64_t b = chs_align_up(p.sum_blocks * 8, 256);
+  if (sort_mode == CHS_SORT_DEPTH_PRESORT)
+    b += chs_align_up((uint64_t)cs::kDigits * p.t_cap * 4, 256) + chs_align_up((uint64_t)d.C * cs::kDigits * 4, 256) +
+         4 * chs_align_up((uint64_t)d.CN * 4, 256);
+  return b + 256;
+}
+
+struct SortPlan {
+  bool multisplit;   // presort with tile ids that fit 16 bits: the two-pass segmented route
+  int nb;            // bands of 256 tile ids per camera
+  int64_t n_seg2;    // C * nb
+  int passes;        // LSD routes: number of 8-bit passes
+  int key_bytes;     // LSD routes: 8 (cam|tile|depth) or 4 (linear keys)
+  uint32_t t_cap;
+  uint64_t sum_blocks;
+};
+SortPlan sort_plan(const ChsDims& d, int sort_mode, uint64_t cap) {
+  SortPlan p;
+  memset(&p, 0, sizeof(p));
+  p.multisplit = sort_mode == CHS_SORT_DEPTH_PRESORT && d.tiles <= 65536;
+  if (p.multisplit) {
+    p.nb = (d.tiles + 255) / 256;
+    p.n_seg2 = (int64_t)d.C * p.nb;
+    p.t_cap = tiles_of(cap) + (uint32_t)p.n_seg2;
+    p.sum_blocks = ((uint64_t)p.n_seg2 * cs::kDigits + cs::kScanTile - 1) / cs::kScanTile;
+  } else {
+    p.key_bytes = sort_mode == CHS_SORT_KEY64 ? 8 : 4;
+    const int bits = sort_mode == CHS_SORT_KEY64 ? 32 + d.tile_bits + d.cam_bits
+                                                 : (d.C * (int64_t)d.tiles > 1 ? chs_bit_length((uint64_t)d.C * d.tiles - 1) : 1);
+    p.passes = (bits + 7) / 8;
+    p.t_cap = tiles_of(cap);
+  }
+  return p;
+}
+uint64_t hw_sort_bytes(const ChsDims& d, int sort_mode, uint64_t cap) {
+  const SortPlan p = sort_plan(d, sort_mode, cap);
+  uint64_t b = chs_align_up((uint64_t)cs::kDigits * p.t_cap * 4, 256);
+  if (p.multisplit) {
+    b += chs_align_up(cap * 2, 256) + 2 * chs_align_up(cap * 4, 256) + chs_align_up(cap, 256);       // tile keys, vals x2, digits
+    b += chs_align_up((uint64_t)d.C * cs::kDigits * 4, 256) + 2 * chs_align_up((uint64_t)(d.C + 1) * 4, 256);  // totals1, tables1
+    b += 2 * chs_align_up((uint64_t)p.n_seg2 * cs::kDigits * 4, 256) + 2 * chs_align_up((uint64_t)(p.n_seg2 + 1) * 4, 256);
+    b += chs_align_up(p.sum_blocks * 8, 256);
+  } else {
+    b += 2 * chs_align_up(cap * p.key_bytes, 256) + chs_align_up(cap * 4, 256) + chs_align_up((uint64_t)cs::kDigits * 4, 256);
+  }
+  return b + 256;
+}
+
+int hw_bin_count(const chs_config* cfg, const ChsDims& d, const int32_t* tiles_touched, const float* depths, uint32_t* isect_offsets,
+                 int32_t* order, int64_t* n_isect_dev, void* workspace, uint64_t workspace_bytes, cudaStream_t s) {
+  const CountPlan p = count_plan(d);
+  ChsArena ar(workspace, workspace_bytes);
+  uint64_t* sums = ar.take<uint64_t>(p.sum_blocks);
+  const int32_t* ord = nullptr;
+  if (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT) {
+    uint32_t* counts = ar.take<uint32_t>((uint64_t)cs::kDigits * p.t_cap);
+    uint32_t* totals = ar.take<uint32_t>((uint64_t)d.C * cs::kDigits);
+    uint32_t* ka = ar.take<uint32_t>(d.CN);
+    uint32_t* kb = ar.take<uint32_t>(d.CN);
+    int32_t* va = ar.take<int32_t>(d.CN);
+    int32_t* vb = ar.take<int32_t>(d.CN);
+    if (!ar.ok) {
+      chs_set_error("chs_bin_count: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+      return CHS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    // cameras are segments of N pairs: four stable LSD passes over the depth bits inside every camera
+    cs::TileMap map;
+    memset(&map, 0, sizeof(map));
+    map.n_seg = d.C; map.seg_len = (uint32_t)d.N; map.tiles_per_seg = p.tps;
+    int st = radix_pass<cs::DepthKeys, uint32_t>(map, cs::DepthKeys{depths, tiles_touched}, nullptr, ka, va, 0, 8, counts, p.t_cap, totals, nullptr, s);
+    if (st) return st;
+    st = radix_pass<cs::ArrayKeys<uint32_t>, uint32_t>(map, cs::ArrayKeys<uint32_t>{ka}, va, kb, vb, 8, 8, counts, p.t_cap, totals, nullptr, s);
+    if (st) return st;
+    st = radix_pass<cs::ArrayKeys<uint32_t>, uint32_t>(map, cs::ArrayKeys<uint32_t>{kb}, vb, ka, va, 16, 8, counts, p.t_cap, totals, nullptr, s);
+    if (st) return st;
+    st = radix_pass<cs::ArrayKeys<uint32_t>, uint32_t>(map, cs::ArrayKeys<uint32_t>{ka}, va, (uint32_t*)nullptr, order, 24, 8, counts, p.t_cap,
+                                                       totals, nullptr, s);
+    if (st) return st;
+    ord = order;
+  }
+  if (!ar.ok) {
+    chs_set_error("chs_bin_count: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+    return CHS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  return exclusive_scan(TouchedIn{tiles_touched, ord}, (uint64_t)d.CN, sums, StoreU32{isect_offsets}, n_isect_dev, s);
+}
+
+// LSD sort of (key, value) pairs over the low 8 * passes bits, one segment whose live length may only exist on the device.
+// The pairs start in (k0, v0); buffers alternate so that the last pass lands in (k_final, v_final).
+template <class KeyT>
+int lsd_sort(int passes, uint64_t cap, const int64_t* n_dev, KeyT* k_a, int32_t* v_a, KeyT* k_final, int32_t* v_final, uint32_t* counts,
+             uint32_t t_cap, uint32_t* totals, cudaStream_t s) {
+  cs::TileMap map;
+  memset(&map, 0, sizeof(map));
+  map.n_seg = 1; map.seg_len = (uint32_t)cap; map.tiles_per_seg = t_cap; map.n_items_dev = n_dev;
+  // the caller emitted into (k_a, v_a) if passes is odd, into (k_final, v_final) if even
+  KeyT* kin = passes % 2 ? k_a : k_final;
+  int32_t* vin = passes % 2 ? v_a : v_final;
+  KeyT* kout = passes % 2 ? k_final : k_a;
+  int32_t* vout = passes % 2 ? v_final : v_a;
+  for (int p = 0; p < passes; ++p) {
+    int st = radix_pass<cs::ArrayKeys<KeyT>, KeyT>(map, cs::ArrayKeys<KeyT>{kin}, vin, kout, vout, 8 * p, 8, counts, t_cap, totals, nullptr, s);
+    if (st) return st;
+    KeyT* tk = kin; kin = kout; kout = tk;
+    int32_t* tv = vin; vin = vout; vout = tv;
+  }
+  return CHS_OK;
+}
+
+int hw_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const int64_t* n_dev, const float* geom, const int32_t* radii,
+                const float* depths, const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted,
+                uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, cudaStream_t s) {
+  const SortPlan p = sort_plan(d, cfg->sort_mode, cap);
+  const int64_t n_lin = (int64_t)d.C * d.tiles;
+  const int tight = cfg->tight_bounds != 0;
+  ChsArena ar(workspace, workspace_bytes);
+  uint32_t* counts = ar.take<uint32_t>((uint64_t)cs::kDigits * p.t_cap);
+#define CHS_SORT_WS_CHECK()                                                                                        \
+  if (!ar.ok) {                                                                                                    \
+    chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);          \
+    return CHS_ERR_WORKSPACE_TOO_SMALL;                                                                            \
+  }
+  if (p.multisplit) {
+    uint16_t* k16 = ar.take<uint16_t>(cap);
+    int32_t* v_in = ar.take<int32_t>(cap);
+    int32_t* v_mid = ar.take<int32_t>(cap);
+    uint8_t* d8 = ar.take<uint8_t>(cap);
+    uint32_t* totals1 = ar.take<uint32_t>((uint64_t)d.C * cs::kDigits);
+    uint32_t* seg_begin1 = ar.take<uint32_t>((uint64_t)d.C + 1);
+    uint32_t* tile_first1 = ar.take<uint32_t>((uint64_t)d.C + 1);
+    uint32_t* totals2 = ar.take<uint32_t>((uint64_t)p.n_seg2 * cs::kDigits);
+    uint32_t* base2 = ar.take<uint32_t>((uint64_t)p.n_seg2 * cs::kDigits);
+    uint32_t* seg_begin2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
+    uint32_t* tile_first2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
+    uint64_t* sums = ar.take<uint64_t>(p.sum_blocks);
+    CHS_SORT_WS_CHECK();
+    emit_kernel<2, uint16_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, tight, (uint32_t)cap,
+                                                                 (const float4*)geom, radii, depths, isect_offsets, order, nullptr, k16, v_in);
+    CHS_LAUNCH_CHECK();
+    // pass 1: inside each camera, by the band tile >> 8
+    segments_kernel<CamLen><<<1, 1024, 0, s>>>(CamLen{isect_offsets, d.N, d.C, n_dev, (uint32_t)cap}, d.C, seg_begin1, tile_first1);
+    CHS_LAUNCH_CHECK();
+    cs::TileMap m1;
+    memset(&m1, 0, sizeof(m1));
+    m1.table = 1; m1.n_seg = d.C; m1.seg_begin = seg_begin1; m1.tile_first = tile_first1;
+    int st = radix_pass<cs::ArrayKeys<uint16_t>, uint8_t>(m1, cs::ArrayKeys<uint16_t>{k16}, v_in, d8, v_mid, 8, p.nb > 1 ? chs_bit_length((uint64_t)p.nb - 1) : 1, counts, p.t_cap,
+                                                          totals1, nullptr, s);
+    if (st) return st;
+    // pass 2: inside each (camera, band) bucket, by tile & 255, straight to every list's final position
+    segments_kernel<BucketLen><<<1, 1024, 0, s>>>(BucketLen{totals1, p.nb}, (int)p.n_seg2, seg_begin2, tile_first2);
+    CHS_LAUNCH_CHECK();
+    cs::TileMap m2;
+    memset(&m2, 0, sizeof(m2));
+    m2.table = 1; m2.n_seg = (int)p.n_seg2; m2.seg_begin = seg_begin2; m2.tile_first = tile_first2;
+    st = launch_count(m2, cs::ArrayKeys<uint8_t>{d8}, 0, counts, p.t_cap, s);
+    if (st) return st;
+    st = launch_colscan(m2, counts, p.t_cap, totals2, s);
+    if (st) return st;
+    st = exclusive_scan(ArrayIn{totals2}, (uint64_t)p.n_seg2 * cs::kDigits, sums, StoreU32{base2}, nullptr, s);
+    if (st) return st;
+    tile_offsets_from_base_kernel<<<grid_for(n_lin + 1), kThreads, 0, s>>>(n_lin, d.tiles, p.nb, base2, seg_begin2, (int)p.n_seg2, tile_offsets);
+    CHS_LAUNCH_CHECK();
+    cs::ScatterArgs<cs::ArrayKeys<uint8_t>, uint8_t> a;
+    a.map = m2; a.keys = cs::ArrayKeys<uint8_t>{d8}; a.vals_in = v_mid; a.keys_out = nullptr; a.vals_out = vals_sorted; a.shift = 0;
+    a.prefix = counts; a.t_cap = p.t_cap; a.totals = totals2; a.digit_base = base2;
+    st = launch_scatter(a, d.tiles > 1 ? chs_bit_length((uint64_t)d.tiles - 1) : 1, s);
+    if (st) return st;
+    if (keys_sorted) {
+      rebuild_keys_from_offsets_kernel<<<(unsigned)n_lin, 128, 0, s>>>(d.tiles, d.tile_bits, tile_offsets, vals_sorted, depths, keys_sorted);
+      CHS_LAUNCH_CHECK();
+    }
+    return CHS_OK;
+  }
+  // LSD routes: the literal 64-bit key sort, or linear cam * tiles + tile keys when tile ids do not fit 16 bits
+  uint32_t* totals = ar.take<uint32_t>(cs::kDigits);
+  int32_t* v_a = ar.take<int32_t>(cap);
+  if (cfg->sort_mode == CHS_SORT_KEY64) {
+    uint64_t* k_a = ar.take<uint64_t>(cap);
+    uint64_t* k_final = keys_sorted ? keys_sorted : ar.take<uint64_t>(cap);
+    CHS_SORT_WS_CHECK();
+    uint64_t* k0 = p.passes % 2 ? k_a : k_final;
+    int32_t* v0 = p.passes % 2 ? v_a : vals_sorted;
+    emit_kernel<0, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, tight, (uint32_t)cap,
+                                                                 (const float4*)geom, radii, depths, isect_offsets, nullptr, k0, nullptr, v0);
+    CHS_LAUNCH_CHECK();
+    int st = lsd_sort<uint64_t>(p.passes, cap, n_dev, k_a, v_a, k_final, vals_sorted, counts, p.t_cap, totals, s);
+    if (st) return st;
+    tile_offsets_kernel<0, uint32_t><<<grid_for(((int64_t)cap + 3) / 4), kThreads, 0, s>>>((int64_t)cap, n_dev, (int)n_lin, d.tile_bits, d.tiles, k_final,
+                                                                                          nullptr, tile_offsets);
+    CHS_LAUNCH_CHECK();
+  } else {
+    uint32_t* k_a = ar.take<uint32_t>(cap);
+    uint32_t* k_final = ar.take<uint32_t>(cap);
+    CHS_SORT_WS_CHECK();
+    uint32_t* k0 = p.passes % 2 ? k_a : k_final;
+    int32_t* v0 = p.passes % 2 ? v_a : vals_sorted;
+    emit_kernel<1, uint32_t><<<grid_for(d.CN), kThreads, 0, s>>>(d.CN, d.N, d.tile_w, d.tile_h, d.tiles, d.tile_bits, tight, (uint32_t)cap,
+                                                                 (const float4*)geom, radii, depths, isect_offsets, order, nullptr, k0, v0);
+    CHS_LAUNCH_CHECK();
+    int st = lsd_sort<uint32_t>(p.passes, cap, n_dev, k_a, v_a, k_final, vals_sorted, counts, p.t_cap, totals, s);
+    if (st) return st;
+    tile_offsets_kernel<1, uint32_t><<<grid_for(((int64_t)cap + 3) / 4), kThreads, 0, s>>>((int64_t)cap, n_dev, (int)n_lin, d.tile_bits, d.tiles, nullptr,
+                                                                                          k_final, tile_offsets);
+    CHS_LAUNCH_CHECK();
+    if (keys_sorted) {
+      rebuild_keys_from_offsets_kernel<<<(unsigned)n_lin, 128, 0, s>>>(d.tiles, d.tile_bits, tile_offsets, vals_sorted, depths, keys_sorted);
+      CHS_LAUNCH_CHECK();
+    }
+  }
+#undef CHS_SORT_WS_CHECK
+  return CHS_OK;
+}
+
+}  // namespace
+
+// exported to chs_api.cu: every route fits the same workspace, so a knob never changes the sizes a caller queried
+int chs_bin_count_bytes(const ChsDims& d, int sort_mode, uint64_t* bytes) {
+  uint64_t b = 0;
+  int st = cub_bin_count_bytes(d, sort_mode, &b);
+  if (st) return st;
+  const uint64_t h = hw_count_bytes(d, sort_mode);
+  *bytes = b > h ? b : h;
+  return CHS_OK;
+}
+
+int chs_bin_sort_bytes(const ChsDims& d, const chs_config* cfg, int64_t M, uint64_t* bytes) {
+  uint64_t b = 0;
+  int st = legacy_bin_sort_bytes(d, cfg, M, &b);
+  if (st) return st;
+  const uint64_t h = hw_sort_bytes(d, cfg->sort_mode, (uint64_t)(M > 0 ? M : 0));
+  *bytes = b > h ? b : h;
+  return CHS_OK;
+}
+
+extern "C" int chs_bin_count(const chs_config* cfg, const int32_t* tiles_touched, const float* depths, uint32_t* isect_offsets,
+                             int32_t* order, int64_t* n_isect_dev, int64_t* n_isect_host, void* workspace,
+                             uint64_t workspace_bytes, void* stream) {
+  if (cfg && cfg->tune_bin == 1)
+    return cub_bin_count(cfg, tiles_touched, depths, isect_offsets, order, n_isect_dev, n_isect_host, workspace, workspace_bytes, stream);
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(tiles_touched && depths && isect_offsets && n_isect_dev && workspace, "chs_bin_count: null pointer");
+  CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || order, "chs_bin_count: order buffer required for CHS_SORT_DEPTH_PRESORT");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d.CN == 0) {
+    CHS_CUDA(cudaMemsetAsync(n_isect_dev, 0, sizeof(int64_t), s));
+    if (n_isect_host) *n_isect_host = 0;
+    return CHS_OK;
+  }
+  st = hw_bin_count(cfg, d, tiles_touched, depths, isect_offsets, order, n_isect_dev, workspace, workspace_bytes, s);
+  if (st) return st;
+  if (n_isect_host) {
+    CHS_CUDA(cudaMemcpyAsync(n_isect_host, n_isect_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CHS_CUDA(cudaStreamSynchronize(s));
+    if (*n_isect_host >= ((int64_t)1 << 32) - 1) {
+      chs_set_error("chs_bin_count: %lld intersections exceed the 2^32 limit of one launch; split the frame batch",
+                    (long long)*n_isect_host);
+      return CHS_ERR_UNSUPPORTED;
+    }
+  }
+  return CHS_OK;
+}
+
+static int bin_sort_common(const chs_config* cfg, int64_t cap, const int64_t* n_dev, const float* geom, const int32_t* radii,
+                           const float* depths, const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted,
+                           int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, void* stream) {
+  ChsDims d;
+  int st = chs_make_dims(cfg, &d);
+  if (st) return st;
+  CHS_REQUIRE(geom && radii && depths && isect_offsets && tile_offsets, "chs_bin_sort: null pointer");
+  CHS_REQUIRE(cap >= 0 && cap < ((int64_t)1 << 32) - 1, "chs_bin_sort: n_isect out of range");
+  CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || order, "chs_bin_sort: order required for CHS_SORT_DEPTH_PRESORT");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cap == 0 || d.CN == 0) {
+    CHS_CUDA(cudaMemsetAsync(tile_offsets, 0, ((size_t)d.C * d.tiles + 1) * sizeof(uint32_t), s));
+    return CHS_OK;
+  }
+  CHS_REQUIRE(vals_sorted && workspace, "chs_bin_sort: null output/workspace");
+  return hw_bin_sort(cfg, d, (uint64_t)cap, n_dev, geom, radii, depths, isect_offsets, order, keys_sorted, vals_sorted, tile_offsets, workspace,
+                     workspace_bytes, s);
+}
+
+extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii, const float* depths,
+                            const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted,
+                            uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, void* stream) {
+  if (cfg && cfg->tune_bin != 0)
+    return legacy_bin_sort(cfg, n_isect, geom, radii, depths, isect_offsets, order, keys_sorted, vals_sorted, tile_offsets, workspace,
+                           workspace_bytes, stream);
+  return bin_sort_common(cfg, n_isect, nullptr, geom, radii, depths, isect_offsets, order, keys_sorted, vals_sorted, tile_offsets, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int chs_bin_sort_dev(const chs_config* cfg, int64_t isect_capacity, const int64_t* n_isect_dev, const float* geom,
+                                const int32_t* radii, const float* depths, const uint32_t* isect_offsets, const int32_t* order,
+                                uint64_t* keys_sorted, int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace,
+                                uint64_t workspace_bytes, void* stream) {
+  CHS_REQUIRE(n_isect_dev, "chs_bin_sort_dev: null n_isect_dev");
+  CHS_REQUIRE(!cfg || cfg->tune_bin == 0, "chs_bin_sort_dev: only the default (hand-written) binning route runs without the host knowing M");
+  return bin_sort_common(cfg, isect_capacity, n_isect_dev, geom, radii, depths, isect_offsets, order, keys_sorted, vals_sorted, tile_offsets,
+                         workspace, workspace_bytes, stream);
+}
+
+// ---- verification helper: the radix machinery on caller-supplied keys (tests/test_gpu_sort.py) ----
+extern "C" int chs_radix_sort_pairs(const uint32_t* keys_in, int32_t n_seg, uint32_t seg_len, int32_t bits, uint32_t* keys_out,
+                                    int32_t* vals_out, void* workspace, uint64_t workspace_bytes, void* stream) {
+  CHS_REQUIRE(n_seg >= 0 && bits >= 1 && bits <= 32, "chs_radix_sort_pairs: bad arguments");
+  const uint64_t n = (uint64_t)n_seg * seg_len;
+  CHS_REQUIRE(n < ((uint64_t)1 << 32) - 1, "chs_radix_sort_pairs: too many items");
+  if (n == 0) return CHS_OK;
+  CHS_REQUIRE(keys_in && keys_out && vals_out && workspace, "chs_radix_sort_pairs: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t tps = tiles_of(seg_len), t_cap = tps * (uint32_t)n_seg;
+  ChsArena ar(workspace, workspace_bytes);
+  uint32_t* counts = ar.take<uint32_t>((uint64_t)cs::kDigits * t_cap);
+  uint32_t* totals = ar.take<uint32_t>((uint64_t)n_seg * cs::kDigits);
+  uint32_t* kt = ar.take<uint32_t>(n);
+  int32_t* vt = ar.take<int32_t>(n);
+  if (!ar.ok) {
+    chs_set_error("chs_radix_sort_pairs: workspace too small (need ~%llu bytes)",
+                  (unsigned long long)(1024 + (uint64_t)cs::kDigits * t_cap * 4 + (uint64_t)n_seg * 1024 + n * 8 + 2048));
+    return CHS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cs::TileMap map;
+  memset(&map, 0, sizeof(map));
+  map.n_seg = n_seg; map.seg_len = seg_len; map.tiles_per_seg = tps;
+  const int passes = (bits + 7) / 8;
+  // buffers alternate so that the last pass lands in the caller's outputs
+  const uint32_t* kin = keys_in;
+  const int32_t* vin = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const bool to_out = (passes - 1 - p) % 2 == 0;
+    uint32_t* ko = to_out ? keys_out : kt;
+    int32_t* vo = to_out ? vals_out : vt;
+    int st = radix_pass<cs::ArrayKeys<uint32_t>, uint32_t>(map, cs::ArrayKeys<uint32_t>{kin}, vin, ko, vo, 8 * p, 8, counts, t_cap, totals, nullptr, s);
+    if (st) return st;
+    kin = ko;
+    vin = vo;
   }
   return CHS_OK;
 }

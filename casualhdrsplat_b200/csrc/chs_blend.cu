@@ -126,8 +126,8 @@ __device__ __forceinline__ P2 pair_power2(const float4 sa, float kc, float lo, f
   dx = sa.x - px;
   dy2 = p2s(sa.y) - py2;
   u2 = fma2(p2s(sa.w), dy2, p2s(dx));
-  const P2 t2 = (p2s(kc) * dy2) * dy2;
-  return fma2(p2s(sa.z) * u2, u2, t2) + p2s(lo);
+  const P2 t2 = fma2(p2s(kc) * dy2, dy2, p2s(lo));
+  return fma2(p2s(sa.z) * u2, u2, t2);
 }
 
 struct BlendFwdArgs {
@@ -777,6 +777,429 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd2_kernel(BlendB
   }
 }
 
+
+// =================================================================================================
+// Round-2 kernels (defaults).  Same tile / warp / pixel-pair layout and the same exact culling as above; what changes is the
+// instruction count of the inner loops (ncu source pages of the r1g kernels, profiles/r1g_ncu_blend.csv):
+//   * SURVIVOR LIST.  The lanes that test 32 staged Gaussians against the warp's block write the survivors' staged indices
+//     compactly to a per-warp shared-memory list (one STS per survivor); the pair loop then reads "next index" with one
+//     broadcast LDS instead of finding and clearing the next set bit of the ballot (FLO/BREV, shifts, masks, address
+//     arithmetic: 6-8 instructions per (warp, Gaussian) in r1).
+//   * Staged record repacked as A = (mx, my, qa, r), B = (kc, lo, cr, cg), C = (cb, 1/opacity, val, rbc): the hot loops read A,
+//     B and one scalar of C.
+//   * Forward: the transmittance is updated as T -= w with w = alpha T (or 0), which replaces the per-pixel select between
+//     "T (1 - alpha)" and "T" (four register moves per pair in r1) and reuses the product the colour sums need anyway; the last
+//     accumulated index is tracked batch-relative.
+//   * Backward, phase A: the three "colour behind" accumulators become ONE scalar R, the colour behind per unit of
+//     transmittance dotted with the pixel's upstream gradient (chs_pair_bwd_scalars_r in chs_math.cuh: R <- R - alpha (R - c.v),
+//     no division, dL/dalpha = T (c.v - R)): 11 packed operations instead of 19.  The table row of a slot is reached through a
+//     running pointer (r1 recomputed the address from the thread id every iteration), a lane's two pixels are adjacent in the
+//     row (two STS.64 instead of four STS.32), and the staged index of the slot rides in the row's padding.
+//   * Backward, phase B: a lane's 128-bit table loads now hold pixel pairs that differ only in the row (y, y + 4), so the row
+//     sums stay packed to the end; sum vs.u is derived as sum vs.dx + r sum vs.dy instead of being accumulated per pixel.
+// =================================================================================================
+template <int kB>
+struct SplatSmem3 {
+  float4 a[kB];  // mx, my, qa, r
+  float4 b[kB];  // kc, lo, cr, cg
+  float4 c[kB];  // cb, 1/opacity, val (int bits; c * N + g), rbc
+};
+
+template <class Smem>
+__device__ __forceinline__ void stage_splat3(Smem& sm, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
+                                             const float* __restrict__ conic_c, const float4* __restrict__ rgbo) {
+  const float4 gm = __ldg(geom + val);
+  const float cc = __ldg(conic_c + val);
+  const float4 col = __ldg(rgbo + (val - cam_base));
+  ChsSplat<float> s;
+  chs_make_splat(gm.x, gm.y, gm.z, gm.w, cc, col.w, col.x, col.y, col.z, s);
+  sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.r);
+  sm.b[slot] = make_float4(s.kc, s.lo, s.cr, s.cg);
+  sm.c[slot] = make_float4(s.cb, s.inv_opac, __int_as_float(val), s.rbc);
+}
+
+template <class Smem>
+__device__ __forceinline__ bool splat_hits_block3(const Smem& sm, int slot, float bx0, float bx1, float by0, float by1) {
+  const float4 a = sm.a[slot];
+  const float2 b = *reinterpret_cast<const float2*>(&sm.b[slot]);
+  ChsSplat<float> s;
+  s.mx = a.x; s.my = a.y; s.qa = a.z; s.r = a.w;
+  s.kc = b.x; s.lo = b.y; s.rbc = sm.c[slot].w;
+  return chs_block_max_power(s, bx0, bx1, by0, by1) >= CHS_LOG2_ALPHA_MIN - 1e-3f;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt_() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ unsigned lanemask_gt_() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+  return m;
+}
+
+// ---- forward ----
+template <int kMinBlocks, bool kPerPoseCrf>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendFwdArgs a) {
+  __shared__ SplatSmem3<kBatch> sm;
+  __shared__ int s_list[kThreads / 32][32];
+  extern __shared__ float s_crf[];  // the CRF parameters [3, stride] when the CRF is learned
+
+  const int tile = blockIdx.x, frame = blockIdx.y;
+  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 8;
+  const int ix = bx + (lane & 7), iyA = by + (lane >> 3), iyB = iyA + 4;
+  const bool insideA = ix < a.W && iyA < a.H, insideB = ix < a.W && iyB < a.H;
+  const float px = ix + 0.5f;
+  const P2 py2 = p2(iyA + 0.5f, iyB + 0.5f);
+  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 7.5f;
+  const int64_t P = (int64_t)a.W * a.H;
+  const int64_t pixA = (int64_t)iyA * a.W + ix, pixB = (int64_t)iyB * a.W + ix;
+  const float kInf = __int_as_float(0x7f800000);
+  const unsigned lt = lanemask_lt_();
+  int* list = s_list[warp];
+
+  const int crf_stride = chs_crf_stride(a.crf_kind, a.crf_hidden);  // 0 for the identity CRF
+  for (int i = tid; i < 3 * crf_stride; i += kThreads) s_crf[i] = a.crf_params[i];
+
+  constexpr bool per_pose_crf = kPerPoseCrf;
+  const float dt = a.exposure[frame];
+  if (per_pose_crf) __syncthreads();  // s_crf is read inside the pose loop
+  P2 sum_r2 = p2s(0.f), sum_g2 = p2s(0.f), sum_b2 = p2s(0.f), sum_al2 = p2s(0.f);
+  for (int k = 0; k < a.n_virtual; ++k) {
+    const int c = frame * a.n_virtual + k;
+    const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;  // index of the camera's first record in rgbo
+    const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
+    const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
+    P2 T2 = p2s(1.f), acc_r2 = p2s(0.f), acc_g2 = p2s(0.f), acc_b2 = p2s(0.f);
+    int lastA = 0, lastB = 0;
+    // "done" is folded into the pixel's alpha threshold: a finished pixel has threshold +inf
+    float thrA = insideA ? CHS_LOG2_ALPHA_MIN : kInf, thrB = insideB ? CHS_LOG2_ALPHA_MIN : kInf;
+    bool warp_done = __all_sync(CHS_FULL_MASK, thrA == kInf && thrB == kInf);
+    for (uint32_t base = start; base < end; base += kBatch) {
+      // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
+      if (__syncthreads_and(thrA == kInf && thrB == kInf)) break;
+      const int cnt = min((uint32_t)kBatch, end - base);
+      for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[base + i], cam_base, a.geom, a.conic_c, a.rgbo);
+      __syncthreads();
+      if (warp_done) continue;
+      const int idx0 = (int)(base - start) + 1;
+      int relA = -1, relB = -1;  // staged index of the last Gaussian accumulated from this batch
+      for (int sub = 0; sub < cnt; sub += 32) {
+        const int j = sub + lane;
+        const bool hit = (j < cnt) && splat_hits_block3(sm, j, bx0, bx1, by0, by1);
+        const unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+        if (mask == 0u) continue;
+        const int n_surv = __popc(mask);
+        if (hit) list[__popc(mask & lt)] = j;  // ascending: front to back
+        __syncwarp();
+        for (int i = 0; i < n_surv; ++i) {
+          const int jj = list[i];
+          const float4 sa = sm.a[jj];
+          const float4 sb = sm.b[jj];  // kc, log2(opacity), cr, cg
+          float dx;
+          P2 dy2, u2;
+          const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+          const float pA = p2lo(pw2), pB = p2hi(pw2);
+          const bool actA = pA >= thrA, actB = pB >= thrB;
+          if (actA || actB) {
+            const float alA = actA ? fminf(CHS_ALPHA_MAX, chs_exp2_fast(pA)) : 0.f;
+            const float alB = actB ? fminf(CHS_ALPHA_MAX, chs_exp2_fast(pB)) : 0.f;
+            const P2 wq2 = p2(alA, alB) * T2;
+            const P2 Tn2 = T2 - wq2;  // = T (1 - alpha)
+            // stop (this Gaussian is not accumulated) when the transmittance would drop to <= 1e-4
+            const bool accA = actA && p2lo(Tn2) > CHS_T_STOP, accB = actB && p2hi(Tn2) > CHS_T_STOP;
+            thrA = (actA && !accA) ? kInf : thrA;
+            thrB = (actB && !accB) ? kInf : thrB;
+            const P2 w2 = p2(accA ? p2lo(wq2) : 0.f, accB ? p2hi(wq2) : 0.f);
+            const float cb = sm.c[jj].x;
+            acc_r2 = fma2(p2s(sb.z), w2, acc_r2);
+            acc_g2 = fma2(p2s(sb.w), w2, acc_g2);
+            acc_b2 = fma2(p2s(cb), w2, acc_b2);
+            T2 = T2 - w2;
+            relA = accA ? jj : relA;
+            relB = accB ? jj : relB;
+          }
+        }
+        __syncwarp();  // the list is rewritten by the next sub-batch
+        if (__all_sync(CHS_FULL_MASK, thrA == kInf && thrB == kInf)) {
+          warp_done = true;
+          break;
+        }
+      }
+      lastA = relA >= 0 ? idx0 + relA : lastA;
+      lastB = relB >= 0 ? idx0 + relB : lastB;
+    }
+    __syncthreads();  // the next pose restages shared memory
+    if (insideA) {
+      a.final_T[(int64_t)c * P + pixA] = p2lo(T2);
+      a.last_id[(int64_t)c * P + pixA] = lastA;
+    }
+    if (insideB) {
+      a.final_T[(int64_t)c * P + pixB] = p2hi(T2);
+      a.last_id[(int64_t)c * P + pixB] = lastB;
+    }
+    const P2 h_r2 = fma2(T2, p2s(a.bg[0]), acc_r2), h_g2 = fma2(T2, p2s(a.bg[1]), acc_g2), h_b2 = fma2(T2, p2s(a.bg[2]), acc_b2);
+    sum_al2 = sum_al2 + (p2s(1.f) - T2);
+    if (!per_pose_crf) {
+      sum_r2 = sum_r2 + h_r2;
+      sum_g2 = sum_g2 + h_g2;
+      sum_b2 = sum_b2 + h_b2;
+    } else {
+      float y[2][3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float hr = h == 0 ? p2lo(h_r2) : p2hi(h_r2), hg = h == 0 ? p2lo(h_g2) : p2hi(h_g2), hb = h == 0 ? p2lo(h_b2) : p2hi(h_b2);
+        y[h][0] = dt * hr; y[h][1] = dt * hg; y[h][2] = dt * hb;
+        if (a.crf_kind != CHS_CRF_IDENTITY) {
+          y[h][0] = chs_crf_fwd(a.crf_kind, y[h][0], s_crf, a.crf_hidden);
+          y[h][1] = chs_crf_fwd(a.crf_kind, y[h][1], s_crf + crf_stride, a.crf_hidden);
+          y[h][2] = chs_crf_fwd(a.crf_kind, y[h][2], s_crf + 2 * crf_stride, a.crf_hidden);
+        }
+        if (h == 0 ? insideA : insideB) {
+          const int64_t o = ((int64_t)c * P + (h == 0 ? pixA : pixB)) * 3;
+          a.hdr_mean[o] = hr; a.hdr_mean[o + 1] = hg; a.hdr_mean[o + 2] = hb;
+        }
+      }
+      sum_r2 = sum_r2 + p2(y[0][0], y[1][0]);
+      sum_g2 = sum_g2 + p2(y[0][1], y[1][1]);
+      sum_b2 = sum_b2 + p2(y[0][2], y[1][2]);
+    }
+  }
+  // formation epilogue (A.7, decision D0): mean over poses, x exposure, CRF
+  const float inv_n = 1.f / (float)a.n_virtual;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (!(h == 0 ? insideA : insideB)) continue;
+    const float hr = (h == 0 ? p2lo(sum_r2) : p2hi(sum_r2)) * inv_n;
+    const float hg = (h == 0 ? p2lo(sum_g2) : p2hi(sum_g2)) * inv_n;
+    const float hb = (h == 0 ? p2lo(sum_b2) : p2hi(sum_b2)) * inv_n;
+    const float al = (h == 0 ? p2lo(sum_al2) : p2hi(sum_al2)) * inv_n;
+    const int64_t pix = h == 0 ? pixA : pixB;
+    if (per_pose_crf) {  // the sums already hold F(dt * H_k)
+      const int64_t o = ((int64_t)frame * P + pix) * 3;
+      a.ldr[o] = hr; a.ldr[o + 1] = hg; a.ldr[o + 2] = hb;
+      a.alpha[(int64_t)frame * P + pix] = al;
+      continue;
+    }
+    float o0 = dt * hr, o1 = dt * hg, o2 = dt * hb;
+    if (a.crf_kind != CHS_CRF_IDENTITY) {
+      o0 = chs_crf_fwd(a.crf_kind, o0, s_crf, a.crf_hidden);
+      o1 = chs_crf_fwd(a.crf_kind, o1, s_crf + crf_stride, a.crf_hidden);
+      o2 = chs_crf_fwd(a.crf_kind, o2, s_crf + 2 * crf_stride, a.crf_hidden);
+    }
+    const int64_t o = ((int64_t)frame * P + pix) * 3;
+    a.ldr[o] = o0; a.ldr[o + 1] = o1; a.ldr[o + 2] = o2;
+    a.hdr_mean[o] = hr; a.hdr_mean[o + 1] = hg; a.hdr_mean[o + 2] = hb;
+    a.alpha[(int64_t)frame * P + pix] = al;
+  }
+}
+
+// ---- backward ----
+constexpr int kRow3 = 68;  // floats per table row: 64 pixel ids (id = 2 lane + h), the slot's staged index, padding to 16 bytes
+
+template <int kSlots>
+struct __align__(16) BwdWarp3 {
+  float nvs[kSlots][kRow3];  // -dL/dsigma of (slot, pixel id); column 64: staged-batch index of the slot's Gaussian (int bits)
+  float nf[kSlots][kRow3];   // -alpha * T of (slot, pixel id)
+  float vh[3][64];           // dL/dH of the warp's pixels by pixel id (r, g, b planes)
+  int list[32];              // survivors of the current 32-entry sub-batch, back to front
+};
+
+// phase B for the n_slots tabled Gaussians of this warp.  Lane = (slot k = lane % 8, part = lane / 8); a part covers the two
+// pixel rows y0 = part and y0 + 4 of the warp's 8x8 block: pixel ids 16 part .. 16 part + 15, i.e. four 128-bit chunks
+// [(x, y0), (x, y0 + 4), (x + 1, y0), (x + 1, y0 + 4)] for x = 0, 2, 4, 6.
+template <int kSlots, class Smem>
+__device__ __forceinline__ void bwd_round3(const Smem& sm, const BwdWarp3<kSlots>& ws, int n_slots, int lane, float bxc, float byc,
+                                           const BlendBwdArgs& a) {
+  static_assert(kSlots == 8, "phase B assigns one lane per (slot, row pair): 8 slots x 4 parts");
+  __syncwarp();
+  const int k = lane & 7, part = lane >> 3;
+  const bool active = k < n_slots;
+  P2 rowvs = p2s(0.f), rowt = p2s(0.f), S_xx = p2s(0.f), G6 = p2s(0.f), G7 = p2s(0.f), G8 = p2s(0.f);
+  float4 sa = make_float4(0.f, 0.f, 0.f, 0.f);
+  float kc = 0.f, inv_opac = 0.f, dy_lo = 0.f;
+  uint32_t val = 0;
+  if (active) {
+    const int jj = __float_as_int(ws.nvs[k][64]);
+    sa = sm.a[jj];  // mx, my, qa, r
+    kc = sm.b[jj].x;
+    const float4 sc = sm.c[jj];  // cb, 1/opacity, val, rbc
+    inv_opac = sc.y;
+    val = (uint32_t)__float_as_int(sc.z);
+    const float dxb = sa.x - bxc;  // mean - centre of pixel column 0
+    dy_lo = sa.y - (byc + (float)part);
+    const float* rv = &ws.nvs[k][16 * part];
+    const float* rf = &ws.nf[k][16 * part];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 vs4 = *reinterpret_cast<const float4*>(rv + 4 * c);
+      const float4 f4 = *reinterpret_cast<const float4*>(rf + 4 * c);
+      const float4 r4 = *reinterpret_cast<const float4*>(&ws.vh[0][16 * part + 4 * c]);
+      const float4 g4 = *reinterpret_cast<const float4*>(&ws.vh[1][16 * part + 4 * c]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&ws.vh[2][16 * part + 4 * c]);
+      const P2 vA = p2(vs4.x, vs4.y), vB = p2(vs4.z, vs4.w);  // columns 2c and 2c + 1, rows (y0, y0 + 4)
+      const P2 dxa = p2s(dxb - (float)(2 * c)), dxc = p2s(dxb - (float)(2 * c + 1));
+      const P2 tA = vA * dxa, tB = vB * dxc;
+      rowvs = rowvs + (vA + vB);
+      rowt = rowt + (tA + tB);
+      S_xx = fma2(tA, dxa, S_xx);
+      S_xx = fma2(tB, dxc, S_xx);
+      const P2 fA = p2(f4.x, f4.y), fB = p2(f4.z, f4.w);
+      G6 = fma2(fA, p2(r4.x, r4.y), G6); G6 = fma2(fB, p2(r4.z, r4.w), G6);
+      G7 = fma2(fA, p2(g4.x, g4.y), G7); G7 = fma2(fB, p2(g4.z, g4.w), G7);
+      G8 = fma2(fA, p2(b4.x, b4.y), G8); G8 = fma2(fB, p2(b4.z, b4.w), G8);
+    }
+  }
+  // the two halves of every packed sum are the rows y0 (dy = dy_lo) and y0 + 4 (dy = dy_lo - 4)
+  const P2 dyv = p2(dy_lo, dy_lo - 4.f);
+  const P2 S_dy = rowvs * dyv, S_xy = rowt * dyv;
+  const P2 S_yy = S_dy * dyv;
+  const float s_dy = p2sum(S_dy);
+  float t[9] = {fmaf(sa.w, s_dy, p2sum(rowt)), s_dy, p2sum(S_xx), p2sum(S_xy), p2sum(S_yy), p2sum(rowvs), p2sum(G6), p2sum(G7), p2sum(G8)};
+#pragma unroll
+  for (int o = 8; o < 32; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t[i] += __shfl_xor_sync(CHS_FULL_MASK, t[i], o);
+  if (active) {
+    ChsSplat<float> sp;
+    sp.qa = sa.z; sp.r = sa.w; sp.kc = kc; sp.inv_opac = inv_opac;
+    float g[9];
+    chs_moments_to_grads_neg(sp, t, g);  // csrc/chs_math.cuh, checked on the host against chs_pair_bwd and the oracle
+    if (part == 0) atomicAdd(a.v_geom + val, make_float4(g[0], g[1], g[2], g[3]));
+    if (part == 1) atomicAdd(a.v_cogr + val, make_float4(g[4], g[5], g[6], g[7]));
+    if (part == 2) atomicAdd(a.v_blue + val, g[8]);
+  }
+  __syncwarp();  // the table is rewritten by the next round
+}
+
+template <int kSlots, int kB, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Smem = SplatSmem3<kB>;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  __shared__ int s_max_last;
+
+  const int tile = blockIdx.x, c = blockIdx.y;
+  const int frame = c / a.n_virtual;
+  const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;
+  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  BwdWarp3<kSlots>& ws = reinterpret_cast<BwdWarp3<kSlots>*>(smem_raw + sizeof(Smem))[warp];
+  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 8;
+  const int ix = bx + (lane & 7), iy0 = by + (lane >> 3);
+  const float px = ix + 0.5f;
+  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 7.5f;
+  const int64_t P = (int64_t)a.W * a.H;
+  const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
+  const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
+  if (end <= start) return;
+
+  const float inv_nv = 1.f / (float)a.n_virtual;
+  const int vimg = a.v_hdr_per_camera ? c : frame;
+  int last[2];
+  int warp_last = 0;
+  float Tf[2] = {1.f, 1.f}, v[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, r0[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int iy = iy0 + 4 * h;
+    last[h] = 0;
+    if (ix < a.W && iy < a.H) {
+      const int64_t pix = (int64_t)iy * a.W + ix;
+      Tf[h] = a.final_T[(int64_t)c * P + pix];
+      last[h] = a.last_id[(int64_t)c * P + pix];
+      const int64_t o = ((int64_t)vimg * P + pix) * 3;
+      v[h][0] = a.v_hdr[o]; v[h][1] = a.v_hdr[o + 1]; v[h][2] = a.v_hdr[o + 2];
+      const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] * inv_nv : 0.f;
+      // behind the last accumulated Gaussian lies the background: R = bg . v_H - v_alpha (chs_pair_bwd_scalars_r)
+      r0[h] = (a.bg[0] * v[h][0] + a.bg[1] * v[h][1] + a.bg[2] * v[h][2]) - v_al;
+    }
+    warp_last = max(warp_last, last[h]);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) ws.vh[ch][2 * lane + h] = v[h][ch];  // pixel id = 2 lane + h  <->  (x, y) = (lane & 7, (lane >> 3) + 4 h)
+  }
+  const P2 py2 = p2(iy0 + 0.5f, iy0 + 4.5f);
+  P2 Tr2 = p2(Tf[0], Tf[1]);
+  P2 R2 = p2(r0[0], r0[1]);
+  const P2 vh_r2 = p2(v[0][0], v[1][0]), vh_g2 = p2(v[0][1], v[1][1]), vh_b2 = p2(v[0][2], v[1][2]);
+  if (tid == 0) s_max_last = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(CHS_FULL_MASK, warp_last, o));
+  if (lane == 0 && warp_last > 0) atomicMax(&s_max_last, warp_last);
+  __syncthreads();
+  const int n_walk = s_max_last;
+
+  const unsigned gt = lanemask_gt_();
+  float* const row0 = &ws.nvs[0][0];
+  float* const row_end = row0 + kSlots * kRow3;
+  float* row = row0;                 // table row of the next slot (running pointer: never recomputed from the thread id)
+  constexpr int kFOff = kSlots * kRow3;  // nf row of a slot = its nvs row + kFOff floats
+  for (int hi = n_walk; hi > 0; hi -= kB) {
+    const int lo = max(0, hi - kB);
+    const int cnt = hi - lo;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[start + lo + i], cam_base, a.geom, a.conic_c, a.rgbo);
+    __syncthreads();
+    if (warp_last <= lo) continue;
+    const int lrA = last[0] - lo - 1, lrB = last[1] - lo - 1;  // staged indices <= lr are inside the pixel's accumulated prefix
+    for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
+      const int sub_lo = max(0, sub_hi - 32);
+      if (warp_last <= lo + sub_lo) continue;
+      const int j = sub_lo + lane;
+      const bool hit = (j < sub_hi) && (lo + j < warp_last) && splat_hits_block3(sm, j, bx0, bx1, by0, by1);
+      const unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+      if (mask == 0u) continue;
+      const int n_surv = __popc(mask);
+      if (hit) ws.list[__popc(mask & gt)] = j;  // descending: back to front
+      __syncwarp();
+      // ---- phase A over the survivors ----
+      for (int i = 0; i < n_surv; ++i) {
+        const int jj = ws.list[i];
+        const float4 sa = sm.a[jj];  // mx, my, qa, r
+        const float4 sb = sm.b[jj];  // kc, log2(opacity), cr, cg
+        float dx;
+        P2 dy2, u2;
+        const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+        const float pA = p2lo(pw2), pB = p2hi(pw2);
+        const bool validA = (jj <= lrA) && pA >= CHS_LOG2_ALPHA_MIN;
+        const bool validB = (jj <= lrB) && pB >= CHS_LOG2_ALPHA_MIN;
+        if (!__any_sync(CHS_FULL_MASK, validA || validB)) continue;
+        const float cb = sm.c[jj].x;
+        const float auA = validA ? chs_exp2_fast(pA) : 0.f;
+        const float auB = validB ? chs_exp2_fast(pB) : 0.f;
+        // packed chs_pair_bwd_scalars_r with na = -alpha: a pixel that does not contribute runs with alpha = 0, which leaves
+        // T and R untouched and tables zeros
+        const P2 na2 = p2(fmaxf(-CHS_ALPHA_MAX, -auA), fmaxf(-CHS_ALPHA_MAX, -auB));
+        const P2 om2 = p2s(1.f) + na2;
+        Tr2 = Tr2 * p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));  // transmittance before this Gaussian
+        const P2 nf2 = na2 * Tr2;
+        const P2 s2 = fma2(p2s(cb), vh_b2, fma2(p2s(sb.w), vh_g2, p2s(sb.z) * vh_r2));
+        const P2 e2 = R2 - s2;
+        R2 = fma2(na2, e2, R2);
+        // no gradient through the 0.999 clamp
+        const P2 gate2 = p2(auA <= CHS_ALPHA_MAX ? 1.f : 0.f, auB <= CHS_ALPHA_MAX ? 1.f : 0.f);
+        const P2 nvs2 = (nf2 * e2) * gate2;
+        *reinterpret_cast<float2*>(row + 2 * lane) = make_float2(p2lo(nvs2), p2hi(nvs2));
+        *reinterpret_cast<float2*>(row + kFOff + 2 * lane) = make_float2(p2lo(nf2), p2hi(nf2));
+        if (lane == 0) row[64] = __int_as_float(jj);
+        row += kRow3;
+        if (row == row_end) {
+          bwd_round3<kSlots>(sm, ws, kSlots, lane, bx0, by0, a);
+          row = row0;
+        }
+      }
+      __syncwarp();  // the list is rewritten by the next sub-batch
+    }
+    if (row != row0) {  // the staged batch is about to be replaced
+      bwd_round3<kSlots>(sm, ws, (int)((row - row0) / kRow3), lane, bx0, by0, a);
+      row = row0;
+    }
+  }
+}
+
 }  // namespace
 
 static size_t crf_smem_bytes(const chs_config* cfg) {
@@ -806,12 +1229,20 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   const size_t dyn = crf_smem_bytes(cfg);
   cudaStream_t s = (cudaStream_t)stream;
   if (cfg->crf_before_average) {
-    blend_fwd_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
+    if (cfg->tune_blend_fwd == 8)
+      blend_fwd_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
+    else
+      blend_fwd2_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
   } else {
     switch (cfg->tune_blend_fwd) {  // development knob (chs_config)
       case 1: blend_fwd_kernel<6, false><<<grid, kThreads, dyn, s>>>(a); break;
       case 3: blend_fwd_kernel<10, false><<<grid, kThreads, dyn, s>>>(a); break;
-      default: blend_fwd_kernel<8, false><<<grid, kThreads, dyn, s>>>(a); break;  // 64 registers, 32 warps/SM: best of the r1d sweep
+      case 8: blend_fwd_kernel<8, false><<<grid, kThreads, dyn, s>>>(a); break;  // the round-1 kernel (64 registers, 32 warps/SM)
+      case 26: blend_fwd2_kernel<6, false><<<grid, kThreads, dyn, s>>>(a); break;
+      case 28: blend_fwd2_kernel<8, false><<<grid, kThreads, dyn, s>>>(a); break;
+      // round 2: survivor list, T -= w.  r2e, c3 (ms per frame): 6 CTAs/SM 2.33 | 7 (72 registers) 2.21 | 8 (64 registers, spills) 2.26;
+      // round-1 kernel 2.50
+      default: blend_fwd2_kernel<7, false><<<grid, kThreads, dyn, s>>>(a); break;
     }
   }
   CHS_LAUNCH_CHECK();
@@ -853,7 +1284,15 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
     case 40: CHS_BWD2_ATTR(16, 256, 4, false); CHS_BWD2_LAUNCH(16, 256, 4, false); break;  // 50 KB of dynamic shared memory: opt in
     case 41: CHS_BWD2_LAUNCH(16, 128, 5, false); break;
     case 45: CHS_BWD2_LAUNCH(8, 128, 7, true); break;
-    default: CHS_BWD2_LAUNCH(8, 128, 7, false); break;  // tabled: 8 slots per round, 128-entry batches, 72 registers, 28 warps/SM
+    case 2: CHS_BWD2_LAUNCH(8, 128, 7, false); break;  // the round-1 default: tabled, 8 slots, 128-entry batches, 72 registers
+#define CHS_BWD3_SMEM(B) (sizeof(SplatSmem3<B>) + 4 * sizeof(BwdWarp3<8>))
+#define CHS_BWD3_LAUNCH(B, MB) blend_bwd3_kernel<8, B, MB><<<grid, kThreads, CHS_BWD3_SMEM(B), s>>>(a)
+    case 36: CHS_BWD3_LAUNCH(128, 6); break;
+    case 38: CHS_BWD3_LAUNCH(128, 8); break;
+    case 37: CHS_BWD3_LAUNCH(64, 7); break;
+    // round 2: division-free colour state, survivor list, running table pointer.  r2e, c3 (ms per frame of 8 poses): batch 128 /
+    // 7 CTAs per SM 4.03 (default) | 128 / 6: 4.19 | 128 / 8 (64 registers): 4.24 | 64 / 7: 4.17; round-1 tabled kernel 4.97
+    default: CHS_BWD3_LAUNCH(128, 7); break;
   }
   CHS_LAUNCH_CHECK();
   return CHS_OK;

@@ -418,7 +418,7 @@ template <class T> CHS_HD T chs_pair_power(const ChsSplat<T>& s, T px, T py, T& 
   dx = s.mx - px;
   dy = s.my - py;
   u = chs_fma(s.r, dy, dx);
-  return chs_fma(s.qa * u, u, (s.kc * dy) * dy) + s.lo;
+  return chs_fma(s.qa * u, u, chs_fma(s.kc * dy, dy, s.lo));
 }
 
 // Sub-tile culling.  Upper bound of log2(alpha) over the axis-aligned rectangle of pixel centres
@@ -513,6 +513,37 @@ template <class T> CHS_HD void chs_moments_to_grads(const ChsSplat<T>& s, const 
   g[6] = m[6];
   g[7] = m[7];
   g[8] = m[8];
+}
+
+// Division-free colour state (round 2, blend_bwd3_kernel).  Dotting the colours with the pixel's upstream gradient first turns
+// the three "colour behind" accumulators into ONE scalar, and normalising it by the transmittance removes every division:
+//   s_i = c_i . v_H,   R_i = (sum_{j>i} alpha_j T_j s_j + T_final (bg . v_H - v_alpha)) / T_{i+1}   ("what lies behind i", per unit
+//   of transmittance),   dL/dalpha_i = T_i (s_i - R_i),   R_{i-1} = alpha_i s_i + (1 - alpha_i) R_i = R_i - alpha_i (R_i - s_i),
+// starting behind the last accumulated Gaussian with R = bg . v_H - v_alpha.  Only T still needs its reciprocal.  The routine
+// returns the NEGATED scalars nvs = -dL/dsigma, nf = -alpha T (the kernel's packed arithmetic produces these signs for free;
+// chs_moments_to_grads_neg undoes them once per Gaussian).
+template <class T>
+CHS_HD void chs_pair_bwd_scalars_r(const ChsSplat<T>& s, T alpha_unclamped, T alpha, T& Tr, T& R, const T vh[3], T& nvs, T& nf) {
+  T ra = chs_rcp_fast(T(1) - alpha);
+  Tr = Tr * ra;  // transmittance before this Gaussian
+  nf = -alpha * Tr;
+  T sv = s.cb * vh[2] + (s.cg * vh[1] + s.cr * vh[0]);
+  T e = R - sv;
+  R = R - alpha * e;
+  nvs = alpha_unclamped <= ChsK<T>::alpha_max ? nf * e : T(0);  // no gradient through the 0.999 clamp
+}
+// as chs_moments_to_grads for moment sums of the negated scalars (nvs, nf)
+template <class T> CHS_HD void chs_moments_to_grads_neg(const ChsSplat<T>& s, const T m[9], T g[9]) {
+  const T k2 = T(2) / ChsK<T>::log2e;
+  g[0] = k2 * s.qa * m[0];
+  g[1] = s.r * g[0] + k2 * s.kc * m[1];
+  g[2] = T(-0.5) * m[2];
+  g[3] = -m[3];
+  g[4] = T(-0.5) * m[4];
+  g[5] = m[5] * s.inv_opac;
+  g[6] = -m[6];
+  g[7] = -m[7];
+  g[8] = -m[8];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -9,9 +9,11 @@
 //     No decoupled look-back, no spinning: a bug can produce wrong output but never a hang.  The price is one extra read of
 //     the keys per pass (2-4 B per item).
 //   * ranking inside a tile is warp-synchronous: the 32 items a warp looks at in one round are consecutive in memory, lanes
-//     with the same digit find each other with one MATCH.ANY, their order is the lane order, and the warp's private digit
-//     counter advances by the group size.  Rounds are in memory order, warps are combined in warp order: stable by
-//     construction, independent of the digit distribution (a tile whose items all share one digit costs the same).
+//     with the same digit find each other with one ballot per digit bit, their order is the lane order, and the warp's private
+//     digit counter advances by the group size.  Rounds are in memory order, warps are combined in warp order: stable by
+//     construction, and the cost does not depend on the digit distribution (a tile whose items all share one digit costs the
+//     same as a uniform one; MATCH.ANY, tried first, resolves one distinct value per iteration and was 3-4x slower on
+//     uniformly distributed digits).
 //   * a reduce-then-scan exclusive scan (block sums -> scan of the sums -> final) with a functor input, used for the
 //     intersection offsets (gathered through the depth order) and for turning per-(camera, tile) counts into tile_offsets.
 #pragma once
@@ -99,10 +101,33 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
+// Lanes holding the same digit, found with one ballot per digit bit (cost independent of how many distinct digits the warp
+// holds: MATCH.ANY resolves one group per iteration and measured 3-4x slower on uniformly distributed digits, r2b).  Four
+// instructions per bit: test, ballot, conditional complement, and.
+template <int kBits>
+__device__ __forceinline__ unsigned match_digit(uint32_t d, bool valid) {
+  unsigned peers = __ballot_sync(CHS_FULL_MASK, valid);
+#pragma unroll
+  for (int b = 0; b < kBits; ++b) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 m;\n\t"
+        "setp.ne.b32 p, %1, 0;\n\t"
+        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+        "@!p not.b32 m, m;\n\t"
+        "and.b32 %0, %0, m;\n\t"
+        "}"
+        : "+r"(peers)
+        : "r"(d & (1u << b)));
+  }
+  return peers;
+}
+
 // Rank the tile's items by digit.  Item (warp w, round k, lane l) is element begin + w * 32 * kItems + k * 32 + l.  On return
 // rank[k] is the item's position among the items OF ITS WARP with the same digit, and warp_hist[w][d] the warp's digit counts.
-template <class Keys, class KeyT>
-__device__ __forceinline__ void rank_tile(const Keys& keys, const TileRange& r, int shift, KeyT key[kItems], uint32_t rank[kItems],
+// kBits: number of significant digit bits (digits < 2^kBits), which bounds the ballots per round.
+template <int kBits, class Keys, class KeyT>
+__device__ __forceinline__ void rank_tile(const Keys& keys, const TileRange& r, int shift, KeyT key[kItems], uint16_t rank[kItems],
                                           uint32_t (*warp_hist)[kDigits]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < kWarps * kDigits; i += kThreads) (&warp_hist[0][0])[i] = 0u;
@@ -118,8 +143,8 @@ __device__ __forceinline__ void rank_tile(const Keys& keys, const TileRange& r, 
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const bool valid = base + k * 32 < r.end;
-    const uint32_t d = valid ? (uint32_t)((key[k] >> shift) & (KeyT)0xFF) : (uint32_t)kDigits;  // items past the end group apart
-    const unsigned peers = __match_any_sync(CHS_FULL_MASK, d);
+    const uint32_t d = (uint32_t)((key[k] >> shift) & (KeyT)0xFF);
+    const unsigned peers = match_digit<kBits>(d, valid);
     const uint32_t before = __popc(peers & lt);
     uint32_t start = 0;
     if (before == 0 && valid) {  // the first lane of the group advances the warp's counter for the whole group
@@ -127,30 +152,36 @@ __device__ __forceinline__ void rank_tile(const Keys& keys, const TileRange& r, 
       wh[d] = start + __popc(peers);
     }
     __syncwarp();
-    rank[k] = __shfl_sync(CHS_FULL_MASK, start, __ffs(peers) - 1) + before;
+    rank[k] = (uint16_t)(__shfl_sync(CHS_FULL_MASK, start, __ffs(peers | (1u << lane)) - 1) + before);
   }
   __syncthreads();
 }
 
-// ---- count: counts[d * t_cap + t] = number of items of tile t with digit d ----
+// ---- count: counts[d * t_cap + t] = number of items of tile t with digit d (order does not matter: shared-memory atomics) ----
 template <class Keys>
 __global__ void __launch_bounds__(kThreads) radix_count_kernel(TileMap map, Keys keys, int shift, uint32_t* __restrict__ counts, uint32_t t_cap) {
   typedef typename Keys::key_type KeyT;
-  __shared__ uint32_t warp_hist[kWarps][kDigits];
+  __shared__ uint32_t hist[kDigits];
   __shared__ TileRange s_range;
   const uint32_t t = blockIdx.x;
   const int d = threadIdx.x;
-  if (!resolve_tile(map, t, &s_range)) {
+  hist[d] = 0u;
+  if (!resolve_tile(map, t, &s_range)) {  // (contains the barrier that publishes the zeroed histogram)
     counts[(size_t)d * t_cap + t] = 0u;
     return;
   }
+  const TileRange r = s_range;
   KeyT key[kItems];
-  uint32_t rank[kItems];
-  rank_tile<Keys, KeyT>(keys, s_range, shift, key, rank, warp_hist);
-  uint32_t c = 0;
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) c += warp_hist[w][d];
-  counts[(size_t)d * t_cap + t] = c;
+  for (int k = 0; k < kItems; ++k) {
+    const uint32_t idx = r.begin + k * kThreads + threadIdx.x;
+    key[k] = idx < r.end ? keys(idx) : (KeyT)0;
+  }
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (r.begin + k * kThreads + threadIdx.x < r.end) atomicAdd(&hist[(uint32_t)((key[k] >> shift) & (KeyT)0xFF)], 1u);
+  __syncthreads();
+  counts[(size_t)d * t_cap + t] = hist[d];
 }
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
@@ -230,8 +261,8 @@ struct ScatterArgs {
   const uint32_t* digit_base;  // [n_seg][256] or null
 };
 
-template <class Keys, class KeyOutT>
-__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(ScatterArgs<Keys, KeyOutT> a) {
+template <int kBits, class Keys, class KeyOutT>
+__global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(ScatterArgs<Keys, KeyOutT> a) {
   typedef typename Keys::key_type KeyT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t(*warp_hist)[kDigits] = reinterpret_cast<uint32_t(*)[kDigits]>(smem_raw);
@@ -247,8 +278,8 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(ScatterArgs<Key
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, d = threadIdx.x;
 
   KeyT key[kItems];
-  uint32_t rank[kItems];
-  rank_tile<Keys, KeyT>(a.keys, r, a.shift, key, rank, warp_hist);
+  uint16_t rank[kItems];
+  rank_tile<kBits, Keys, KeyT>(a.keys, r, a.shift, key, rank, warp_hist);
 
   // per digit: exclusive prefix over the warps, tile count
   uint32_t cnt = 0;
@@ -359,23 +390,40 @@ __global__ void __launch_bounds__(1024) scan_of_sums_kernel(uint64_t* __restrict
   }
 }
 
-// out(i, exclusive prefix) for every i; blocked arrangement (thread owns kItems consecutive items) so the running sum is local
+// out(i, exclusive prefix) for every i.  Loads and stores are striped (coalesced, and the gathers of a functor input are all
+// in flight at once); the scan itself runs blocked (thread owns kItems consecutive items) out of shared memory, whose rows are
+// padded by one word per 16 so that both access patterns are conflict-free.
+__device__ __forceinline__ int scan_slot(int j) { return j + (j >> 4); }
+
 template <class In, class Out>
 __global__ void __launch_bounds__(kThreads) scan_final_kernel(In in, uint64_t n, const uint64_t* __restrict__ sums, Out out) {
   __shared__ uint32_t s_scan[kWarps + 1];
-  const uint64_t b0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kItems;
+  __shared__ uint32_t s_v[kScanTile + kScanTile / 16];
+  const uint64_t b0 = (uint64_t)blockIdx.x * kScanTile;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const int j = k * kThreads + threadIdx.x;
+    s_v[scan_slot(j)] = b0 + j < n ? in(b0 + j) : 0u;
+  }
+  __syncthreads();
   uint32_t v[kItems];
   uint32_t mine = 0;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    v[k] = b0 + k < n ? in(b0 + k) : 0u;
+    v[k] = s_v[scan_slot(threadIdx.x * kItems + k)];
     mine += v[k];
   }
   uint32_t run = block_exclusive_scan(mine, s_scan, nullptr) + (uint32_t)sums[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    if (b0 + k < n) out(b0 + k, run);
+    s_v[scan_slot(threadIdx.x * kItems + k)] = run;
     run += v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const int j = k * kThreads + threadIdx.x;
+    if (b0 + j < n) out(b0 + j, s_v[scan_slot(j)]);
   }
 }
 

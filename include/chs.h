@@ -183,6 +183,15 @@ CHS_API int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float* ge
                  uint64_t* keys_sorted, int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace,
                  uint64_t workspace_bytes, void* stream);
 
+/* chs_bin_sort without the host knowing M: the intersection buffers (vals_sorted, the bin_sort part of the workspace) hold
+ * `isect_capacity` entries, the live count is read from n_isect_dev (what chs_bin_count wrote) ON THE DEVICE, and the call
+ * never synchronises.  If M exceeds the capacity the lists are truncated consistently (no out-of-bounds access); the caller
+ * detects that whenever it next reads *n_isect_dev and repeats the step with larger buffers. */
+CHS_API int chs_bin_sort_dev(const chs_config* cfg, int64_t isect_capacity, const int64_t* n_isect_dev, const float* geom,
+                     const int32_t* radii, const float* depths, const uint32_t* isect_offsets, const int32_t* order,
+                     uint64_t* keys_sorted, int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace,
+                     uint64_t workspace_bytes, void* stream);
+
 /* ---- K6: blend forward + formation epilogue -----------------------------------------------------
  * Per (frame, tile): for each virtual pose, front-to-back alpha blending in linear HDR; then
  * mean over poses, x exposure, CRF.  Outputs: ldr [B,H,W,3], alpha [B,H,W], hdr_mean [B,H,W,3]
@@ -216,6 +225,13 @@ CHS_API int chs_blend_bwd(const chs_config* cfg, const float* geom, const float*
 CHS_API int chs_bin_emit_keys(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii,
                       const float* depths, const uint32_t* isect_offsets, const int32_t* order,
                       uint64_t* keys, int32_t* vals, void* stream);
+
+/* ---- test / verification helper: the hand-written radix passes of the binning stage on caller-supplied keys ----
+ * Stable ascending sort of the low `bits` bits of keys_in [n_seg * seg_len] INSIDE each of the n_seg segments of seg_len items
+ * (segments never mix: this is how cameras stay apart in the depth presort).  vals_out receives each sorted item's original
+ * index.  workspace: 8 * n + 1024 * (n_seg * ceil(seg_len / 4096) + n_seg) + 4096 bytes. */
+CHS_API int chs_radix_sort_pairs(const uint32_t* keys_in, int32_t n_seg, uint32_t seg_len, int32_t bits, uint32_t* keys_out,
+                         int32_t* vals_out, void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* ---- K10: gradient all-reduce over NCCL (one process per GPU) ----------------------------------
  * The NCCL library already loaded in the process is used (dlopen of libnccl.so.2).  unique_id is

@@ -75,7 +75,8 @@ static void project_bwd_impl(int N, int C, int W, int H, T eps2d, const T* means
 
 // One tile list blended over a set of pixels, forward then backward, the way the kernels walk it.
 // splat params per list entry: mean2d (2), conic (3), opacity, rgb (3) = 9 numbers.
-// tabled != 0: the backward in the form blend_bwd2_kernel uses (per-pair scalars -> moment sums -> gradients)
+// tabled != 0: the backward in the form blend_bwd2_kernel uses (per-pair scalars -> moment sums -> gradients);
+// tabled == 4: the division-free form of blend_bwd3_kernel (chs_pair_bwd_scalars_r, negated scalars, chs_moments_to_grads_neg)
 template <class T>
 static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, const T* bg, const T* v_hdr, const T* v_alpha,
                        T* out_hdr, T* out_alpha, int32_t* out_last, T* v_params, int tabled = 0) {
@@ -115,11 +116,18 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
     const T vh[3] = {v_hdr[p * 3], v_hdr[p * 3 + 1], v_hdr[p * 3 + 2]};
     T va_t = Tr * (v_alpha[p] - (bg[0] * vh[0] + bg[1] * vh[1] + bg[2] * vh[2]));
     T buf[3] = {0, 0, 0};
+    T Rn = (bg[0] * vh[0] + bg[1] * vh[1] + bg[2] * vh[2]) - v_alpha[p];  // behind the last Gaussian: the background
     for (int j = last - 1; j >= 0; --j) {
       T dx, dy, u;
       T power = chs_pair_power(sp[j], px, py, dx, dy, u);
       if (!(power >= thr)) continue;
       T au = chs_exp2_fast(power);
+      if (tabled == 4) {
+        T nvs, nf;
+        chs_pair_bwd_scalars_r(sp[j], au, chs_min(ChsK<T>::alpha_max, au), Tr, Rn, vh, nvs, nf);
+        chs_pair_moments(nvs, nf, dx, dy, u, vh, &moments[(size_t)j * 9]);
+        continue;
+      }
       if (tabled) {
         T vs, f;
         chs_pair_bwd_scalars(sp[j], au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, vs, f);
@@ -148,7 +156,9 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
       for (int k = 0; k < 9; ++k) v_params[j * 9 + k] += g[k];
     }
   }
-  if (tabled)
+  if (tabled == 4)
+    for (int j = 0; j < n_list; ++j) chs_moments_to_grads_neg(sp[j], &moments[(size_t)j * 9], v_params + (size_t)j * 9);
+  else if (tabled)
     for (int j = 0; j < n_list; ++j) chs_moments_to_grads(sp[j], &moments[(size_t)j * 9], v_params + (size_t)j * 9);
 }
 
@@ -191,6 +201,14 @@ void hs_blend_tabled_f64(int n_list, const double* params, int n_pix, const doub
 void hs_blend_tabled_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
                          const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
   blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 1);
+}
+void hs_blend_tabled_r_f64(int n_list, const double* params, int n_pix, const double* pix_xy, const double* bg, const double* v_hdr,
+                           const double* v_alpha, double* out_hdr, double* out_alpha, int32_t* out_last, double* v_params) {
+  blend_impl<double>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 4);
+}
+void hs_blend_tabled_r_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
+                           const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
+  blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 4);
 }
 // design study (DESIGN.md "next levers"): mode 2 = table in fp16, 3 = bf16
 void hs_blend_tabled_lowp_f32(int mode, int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,

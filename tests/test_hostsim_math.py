@@ -229,11 +229,12 @@ def _tile_case(seed=0, n_list=60, bg=(0.1, 0.3, 0.2)):
     return m, conic, o, col, pix, torch.tensor(bg)
 
 
-@pytest.mark.parametrize("form", ["direct", "tabled"])
+@pytest.mark.parametrize("form", ["direct", "tabled", "tabled_r"])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 def test_blend_pair_math_matches_oracle(dtype, form):
     """form "direct": chs_pair_bwd (nine partials per pair); form "tabled": the per-pair scalars, moment sums and final
-    scaling blend_bwd2_kernel uses (chs_pair_bwd_scalars / chs_pair_moments / chs_moments_to_grads)."""
+    scaling blend_bwd2_kernel uses (chs_pair_bwd_scalars / chs_pair_moments / chs_moments_to_grads); form "tabled_r": the
+    division-free normalised-colour recurrence of blend_bwd3_kernel (chs_pair_bwd_scalars_r / chs_moments_to_grads_neg)."""
     m, conic, o, col, pix, bg = _tile_case()
     n_list, n_pix = m.shape[0], pix.shape[0]
     leaves = [t.clone().requires_grad_(True) for t in (m, conic, o, col)]
@@ -247,7 +248,7 @@ def test_blend_pair_math_matches_oracle(dtype, form):
     arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np_t))
     params = arr(torch.cat([m, conic, o[:, None], col], 1))
     o_h = np.zeros((n_pix, 3), np_t); o_a = np.zeros(n_pix, np_t); o_l = np.zeros(n_pix, np.int32); o_v = np.zeros((n_list, 9), np_t)
-    getattr(HS, f"hs_blend_{dtype}" if form == "direct" else f"hs_blend_tabled_{dtype}")(n_list, _p(params), n_pix, _p(arr(pix)), _p(arr(bg)), _p(arr(vh.reshape(-1, 3))),
+    getattr(HS, f"hs_blend_{dtype}" if form == "direct" else f"hs_blend_{form}_{dtype}")(n_list, _p(params), n_pix, _p(arr(pix)), _p(arr(bg)), _p(arr(vh.reshape(-1, 3))),
                                      _p(arr(va.reshape(-1))), _p(o_h), _p(o_a), _p(o_l), _p(o_v))
     assert (o_l > -1000000).all(), "sub-tile cull dropped a contributing pair"
     tol = 1e-11 if dtype == "f64" else 2e-5

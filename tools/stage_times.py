@@ -22,10 +22,16 @@ def main():
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     over = {}
     tight = False
-    for a in sys.argv[4:]:  # e.g. n_frames=1 n_gauss=2000000 tight=1
+    tuning = {}
+    fused = False
+    for a in sys.argv[4:]:  # e.g. n_frames=1 n_gauss=2000000 tight=1 tune_bin=1 tune_blend_bwd=40 pose_fused=1
         k, v = a.split("=")
         if k == "tight":
             tight = bool(int(v))
+        elif k == "pose_fused":
+            fused = bool(int(v))
+        elif k.startswith("tune_"):
+            tuning[k[5:]] = int(v)
         else:
             over[k] = int(v)
     t0 = time.time()
@@ -63,7 +69,7 @@ def main():
         e0.record()
         ldr, alpha, meta = rasterize(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"], None, sc.Ks,
                                      sc.width, sc.height, leaves["exposure_times"], sc.n_virtual, sc.crf_kind, crf, spline=sp,
-                                     sort_mode=sort_mode, tight_bounds=tight)
+                                     sort_mode=sort_mode, tight_bounds=tight, tuning=tuning, pose_fused=fused)
         (ldr * sc.v_ldr).sum().backward()
         e1.record()
         torch.cuda.synchronize()
@@ -74,7 +80,7 @@ def main():
             print(json.dumps({"iter": it, "total_ms": round(total[-1], 3), **{k[4:]: round(v, 3) for k, v in row.items()}}), flush=True)
         del ldr, alpha, meta
     st = sorted(total)
-    tt = {"config": name, "sort_mode": sort_mode, "tight_bounds": tight, "M": M, "median_ms": st[len(st) // 2], "min_ms": st[0],
+    tt = {"config": name, "sort_mode": sort_mode, "tight_bounds": tight, "tuning": tuning, "pose_fused": fused, "M": M, "median_ms": st[len(st) // 2], "min_ms": st[0],
           "frames_per_s": sc.n_frames / (st[len(st) // 2] / 1e3), "mem_GB": torch.cuda.max_memory_allocated() / 1e9}
     print(json.dumps(tt), flush=True)
 
