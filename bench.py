@@ -11,9 +11,14 @@ A step = fwd+bwd of the whole batch (K0..K9 of SURVEY.md section 3.1) + the all-
     value : frames/s with every input resident in HBM (upstream gradient = the fixed seed-2 v_B)
     e2e   : the same step through the public step API with HOST (pinned) buffers: H2D of all
             parameters and of the batch's target frames, L2 loss on device, D2H of the flat gradient
-            buffer and the loss — copies inside the timed region
-    roofline : blend_bwd (K8), the dominant kernel; algorithmic bytes over its
-            CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json
+            buffer and the loss — copies inside the timed region.  With G ranks every byte still crosses
+            PCIe once per step, not G times: rank r uploads slice r of the flat parameter buffer and the
+            slices are exchanged over NVLink (chs_nvls_broadcast), rank r reads back slice r of the reduced
+            gradients (casualhdrsplat_b200.parallel.ShardedHostParams)
+    roofline : blend_bwd (K8), the dominant kernel; algorithmic bytes of the units
+            the launch actually processes (emitted intersections) over its CUDA-event duration measured
+            inside the timed region, against MEASURED_PEAKS.json; issue_frac = its warp instructions over
+            the SM issue slots of that duration (the bound that actually limits it)
     cpu_baseline : the float64 oracle on the host cores, on a bounded sample (stated), extrapolated
 `--impl reference` times that CPU oracle alone (the reference ships no implementation to run).
 """
@@ -206,7 +211,7 @@ def main():
     import torch.distributed as dist
 
     from casualhdrsplat_b200 import _lib
-    from casualhdrsplat_b200.parallel import ChsComm, NvlsComm, TorchComm, formation_step, shard_frames
+    from casualhdrsplat_b200.parallel import ChsComm, NvlsComm, ShardedHostParams, TorchComm, formation_step, shard_frames
     from casualhdrsplat_b200.scene import make_config
 
     if not torch.cuda.is_available():
@@ -238,8 +243,14 @@ def main():
     B, n, N, W, H = sc.n_frames, sc.n_virtual, sc.means.shape[0], sc.width, sc.height
     ids = list(shard_frames(B, rank, world))
     names = ["means", "quats", "scales", "opacities", "colors", "knots", "frame_times", "exposure_times", "Ks", "crf_params"]
-    host = {k: getattr(sc, k).contiguous().pin_memory() for k in names if getattr(sc, k) is not None}
-    P = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    host = {k: getattr(sc, k).contiguous() for k in names if getattr(sc, k) is not None}
+    # all parameters in one flat buffer per pipeline slot; rank r holds (and uploads) slice r on the host side
+    param_group = dist.new_group() if (world > 1 and not isinstance(comm, NvlsComm)) else None
+    shp = ShardedHostParams(host, dev, rank, world, comm=comm, n_slots=2, group=param_group)
+    shp.upload_(0)
+    shp.upload_(1)
+    torch.cuda.synchronize()
+    P = shp.views(0)
     v_ldr_local = {i: sc.v_ldr[i].to(dev) for i in ids}
     spline_meta = {"knot_t0": sc.knot_t0, "knot_dt": sc.knot_dt, "kind": sc.spline_kind}
 
@@ -330,6 +341,10 @@ def main():
     bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_calls) / max(len(bwd_calls), 1)
     for k, f in orig.items():
         setattr(L, k, f)
+    # the reduced flat gradient buffer after the last timed step (bit-identical on every rank with the NVLS all-reduce): these two
+    # numbers must agree between N = 1, 2, 4, 8 up to summation order (different frames are summed in a different order)
+    fl64 = flat[: layout.total].double()
+    grad_checksum = {"sum": float(fl64.sum()), "l2": float(fl64.norm()), "n": int(layout.total)}
 
     # ---- e2e: host buffers in, host gradients out ----
     # Every step moves ALL parameters + the step's captured frames host->device and the whole gradient buffer + the loss
@@ -341,14 +356,15 @@ def main():
         from casualhdrsplat_b200.train import LOSS_L2, photometric_loss
 
         targets_host = {i: (sc.v_ldr[i] * 0.05 + 0.2).contiguous().pin_memory() for i in ids}  # synthetic "captured" frames
-        h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(v.numel() * 4 for v in targets_host.values())
-        d2h = layout.total * 4 + 8
+        g_lo, g_hi = shp.grad_slice(layout.total)  # the slice of the reduced gradient buffer this rank reads back
+        h2d = shp.h2d_bytes + sum(v.numel() * 4 for v in targets_host.values())
+        d2h = (g_hi - g_lo) * 4 + 8
         cur = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        P2 = [P, {k: torch.empty_like(v) for k, v in P.items()}]
+        P2 = [shp.views(0), shp.views(1)]
         tg2 = [{i: torch.empty(targets_host[i].shape, dtype=torch.float32, device=dev) for i in ids} for _ in range(2)]
-        stage_g = [torch.empty(layout.total, dtype=torch.float32, device=dev) for _ in range(2)]
-        grads_host2 = [torch.empty(layout.total, dtype=torch.float32).pin_memory() for _ in range(2)]
+        stage_g = [torch.empty(max(g_hi - g_lo, 1), dtype=torch.float32, device=dev) for _ in range(2)]
+        grads_host2 = [torch.empty(max(g_hi - g_lo, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
         loss_dev2 = [torch.zeros((), dtype=torch.float64, device=dev) for _ in range(2)]
         loss_host2 = [torch.zeros((), dtype=torch.float64).pin_memory() for _ in range(2)]
         mk = lambda: [torch.cuda.Event() for _ in range(2)]  # noqa: E731
@@ -361,8 +377,7 @@ def main():
                     s_in.wait_event(after)
                 if j >= 2:
                     s_in.wait_event(ev_free[sl])  # step j-2 has finished reading this input slot
-                for k, v in host.items():
-                    P2[sl][k].copy_(v, non_blocking=True)
+                shp.upload_(sl)  # H2D of this rank's parameter slice + slice exchange over NVLink
                 for i in ids:
                     tg2[sl][i].copy_(targets_host[i], non_blocking=True)
                 ev_in[sl].record(s_in)
@@ -380,7 +395,7 @@ def main():
                 v, _ = photometric_loss(ldr, tgt, LOSS_L2, scale=1.0, loss_acc=loss_dev2[sl])
                 return v
             step(upstream_l2, params=P2[sl])
-            stage_g[sl].copy_(flat)
+            stage_g[sl][: g_hi - g_lo].copy_(flat[g_lo:g_hi])
             ev_comp[sl].record(cur)
             ev_free[sl].record(cur)
 
@@ -422,15 +437,28 @@ def main():
             barrier()
             return max_over_ranks(t0.elapsed_time(t1)) / k_steps, losses
 
+        def sum_over_ranks(x):
+            if world == 1:
+                return x
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+
         e2e_run(2, True)
         e2e_ms, losses = e2e_run(args.steps, True)
         e2e_run(1, False)
         serial_ms, losses_serial = e2e_run(args.steps, False)
-        e2e = {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_ms, "pipeline": "depth-2 double-buffered H2D / D2H on copy streams, every step copies all "
-               "parameters + captured frames in and all gradients + loss out",
+        # the gradient the hosts hold after the last step, slice by slice: must be the same numbers at every N
+        gh = grads_host2[0][: g_hi - g_lo].double()
+        e2e = {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)), "d2h_bytes_per_step": int(sum_over_ranks(d2h)),
+               "h2d_bytes_per_step_per_rank": int(h2d), "d2h_bytes_per_step_per_rank": int(d2h),
+               "ms_per_step": e2e_ms, "pipeline": "depth-2 double-buffered H2D / D2H on copy streams; every step all parameters + captured frames "
+               "go in and all gradients + loss come out, each byte once: rank r uploads slice r of the flat parameter buffer (slices exchanged over "
+               "NVLink: " + ("chs_nvls_broadcast" if shp.nvls else "all_gather" if world > 1 else "n/a") + ") and reads back slice r of the reduced gradients",
                "serial_value": B / (serial_ms / 1e3), "serial_ms_per_step": serial_ms,
-               "loss_local_frames": losses[-1], "loss_matches_serial": bool(abs(losses[-1] - losses_serial[-1]) <= 1e-9 * abs(losses_serial[-1]))}
+               "loss_all_frames": sum_over_ranks(losses[-1]),
+               "host_grad_checksum": {"sum": sum_over_ranks(float(gh.sum())), "l2": sum_over_ranks(float((gh * gh).sum())) ** 0.5},
+               "loss_matches_serial": bool(abs(losses[-1] - losses_serial[-1]) <= 1e-9 * abs(losses_serial[-1]))}
 
     # ---- roofline of the dominant kernel (one launch = one frame = n cameras) ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -439,24 +467,43 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     n_local = max(len(ids), 1)
-    M_f = m_ref / n_local
+    M_ref_f = m_ref / n_local        # intersections of the reference (3-sigma square) binning, per frame
+    M_f = m_emitted / n_local        # intersections the launch actually walks (tight bounds emit fewer)
     Mg_f = stats["m_g"] / n_local
     Ppix = W * H
-    bwd_bytes = 40 * M_f + 36 * Mg_f + 8 * n * Ppix + 12 * 1 * Ppix
+    tiles_img = ((W + 15) // 16) * ((H + 15) // 16)
+
+    def k8_bytes(m):
+        return 40 * m + 36 * Mg_f + 8 * n * Ppix + 12 * 1 * Ppix
+
+    bwd_bytes = k8_bytes(M_f)
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "blend_bwd_traffic.json")
+    # static facts of one K8 launch from the committed ncu capture of this kernel revision (not re-measured per run)
+    prof, prof_src = {}, None
+    tpath = os.path.join(ROOT, "profiles", "blend_bwd_profile.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "blend_bwd2_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
-                "launch_ms": bwd_ms, "isects_per_launch": M_f}
-    # whole-step algorithmic bytes, per frame
+        prof = json.load(open(tpath))
+        prof_src = "profiles/blend_bwd_profile.json: " + prof.get("source", "ncu capture, static")
+    clk = sampler.result()
+    sm_hz = (clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965) * 1e6
+    issue_frac = None
+    if prof.get("warp_inst_per_launch") and bwd_ms > 0 and args.workload in ("c3", "c4"):
+        issue_frac = prof["warp_inst_per_launch"] / (148 * 4 * sm_hz * bwd_ms * 1e-3)
+    roofline = {"bound": "hbm", "kernel": "blend_bwd3_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch") if args.workload in ("c3", "c4") else None,
+                "traffic_source": prof_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
+                "launch_ms": bwd_ms, "isects_per_launch": M_f,
+                "frac_at_reference_isects": k8_bytes(M_ref_f) / (bwd_ms * 1e-3) / 1e9 / peak if bwd_ms > 0 else 0.0,
+                "reference_isects_per_launch": M_ref_f,
+                "issue_frac": issue_frac, "issue_frac_note": "warp instructions of one launch (static, ncu) / (148 SMs x 4 schedulers x SM clock x "
+                "launch time): the kernel is issue-bound, not HBM-bound (DRAM traffic is below the algorithmic bytes: the per-camera records "
+                "stay in L2)"}
+    # bytes the EXECUTED algorithm must move per frame (not the 7-pass 64-bit sort A.4 specifies): K2 = 4 passes of 8-byte pairs over
+    # the C*N depth keys + the gathered scan; K3-K5 = emit (6 B) + two multisplit passes (count 2 + 11 B, count 1 + 9 B)
     Cn = n
-    key_passes = 2 if args.sort_mode == "presort" else 7
-    step_bytes = {"K1": 44 * N + 32 * Cn * N, "K2": 8 * Cn * N, "K3": 12 * M_f + 20 * Cn * N,
-                  "K4": 8 * M_f + 24 * M_f * 7, "K5": 8 * M_f + 4 * Cn * 8160, "K6": 40 * M_f + 8 * Cn * Ppix + 24 * Ppix,
-                  "K7": 36 * Ppix, "K8": bwd_bytes, "K9": 68 * Cn * N + 100 * N}
+    step_bytes = {"K1": 44 * N + 32 * Cn * N, "K2": (8 + 3 * 4 + 4 * 16 + 16) * Cn * N, "K3": 6 * M_f + 24 * Cn * N,
+                  "K4": (2 + 11 + 1 + 9) * M_f if args.sort_mode == "presort" else (12 + 24 * 7) * M_f, "K5": 4 * Cn * tiles_img,
+                  "K6": 40 * M_f + 8 * Cn * Ppix + 24 * Ppix, "K7": 36 * Ppix, "K8": bwd_bytes, "K9": 68 * Cn * N + 100 * N}
     frame_bytes = float(sum(step_bytes.values()))
     step_frac = (frame_bytes * n_local) / (ms_per_step * 1e-3) / 1e9 / peak
 
@@ -474,7 +521,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"{args.workload}: BASELINE.json configs[3] — {N} Gaussians, {W}x{H}, {n} virtual poses/frame, "
+                "config": {"workload": f"{args.workload}: BASELINE.json configs[{ {'c1': 0, 'c2': 1, 'c3': 2, 'c4': 3, 'c5': 4}.get(args.workload, '?') }] — {N} Gaussians, {W}x{H}, {n} virtual poses/frame, "
                                        f"global batch {B} frames sharded by frame, fwd+bwd incl. pose/exposure/CRF grads",
                            "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode, "tile_bounds": args.bounds,
                            "isects_emitted_per_frame": m_emitted / n_local,
@@ -483,11 +530,14 @@ def main():
                                                                  "NVLS multimem one-shot all-reduce kernel (libchs)" if isinstance(comm, NvlsComm)
                                                                  else "torch.distributed all_reduce"),
                            "parallelism": f"dp{world} over frames"},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
                 "cpu_baseline": cpu_baseline,
                 "extra": {"stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
-                          "step_algorithmic_bytes_per_frame": frame_bytes, "step_roofline_frac": step_frac,
-                          "sort_passes_actual": key_passes, "mem_GB": torch.cuda.max_memory_allocated() / 1e9}}
+                          "grad_checksum": grad_checksum,
+                          "step_executed_bytes_per_frame": frame_bytes, "step_executed_bytes_frac_of_hbm_peak": step_frac,
+                          "step_bytes_note": "minimum bytes of the kernels as executed (not of the 7-pass 64-bit sort A.4 specifies); the blend "
+                          "kernels read most of theirs from L2, so this is not achieved DRAM bandwidth",
+                          "mem_GB": torch.cuda.max_memory_allocated() / 1e9}}
         emit(line)
     if comm is not None:
         comm.close()

@@ -73,6 +73,7 @@ SIGNATURES = {
     "chs_allreduce_grads": (ctypes.c_int, [P, P, c_uint64, P]),
     "chs_comm_destroy": (ctypes.c_int, [P]),
     "chs_nvls_allreduce": (ctypes.c_int, [P, c_uint64, c_int32, c_int32, P]),
+    "chs_nvls_broadcast": (ctypes.c_int, [P, P, c_uint64, c_uint64, P]),
     "chs_sh_fwd": (ctypes.c_int, [CFG, c_int32, P, P, P, P, P, P]),
     "chs_sh_bwd": (ctypes.c_int, [CFG, c_int32] + [P] * 10 + [c_uint64, P]),
     "chs_loss": (ctypes.c_int, [c_int32, P, P, c_uint64, c_float, P, P, P]),

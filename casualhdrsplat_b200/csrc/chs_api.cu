@@ -216,6 +216,38 @@ extern "C" int chs_nvls_allreduce(float* mc_ptr, uint64_t count, int32_t rank, i
   return CHS_OK;
 }
 
+// Broadcast of this rank's slice of a symmetric buffer to every rank through the multicast address (parameter replication:
+// each rank uploads 1/G of the parameters from its host and the switch fans the slice out).
+namespace {
+__global__ void __launch_bounds__(256) nvls_broadcast_kernel(float* mc, const float* __restrict__ local, uint64_t begin, uint64_t end) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t b4 = (begin + 3) / 4, e4 = end / 4;  // whole float4 inside [begin, end)
+  for (uint64_t i = b4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(local)[i];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + i * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+  // scalar head and tail
+  const uint64_t head_end = b4 * 4 < end ? b4 * 4 : end, tail_begin = e4 * 4 > begin ? e4 * 4 : begin;
+  for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < head_end; i += stride)
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(local[i]) : "memory");
+  if (e4 >= b4)
+    for (uint64_t i = tail_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride)
+      asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(local[i]) : "memory");
+}
+}  // namespace
+
+extern "C" int chs_nvls_broadcast(float* mc_ptr, const float* local_ptr, uint64_t begin, uint64_t count, void* stream) {
+  CHS_REQUIRE(mc_ptr && local_ptr, "chs_nvls_broadcast: null pointer (no NVLS multicast support?)");
+  CHS_REQUIRE(((uintptr_t)mc_ptr) % 16 == 0 && ((uintptr_t)local_ptr) % 16 == 0, "chs_nvls_broadcast: pointers must be 16-byte aligned");
+  if (count == 0) return CHS_OK;
+  int blocks = (int)((count / 4 + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  nvls_broadcast_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mc_ptr, local_ptr, begin, begin + count);
+  CHS_LAUNCH_CHECK();
+  return CHS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // one-shot entry points
 // ---------------------------------------------------------------------------------------------

@@ -1005,7 +1005,7 @@ struct __align__(16) BwdWarp3 {
   float nvs[kSlots][kRow3];  // -dL/dsigma of (slot, pixel id); column 64: staged-batch index of the slot's Gaussian (int bits)
   float nf[kSlots][kRow3];   // -alpha * T of (slot, pixel id)
   float vh[3][64];           // dL/dH of the warp's pixels by pixel id (r, g, b planes)
-  int list[32];              // survivors of the current 32-entry sub-batch, back to front
+  int list[36];              // survivors of the current 32-entry sub-batch, back to front (+ spare entries: the loop reads one ahead)
 };
 
 // phase B for the n_slots tabled Gaussians of this warp.  Lane = (slot k = lane % 8, part = lane / 8); a part covers the two
@@ -1075,7 +1075,7 @@ __device__ __forceinline__ void bwd_round3(const Smem& sm, const BwdWarp3<kSlots
   __syncwarp();  // the table is rewritten by the next round
 }
 
-template <int kSlots, int kB, int kMinBlocks>
+template <int kSlots, int kB, int kMinBlocks, bool kPrefetch>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendBwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Smem = SplatSmem3<kB>;
@@ -1120,6 +1120,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) ws.vh[ch][2 * lane + h] = v[h][ch];  // pixel id = 2 lane + h  <->  (x, y) = (lane & 7, (lane >> 3) + 4 h)
   }
+  ws.list[lane] = 0;  // entries read ahead of the valid ones must always be in-bounds staged indices
+  if (lane < 4) ws.list[32 + lane] = 0;
   const P2 py2 = p2(iy0 + 0.5f, iy0 + 4.5f);
   P2 Tr2 = p2(Tf[0], Tf[1]);
   P2 R2 = p2(r0[0], r0[1]);
@@ -1133,10 +1135,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
   const int n_walk = s_max_last;
 
   const unsigned gt = lanemask_gt_();
-  float* const row0 = &ws.nvs[0][0];
-  float* const row_end = row0 + kSlots * kRow3;
-  float* row = row0;                 // table row of the next slot (running pointer: never recomputed from the thread id)
-  constexpr int kFOff = kSlots * kRow3;  // nf row of a slot = its nvs row + kFOff floats
+  // The table is written through a 32-bit shared-memory address that is carried across iterations (the lane's float2 slot in the
+  // next free row): one add per tabled Gaussian, no address arithmetic from the thread id inside the loop.
+  const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(&ws.nvs[0][0]) + 8u * (uint32_t)lane;
+  constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = kSlots * kRow3 * 4;
+  const uint32_t tab_end = tab0 + kSlots * kRowBytes;
+  uint32_t tab = tab0;
   for (int hi = n_walk; hi > 0; hi -= kB) {
     const int lo = max(0, hi - kB);
     const int cnt = hi - lo;
@@ -1156,10 +1160,33 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
       if (hit) ws.list[__popc(mask & gt)] = j;  // descending: back to front
       __syncwarp();
       // ---- phase A over the survivors ----
+      // (the list has spare entries) kPrefetch: the next Gaussian's record is fetched while this one is processed, the index
+      // after it is already in flight; otherwise only the next index is fetched ahead
+      int jn = ws.list[0];
+      float4 san = make_float4(0.f, 0.f, 0.f, 0.f), sbn = san;
+      if (kPrefetch) {
+        san = sm.a[jn];
+        sbn = sm.b[jn];
+        jn = ws.list[1];
+      }
+      int jcur = ws.list[0];
       for (int i = 0; i < n_surv; ++i) {
-        const int jj = ws.list[i];
-        const float4 sa = sm.a[jj];  // mx, my, qa, r
-        const float4 sb = sm.b[jj];  // kc, log2(opacity), cr, cg
+        int jj;
+        float4 sa, sb;  // (mx, my, qa, r), (kc, log2(opacity), cr, cg)
+        if (kPrefetch) {
+          jj = jcur;
+          sa = san;
+          sb = sbn;
+          jcur = jn;
+          san = sm.a[jn];  // past the end: a stale (but in-bounds) staged index, never used
+          sbn = sm.b[jn];
+          jn = ws.list[i + 2];
+        } else {
+          jj = jn;
+          jn = ws.list[i + 1];
+          sa = sm.a[jj];
+          sb = sm.b[jj];
+        }
         float dx;
         P2 dy2, u2;
         const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
@@ -1182,20 +1209,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
         // no gradient through the 0.999 clamp
         const P2 gate2 = p2(auA <= CHS_ALPHA_MAX ? 1.f : 0.f, auB <= CHS_ALPHA_MAX ? 1.f : 0.f);
         const P2 nvs2 = (nf2 * e2) * gate2;
-        *reinterpret_cast<float2*>(row + 2 * lane) = make_float2(p2lo(nvs2), p2hi(nvs2));
-        *reinterpret_cast<float2*>(row + kFOff + 2 * lane) = make_float2(p2lo(nf2), p2hi(nf2));
-        if (lane == 0) row[64] = __int_as_float(jj);
-        row += kRow3;
-        if (row == row_end) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab), "f"(p2lo(nvs2)), "f"(p2hi(nvs2)) : "memory");
+        asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(tab), "f"(p2lo(nf2)), "f"(p2hi(nf2)), "n"(kFOffBytes) : "memory");
+        if (lane == 0) asm volatile("st.shared.b32 [%0+256], %1;" ::"r"(tab), "r"(jj) : "memory");  // lane 0: tab = start of the row
+        tab += kRowBytes;
+        if (tab == tab_end) {
           bwd_round3<kSlots>(sm, ws, kSlots, lane, bx0, by0, a);
-          row = row0;
+          tab = tab0;
         }
       }
       __syncwarp();  // the list is rewritten by the next sub-batch
     }
-    if (row != row0) {  // the staged batch is about to be replaced
-      bwd_round3<kSlots>(sm, ws, (int)((row - row0) / kRow3), lane, bx0, by0, a);
-      row = row0;
+    if (tab != tab0) {  // the staged batch is about to be replaced
+      bwd_round3<kSlots>(sm, ws, (int)((tab - tab0) / kRowBytes), lane, bx0, by0, a);
+      tab = tab0;
     }
   }
 }
@@ -1286,10 +1313,12 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
     case 45: CHS_BWD2_LAUNCH(8, 128, 7, true); break;
     case 2: CHS_BWD2_LAUNCH(8, 128, 7, false); break;  // the round-1 default: tabled, 8 slots, 128-entry batches, 72 registers
 #define CHS_BWD3_SMEM(B) (sizeof(SplatSmem3<B>) + 4 * sizeof(BwdWarp3<8>))
-#define CHS_BWD3_LAUNCH(B, MB) blend_bwd3_kernel<8, B, MB><<<grid, kThreads, CHS_BWD3_SMEM(B), s>>>(a)
+#define CHS_BWD3_LAUNCH(B, MB) blend_bwd3_kernel<8, B, MB, false><<<grid, kThreads, CHS_BWD3_SMEM(B), s>>>(a)
     case 36: CHS_BWD3_LAUNCH(128, 6); break;
     case 38: CHS_BWD3_LAUNCH(128, 8); break;
     case 37: CHS_BWD3_LAUNCH(64, 7); break;
+    case 39: blend_bwd3_kernel<8, 128, 7, true><<<grid, kThreads, CHS_BWD3_SMEM(128), s>>>(a); break;  // + record prefetch
+    case 35: blend_bwd3_kernel<8, 128, 6, true><<<grid, kThreads, CHS_BWD3_SMEM(128), s>>>(a); break;
     // round 2: division-free colour state, survivor list, running table pointer.  r2e, c3 (ms per frame of 8 poses): batch 128 /
     // 7 CTAs per SM 4.03 (default) | 128 / 6: 4.19 | 128 / 8 (64 registers): 4.24 | 64 / 7: 4.17; round-1 tabled kernel 4.97
     default: CHS_BWD3_LAUNCH(128, 7); break;

@@ -84,12 +84,14 @@ class ChsComm:
 
 
 class NvlsComm:
-    """Hand-written one-shot all-reduce through the NVSwitch multicast mapping (NVLS), no NCCL in the data path.
+    """Hand-written one-shot collectives through the NVSwitch multicast mapping (NVLS), no NCCL in the data path.
 
     The flat gradient buffer itself lives in symmetric memory (torch.distributed._symmetric_memory owns the allocation
     and the rendezvous — plumbing), so K9 / the accumulations write straight into it; ``allreduce_`` is then
     barrier -> ``chs_nvls_allreduce`` (multimem.ld_reduce + multimem.st on this rank's slice) -> barrier.
-    Every rank ends with bit-identical sums.  Raises if the fabric has no multicast support.
+    Every rank ends with bit-identical sums.  ``symmetric(name, n)`` hands out further symmetric buffers (e.g. the replicated
+    parameters) and ``broadcast_slice_`` fans this rank's slice of one out to every rank (``chs_nvls_broadcast``).
+    Raises if the fabric has no multicast support.
     """
 
     def __init__(self, rank: int, world: int, device: torch.device, group=None):
@@ -99,29 +101,50 @@ class NvlsComm:
         self._symm, self._dist = symm, dist
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world, self.device = rank, world, device
-        self._buf = None
-        self._hdl = None
+        self._bufs = {}  # name -> (tensor, handle)
+
+    def symmetric(self, name: str, n_floats: int) -> torch.Tensor:
+        """A symmetric [n_floats] fp32 buffer with a multicast mapping (allocated and rendezvoused once per name)."""
+        cur = self._bufs.get(name)
+        if cur is None or cur[0].numel() < n_floats:
+            padded = (n_floats + 1023) // 1024 * 1024
+            buf = self._symm.empty(padded, dtype=torch.float32, device=self.device)
+            hdl = self._symm.rendezvous(buf, self.group.group_name)
+            if not hdl.multicast_ptr:
+                raise RuntimeError("NvlsComm: this fabric/driver exposes no multicast (NVLS) mapping; use ChsComm (NCCL)")
+            self._bufs[name] = cur = (buf, hdl)
+        return cur[0][:n_floats]
 
     def flat_buffer(self, n_floats: int) -> torch.Tensor:
-        """The symmetric [n_floats] fp32 buffer (allocated and rendezvoused once, reused every step)."""
-        if self._buf is None or self._buf.numel() < n_floats:
-            padded = (n_floats + 1023) // 1024 * 1024
-            self._buf = self._symm.empty(padded, dtype=torch.float32, device=self.device)
-            self._hdl = self._symm.rendezvous(self._buf, self.group.group_name)
-            if not self._hdl.multicast_ptr:
-                raise RuntimeError("NvlsComm: this fabric/driver exposes no multicast (NVLS) mapping; use ChsComm (NCCL)")
-        return self._buf[:n_floats]
+        """The symmetric gradient buffer (reused every step)."""
+        return self.symmetric("grads", n_floats)
 
-    def allreduce_(self, buf: torch.Tensor) -> None:
-        if self._buf is None or buf.data_ptr() != self._buf.data_ptr():
-            raise RuntimeError("NvlsComm.allreduce_: the buffer must be the one returned by flat_buffer()")
-        self._hdl.barrier(channel=0)  # every rank's partial sums are in its symmetric buffer
-        _lib.check(_lib.lib().chs_nvls_allreduce(ctypes.c_void_p(self._hdl.multicast_ptr), buf.numel(), self.rank, self.world,
-                                                 _stream()), "chs_nvls_allreduce")
-        self._hdl.barrier(channel=1)  # every slice has been broadcast
+    def _find(self, buf: torch.Tensor):
+        for b, h in self._bufs.values():
+            if b.data_ptr() == buf.data_ptr():
+                return b, h
+        raise RuntimeError("NvlsComm: the buffer must come from flat_buffer() / symmetric()")
+
+    def allreduce_(self, buf: torch.Tensor, begin: int = 0, count: Optional[int] = None, channel: int = 0) -> None:
+        """Sum floats [begin, begin + count) of the symmetric buffer over all ranks (default: all of ``buf``)."""
+        base, hdl = self._find(buf)
+        count = buf.numel() - begin if count is None else count
+        if begin % 4:
+            raise RuntimeError("NvlsComm.allreduce_: begin must be a multiple of 4 floats")
+        hdl.barrier(channel=channel)  # every rank's partial sums are in its symmetric buffer
+        _lib.check(_lib.lib().chs_nvls_allreduce(ctypes.c_void_p(hdl.multicast_ptr + 4 * begin), count, self.rank, self.world, _stream()),
+                   "chs_nvls_allreduce")
+        hdl.barrier(channel=channel + 1)  # every slice has been broadcast
+
+    def broadcast_slice_(self, buf: torch.Tensor, begin: int, count: int, channel: int = 2) -> None:
+        """Every rank calls this with ITS slice [begin, begin + count): afterwards all ranks hold all slices."""
+        base, hdl = self._find(buf)
+        _lib.check(_lib.lib().chs_nvls_broadcast(ctypes.c_void_p(hdl.multicast_ptr), _lib.ptr(base), begin, count, _stream()),
+                   "chs_nvls_broadcast")
+        hdl.barrier(channel=channel)  # every rank's slice has landed everywhere
 
     def close(self) -> None:
-        self._buf, self._hdl = None, None
+        self._bufs = {}
 
 
 class TorchComm:
@@ -143,13 +166,15 @@ class TorchComm:
 def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: int, height: int, n_virtual: int, crf_kind: int,
                    frame_ids: Sequence[int], upstream: Callable[[Sequence[int], torch.Tensor], torch.Tensor], *,
                    micro_batch: int = 1, sort_mode: str = "presort", comm=None, background=None, out: Optional[torch.Tensor] = None,
-                   stats: Optional[dict] = None, crf_before_average: bool = False, tight_bounds: bool = False):
+                   stats: Optional[dict] = None, crf_before_average: bool = False, tight_bounds: bool = False,
+                   pose_fused: bool = False, tuning: Optional[dict] = None):
     """One fwd+bwd training step over this rank's frames, then the gradient all-reduce.
 
     params: CUDA fp32 tensors means [N,3], quats [N,4], scales [N,3], opacities [N], colors [N,3], knots [K,7],
             frame_times [B], exposure_times [B], Ks [B,3,3], crf_params [3,3Hd+1] (or absent for the identity CRF);
             B is the GLOBAL batch.  spline_meta: knot_t0, knot_dt, kind.
     tight_bounds: opacity-aware tile bounds (``rasterize``): same gradients, shorter tile lists.
+    pose_fused / tuning: as in ``rasterize`` (chs_config.pose_fused, chs_config.tune_*).
     frame_ids: the frames this rank renders (``shard_frames``).  ``upstream(ids, ldr[len(ids),H,W,3])`` returns the
             gradient of the loss w.r.t. those LDR frames (same shape).
     Returns (GradLayout, flat gradient buffer summed over all ranks).
@@ -177,7 +202,7 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
         cfg = _lib.make_config(N, len(ids), n_virtual, width, height, crf_kind=crf_kind,
                                crf_hidden=_lib.crf_size(crf_kind, crf_params),
                                sort_mode=_SORT[sort_mode], background=background, crf_before_average=crf_before_average,
-                               tight_bounds=tight_bounds)
+                               tight_bounds=tight_bounds, pose_fused=pose_fused, tuning=tuning)
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
         st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline)
         v_ldr = upstream(ids, st.ldr).contiguous()
@@ -211,3 +236,67 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
         if stats.get("count_pairs"):
             stats["m_g"] = m_g_total
     return layout, flat
+
+
+class ShardedHostParams:
+    """Host-resident parameters of a frame-sharded job, replicated on the GPUs without every rank uploading everything.
+
+    All parameter tensors live in ONE flat fp32 device buffer (views per tensor).  Each step rank r copies only slice r (1/G of
+    the buffer) from its pinned host copy and the slices are exchanged over NVLink: ``chs_nvls_broadcast`` (multimem.st through
+    the NVSwitch) when the communicator is an ``NvlsComm``, else ``all_gather_into_tensor``.  Host traffic per step is the
+    parameter bytes once in total instead of once per rank.  The reduced gradient buffer is read back the same way: rank r
+    downloads slice r (``grad_slice``).
+    """
+
+    def __init__(self, host: Dict[str, torch.Tensor], device: torch.device, rank: int, world: int, comm=None, n_slots: int = 2, group=None):
+        self.names = list(host)
+        self.shapes = {k: tuple(v.shape) for k, v in host.items()}
+        sizes = [int(v.numel()) for v in host.values()]
+        self.offsets, off = {}, 0
+        for k, n in zip(self.names, sizes):
+            self.offsets[k] = off
+            off += (n + 3) // 4 * 4  # every tensor starts 16-byte aligned
+        self.rank, self.world, self.comm, self.group = rank, world, comm, group
+        per = (off + world - 1) // world
+        self.per = (per + 3) // 4 * 4
+        self.total = self.per * world
+        self.host_flat = torch.zeros(self.total, dtype=torch.float32)
+        if torch.cuda.is_available():
+            self.host_flat = self.host_flat.pin_memory()
+        for k, v in host.items():
+            self.host_flat[self.offsets[k]:self.offsets[k] + v.numel()].copy_(v.reshape(-1))
+        self.nvls = isinstance(comm, NvlsComm) and world > 1
+        self.dev_flat = []
+        for s in range(n_slots):
+            if self.nvls:
+                self.dev_flat.append(comm.symmetric(f"params{s}", self.total))
+            else:
+                self.dev_flat.append(torch.empty(self.total, dtype=torch.float32, device=device))
+        self.h2d_bytes = self.per * 4 if world > 1 else off * 4
+
+    def views(self, slot: int) -> Dict[str, torch.Tensor]:
+        import math
+
+        f = self.dev_flat[slot]
+        return {k: f[self.offsets[k]:self.offsets[k] + math.prod(self.shapes[k])].view(self.shapes[k]) for k in self.names}
+
+    def upload_(self, slot: int) -> None:
+        """Stream-ordered on the current stream: H2D of this rank's slice, then the slice exchange."""
+        f = self.dev_flat[slot]
+        b = self.rank * self.per
+        if self.world == 1:
+            f.copy_(self.host_flat, non_blocking=True)
+            return
+        f[b:b + self.per].copy_(self.host_flat[b:b + self.per], non_blocking=True)
+        if self.nvls:
+            self.comm.broadcast_slice_(f, b, self.per, channel=2 + slot)
+        else:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(f, f[b:b + self.per].clone(), group=self.group)
+
+    def grad_slice(self, n_floats: int):
+        """[begin, end) of the flat gradient buffer this rank reads back to its host."""
+        per = ((n_floats + self.world - 1) // self.world + 3) // 4 * 4
+        b = min(self.rank * per, n_floats)
+        return b, min(b + per, n_floats)

@@ -316,6 +316,10 @@ CHS_API int chs_adam_step(float* param, const float* grad, float* m, float* v, u
  * (multimem.st), so all ranks end with bit-identical buffers.  The caller must place a cross-rank
  * barrier before (all partials written) and after (all slices broadcast) this call. count in floats. */
 CHS_API int chs_nvls_allreduce(float* mc_ptr, uint64_t count, int32_t rank, int32_t world, void* stream);
+/* Fan-out of the floats [begin, begin + count) of this rank's copy (local_ptr, the rank's own mapping of the symmetric buffer)
+ * to the same offsets on every rank (multimem.st).  Parameter replication of the frame-sharded step: each rank uploads 1/G of
+ * the parameters from its host and broadcasts its slice.  Barriers before / after as for chs_nvls_allreduce. */
+CHS_API int chs_nvls_broadcast(float* mc_ptr, const float* local_ptr, uint64_t begin, uint64_t count, void* stream);
 
 #ifdef __cplusplus
 }

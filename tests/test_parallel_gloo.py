@@ -91,3 +91,48 @@ def test_sharded_gradients_sum_to_full_batch(tmp_path):
     for k in ["means", "quats", "scales", "opacities", "colors", "knots", "exposure_times", "frame_times"]:
         assert torch.allclose(v[k], full[k], rtol=1e-9, atol=1e-12 * float(full[k].abs().max())), k
     assert torch.allclose(v["crf_params"], full["crf_params"].reshape(-1), rtol=1e-9, atol=1e-12)
+
+
+def _params_worker(rank, world, port, out_dir):
+    from casualhdrsplat_b200.parallel import ShardedHostParams
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        host = {"means": torch.randn(37, 3, generator=g), "opacities": torch.rand(37, generator=g), "crf": torch.randn(3, 7, generator=g),
+                "scalar": torch.randn((), generator=g)}
+        sp = ShardedHostParams(host, torch.device("cpu"), rank, world, comm=None, n_slots=2)
+        # a rank only has to hold ITS slice on the host: wipe the rest to prove the exchange supplies it
+        keep = sp.host_flat[rank * sp.per:(rank + 1) * sp.per].clone()
+        sp.host_flat.zero_()
+        sp.host_flat[rank * sp.per:(rank + 1) * sp.per] = keep
+        for slot in range(2):
+            sp.upload_(slot)
+            v = sp.views(slot)
+            for k in host:
+                assert torch.equal(v[k], host[k]), (rank, slot, k)
+        n = 14 * 37 + 11
+        slices = [None] * world
+        dist.all_gather_object(slices, sp.grad_slice(n))
+        assert sp.h2d_bytes == sp.per * 4 and sp.per * world >= sum(v.numel() for v in host.values())
+        if rank == 0:
+            torch.save(slices, os.path.join(out_dir, "slices.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_host_params_replicate_and_gradient_slices_cover(tmp_path):
+    """Each rank uploads 1/G of the flat parameter buffer and the exchange rebuilds every tensor on every rank; the gradient
+    read-back slices of the ranks tile the flat gradient buffer exactly once."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_params_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    slices = torch.load(os.path.join(str(tmp_path), "slices.pt"))
+    n = 14 * 37 + 11
+    assert slices[0][0] == 0 and slices[-1][1] == n
+    for a, b in zip(slices[:-1], slices[1:]):
+        assert a[1] == b[0] and a[0] % 4 == 0
