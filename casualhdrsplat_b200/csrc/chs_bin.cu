@@ -706,7 +706,7 @@ struct BucketLen {
 
 // single block: seg_begin = exclusive scan of the lengths, tile_first = exclusive scan of ceil(length / tile); entry n_seg = totals
 template <class LenFn>
-__global__ void __launch_bounds__(1024) segments_kernel(LenFn len_of, int n_seg, uint32_t* __restrict__ seg_begin,
+__global__ void __launch_bounds__(1024) segments_kernel(LenFn len_of, int n_seg, uint32_t tile_items, uint32_t* __restrict__ seg_begin,
                                                         uint32_t* __restrict__ tile_first) {
   __shared__ uint64_t s_warp[33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(1024) segments_kernel(LenFn len_of, int n_seg,
   for (int b0 = 0; b0 < n_seg; b0 += 1024) {
     const int i = b0 + threadIdx.x;
     const uint32_t len = i < n_seg ? len_of(i) : 0u;
-    const uint64_t v = ((uint64_t)((len + cs::kTile - 1) / cs::kTile) << 40) | (uint64_t)len;
+    const uint64_t v = ((uint64_t)((len + tile_items - 1) / tile_items) << 40) | (uint64_t)len;
     uint64_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -824,6 +824,293 @@ int exclusive_scan(In in, uint64_t n, uint64_t* sums, Out out, int64_t* total_ou
   return CHS_OK;
 }
 
+
+// =================================================================================================
+// Banded placement (default route of CHS_SORT_DEPTH_PRESORT): the tile lists without emitting or sorting intersections.
+//
+// With the pairs of a camera in depth order, the list of tile t is "the pairs whose rectangle covers t, in that order".  The
+// rank of a pair in a list is a COUNT of earlier pairs, and counting over a fixed chunk is a population count over a bit
+// matrix: bit p of row t says "pair p of the chunk covers t".  Two levels keep the bit matrices in shared memory:
+//   P1  band split.  A band is BR consecutive tile rows with BR * tile_w <= 256 tiles (two rows at 1080p).  For a chunk of 1024
+//       depth-ordered pairs the kernel sets bm[band][pair] for every band a pair's rectangle reaches (1.9 per pair at c3), takes
+//       per-band word prefixes, and writes one 8-byte record (pair id, sub-rectangle inside the band) per (pair, band) to the
+//       band's bucket at  bucket start + chunk prefix + rank.  ~15 M records instead of 62.6 M intersections.
+//   P2  tile placement.  A chunk of 1024 records of ONE bucket sets bm[tile][record] for the <= 256 tiles of the band, takes
+//       per-tile word prefixes, and writes the pair id of every (record, tile) straight to its final position
+//       tile_offsets[tile] + chunk prefix + rank.  The destination of a bucket is its own ~1 MB region, which stays in L2 while
+//       the bucket's chunks are processed.
+// Chunk prefixes come from a count kernel + the column scan of chs_sort.cuh at each level; the column totals of P2 are the
+// per-(camera, tile) counts, so tile_offsets is their exclusive scan.  Nothing is keyed, ranked by ballots or moved twice:
+// per intersection the work is one shared-memory atomicOr, two shared loads, a popc and one 4-byte store.
+// =================================================================================================
+constexpr int kBandChunk = 1024;  // pairs per P1 chunk = records per P2 chunk = 32 words of a bit-matrix row
+constexpr int kBandWords = kBandChunk / 32;
+constexpr int kBandRow = kBandWords + 1;  // padded row: the per-row prefix walk is bank-conflict free
+
+struct BandGeom {
+  int ok, BR, band_tiles, n_bands;
+};
+BandGeom band_geom(const ChsDims& d) {
+  BandGeom g;
+  g.ok = d.tile_w >= 1 && d.tile_w <= 256;
+  g.BR = 1; g.band_tiles = d.tile_w; g.n_bands = d.tile_h;
+  if (!g.ok) return g;
+  g.BR = 256 / d.tile_w;
+  if (g.BR > d.tile_h) g.BR = d.tile_h;
+  if (g.BR < 1) g.BR = 1;
+  g.band_tiles = g.BR * d.tile_w;
+  g.n_bands = (d.tile_h + g.BR - 1) / g.BR;
+  g.ok = g.n_bands <= 256;
+  return g;
+}
+
+bool uses_band_route(const chs_config* cfg, const ChsDims& d) {
+  return cfg->sort_mode == CHS_SORT_DEPTH_PRESORT && cfg->tune_bin == 0 && band_geom(d).ok;
+}
+
+struct BandArgs {
+  int N, C, tile_w, tile_h, tight, BR, n_bands, chunks1;  // chunks1 = chunks per camera in P1
+  uint32_t t_cap1, t_cap2, rec_cap, val_cap;
+  const float4* geom;
+  const int32_t* radii;
+  const int32_t* order;
+  ushort4* rects;            // [C * N] depth order (written by the P1 count, read by the P1 scatter)
+  uint32_t* counts1;         // [256][t_cap1]
+  const uint32_t* seg_begin2;  // [C * n_bands + 1] bucket starts in the record array
+  uint2* recs;               // [rec_cap] (pair id, box)
+  uint4* desc;               // [t_cap2] P2 chunks: (bucket, begin, end, 0); bucket = 0xffffffff past the end
+  uint32_t* counts2;         // [256][t_cap2]
+  const uint32_t* base2;     // [C * n_bands][256] final list starts
+  int32_t* vals;             // [val_cap]
+};
+
+// box of a record: x0 | (x1 - 1) << 8 | ry0 << 16 | (ry1 - 1) << 24, rows relative to the band
+__device__ __forceinline__ uint32_t make_box(int x0, int x1, int ry0, int ry1) {
+  return (uint32_t)x0 | ((uint32_t)(x1 - 1) << 8) | ((uint32_t)ry0 << 16) | ((uint32_t)(ry1 - 1) << 24);
+}
+
+// P1 count: bands reached by the chunk's pairs -> counts1[band][chunk]; also leaves every pair's rectangle in depth order
+__global__ void __launch_bounds__(256) band_count_kernel(BandArgs a) {
+  __shared__ uint32_t hist[256];
+  const int t = blockIdx.x;  // = c * chunks1 + q
+  const int c = t / a.chunks1, q = t - c * a.chunks1;
+  hist[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t seg = (int64_t)c * a.N;
+#pragma unroll
+  for (int k = 0; k < kBandChunk / 256; ++k) {
+    const int i = q * kBandChunk + k * 256 + threadIdx.x;
+    if (i >= a.N) continue;
+    const int32_t id = a.order[seg + i];
+    const int radius = a.radii[id];
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
+    if (radius != 0) {
+      const float4 gm = a.geom[id];
+      const ChsTileRect r = chs_tile_bounds_of(gm.x, gm.y, radius, a.tight, a.tile_w, a.tile_h);
+      if (r.x1 > r.x0 && r.y1 > r.y0) {
+        rc = make_ushort4((unsigned short)r.x0, (unsigned short)r.y0, (unsigned short)r.x1, (unsigned short)r.y1);
+        const int b1 = (r.y1 - 1) / a.BR;
+        for (int b = r.y0 / a.BR; b <= b1; ++b) atomicAdd(&hist[b], 1u);
+      }
+    }
+    a.rects[seg + i] = rc;
+  }
+  __syncthreads();
+  a.counts1[(size_t)threadIdx.x * a.t_cap1 + t] = hist[threadIdx.x];
+}
+
+// P1 scatter: one record per (pair, band) at bucket start + chunk prefix + rank
+__global__ void __launch_bounds__(256) band_scatter_kernel(BandArgs a) {
+  extern __shared__ uint32_t smem_band[];
+  uint32_t* bm = smem_band;                        // [n_bands][kBandRow]
+  uint32_t* pfx = bm + a.n_bands * kBandRow;       // [n_bands][kBandRow]
+  uint32_t* base = pfx + a.n_bands * kBandRow;     // [n_bands]
+  const int t = blockIdx.x;
+  const int c = t / a.chunks1, q = t - c * a.chunks1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < a.n_bands * kBandRow; i += 256) bm[i] = 0u;
+  for (int b = threadIdx.x; b < a.n_bands; b += 256) base[b] = a.seg_begin2[c * a.n_bands + b] + a.counts1[(size_t)b * a.t_cap1 + t];
+  __syncthreads();
+  const int64_t seg = (int64_t)c * a.N;
+  ushort4 rc[kBandChunk / 256];
+#pragma unroll
+  for (int k = 0; k < kBandChunk / 256; ++k) {
+    const int i = q * kBandChunk + k * 256 + threadIdx.x;  // pair p = k * 256 + tid of the chunk: word p >> 5 = k * 8 + warp, bit = lane
+    rc[k] = i < a.N ? a.rects[seg + i] : make_ushort4(0, 0, 0, 0);
+    if (rc[k].z > rc[k].x) {
+      const int b1 = ((int)rc[k].w - 1) / a.BR;
+      for (int b = (int)rc[k].y / a.BR; b <= b1; ++b) atomicOr(&bm[b * kBandRow + k * 8 + warp], 1u << lane);
+    }
+  }
+  __syncthreads();
+  for (int b = warp; b < a.n_bands; b += 8) {  // exclusive prefix of the row's word populations
+    const uint32_t cnt = __popc(bm[b * kBandRow + lane]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(CHS_FULL_MASK, incl, o);
+      if (lane >= o) incl += u;
+    }
+    pfx[b * kBandRow + lane] = incl - cnt;
+  }
+  __syncthreads();
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int k = 0; k < kBandChunk / 256; ++k) {
+    if (rc[k].z <= rc[k].x) continue;
+    const int i = q * kBandChunk + k * 256 + threadIdx.x;
+    const int32_t id = a.order[seg + i];
+    const int w = k * 8 + warp;
+    const int y0 = rc[k].y, y1 = rc[k].w;
+    const int b1 = (y1 - 1) / a.BR;
+    for (int b = y0 / a.BR; b <= b1; ++b) {
+      const uint32_t rank = pfx[b * kBandRow + w] + __popc(bm[b * kBandRow + w] & lt);
+      const uint32_t dst = base[b] + rank;
+      const int r0 = b * a.BR;
+      if (dst < a.rec_cap) a.recs[dst] = make_uint2((uint32_t)id, make_box(rc[k].x, rc[k].z, max(y0, r0) - r0, min(y1, r0 + a.BR) - r0));
+    }
+  }
+}
+
+// P2 chunk descriptors: chunk t -> (bucket, first record, end record); one thread per chunk does the table search once
+__global__ void __launch_bounds__(256) chunk_desc_kernel(int n_seg2, const uint32_t* __restrict__ seg_begin2, const uint32_t* __restrict__ tile_first2,
+                                                         uint32_t t_cap2, uint32_t rec_cap, uint4* __restrict__ desc) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= t_cap2) return;
+  uint4 r = make_uint4(0xffffffffu, 0u, 0u, 0u);
+  if (t < tile_first2[n_seg2]) {
+    int lo = 0, hi = n_seg2 - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tile_first2[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const uint64_t b = (uint64_t)seg_begin2[lo] + (uint64_t)(t - tile_first2[lo]) * kBandChunk;
+    const uint64_t e = min((uint64_t)seg_begin2[lo + 1], b + kBandChunk);
+    r = make_uint4((uint32_t)lo, (uint32_t)min(b, (uint64_t)rec_cap), (uint32_t)min(e, (uint64_t)rec_cap), 0u);
+  }
+  desc[t] = r;
+}
+
+// P2 count: tiles covered by the chunk's records -> counts2[tile in band][chunk]
+__global__ void __launch_bounds__(256) tile_count_kernel(BandArgs a) {
+  __shared__ uint32_t hist[256];
+  const uint32_t t = blockIdx.x;
+  const uint4 ds = a.desc[t];
+  hist[threadIdx.x] = 0u;
+  __syncthreads();
+  if (ds.x != 0xffffffffu) {
+#pragma unroll
+    for (int k = 0; k < kBandChunk / 256; ++k) {
+      const uint32_t i = ds.y + k * 256 + threadIdx.x;
+      if (i >= ds.z) continue;
+      const uint32_t box = a.recs[i].y;
+      const int x0 = box & 0xff, x1 = (box >> 8) & 0xff, ry0 = (box >> 16) & 0xff, ry1 = box >> 24;
+      for (int ry = ry0; ry <= ry1; ++ry)
+        for (int x = x0; x <= x1; ++x) atomicAdd(&hist[ry * a.tile_w + x], 1u);
+    }
+  }
+  __syncthreads();
+  a.counts2[(size_t)threadIdx.x * a.t_cap2 + t] = hist[threadIdx.x];
+}
+
+// P2 scatter: every (record, tile) of the chunk straight to its final position in the tile's list
+__global__ void __launch_bounds__(256) tile_scatter_kernel(BandArgs a) {
+  extern __shared__ uint32_t smem_tile[];
+  uint32_t* bm = smem_tile;                                                       // [256][kBandRow]
+  uint32_t* cursor = bm + 256 * kBandRow;                                         // [256]
+  unsigned short* pfx = reinterpret_cast<unsigned short*>(cursor + 256);          // [256][kBandWords + 2] (padded: conflict-free walk)
+  constexpr int kPfxRow = kBandWords + 2;
+  const uint32_t t = blockIdx.x;
+  const uint4 ds = a.desc[t];
+  if (ds.x == 0xffffffffu) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cursor[threadIdx.x] = a.base2[(size_t)ds.x * 256 + threadIdx.x] + a.counts2[(size_t)threadIdx.x * a.t_cap2 + t];
+  for (int i = threadIdx.x; i < 256 * kBandRow; i += 256) bm[i] = 0u;
+  __syncthreads();
+  uint2 rec[kBandChunk / 256];
+#pragma unroll
+  for (int k = 0; k < kBandChunk / 256; ++k) {
+    const uint32_t i = ds.y + k * 256 + threadIdx.x;  // record p = k * 256 + tid of the chunk: word k * 8 + warp, bit = lane
+    rec[k] = i < ds.z ? a.recs[i] : make_uint2(0u, 0xffffffffu);
+    if (i < ds.z) {
+      const uint32_t box = rec[k].y;
+      const int x0 = box & 0xff, x1 = (box >> 8) & 0xff, ry0 = (box >> 16) & 0xff, ry1 = box >> 24;
+      for (int ry = ry0; ry <= ry1; ++ry)
+        for (int x = x0; x <= x1; ++x) atomicOr(&bm[(ry * a.tile_w + x) * kBandRow + k * 8 + warp], 1u << lane);
+    }
+  }
+  __syncthreads();
+  {  // thread = tile of the band: exclusive prefix of its row's word populations
+    uint32_t run = 0;
+#pragma unroll 8
+    for (int w = 0; w < kBandWords; ++w) {
+      pfx[threadIdx.x * kPfxRow + w] = (unsigned short)run;
+      run += __popc(bm[threadIdx.x * kBandRow + w]);
+    }
+  }
+  __syncthreads();
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int k = 0; k < kBandChunk / 256; ++k) {
+    const uint32_t i = ds.y + k * 256 + threadIdx.x;
+    if (i >= ds.z) continue;
+    const uint32_t box = rec[k].y;
+    const int w = k * 8 + warp;
+    const int x0 = box & 0xff, x1 = (box >> 8) & 0xff, ry0 = (box >> 16) & 0xff, ry1 = box >> 24;
+    for (int ry = ry0; ry <= ry1; ++ry)
+      for (int x = x0; x <= x1; ++x) {
+        const int tl = ry * a.tile_w + x;
+        const uint32_t dst = cursor[tl] + (uint32_t)pfx[tl * kPfxRow + w] + __popc(bm[tl * kBandRow + w] & lt);
+        if (dst < a.val_cap) a.vals[dst] = (int32_t)rec[k].x;
+      }
+  }
+}
+
+// K5 of the banded route: list starts of every (camera, tile) from the scanned column totals of P2 (clamped to the capacity of
+// the value buffer, so that a step whose M outgrew it walks truncated lists instead of reading past the end)
+__global__ void __launch_bounds__(kThreads) band_tile_offsets_kernel(int64_t n_lin, int tiles, int tile_w, int BR, int n_bands,
+                                                                      const uint32_t* __restrict__ base2, const uint64_t* __restrict__ total,
+                                                                      uint32_t val_cap, uint32_t* __restrict__ tile_offsets) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lin) {
+    const int64_t c = i / tiles;
+    const int t = (int)(i - c * tiles);
+    const int b = (t / tile_w) / BR;
+    tile_offsets[i] = min(base2[(c * n_bands + b) * 256 + (t - b * BR * tile_w)], val_cap);
+  } else if (i == n_lin) {
+    const uint64_t m = *total;
+    tile_offsets[n_lin] = m < (uint64_t)val_cap ? (uint32_t)m : val_cap;
+  }
+}
+
+struct BandPlan {
+  BandGeom g;
+  int chunks1;
+  int64_t n_seg2;
+  uint32_t t_cap1, t_cap2;
+  uint64_t sum_blocks;
+};
+BandPlan band_plan(const ChsDims& d, uint64_t cap) {
+  BandPlan p;
+  memset(&p, 0, sizeof(p));
+  p.g = band_geom(d);
+  p.chunks1 = (d.N + kBandChunk - 1) / kBandChunk;
+  p.t_cap1 = (uint32_t)p.chunks1 * (uint32_t)d.C;
+  p.n_seg2 = (int64_t)d.C * p.g.n_bands;
+  p.t_cap2 = (uint32_t)((cap + kBandChunk - 1) / kBandChunk) + (uint32_t)p.n_seg2;
+  p.sum_blocks = ((uint64_t)p.n_seg2 * 256 + cs::kScanTile - 1) / cs::kScanTile;
+  return p;
+}
+uint64_t band_bytes(const ChsDims& d, uint64_t cap) {
+  const BandPlan p = band_plan(d, cap);
+  uint64_t b = chs_align_up((uint64_t)d.CN * sizeof(ushort4), 256) + chs_align_up((uint64_t)256 * p.t_cap1 * 4, 256);
+  b += chs_align_up((uint64_t)d.C * 256 * 4, 256) + 2 * chs_align_up((uint64_t)(p.n_seg2 + 1) * 4, 256);
+  b += chs_align_up(cap * sizeof(uint2), 256) + chs_align_up((uint64_t)p.t_cap2 * sizeof(uint4), 256);
+  b += chs_align_up((uint64_t)256 * p.t_cap2 * 4, 256) + 2 * chs_align_up((uint64_t)p.n_seg2 * 256 * 4, 256);
+  b += chs_align_up((p.sum_blocks + 1) * 8, 256);
+  return b + 256;
+}
+
 inline uint32_t tiles_of(uint64_t n) { return (uint32_t)((n + cs::kTile - 1) / cs::kTile); }
 
 // ---- workspace layouts (one definition for the size query and for the launch) ----
@@ -924,6 +1211,14 @@ int hw_bin_count(const chs_config* cfg, const ChsDims& d, const int32_t* tiles_t
     chs_set_error("chs_bin_count: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
     return CHS_ERR_WORKSPACE_TOO_SMALL;
   }
+  if (uses_band_route(cfg, d)) {  // the banded placement never reads isect_offsets: M is a plain (coalesced) sum
+    const uint32_t blocks = (uint32_t)p.sum_blocks;
+    cs::scan_sums_kernel<TouchedIn><<<blocks, cs::kThreads, 0, s>>>(TouchedIn{tiles_touched, nullptr}, (uint64_t)d.CN, sums);
+    CHS_LAUNCH_CHECK();
+    cs::scan_of_sums_kernel<<<1, 1024, 0, s>>>(sums, blocks, n_isect_dev, nullptr);
+    CHS_LAUNCH_CHECK();
+    return CHS_OK;
+  }
   return exclusive_scan(TouchedIn{tiles_touched, ord}, (uint64_t)d.CN, sums, StoreU32{isect_offsets}, n_isect_dev, s);
 }
 
@@ -949,9 +1244,80 @@ int lsd_sort(int passes, uint64_t cap, const int64_t* n_dev, KeyT* k_a, int32_t*
   return CHS_OK;
 }
 
+int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const float4* geom, const int32_t* radii, const float* depths,
+                  const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace,
+                  uint64_t workspace_bytes, cudaStream_t s) {
+  const BandPlan p = band_plan(d, cap);
+  const int64_t n_lin = (int64_t)d.C * d.tiles;
+  ChsArena ar(workspace, workspace_bytes);
+  ushort4* rects = ar.take<ushort4>(d.CN);
+  uint32_t* counts1 = ar.take<uint32_t>((uint64_t)256 * p.t_cap1);
+  uint32_t* totals1 = ar.take<uint32_t>((uint64_t)d.C * 256);
+  uint32_t* seg_begin2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
+  uint32_t* tile_first2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
+  uint2* recs = ar.take<uint2>(cap);
+  uint4* desc = ar.take<uint4>(p.t_cap2);
+  uint32_t* counts2 = ar.take<uint32_t>((uint64_t)256 * p.t_cap2);
+  uint32_t* totals2 = ar.take<uint32_t>((uint64_t)p.n_seg2 * 256);
+  uint32_t* base2 = ar.take<uint32_t>((uint64_t)p.n_seg2 * 256);
+  uint64_t* sums = ar.take<uint64_t>(p.sum_blocks + 1);
+  if (!ar.ok) {
+    chs_set_error("chs_bin_sort: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
+    return CHS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  int64_t* total = reinterpret_cast<int64_t*>(sums + p.sum_blocks);
+  BandArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d.N; a.C = d.C; a.tile_w = d.tile_w; a.tile_h = d.tile_h; a.tight = cfg->tight_bounds != 0; a.BR = p.g.BR; a.n_bands = p.g.n_bands;
+  a.chunks1 = p.chunks1; a.t_cap1 = p.t_cap1; a.t_cap2 = p.t_cap2; a.rec_cap = (uint32_t)cap; a.val_cap = (uint32_t)cap;
+  a.geom = geom; a.radii = radii; a.order = order; a.rects = rects; a.counts1 = counts1; a.seg_begin2 = seg_begin2; a.recs = recs;
+  a.desc = desc; a.counts2 = counts2; a.base2 = base2; a.vals = vals_sorted;
+  // P1: band split
+  band_count_kernel<<<p.t_cap1, 256, 0, s>>>(a);
+  CHS_LAUNCH_CHECK();
+  cs::TileMap m1;
+  memset(&m1, 0, sizeof(m1));
+  m1.n_seg = d.C; m1.tiles_per_seg = (uint32_t)p.chunks1;
+  int st = launch_colscan(m1, counts1, p.t_cap1, totals1, s);
+  if (st) return st;
+  segments_kernel<BucketLen><<<1, 1024, 0, s>>>(BucketLen{totals1, p.g.n_bands}, (int)p.n_seg2, kBandChunk, seg_begin2, tile_first2);
+  CHS_LAUNCH_CHECK();
+  const size_t smem1 = ((size_t)2 * p.g.n_bands * kBandRow + p.g.n_bands) * sizeof(uint32_t);
+  if (smem1 > 48 * 1024) CHS_CUDA(cudaFuncSetAttribute(band_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  band_scatter_kernel<<<p.t_cap1, 256, smem1, s>>>(a);
+  CHS_LAUNCH_CHECK();
+  // P2: tile placement inside every (camera, band) bucket
+  chunk_desc_kernel<<<(p.t_cap2 + 255) / 256, 256, 0, s>>>((int)p.n_seg2, seg_begin2, tile_first2, p.t_cap2, (uint32_t)cap, desc);
+  CHS_LAUNCH_CHECK();
+  tile_count_kernel<<<p.t_cap2, 256, 0, s>>>(a);
+  CHS_LAUNCH_CHECK();
+  cs::TileMap m2;
+  memset(&m2, 0, sizeof(m2));
+  m2.table = 1; m2.n_seg = (int)p.n_seg2; m2.seg_begin = seg_begin2; m2.tile_first = tile_first2;
+  st = launch_colscan(m2, counts2, p.t_cap2, totals2, s);
+  if (st) return st;
+  st = exclusive_scan(ArrayIn{totals2}, (uint64_t)p.n_seg2 * 256, sums, StoreU32{base2}, total, s);
+  if (st) return st;
+  band_tile_offsets_kernel<<<grid_for(n_lin + 1), kThreads, 0, s>>>(n_lin, d.tiles, d.tile_w, p.g.BR, p.g.n_bands, base2,
+                                                                     reinterpret_cast<const uint64_t*>(total), (uint32_t)cap, tile_offsets);
+  CHS_LAUNCH_CHECK();
+  const size_t smem2 = (size_t)256 * kBandRow * 4 + 256 * 4 + (size_t)256 * (kBandWords + 2) * 2;
+  CHS_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  tile_scatter_kernel<<<p.t_cap2, 256, smem2, s>>>(a);
+  CHS_LAUNCH_CHECK();
+  if (keys_sorted) {
+    rebuild_keys_from_offsets_kernel<<<(unsigned)n_lin, 128, 0, s>>>(d.tiles, d.tile_bits, tile_offsets, vals_sorted, depths, keys_sorted);
+    CHS_LAUNCH_CHECK();
+  }
+  return CHS_OK;
+}
+
 int hw_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const int64_t* n_dev, const float* geom, const int32_t* radii,
                 const float* depths, const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted,
                 uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, cudaStream_t s) {
+  if (uses_band_route(cfg, d))  // default: banded placement (no keys, no emitted intersections; isect_offsets is not read)
+    return band_bin_sort(cfg, d, cap, (const float4*)geom, radii, depths, order, keys_sorted, vals_sorted, tile_offsets, workspace,
+                         workspace_bytes, s);
   const SortPlan p = sort_plan(d, cfg->sort_mode, cap);
   const int64_t n_lin = (int64_t)d.C * d.tiles;
   const int tight = cfg->tight_bounds != 0;
@@ -980,7 +1346,7 @@ int hw_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const int
                                                                  (const float4*)geom, radii, depths, isect_offsets, order, nullptr, k16, v_in);
     CHS_LAUNCH_CHECK();
     // pass 1: inside each camera, by the band tile >> 8
-    segments_kernel<CamLen><<<1, 1024, 0, s>>>(CamLen{isect_offsets, d.N, d.C, n_dev, (uint32_t)cap}, d.C, seg_begin1, tile_first1);
+    segments_kernel<CamLen><<<1, 1024, 0, s>>>(CamLen{isect_offsets, d.N, d.C, n_dev, (uint32_t)cap}, d.C, cs::kTile, seg_begin1, tile_first1);
     CHS_LAUNCH_CHECK();
     cs::TileMap m1;
     memset(&m1, 0, sizeof(m1));
@@ -989,7 +1355,7 @@ int hw_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const int
                                                           totals1, nullptr, s);
     if (st) return st;
     // pass 2: inside each (camera, band) bucket, by tile & 255, straight to every list's final position
-    segments_kernel<BucketLen><<<1, 1024, 0, s>>>(BucketLen{totals1, p.nb}, (int)p.n_seg2, seg_begin2, tile_first2);
+    segments_kernel<BucketLen><<<1, 1024, 0, s>>>(BucketLen{totals1, p.nb}, (int)p.n_seg2, cs::kTile, seg_begin2, tile_first2);
     CHS_LAUNCH_CHECK();
     cs::TileMap m2;
     memset(&m2, 0, sizeof(m2));
@@ -1069,7 +1435,11 @@ int chs_bin_sort_bytes(const ChsDims& d, const chs_config* cfg, int64_t M, uint6
   uint64_t b = 0;
   int st = legacy_bin_sort_bytes(d, cfg, M, &b);
   if (st) return st;
-  const uint64_t h = hw_sort_bytes(d, cfg->sort_mode, (uint64_t)(M > 0 ? M : 0));
+  uint64_t h = hw_sort_bytes(d, cfg->sort_mode, (uint64_t)(M > 0 ? M : 0));
+  if (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT && band_geom(d).ok) {
+    const uint64_t bb = band_bytes(d, (uint64_t)(M > 0 ? M : 0));
+    if (bb > h) h = bb;
+  }
   *bytes = b > h ? b : h;
   return CHS_OK;
 }
@@ -1126,7 +1496,7 @@ static int bin_sort_common(const chs_config* cfg, int64_t cap, const int64_t* n_
 extern "C" int chs_bin_sort(const chs_config* cfg, int64_t n_isect, const float* geom, const int32_t* radii, const float* depths,
                             const uint32_t* isect_offsets, const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted,
                             uint32_t* tile_offsets, void* workspace, uint64_t workspace_bytes, void* stream) {
-  if (cfg && cfg->tune_bin != 0)
+  if (cfg && (cfg->tune_bin == 1 || cfg->tune_bin == 2))
     return legacy_bin_sort(cfg, n_isect, geom, radii, depths, isect_offsets, order, keys_sorted, vals_sorted, tile_offsets, workspace,
                            workspace_bytes, stream);
   return bin_sort_common(cfg, n_isect, nullptr, geom, radii, depths, isect_offsets, order, keys_sorted, vals_sorted, tile_offsets, workspace,
@@ -1138,7 +1508,7 @@ extern "C" int chs_bin_sort_dev(const chs_config* cfg, int64_t isect_capacity, c
                                 uint64_t* keys_sorted, int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace,
                                 uint64_t workspace_bytes, void* stream) {
   CHS_REQUIRE(n_isect_dev, "chs_bin_sort_dev: null n_isect_dev");
-  CHS_REQUIRE(!cfg || cfg->tune_bin == 0, "chs_bin_sort_dev: only the default (hand-written) binning route runs without the host knowing M");
+  CHS_REQUIRE(!cfg || cfg->tune_bin == 0 || cfg->tune_bin == 3, "chs_bin_sort_dev: only the hand-written binning routes run without the host knowing M");
   return bin_sort_common(cfg, isect_capacity, n_isect_dev, geom, radii, depths, isect_offsets, order, keys_sorted, vals_sorted, tile_offsets,
                          workspace, workspace_bytes, stream);
 }

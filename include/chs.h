@@ -104,7 +104,8 @@ typedef struct chs_config {
   int32_t tune_blend_fwd;     /* 1 / 3: 6 / 10 CTAs per SM */
   int32_t tune_blend_bwd;     /* 1: direct kernel; 22: direct, four pixels per thread; 40 / 41: tabled, 16 slots */
   int32_t tune_crf_bwd;       /* resident blocks per SM (2, 3, 4) */
-  int32_t tune_bin;           /* 1: CUB radix passes instead of the hand-written ones; 2: counting placement */
+  int32_t tune_bin;           /* CHS_SORT_DEPTH_PRESORT routes.  0: banded placement (default); 3: hand-written two-pass radix multisplit
+                               * over emitted intersections; 1: cub::DeviceRadixSort baseline; 2: round-1 counting placement */
   int32_t tune_bin_chunk;     /* counting placement: pairs per chunk */
   int32_t reserved[2];
 } chs_config;
@@ -164,7 +165,9 @@ CHS_API int chs_project_bwd(const chs_config* cfg, const float* means, const flo
                     void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* ---- K2: intersection count --------------------------------------------------------------------
- * isect_offsets uint32 [C*N]: exclusive scan of tiles_touched in emission order.
+ * isect_offsets uint32 [C*N]: exclusive scan of tiles_touched in emission order.  Only the routes that emit intersections read
+ * it (CHS_SORT_KEY64, tune_bin != 0); the default banded placement of CHS_SORT_DEPTH_PRESORT needs just M and leaves the
+ * buffer untouched.
  * order int32 [C*N]: emission order (identity for CHS_SORT_KEY64; the (cam, depth)-sorted
  * permutation of c*N+g for CHS_SORT_DEPTH_PRESORT).
  * n_isect_dev: device int64 receiving M.  If n_isect_host != NULL the call synchronises the stream

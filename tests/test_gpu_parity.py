@@ -61,10 +61,12 @@ def test_projection_parity(name):
 # ------------------------------------------------------------------------------------------------
 # K2-K5 binning: bit exact, both sort strategies
 # ------------------------------------------------------------------------------------------------
-# sort routes: the literal 64-bit key sort; depth presort + hand-written multisplit (default); the same with CUB radix passes
-# (chs_config.tune_bin = 1); the sort-free counting placement (tune_bin = 2, small chunks so even tiny scenes have many)
-BIN_ROUTES = {"key64": ("key64", None), "presort": ("presort", None), "presort-cub": ("presort", {"bin": 1}),
-              "presort-place": ("presort", {"bin": 2, "bin_chunk": 96}), "key64-cub": ("key64", {"bin": 1})}
+# sort routes: the literal 64-bit key sort (hand-written LSD passes); depth presort + banded placement (default); depth presort +
+# hand-written two-pass radix multisplit (chs_config.tune_bin = 3); the CUB baselines (tune_bin = 1); the round-1 counting
+# placement (tune_bin = 2, small chunks so even tiny scenes have many)
+BIN_ROUTES = {"key64": ("key64", None), "presort": ("presort", None), "presort-radix": ("presort", {"bin": 3}),
+              "presort-cub": ("presort", {"bin": 1}), "presort-place": ("presort", {"bin": 2, "bin_chunk": 96}),
+              "key64-cub": ("key64", {"bin": 1})}
 
 
 @pytest.mark.parametrize("route", list(BIN_ROUTES))
