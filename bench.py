@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--bounds", default="tight", choices=["tight", "square"],
                     help="tile bounds used for binning: classic 3-sigma square, or the opacity-aware per-axis box (same images and "
                          "gradients, fewer intersections)")
+    ap.add_argument("--host-sync", action="store_true", help="size the intersection buffers from a host read of M every frame (round-1 "
+                    "behaviour) instead of the sync-free step (capacity from the previous step, count kept on the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-tiles", type=int, default=48, help="tiles in the CPU-oracle sample")
@@ -211,7 +213,7 @@ def main():
     import torch.distributed as dist
 
     from casualhdrsplat_b200 import _lib
-    from casualhdrsplat_b200.parallel import ChsComm, NvlsComm, ShardedHostParams, TorchComm, formation_step, shard_frames
+    from casualhdrsplat_b200.parallel import ChsComm, NvlsComm, ShardedHostParams, StepState, TorchComm, formation_step, shard_frames
     from casualhdrsplat_b200.scene import make_config
 
     if not torch.cuda.is_available():
@@ -262,10 +264,13 @@ def main():
 
     tight = args.bounds == "tight"
 
+    step_state = None  # created after the warm-up that measures M
+
     def step(upstream, st=None, params=None, tight_bounds=None):
         nonlocal flat
         layout, flat = formation_step(P if params is None else params, spline_meta, W, H, n, sc.crf_kind, ids, upstream, micro_batch=1, sort_mode=args.sort_mode,
-                                      comm=comm, out=flat, stats=st, tight_bounds=tight if tight_bounds is None else tight_bounds)
+                                      comm=comm, out=flat, stats=st, tight_bounds=tight if tight_bounds is None else tight_bounds,
+                                      state=step_state if tight_bounds is None else None)
         return layout
 
     def barrier():
@@ -295,13 +300,19 @@ def main():
     m_emitted = stats["n_isect"]
     if m_ref is None:
         m_ref = m_emitted
+    if not args.host_sync:
+        # sync-free steps from here on: stage buffers from a pool, capacities from the previous step's M (+3 %), K2's count on the device
+        step_state = StepState()
+        for _ in range(2):
+            step(upstream_fixed, stats)
+        step_state.verify()
 
     # ---- per-kernel events for the dominant kernel (K8 blend_bwd), recorded on the launching stream ----
     bwd_events = []
     stage_events = {}
     orig = {}
-    for name_ in ["chs_spline_fwd", "chs_project_fwd", "chs_bin_count", "chs_bin_sort", "chs_blend_fwd", "chs_crf_bwd", "chs_blend_bwd",
-                  "chs_project_bwd", "chs_spline_bwd"]:
+    for name_ in ["chs_spline_fwd", "chs_project_fwd", "chs_bin_count", "chs_bin_sort", "chs_bin_sort_dev", "chs_blend_fwd", "chs_crf_bwd",
+                  "chs_blend_bwd", "chs_project_bwd", "chs_spline_bwd"]:
         orig[name_] = getattr(L, name_)
         stage_events[name_] = []
 
@@ -331,11 +342,14 @@ def main():
     e1.record()
     barrier()
     sampler.stop_flag = True
+    if step_state is not None:
+        step_state.verify()  # no frame outgrew its intersection buffers during the timed steps
     launches = L.chs_launch_count() - launches0
     ms = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms / args.steps
     value = B / (ms_per_step / 1e3)
     stage_ms = {k[4:]: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in stage_events.items()}
+    stage_ms["bin_sort"] += stage_ms.pop("bin_sort_dev")
     stage_ms["allreduce"] = sum(a.elapsed_time(b) for a, b in stats["events"]) / args.steps if stats["events"] else 0.0
     bwd_calls = stage_events["chs_blend_bwd"]
     bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_calls) / max(len(bwd_calls), 1)
@@ -448,6 +462,8 @@ def main():
         e2e_ms, losses = e2e_run(args.steps, True)
         e2e_run(1, False)
         serial_ms, losses_serial = e2e_run(args.steps, False)
+        if step_state is not None:
+            step_state.verify()
         # the gradient the hosts hold after the last step, slice by slice: must be the same numbers at every N
         gh = grads_host2[0][: g_hi - g_lo].double()
         e2e = {"value": B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)), "d2h_bytes_per_step": int(sum_over_ranks(d2h)),
@@ -524,6 +540,7 @@ def main():
                 "config": {"workload": f"{args.workload}: BASELINE.json configs[{ {'c1': 0, 'c2': 1, 'c3': 2, 'c4': 3, 'c5': 4}.get(args.workload, '?') }] — {N} Gaussians, {W}x{H}, {n} virtual poses/frame, "
                                        f"global batch {B} frames sharded by frame, fwd+bwd incl. pose/exposure/CRF grads",
                            "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode, "tile_bounds": args.bounds,
+                           "host_syncs_per_step": len(ids) if args.host_sync else 0,
                            "isects_emitted_per_frame": m_emitted / n_local,
                            "isects_per_frame": M_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
                            "collective": None if world == 1 else ("ncclAllReduce via libchs C ABI" if isinstance(comm, ChsComm) else

@@ -46,17 +46,60 @@ def _empty(shape, dtype, device):
 class _State:
     """Everything one forward produced that the backward (and tests) need."""
     __slots__ = ("cfg", "spline", "viewmats", "Ks", "geom", "conic_c", "depths", "radii", "tiles_touched", "rgbo",
-                 "isect_offsets", "order", "n_isect", "keys_sorted", "vals_sorted", "tile_offsets", "ldr", "alpha", "hdr_mean",
-                 "final_T", "last_id", "n_knots", "sh", "sh_degree", "rgbo_c")
+                 "isect_offsets", "order", "_n_isect", "_n_pinned", "_n_event", "isect_capacity", "keys_sorted", "vals_sorted",
+                 "tile_offsets", "ldr", "alpha", "hdr_mean", "final_T", "last_id", "n_knots", "sh", "sh_degree", "rgbo_c")
+
+    @property
+    def n_isect(self) -> int:
+        """M.  In the sync-free mode (``isect_capacity`` given) the count travels to the host asynchronously and the first
+        read waits for that copy only."""
+        if self._n_isect is None:
+            self._n_event.synchronize()
+            self._n_isect = int(self._n_pinned.item())
+        return self._n_isect
+
+    @property
+    def overflowed(self) -> bool:
+        """Sync-free mode: did the frame need more intersections than the buffers held (its lists were then truncated)?"""
+        return self.isect_capacity is not None and self.n_isect > self.isect_capacity
+
+
+class BufferPool:
+    """Stage buffers allocated once per (name, shape, dtype) and reused by later calls ON THE SAME STREAM (a training step
+    runs forward and backward of one frame batch before the next one starts, so stream order makes the reuse safe)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, shape, dtype, device):
+        key = (name, tuple(shape), dtype, str(device))
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.empty(tuple(shape), dtype=dtype, device=device)
+        return t
+
+    def bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
 
 
 def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposure, crf_params, cfg, spline=None,
-                   want_keys=False, sh=None, sh_degree=0) -> _State:
+                   want_keys=False, sh=None, sh_degree=0, isect_capacity=None, pool=None) -> _State:
     """Run K0-K6 through the C ABI. All tensors CUDA fp32 contiguous. Returns the stage buffers.
-    With ``sh`` [N,K,3] the colours are view dependent (chs_sh_fwd, per-camera records) and ``colors`` is ignored."""
+    With ``sh`` [N,K,3] the colours are view dependent (chs_sh_fwd, per-camera records) and ``colors`` is ignored.
+    ``isect_capacity``: size the intersection buffers for that many entries and never synchronise with the host (K2's count
+    stays on the device, chs_bin_sort_dev reads it there; ``st.n_isect`` / ``st.overflowed`` resolve it lazily).
+    ``pool``: a BufferPool to take the stage buffers from instead of allocating them."""
     L = _lib.lib()
     dev = means.device
+
+    def _empty(shape, dtype, device, name=None, _n=[0]):  # noqa: B006  (call counter names anonymous buffers in call order)
+        _n[0] += 1
+        if pool is None:
+            return torch.empty(shape, dtype=dtype, device=device)
+        return pool.get(name or f"fwd{_n[0]}", shape, dtype, device)
+
     st = _State()
+    st.isect_capacity = None if isect_capacity is None else int(isect_capacity)
     st.cfg, st.spline, st.Ks = cfg, spline, Ks
     N, B, n = cfg.n_gauss, cfg.n_frames, cfg.n_virtual
     C = B * n
@@ -94,19 +137,35 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     st.isect_offsets = _empty((C * N,), torch.int32, dev)
     st.order = _empty((C * N,), torch.int32, dev) if cfg.sort_mode == _lib.CHS_SORT_DEPTH_PRESORT else None
     n_dev = _empty((1,), torch.int64, dev)
-    n_host = c_int64(0)
-    check(L.chs_bin_count(byref(cfg), ptr(st.tiles_touched), ptr(st.depths), ptr(st.isect_offsets), ptr(st.order), ptr(n_dev),
-                          byref(n_host), ptr(work), work.numel(), s), "chs_bin_count")
-    M = int(n_host.value)
-    st.n_isect = M
+    st._n_pinned = st._n_event = None
+    if st.isect_capacity is None:
+        n_host = c_int64(0)
+        check(L.chs_bin_count(byref(cfg), ptr(st.tiles_touched), ptr(st.depths), ptr(st.isect_offsets), ptr(st.order), ptr(n_dev),
+                              byref(n_host), ptr(work), work.numel(), s), "chs_bin_count")
+        M = int(n_host.value)
+        st._n_isect = M
+    else:  # sync-free: M stays on the device; a pinned copy follows asynchronously for the caller's overflow check
+        check(L.chs_bin_count(byref(cfg), ptr(st.tiles_touched), ptr(st.depths), ptr(st.isect_offsets), ptr(st.order), ptr(n_dev),
+                              None, ptr(work), work.numel(), s), "chs_bin_count")
+        M = st.isect_capacity
+        st._n_isect = None
+        st._n_pinned = torch.empty((1,), dtype=torch.int64).pin_memory()
+        st._n_pinned.copy_(n_dev, non_blocking=True)
+        st._n_event = torch.cuda.Event()
+        st._n_event.record()
     # K3-K5
     ws = _lib.workspace_sizes(cfg, M, st.n_knots)
     work = _empty((max(int(ws.bin_sort_bytes), 256),), torch.uint8, dev)
     st.keys_sorted = _empty((M,), torch.int64, dev) if want_keys else None
     st.vals_sorted = _empty((max(M, 1),), torch.int32, dev)
     st.tile_offsets = _empty((C * tiles + 1,), torch.int32, dev)
-    check(L.chs_bin_sort(byref(cfg), M, ptr(st.geom), ptr(st.radii), ptr(st.depths), ptr(st.isect_offsets), ptr(st.order),
-                         ptr(st.keys_sorted), ptr(st.vals_sorted), ptr(st.tile_offsets), ptr(work), work.numel(), s), "chs_bin_sort")
+    if st.isect_capacity is None:
+        check(L.chs_bin_sort(byref(cfg), M, ptr(st.geom), ptr(st.radii), ptr(st.depths), ptr(st.isect_offsets), ptr(st.order),
+                             ptr(st.keys_sorted), ptr(st.vals_sorted), ptr(st.tile_offsets), ptr(work), work.numel(), s), "chs_bin_sort")
+    else:
+        check(L.chs_bin_sort_dev(byref(cfg), M, ptr(n_dev), ptr(st.geom), ptr(st.radii), ptr(st.depths), ptr(st.isect_offsets),
+                                 ptr(st.order), ptr(st.keys_sorted), ptr(st.vals_sorted), ptr(st.tile_offsets), ptr(work), work.numel(), s),
+              "chs_bin_sort_dev")
     del work
     # K6
     st.ldr = _empty((B, H, W, 3), torch.float32, dev)
@@ -122,11 +181,19 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     return st
 
 
-def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ldr, v_alpha, v_hdr_out=None, grads_out=None):
-    """Run K7-K9 (+K0 bwd). Returns dict of gradients; ``grads_flat`` is the [14N] buffer that multi-GPU runs all-reduce."""
+def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ldr, v_alpha, v_hdr_out=None, grads_out=None, pool=None):
+    """Run K7-K9 (+K0 bwd). Returns dict of gradients; ``grads_flat`` is the [14N] buffer that multi-GPU runs all-reduce.
+    ``pool``: a BufferPool for the backward's stage buffers (the returned gradient tensors then alias pool memory)."""
     L = _lib.lib()
     cfg = st.cfg
     dev = means.device
+
+    def _empty(shape, dtype, device, _n=[0]):  # noqa: B006
+        _n[0] += 1
+        if pool is None:
+            return torch.empty(shape, dtype=dtype, device=device)
+        return pool.get(f"bwd{_n[0]}", shape, dtype, device)
+
     N, B, n = cfg.n_gauss, cfg.n_frames, cfg.n_virtual
     C = B * n
     s = _stream()
@@ -134,7 +201,7 @@ def backward_stages(st: _State, means, quats, scales, exposure, crf_params, v_ld
     red = _empty((int(ws.reduce_bytes),), torch.uint8, dev)
     # K7
     v_hdr = _empty((C if cfg.crf_before_average else B, cfg.height, cfg.width, 3), torch.float32, dev)
-    v_crf = torch.zeros_like(crf_params) if crf_params is not None else None
+    v_crf = _empty(tuple(crf_params.shape), torch.float32, dev) if crf_params is not None else None  # overwritten by chs_crf_bwd
     v_exposure = _empty((B,), torch.float32, dev)
     check(L.chs_crf_bwd(byref(cfg), ptr(st.hdr_mean), ptr(exposure), ptr(crf_params), ptr(v_ldr), ptr(v_hdr), ptr(v_crf),
                         ptr(v_exposure), ptr(red), red.numel(), s), "chs_crf_bwd")

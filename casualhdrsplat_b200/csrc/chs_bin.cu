@@ -1088,7 +1088,7 @@ struct BandPlan {
   int chunks1;
   int64_t n_seg2;
   uint32_t t_cap1, t_cap2;
-  uint64_t sum_blocks;
+  uint64_t rec_cap, sum_blocks;
 };
 BandPlan band_plan(const ChsDims& d, uint64_t cap) {
   BandPlan p;
@@ -1097,7 +1097,11 @@ BandPlan band_plan(const ChsDims& d, uint64_t cap) {
   p.chunks1 = (d.N + kBandChunk - 1) / kBandChunk;
   p.t_cap1 = (uint32_t)p.chunks1 * (uint32_t)d.C;
   p.n_seg2 = (int64_t)d.C * p.g.n_bands;
-  p.t_cap2 = (uint32_t)((cap + kBandChunk - 1) / kBandChunk) + (uint32_t)p.n_seg2;
+  // a pair whose rectangle spans r tile rows reaches at most r / BR + 2 bands and has at least r intersections, so the number of
+  // (pair, band) records is bounded by M / BR + 2 C N (and by M): the bound sizes the record array and the P2 grid
+  p.rec_cap = cap / (uint64_t)p.g.BR + 2 * (uint64_t)d.CN;
+  if (p.rec_cap > cap) p.rec_cap = cap;
+  p.t_cap2 = (uint32_t)((p.rec_cap + kBandChunk - 1) / kBandChunk) + (uint32_t)p.n_seg2;
   p.sum_blocks = ((uint64_t)p.n_seg2 * 256 + cs::kScanTile - 1) / cs::kScanTile;
   return p;
 }
@@ -1105,7 +1109,7 @@ uint64_t band_bytes(const ChsDims& d, uint64_t cap) {
   const BandPlan p = band_plan(d, cap);
   uint64_t b = chs_align_up((uint64_t)d.CN * sizeof(ushort4), 256) + chs_align_up((uint64_t)256 * p.t_cap1 * 4, 256);
   b += chs_align_up((uint64_t)d.C * 256 * 4, 256) + 2 * chs_align_up((uint64_t)(p.n_seg2 + 1) * 4, 256);
-  b += chs_align_up(cap * sizeof(uint2), 256) + chs_align_up((uint64_t)p.t_cap2 * sizeof(uint4), 256);
+  b += chs_align_up(p.rec_cap * sizeof(uint2), 256) + chs_align_up((uint64_t)p.t_cap2 * sizeof(uint4), 256);
   b += chs_align_up((uint64_t)256 * p.t_cap2 * 4, 256) + 2 * chs_align_up((uint64_t)p.n_seg2 * 256 * 4, 256);
   b += chs_align_up((p.sum_blocks + 1) * 8, 256);
   return b + 256;
@@ -1255,7 +1259,7 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
   uint32_t* totals1 = ar.take<uint32_t>((uint64_t)d.C * 256);
   uint32_t* seg_begin2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
   uint32_t* tile_first2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
-  uint2* recs = ar.take<uint2>(cap);
+  uint2* recs = ar.take<uint2>(p.rec_cap);
   uint4* desc = ar.take<uint4>(p.t_cap2);
   uint32_t* counts2 = ar.take<uint32_t>((uint64_t)256 * p.t_cap2);
   uint32_t* totals2 = ar.take<uint32_t>((uint64_t)p.n_seg2 * 256);
@@ -1269,7 +1273,7 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
   BandArgs a;
   memset(&a, 0, sizeof(a));
   a.N = d.N; a.C = d.C; a.tile_w = d.tile_w; a.tile_h = d.tile_h; a.tight = cfg->tight_bounds != 0; a.BR = p.g.BR; a.n_bands = p.g.n_bands;
-  a.chunks1 = p.chunks1; a.t_cap1 = p.t_cap1; a.t_cap2 = p.t_cap2; a.rec_cap = (uint32_t)cap; a.val_cap = (uint32_t)cap;
+  a.chunks1 = p.chunks1; a.t_cap1 = p.t_cap1; a.t_cap2 = p.t_cap2; a.rec_cap = (uint32_t)p.rec_cap; a.val_cap = (uint32_t)cap;
   a.geom = geom; a.radii = radii; a.order = order; a.rects = rects; a.counts1 = counts1; a.seg_begin2 = seg_begin2; a.recs = recs;
   a.desc = desc; a.counts2 = counts2; a.base2 = base2; a.vals = vals_sorted;
   // P1: band split
@@ -1287,7 +1291,7 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
   band_scatter_kernel<<<p.t_cap1, 256, smem1, s>>>(a);
   CHS_LAUNCH_CHECK();
   // P2: tile placement inside every (camera, band) bucket
-  chunk_desc_kernel<<<(p.t_cap2 + 255) / 256, 256, 0, s>>>((int)p.n_seg2, seg_begin2, tile_first2, p.t_cap2, (uint32_t)cap, desc);
+  chunk_desc_kernel<<<(p.t_cap2 + 255) / 256, 256, 0, s>>>((int)p.n_seg2, seg_begin2, tile_first2, p.t_cap2, (uint32_t)p.rec_cap, desc);
   CHS_LAUNCH_CHECK();
   tile_count_kernel<<<p.t_cap2, 256, 0, s>>>(a);
   CHS_LAUNCH_CHECK();

@@ -19,7 +19,7 @@ from typing import Callable, Dict, Optional, Sequence
 import torch
 
 from . import _lib
-from .api import _stream, backward_stages, forward_stages
+from .api import BufferPool, _stream, backward_stages, forward_stages
 
 _SORT = {"key64": _lib.CHS_SORT_KEY64, "presort": _lib.CHS_SORT_DEPTH_PRESORT}
 
@@ -167,7 +167,7 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
                    frame_ids: Sequence[int], upstream: Callable[[Sequence[int], torch.Tensor], torch.Tensor], *,
                    micro_batch: int = 1, sort_mode: str = "presort", comm=None, background=None, out: Optional[torch.Tensor] = None,
                    stats: Optional[dict] = None, crf_before_average: bool = False, tight_bounds: bool = False,
-                   pose_fused: bool = False, tuning: Optional[dict] = None):
+                   pose_fused: bool = False, tuning: Optional[dict] = None, state: Optional["StepState"] = None):
     """One fwd+bwd training step over this rank's frames, then the gradient all-reduce.
 
     params: CUDA fp32 tensors means [N,3], quats [N,4], scales [N,3], opacities [N], colors [N,3], knots [K,7],
@@ -175,6 +175,10 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
             B is the GLOBAL batch.  spline_meta: knot_t0, knot_dt, kind.
     tight_bounds: opacity-aware tile bounds (``rasterize``): same gradients, shorter tile lists.
     pose_fused / tuning: as in ``rasterize`` (chs_config.pose_fused, chs_config.tune_*).
+    state: a ``StepState`` kept by the caller across steps.  With it the step never synchronises with the host (after the
+            first step has learnt every frame's intersection count M, the buffers are sized from the previous step's M plus a
+            margin and K2's count stays on the device) and every stage buffer comes from a pool instead of the allocator.
+            Call ``state.verify()`` before trusting a step's gradients: it raises if a frame outgrew its buffers.
     frame_ids: the frames this rank renders (``shard_frames``).  ``upstream(ids, ldr[len(ids),H,W,3])`` returns the
             gradient of the loss w.r.t. those LDR frames (same shape).
     Returns (GradLayout, flat gradient buffer summed over all ranks).
@@ -204,10 +208,14 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
                                sort_mode=_SORT[sort_mode], background=background, crf_before_average=crf_before_average,
                                tight_bounds=tight_bounds, pose_fused=pose_fused, tuning=tuning)
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
-        st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline)
+        cap = state.capacity(tuple(ids)) if state is not None else None
+        pool = state.pool if state is not None else None
+        st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline, isect_capacity=cap, pool=pool)
+        if state is not None:
+            state.track(tuple(ids), st)
         v_ldr = upstream(ids, st.ldr).contiguous()
         # the first micro-batch writes K9's output straight into the flat buffer (which may be symmetric memory)
-        g = backward_stages(st, means, quats, scales, ex, crf_params, v_ldr, None, grads_out=flat[:14 * N] if first else None)
+        g = backward_stages(st, means, quats, scales, ex, crf_params, v_ldr, None, grads_out=flat[:14 * N] if first else None, pool=pool)
         if first:
             first = False
         else:
@@ -217,7 +225,8 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
             v["crf_params"].add_(g["v_crf"].reshape(-1))
         v["exposure_times"][idx] = g["v_exposure"]
         v["frame_times"][idx] = g["v_frame_times"]
-        n_isect_total += st.n_isect
+        if state is None or cap is None:
+            n_isect_total += st.n_isect  # (in the sync-free mode reading M would wait for the GPU: StepState reports it one step late)
         if stats is not None and stats.get("count_pairs"):
             m_g_total += int((st.tiles_touched > 0).sum())
     if first:
@@ -232,7 +241,7 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
         else:
             comm.allreduce_(flat)
     if stats is not None:
-        stats["n_isect"] = n_isect_total
+        stats["n_isect"] = n_isect_total if (state is None or n_isect_total > 0) else state.last_total()
         if stats.get("count_pairs"):
             stats["m_g"] = m_g_total
     return layout, flat
@@ -300,3 +309,56 @@ class ShardedHostParams:
         per = ((n_floats + self.world - 1) // self.world + 3) // 4 * 4
         b = min(self.rank * per, n_floats)
         return b, min(b + per, n_floats)
+
+
+class StepState:
+    """What ``formation_step`` keeps between steps to run without host synchronisation: the stage-buffer pool, every frame
+    batch's intersection capacity (the previous M plus ``margin``) and the forward states whose M has not been checked yet."""
+
+    def __init__(self, margin: float = 0.03, slack: int = 65536):
+        self.pool = BufferPool()
+        self.margin, self.slack = margin, slack
+        self._cap = {}       # frame ids -> capacity for the next step (None until M is known)
+        self._last = {}      # frame ids -> last resolved M
+        self._pending = []   # (frame ids, forward state) of steps not verified yet
+        self.overflows = []  # (frame ids, M, capacity) of frames that outgrew their buffers
+
+    def capacity(self, ids):
+        self._resolve(keep_last=True)
+        if self._cap.get(ids) is None:
+            return None
+        # one capacity for all frame batches (rounded up to 1 Mi entries), so that the pooled buffers have one shape
+        return (max(c for c in self._cap.values() if c) + (1 << 20) - 1) >> 20 << 20
+
+    def track(self, ids, st) -> None:
+        self._pending.append((ids, st))
+
+    def _resolve(self, keep_last: bool) -> None:
+        # states of EARLIER steps only: their K2 finished long ago, so reading M does not stall the stream being fed now
+        done, keep = self._pending, []
+        if keep_last:
+            seen = set()
+            for item in reversed(self._pending):  # the newest state of each frame batch belongs to the step in flight
+                if item[0] not in seen and item[1]._n_isect is None and not item[1]._n_event.query():
+                    keep.append(item)
+                    seen.add(item[0])
+            done = [it for it in self._pending if it not in keep]
+        for ids, st in done:
+            m = st.n_isect
+            self._last[ids] = m
+            if st.overflowed:
+                self.overflows.append((ids, m, st.isect_capacity))
+            want = int(m * (1.0 + self.margin)) + self.slack
+            self._cap[ids] = max(want, self._cap.get(ids) or 0) if not st.overflowed else int(m * (1.0 + 2 * self.margin)) + self.slack
+        self._pending = keep
+
+    def verify(self) -> None:
+        """Wait for every tracked step's intersection count and raise if one exceeded its capacity (that step's lists were
+        truncated, so its gradients must be recomputed; the capacity has been raised for the retry)."""
+        self._resolve(keep_last=False)
+        if self.overflows:
+            o, self.overflows = self.overflows, []
+            raise RuntimeError(f"formation_step: intersection buffers overflowed for {o}; re-run the step")
+
+    def last_total(self) -> int:
+        return int(sum(self._last.values()))
