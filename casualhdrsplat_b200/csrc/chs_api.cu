@@ -46,6 +46,10 @@ int chs_make_dims(const chs_config* cfg, ChsDims* d) {
   d->cam_bits = chs_bit_length((uint64_t)d->C);
   d->CN = (int64_t)d->C * d->N;
   d->P = (int64_t)d->W * d->H;
+  d->Cb = cfg->pose_fused ? d->B : d->C;
+  d->CbN = (int64_t)d->Cb * d->N;
+  CHS_REQUIRE(!cfg->pose_fused || (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT && cfg->tune_bin == 0 && d->tile_w <= 256),
+              "pose_fused needs the default binning route (CHS_SORT_DEPTH_PRESORT, tune_bin = 0, width <= 4096)");
   // the projection kernels keep the whole camera table in shared memory (112 B per camera in the backward)
   CHS_REQUIRE(d->C <= 1024, "too many cameras in one call (%d > 1024 = frames x virtual poses); split the frame batch", d->C);
   CHS_REQUIRE(d->CN < ((int64_t)1 << 31), "C*N = %lld exceeds int32 ids; split the frame batch", (long long)d->CN);

@@ -869,7 +869,8 @@ bool uses_band_route(const chs_config* cfg, const ChsDims& d) {
 }
 
 struct BandArgs {
-  int N, C, tile_w, tile_h, tight, BR, n_bands, chunks1;  // chunks1 = chunks per camera in P1
+  int N, C, tile_w, tile_h, tight, BR, n_bands, chunks1;  // C = binning cameras (frames when fused); chunks1 = chunks per camera in P1
+  int fused, n_virtual;      // pose_fused: pair (frame f, g) covers the union of the rectangles of cameras f * n_virtual + k
   uint32_t t_cap1, t_cap2, rec_cap, val_cap;
   const float4* geom;
   const int32_t* radii;
@@ -902,16 +903,35 @@ __global__ void __launch_bounds__(256) band_count_kernel(BandArgs a) {
     const int i = q * kBandChunk + k * 256 + threadIdx.x;
     if (i >= a.N) continue;
     const int32_t id = a.order[seg + i];
-    const int radius = a.radii[id];
-    ushort4 rc = make_ushort4(0, 0, 0, 0);
-    if (radius != 0) {
-      const float4 gm = a.geom[id];
-      const ChsTileRect r = chs_tile_bounds_of(gm.x, gm.y, radius, a.tight, a.tile_w, a.tile_h);
-      if (r.x1 > r.x0 && r.y1 > r.y0) {
-        rc = make_ushort4((unsigned short)r.x0, (unsigned short)r.y0, (unsigned short)r.x1, (unsigned short)r.y1);
-        const int b1 = (r.y1 - 1) / a.BR;
-        for (int b = r.y0 / a.BR; b <= b1; ++b) atomicAdd(&hist[b], 1u);
+    ChsTileRect r;
+    r.x0 = r.y0 = r.x1 = r.y1 = 0;
+    if (!a.fused) {
+      const int radius = a.radii[id];
+      if (radius != 0) {
+        const float4 gm = a.geom[id];
+        r = chs_tile_bounds_of(gm.x, gm.y, radius, a.tight, a.tile_w, a.tile_h);
       }
+    } else {  // union over the frame's poses that see the Gaussian
+      const int64_t first = ((int64_t)c * a.n_virtual) * a.N + (id - (int32_t)seg);
+      for (int k = 0; k < a.n_virtual; ++k) {
+        const int64_t cid = first + (int64_t)k * a.N;
+        const int radius = a.radii[cid];
+        if (radius == 0) continue;
+        const float4 gm = a.geom[cid];
+        const ChsTileRect q2 = chs_tile_bounds_of(gm.x, gm.y, radius, a.tight, a.tile_w, a.tile_h);
+        if (q2.x1 <= q2.x0 || q2.y1 <= q2.y0) continue;
+        if (r.x1 > r.x0) {
+          r.x0 = min(r.x0, q2.x0); r.y0 = min(r.y0, q2.y0); r.x1 = max(r.x1, q2.x1); r.y1 = max(r.y1, q2.y1);
+        } else {
+          r = q2;
+        }
+      }
+    }
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
+    if (r.x1 > r.x0 && r.y1 > r.y0) {
+      rc = make_ushort4((unsigned short)r.x0, (unsigned short)r.y0, (unsigned short)r.x1, (unsigned short)r.y1);
+      const int b1 = (r.y1 - 1) / a.BR;
+      for (int b = r.y0 / a.BR; b <= b1; ++b) atomicAdd(&hist[b], 1u);
     }
     a.rects[seg + i] = rc;
   }
@@ -1095,11 +1115,11 @@ BandPlan band_plan(const ChsDims& d, uint64_t cap) {
   memset(&p, 0, sizeof(p));
   p.g = band_geom(d);
   p.chunks1 = (d.N + kBandChunk - 1) / kBandChunk;
-  p.t_cap1 = (uint32_t)p.chunks1 * (uint32_t)d.C;
-  p.n_seg2 = (int64_t)d.C * p.g.n_bands;
+  p.t_cap1 = (uint32_t)p.chunks1 * (uint32_t)d.Cb;
+  p.n_seg2 = (int64_t)d.Cb * p.g.n_bands;
   // a pair whose rectangle spans r tile rows reaches at most r / BR + 2 bands and has at least r intersections, so the number of
   // (pair, band) records is bounded by M / BR + 2 C N (and by M): the bound sizes the record array and the P2 grid
-  p.rec_cap = cap / (uint64_t)p.g.BR + 2 * (uint64_t)d.CN;
+  p.rec_cap = cap / (uint64_t)p.g.BR + 2 * (uint64_t)d.CbN;
   if (p.rec_cap > cap) p.rec_cap = cap;
   p.t_cap2 = (uint32_t)((p.rec_cap + kBandChunk - 1) / kBandChunk) + (uint32_t)p.n_seg2;
   p.sum_blocks = ((uint64_t)p.n_seg2 * 256 + cs::kScanTile - 1) / cs::kScanTile;
@@ -1107,8 +1127,8 @@ BandPlan band_plan(const ChsDims& d, uint64_t cap) {
 }
 uint64_t band_bytes(const ChsDims& d, uint64_t cap) {
   const BandPlan p = band_plan(d, cap);
-  uint64_t b = chs_align_up((uint64_t)d.CN * sizeof(ushort4), 256) + chs_align_up((uint64_t)256 * p.t_cap1 * 4, 256);
-  b += chs_align_up((uint64_t)d.C * 256 * 4, 256) + 2 * chs_align_up((uint64_t)(p.n_seg2 + 1) * 4, 256);
+  uint64_t b = chs_align_up((uint64_t)d.CbN * sizeof(ushort4), 256) + chs_align_up((uint64_t)256 * p.t_cap1 * 4, 256);
+  b += chs_align_up((uint64_t)d.Cb * 256 * 4, 256) + 2 * chs_align_up((uint64_t)(p.n_seg2 + 1) * 4, 256);
   b += chs_align_up(p.rec_cap * sizeof(uint2), 256) + chs_align_up((uint64_t)p.t_cap2 * sizeof(uint4), 256);
   b += chs_align_up((uint64_t)256 * p.t_cap2 * 4, 256) + 2 * chs_align_up((uint64_t)p.n_seg2 * 256 * 4, 256);
   b += chs_align_up((p.sum_blocks + 1) * 8, 256);
@@ -1125,16 +1145,16 @@ struct CountPlan {
 CountPlan count_plan(const ChsDims& d) {
   CountPlan p;
   p.tps = tiles_of((uint64_t)d.N);
-  p.t_cap = p.tps * (uint32_t)d.C;
-  p.sum_blocks = ((uint64_t)d.CN + cs::kScanTile - 1) / cs::kScanTile;
+  p.t_cap = p.tps * (uint32_t)d.Cb;
+  p.sum_blocks = ((uint64_t)d.CbN + cs::kScanTile - 1) / cs::kScanTile;
   return p;
 }
 uint64_t hw_count_bytes(const ChsDims& d, int sort_mode) {
   const CountPlan p = count_plan(d);
   uint64_t b = chs_align_up(p.sum_blocks * 8, 256);
   if (sort_mode == CHS_SORT_DEPTH_PRESORT)
-    b += chs_align_up((uint64_t)cs::kDigits * p.t_cap * 4, 256) + chs_align_up((uint64_t)d.C * cs::kDigits * 4, 256) +
-         4 * chs_align_up((uint64_t)d.CN * 4, 256);
+    b += chs_align_up((uint64_t)cs::kDigits * p.t_cap * 4, 256) + chs_align_up((uint64_t)d.Cb * cs::kDigits * 4, 256) +
+         4 * chs_align_up((uint64_t)d.CbN * 4, 256);
   return b + 256;
 }
 
@@ -1187,20 +1207,25 @@ int hw_bin_count(const chs_config* cfg, const ChsDims& d, const int32_t* tiles_t
   const int32_t* ord = nullptr;
   if (cfg->sort_mode == CHS_SORT_DEPTH_PRESORT) {
     uint32_t* counts = ar.take<uint32_t>((uint64_t)cs::kDigits * p.t_cap);
-    uint32_t* totals = ar.take<uint32_t>((uint64_t)d.C * cs::kDigits);
-    uint32_t* ka = ar.take<uint32_t>(d.CN);
-    uint32_t* kb = ar.take<uint32_t>(d.CN);
-    int32_t* va = ar.take<int32_t>(d.CN);
-    int32_t* vb = ar.take<int32_t>(d.CN);
+    uint32_t* totals = ar.take<uint32_t>((uint64_t)d.Cb * cs::kDigits);
+    uint32_t* ka = ar.take<uint32_t>(d.CbN);
+    uint32_t* kb = ar.take<uint32_t>(d.CbN);
+    int32_t* va = ar.take<int32_t>(d.CbN);
+    int32_t* vb = ar.take<int32_t>(d.CbN);
     if (!ar.ok) {
       chs_set_error("chs_bin_count: workspace too small (%llu bytes)", (unsigned long long)workspace_bytes);
       return CHS_ERR_WORKSPACE_TOO_SMALL;
     }
-    // cameras are segments of N pairs: four stable LSD passes over the depth bits inside every camera
+    // cameras (frames with pose_fused) are segments of N pairs: four stable LSD passes over the depth bits inside every segment
     cs::TileMap map;
     memset(&map, 0, sizeof(map));
-    map.n_seg = d.C; map.seg_len = (uint32_t)d.N; map.tiles_per_seg = p.tps;
-    int st = radix_pass<cs::DepthKeys, uint32_t>(map, cs::DepthKeys{depths, tiles_touched}, nullptr, ka, va, 0, 8, counts, p.t_cap, totals, nullptr, s);
+    map.n_seg = d.Cb; map.seg_len = (uint32_t)d.N; map.tiles_per_seg = p.tps;
+    int st;
+    if (cfg->pose_fused)
+      st = radix_pass<cs::FusedDepthKeys, uint32_t>(map, cs::FusedDepthKeys{depths, tiles_touched, d.N, d.n}, nullptr, ka, va, 0, 8, counts, p.t_cap,
+                                                    totals, nullptr, s);
+    else
+      st = radix_pass<cs::DepthKeys, uint32_t>(map, cs::DepthKeys{depths, tiles_touched}, nullptr, ka, va, 0, 8, counts, p.t_cap, totals, nullptr, s);
     if (st) return st;
     st = radix_pass<cs::ArrayKeys<uint32_t>, uint32_t>(map, cs::ArrayKeys<uint32_t>{ka}, va, kb, vb, 8, 8, counts, p.t_cap, totals, nullptr, s);
     if (st) return st;
@@ -1217,7 +1242,7 @@ int hw_bin_count(const chs_config* cfg, const ChsDims& d, const int32_t* tiles_t
   }
   if (uses_band_route(cfg, d)) {  // the banded placement never reads isect_offsets: M is a plain (coalesced) sum
     const uint32_t blocks = (uint32_t)p.sum_blocks;
-    cs::scan_sums_kernel<TouchedIn><<<blocks, cs::kThreads, 0, s>>>(TouchedIn{tiles_touched, nullptr}, (uint64_t)d.CN, sums);
+    cs::scan_sums_kernel<TouchedIn><<<blocks, cs::kThreads, 0, s>>>(TouchedIn{tiles_touched, nullptr}, (uint64_t)d.CbN, sums);
     CHS_LAUNCH_CHECK();
     cs::scan_of_sums_kernel<<<1, 1024, 0, s>>>(sums, blocks, n_isect_dev, nullptr);
     CHS_LAUNCH_CHECK();
@@ -1252,11 +1277,11 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
                   const int32_t* order, uint64_t* keys_sorted, int32_t* vals_sorted, uint32_t* tile_offsets, void* workspace,
                   uint64_t workspace_bytes, cudaStream_t s) {
   const BandPlan p = band_plan(d, cap);
-  const int64_t n_lin = (int64_t)d.C * d.tiles;
+  const int64_t n_lin = (int64_t)d.Cb * d.tiles;
   ChsArena ar(workspace, workspace_bytes);
-  ushort4* rects = ar.take<ushort4>(d.CN);
+  ushort4* rects = ar.take<ushort4>(d.CbN);
   uint32_t* counts1 = ar.take<uint32_t>((uint64_t)256 * p.t_cap1);
-  uint32_t* totals1 = ar.take<uint32_t>((uint64_t)d.C * 256);
+  uint32_t* totals1 = ar.take<uint32_t>((uint64_t)d.Cb * 256);
   uint32_t* seg_begin2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
   uint32_t* tile_first2 = ar.take<uint32_t>((uint64_t)p.n_seg2 + 1);
   uint2* recs = ar.take<uint2>(p.rec_cap);
@@ -1272,7 +1297,8 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
   int64_t* total = reinterpret_cast<int64_t*>(sums + p.sum_blocks);
   BandArgs a;
   memset(&a, 0, sizeof(a));
-  a.N = d.N; a.C = d.C; a.tile_w = d.tile_w; a.tile_h = d.tile_h; a.tight = cfg->tight_bounds != 0; a.BR = p.g.BR; a.n_bands = p.g.n_bands;
+  a.N = d.N; a.C = d.Cb; a.tile_w = d.tile_w; a.tile_h = d.tile_h; a.tight = cfg->tight_bounds != 0; a.BR = p.g.BR; a.n_bands = p.g.n_bands;
+  a.fused = cfg->pose_fused != 0; a.n_virtual = d.n;
   a.chunks1 = p.chunks1; a.t_cap1 = p.t_cap1; a.t_cap2 = p.t_cap2; a.rec_cap = (uint32_t)p.rec_cap; a.val_cap = (uint32_t)cap;
   a.geom = geom; a.radii = radii; a.order = order; a.rects = rects; a.counts1 = counts1; a.seg_begin2 = seg_begin2; a.recs = recs;
   a.desc = desc; a.counts2 = counts2; a.base2 = base2; a.vals = vals_sorted;
@@ -1281,7 +1307,7 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
   CHS_LAUNCH_CHECK();
   cs::TileMap m1;
   memset(&m1, 0, sizeof(m1));
-  m1.n_seg = d.C; m1.tiles_per_seg = (uint32_t)p.chunks1;
+  m1.n_seg = d.Cb; m1.tiles_per_seg = (uint32_t)p.chunks1;
   int st = launch_colscan(m1, counts1, p.t_cap1, totals1, s);
   if (st) return st;
   segments_kernel<BucketLen><<<1, 1024, 0, s>>>(BucketLen{totals1, p.g.n_bands}, (int)p.n_seg2, kBandChunk, seg_begin2, tile_first2);
@@ -1459,7 +1485,7 @@ extern "C" int chs_bin_count(const chs_config* cfg, const int32_t* tiles_touched
   CHS_REQUIRE(tiles_touched && depths && isect_offsets && n_isect_dev && workspace, "chs_bin_count: null pointer");
   CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || order, "chs_bin_count: order buffer required for CHS_SORT_DEPTH_PRESORT");
   cudaStream_t s = (cudaStream_t)stream;
-  if (d.CN == 0) {
+  if (d.CbN == 0) {
     CHS_CUDA(cudaMemsetAsync(n_isect_dev, 0, sizeof(int64_t), s));
     if (n_isect_host) *n_isect_host = 0;
     return CHS_OK;
@@ -1489,7 +1515,7 @@ static int bin_sort_common(const chs_config* cfg, int64_t cap, const int64_t* n_
   CHS_REQUIRE(cfg->sort_mode == CHS_SORT_KEY64 || order, "chs_bin_sort: order required for CHS_SORT_DEPTH_PRESORT");
   cudaStream_t s = (cudaStream_t)stream;
   if (cap == 0 || d.CN == 0) {
-    CHS_CUDA(cudaMemsetAsync(tile_offsets, 0, ((size_t)d.C * d.tiles + 1) * sizeof(uint32_t), s));
+    CHS_CUDA(cudaMemsetAsync(tile_offsets, 0, ((size_t)d.Cb * d.tiles + 1) * sizeof(uint32_t), s));
     return CHS_OK;
   }
   CHS_REQUIRE(vals_sorted && workspace, "chs_bin_sort: null output/workspace");

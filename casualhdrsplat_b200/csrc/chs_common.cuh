@@ -46,6 +46,8 @@ struct ChsDims {
   int tile_bits, cam_bits;
   int64_t CN;  // C * N
   int64_t P;   // W * H
+  int Cb;       // cameras of the BINNING stage: C, or B with cfg->pose_fused (one tile list per frame)
+  int64_t CbN;  // Cb * N
 };
 
 static inline int chs_bit_length(uint64_t v) {

@@ -40,7 +40,7 @@ __device__ __forceinline__ void read_camera(const float* s_cam, int c, ChsCam<fl
 }
 
 struct ProjectFwdArgs {
-  int N, C, n_virtual, ks_per_camera, tile_w, tile_h, tight_bounds;
+  int N, C, n_virtual, ks_per_camera, tile_w, tile_h, tight_bounds, pose_fused;
   float width, height, near_plane, far_plane, eps2d;
   const float *means, *quats, *scales, *opacities, *colors, *viewmats, *Ks;
   float4* geom;
@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(kThreads) project_fwd_kernel(ProjectFwdArgs a)
   const float opac = a.opacities[g];
   a.rgbo[g] = make_float4(s_colors[t * 3], s_colors[t * 3 + 1], s_colors[t * 3 + 2], opac);
 
+  // pose_fused: the union of the frame's per-pose tile rectangles (poses where the Gaussian is live)
+  int ux0 = 0, uy0 = 0, ux1 = 0, uy1 = 0, k = 0;
   for (int c = 0; c < a.C; ++c) {
     ChsCam<float> cam;
     read_camera(s_cam, c, cam);
@@ -85,16 +87,40 @@ __global__ void __launch_bounds__(kThreads) project_fwd_kernel(ProjectFwdArgs a)
     int radius = chs_project_fwd(mu, S, cam, a.width, a.height, a.near_plane, a.far_plane, a.eps2d, pr);
     if (radius > 0 && a.tight_bounds) radius = chs_tight_radii(pr.sxx, pr.syy, opac, radius);  // packed rx | ry << 16, or 0
     int touched = 0;
+    ChsTileRect r;
+    r.x0 = r.y0 = r.x1 = r.y1 = 0;
     if (radius != 0) {  // packed tight radii are an unsigned pair: ry >= 32768 sets bit 31
-      ChsTileRect r = chs_tile_bounds_of(pr.mx, pr.my, radius, a.tight_bounds, a.tile_w, a.tile_h);
+      r = chs_tile_bounds_of(pr.mx, pr.my, radius, a.tight_bounds, a.tile_w, a.tile_h);
       touched = (r.x1 - r.x0) * (r.y1 - r.y0);
     }
     const int64_t o = (int64_t)c * a.N + g;
-    a.geom[o] = make_float4(pr.mx, pr.my, pr.ca, pr.cb);
-    a.conic_c[o] = pr.cc;
     a.depths[o] = pr.depth;
     a.radii[o] = radius;
-    a.tiles_touched[o] = touched;
+    if (!a.pose_fused) {
+      a.geom[o] = make_float4(pr.mx, pr.my, pr.ca, pr.cb);
+      a.conic_c[o] = pr.cc;
+      a.tiles_touched[o] = touched;
+      continue;
+    }
+    if (touched > 0) {
+      a.geom[o] = make_float4(pr.mx, pr.my, pr.ca, pr.cb);
+      a.conic_c[o] = pr.cc;
+      if (ux1 > ux0) {
+        ux0 = min(ux0, r.x0); uy0 = min(uy0, r.y0); ux1 = max(ux1, r.x1); uy1 = max(uy1, r.y1);
+      } else {
+        ux0 = r.x0; uy0 = r.y0; ux1 = r.x1; uy1 = r.y1;
+      }
+    } else {
+      // a pose that does not see the Gaussian still walks the frame's list: give it a record whose alpha is 0 everywhere
+      // (mean far off screen under a unit conic: the exponent is ~ -1e12)
+      a.geom[o] = make_float4(-1e6f, -1e6f, 1.f, 0.f);
+      a.conic_c[o] = 1.f;
+    }
+    if (++k == a.n_virtual) {
+      a.tiles_touched[(int64_t)(c / a.n_virtual) * a.N + g] = (ux1 - ux0) * (uy1 - uy0);
+      ux0 = uy0 = ux1 = uy1 = 0;
+      k = 0;
+    }
   }
 }
 
@@ -227,6 +253,7 @@ extern "C" int chs_project_fwd(const chs_config* cfg, const float* means, const 
   ProjectFwdArgs a;
   a.N = d.N; a.C = d.C; a.n_virtual = d.n; a.ks_per_camera = cfg->ks_per_camera; a.tile_w = d.tile_w; a.tile_h = d.tile_h;
   a.tight_bounds = cfg->tight_bounds != 0;
+  a.pose_fused = cfg->pose_fused != 0;
   a.width = (float)d.W; a.height = (float)d.H; a.near_plane = cfg->near_plane; a.far_plane = cfg->far_plane; a.eps2d = cfg->eps2d;
   a.means = means; a.quats = quats; a.scales = scales; a.opacities = opacities; a.colors = colors; a.viewmats = viewmats; a.Ks = Ks;
   a.geom = (float4*)geom; a.conic_c = conic_c; a.depths = depths; a.radii = radii; a.tiles_touched = tiles_touched; a.rgbo = (float4*)rgbo;

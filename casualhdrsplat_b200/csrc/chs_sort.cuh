@@ -95,6 +95,20 @@ struct DepthKeys {
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return touched[i] > 0 ? __float_as_uint(depths[i]) : 0xFFFFFFFFu; }
 };
 
+// pose_fused (one tile list per frame): pair i = frame * N + g is keyed by its depth at the frame's middle pose; `touched` is
+// the per-frame union count [B, N]
+struct FusedDepthKeys {
+  const float* depths;      // [C, N]
+  const int32_t* touched;   // [B, N]
+  int N, n_virtual;
+  typedef uint32_t key_type;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+    if (touched[i] <= 0) return 0xFFFFFFFFu;
+    const uint32_t f = i / (uint32_t)N, g = i - f * (uint32_t)N;
+    return __float_as_uint(depths[((size_t)f * n_virtual + n_virtual / 2) * N + g]);
+  }
+};
+
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -8,6 +8,6 @@ PARITY UNPINNED: the reference ships no code, tests or golden vectors (see oracl
 """
 from . import se3  # noqa: F401
 from .formation import (  # noqa: F401
-    CRF_IDENTITY, CRF_LUT, CRF_MLP, TIGHT_MARGIN, bin_tiles, blend, blend_pixel_loop, crf_apply, formation, key_bits, project,
+    CRF_IDENTITY, CRF_LUT, CRF_MLP, TIGHT_MARGIN, bin_tiles, bin_tiles_fused, blend, blend_pixel_loop, crf_apply, formation, key_bits, project,
     rasterize, tile_bounds, tile_grid,
 )

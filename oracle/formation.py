@@ -214,17 +214,70 @@ def bin_tiles(means2d_f32, radii_i32, depths_f32, width, height, tile=TILE, tigh
     }
 
 
+def bin_tiles_fused(means2d_f32, radii_i32, depths_f32, width, height, n_virtual, tile=TILE, tight=False):
+    """Pose-fused binning (``pose_fused=True``): ONE tile list per (frame, tile).
+
+    The n virtual poses of a frame see the scene from millimetres apart (/root/reference/assets/pipeline.png: the virtual camera
+    poses sit on one exposure-time arc), so their tile lists are almost the same lists.  The fused definition bins a Gaussian
+    once per frame: its rectangle is the union (bounding box) of its per-pose tile rectangles over the poses where it is live,
+    its depth key is its camera-space depth at the frame's middle pose k = n // 2 (taken whether or not that pose culls it), and
+    key = frame << (32 + tile_bits) | tile << 32 | depth bits, val = frame * N + g, stable sort.  Every pose then walks the
+    frame's list with its OWN projection (mean2d, conic) and alpha tests; a pose that culls the Gaussian skips it.
+    Returns the same dict as ``bin_tiles`` with frames in the role of cameras, plus ``live`` [C,N].
+    """
+    C, N = radii_i32.shape
+    B = C // n_virtual
+    tile_w, tile_h = tile_grid(width, height, tile)
+    tiles = tile_w * tile_h
+    tile_bits, frame_bits = key_bits(B, width, height, tile)
+    min_x, min_y, max_x, max_y, touched = tile_bounds(means2d_f32, radii_i32, width, height, tile, tight)
+    live = touched > 0
+    big = torch.iinfo(torch.int32).max
+
+    def fuse(v, lo):
+        v = torch.where(live, v, torch.full_like(v, big if lo else -1)).reshape(B, n_virtual, N)
+        return v.min(dim=1).values if lo else v.max(dim=1).values
+
+    fx0, fy0, fx1, fy1 = fuse(min_x, True), fuse(min_y, True), fuse(max_x, False), fuse(max_y, False)
+    any_live = live.reshape(B, n_virtual, N).any(dim=1)
+    f_touched = torch.where(any_live, (fx1 - fx0) * (fy1 - fy0), torch.zeros_like(fx0))
+    counts = f_touched.reshape(-1).to(torch.int64)
+    offsets = torch.cumsum(counts, 0) - counts
+    M = int(counts.sum())
+    rep = torch.repeat_interleave(torch.arange(B * N, dtype=torch.int64), counts)
+    local = torch.arange(M, dtype=torch.int64) - offsets[rep]
+    bw = (fx1 - fx0).reshape(-1).to(torch.int64)[rep]
+    ti = fy0.reshape(-1).to(torch.int64)[rep] + local // torch.clamp(bw, min=1)
+    tj = fx0.reshape(-1).to(torch.int64)[rep] + local % torch.clamp(bw, min=1)
+    tile_id = ti * tile_w + tj
+    frame = rep // N
+    mid = depths_f32.reshape(B, n_virtual, N)[:, n_virtual // 2, :].contiguous()
+    depth_bits = mid.view(torch.int32).reshape(-1).to(torch.int64)[rep] & 0xFFFFFFFF
+    keys = (frame << (32 + tile_bits)) | (tile_id << 32) | depth_bits
+    vals = rep.to(torch.int32)
+    keys_sorted, perm = torch.sort(keys, stable=True)
+    vals_sorted = vals[perm]
+    bucket = keys_sorted >> 32
+    wanted = (torch.arange(B, dtype=torch.int64)[:, None] << tile_bits) | torch.arange(tiles, dtype=torch.int64)[None, :]
+    tile_offsets = torch.searchsorted(bucket, wanted.reshape(-1), right=False)
+    tile_offsets = torch.cat([tile_offsets, torch.tensor([M], dtype=torch.int64)])
+    return {"tiles_touched": f_touched, "offsets": offsets, "n_isect": M, "keys": keys, "vals": vals, "keys_sorted": keys_sorted,
+            "vals_sorted": vals_sorted, "tile_offsets": tile_offsets, "tile_bits": tile_bits, "cam_bits": frame_bits, "live": live}
+
+
 # ----------------------------------------------------------------------------------------------
 # A.5 blend forward (vectorised per tile; validated against the literal loop in tests)
 # ----------------------------------------------------------------------------------------------
 def blend(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss, width, height,
-          background=None, tile=TILE, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP):
+          background=None, tile=TILE, tile_subset=None, alpha_min=ALPHA_MIN, t_stop=T_STOP, fused_n=None, live=None):
     """Front-to-back alpha blending of every camera's sorted tile lists in linear HDR radiance.
 
     means2d [C,N,2], conics [C,N,3], opacities [N], colors [N,3] (or per camera [C,N,3], e.g. from SH) float64.
     Returns hdr [C,H,W,3], alpha [C,H,W], last_id [C,H,W] (sorted index of the last accumulated
     Gaussian, -1 if none).  ``tile_subset``: optional iterable of (c, tile_id) to restrict work
     (used for the bounded CPU-baseline timing); other pixels stay at background.
+    ``fused_n`` = n_virtual with the lists of ``bin_tiles_fused``: camera c walks the list of frame c // fused_n (entries
+    frame * N + g) and skips the Gaussians it culls (``live`` [C,N]); last_id then indexes the frame's list.
     """
     means2d, conics, opacities, colors = map(_f64, (means2d, conics, opacities, colors))
     C = means2d.shape[0]
@@ -239,7 +292,8 @@ def blend(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss
     to = tile_offsets.tolist()
     pieces = []
     for c, tid in todo:
-        start, end = to[c * tiles + tid], to[c * tiles + tid + 1]
+        lc = c if fused_n is None else c // fused_n  # whose list this camera walks
+        start, end = to[lc * tiles + tid], to[lc * tiles + tid + 1]
         if end <= start:
             continue
         ty, tx = divmod(tid, tile_w)
@@ -250,7 +304,7 @@ def blend(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss
         PY, PX = torch.meshgrid(py, px, indexing="ij")
         PX, PY = PX.reshape(-1), PY.reshape(-1)
         ids = vals_sorted[start:end].to(torch.int64)
-        g = ids - c * N
+        g = ids - lc * N
         m = means2d[c, g]
         q = conics[c, g]
         o = opacities[g]
@@ -260,6 +314,8 @@ def blend(means2d, conics, opacities, colors, vals_sorted, tile_offsets, n_gauss
         sigma = 0.5 * (q[:, 0, None] * dx * dx + q[:, 2, None] * dy * dy) + q[:, 1, None] * dx * dy
         a = torch.clamp(o[:, None] * torch.exp(-sigma), max=ALPHA_MAX)
         skip = (sigma < 0) | (a < alpha_min)
+        if live is not None:
+            skip = skip | ~live[c, g][:, None]
         a_eff = torch.where(skip, torch.zeros_like(a), a)
         t_after = torch.cumprod(1 - a_eff.detach(), dim=0)
         stopped = t_after <= t_stop
@@ -376,7 +432,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
               background=None, near=0.01, far=1e10, eps2d=0.3, tile_size=TILE, crf_before_average=False,
               projection_override=None, binning_override=None, straight_through=False, tile_subset=None,
               sh_coeffs=None, sh_degree=0, alpha_min=ALPHA_MIN, t_stop=T_STOP,
-              radius_sigmas=3.0, tight_bounds=False):
+              radius_sigmas=3.0, tight_bounds=False, pose_fused=False):
     """Oracle of ``casualhdrsplat_b200.rasterize`` (same arguments and meaning; float64 CPU).
 
     ``spline`` = dict(knots [K,7], knot_t0, knot_dt, frame_times [B], kind) or explicit
@@ -400,6 +456,7 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
     ``sh_coeffs`` [N,K,3] + ``sh_degree``: view-dependent colours, evaluated per virtual camera
     (oracle/sh.py); ``colors`` is then ignored.
     ``tight_bounds``: opacity-aware per-axis tile bounds (see ``project``); same images, shorter tile lists.
+    ``pose_fused``: one tile list per (frame, tile) shared by the frame's virtual poses (``bin_tiles_fused``).
     Returns (ldr [B,H,W,3], alpha [B,H,W,1], meta dict).
     """
     means, quats, scales, opacities, colors = map(_f64, (means, quats, scales, opacities, colors))
@@ -444,9 +501,14 @@ def rasterize(means, quats, scales, opacities, colors, viewmats=None, Ks=None, w
         m2d_f32 = binning_override["means2d"].to(torch.float32)
         dep_f32 = binning_override["depths"].to(torch.float32)
         radii = binning_override["radii"].to(torch.int32)
-    bins = bin_tiles(m2d_f32, radii, dep_f32, width, height, tile_size, tight_bounds)
-    hdr, alpha_c, last_id = blend(m2d, con, opacities, colors, bins["vals_sorted"], bins["tile_offsets"], N,
-                                  width, height, background, tile_size, tile_subset, alpha_min, t_stop)
+    if pose_fused:
+        bins = bin_tiles_fused(m2d_f32, radii, dep_f32, width, height, n_virtual, tile_size, tight_bounds)
+        hdr, alpha_c, last_id = blend(m2d, con, opacities, colors, bins["vals_sorted"], bins["tile_offsets"], N, width, height, background,
+                                      tile_size, tile_subset, alpha_min, t_stop, fused_n=n_virtual, live=bins["live"])
+    else:
+        bins = bin_tiles(m2d_f32, radii, dep_f32, width, height, tile_size, tight_bounds)
+        hdr, alpha_c, last_id = blend(m2d, con, opacities, colors, bins["vals_sorted"], bins["tile_offsets"], N,
+                                      width, height, background, tile_size, tile_subset, alpha_min, t_stop)
     ldr, alpha, hdr_mean = formation(hdr, alpha_c, exposure, n_virtual, crf_kind, crf_params, crf_before_average)
     meta = {"viewmats": viewmats, "proj": proj, "bins": bins, "hdr_cams": hdr, "alpha_cams": alpha_c,
             "last_id": last_id, "hdr_mean": hdr_mean, "n_isect": bins["n_isect"]}
