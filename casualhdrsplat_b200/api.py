@@ -103,6 +103,7 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     st.cfg, st.spline, st.Ks = cfg, spline, Ks
     N, B, n = cfg.n_gauss, cfg.n_frames, cfg.n_virtual
     C = B * n
+    Cb = B if cfg.pose_fused else C  # cameras of the binning stage: with pose_fused the tile lists are per frame
     W, H = cfg.width, cfg.height
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     s = _stream()
@@ -126,7 +127,7 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     st.conic_c = _empty((C, N), torch.float32, dev)
     st.depths = _empty((C, N), torch.float32, dev)
     st.radii = _empty((C, N), torch.int32, dev)
-    st.tiles_touched = _empty((C, N), torch.int32, dev)
+    st.tiles_touched = _empty((Cb, N), torch.int32, dev)
     st.rgbo = _empty((N, 4), torch.float32, dev)
     check(L.chs_project_fwd(byref(cfg), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors), ptr(viewmats), ptr(Ks),
                             ptr(st.geom), ptr(st.conic_c), ptr(st.depths), ptr(st.radii), ptr(st.tiles_touched), ptr(st.rgbo), s),
@@ -134,8 +135,8 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     # K2 (the one host sync of the step: M sizes the intersection buffers)
     ws = _lib.workspace_sizes(cfg, 0, st.n_knots)
     work = _empty((max(int(ws.bin_count_bytes), 256),), torch.uint8, dev)
-    st.isect_offsets = _empty((C * N,), torch.int32, dev)
-    st.order = _empty((C * N,), torch.int32, dev) if cfg.sort_mode == _lib.CHS_SORT_DEPTH_PRESORT else None
+    st.isect_offsets = _empty((Cb * N,), torch.int32, dev)
+    st.order = _empty((Cb * N,), torch.int32, dev) if cfg.sort_mode == _lib.CHS_SORT_DEPTH_PRESORT else None
     n_dev = _empty((1,), torch.int64, dev)
     st._n_pinned = st._n_event = None
     if st.isect_capacity is None:
@@ -158,7 +159,7 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
     work = _empty((max(int(ws.bin_sort_bytes), 256),), torch.uint8, dev)
     st.keys_sorted = _empty((M,), torch.int64, dev) if want_keys else None
     st.vals_sorted = _empty((max(M, 1),), torch.int32, dev)
-    st.tile_offsets = _empty((C * tiles + 1,), torch.int32, dev)
+    st.tile_offsets = _empty((Cb * tiles + 1,), torch.int32, dev)
     if st.isect_capacity is None:
         check(L.chs_bin_sort(byref(cfg), M, ptr(st.geom), ptr(st.radii), ptr(st.depths), ptr(st.isect_offsets), ptr(st.order),
                              ptr(st.keys_sorted), ptr(st.vals_sorted), ptr(st.tile_offsets), ptr(work), work.numel(), s), "chs_bin_sort")

@@ -362,14 +362,20 @@ __global__ void __launch_bounds__(kThreads) column_scan_kernel(int64_t n_lin, in
 }
 
 // keys of the sorted list from (tile_offsets, vals): one block per (camera, tile) bucket
+// fused_n > 0 (pose_fused): a list entry frame * N + g is keyed by its depth at the frame's middle pose
 __global__ void __launch_bounds__(128) rebuild_keys_from_offsets_kernel(int tiles, int tile_bits, const uint32_t* __restrict__ tile_offsets,
                                                                        const int32_t* __restrict__ vals_sorted,
-                                                                       const float* __restrict__ depths, uint64_t* __restrict__ keys_sorted) {
+                                                                       const float* __restrict__ depths, uint64_t* __restrict__ keys_sorted,
+                                                                       int fused_n = 0, int N = 0) {
   const uint32_t lin = blockIdx.x;
   const uint64_t c = lin / (uint32_t)tiles, t = lin % (uint32_t)tiles;
   const uint64_t hi = (c << (32 + tile_bits)) | (t << 32);
   const uint32_t e = tile_offsets[lin + 1];
-  for (uint32_t i = tile_offsets[lin] + threadIdx.x; i < e; i += blockDim.x) keys_sorted[i] = hi | (uint64_t)__float_as_uint(depths[vals_sorted[i]]);
+  for (uint32_t i = tile_offsets[lin] + threadIdx.x; i < e; i += blockDim.x) {
+    int64_t id = vals_sorted[i];
+    if (fused_n > 0) id = ((int64_t)c * fused_n + fused_n / 2) * N + (id - (int64_t)c * N);
+    keys_sorted[i] = hi | (uint64_t)__float_as_uint(depths[id]);
+  }
 }
 
 size_t place_scan_temp(int64_t n) {
@@ -1336,7 +1342,8 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
   tile_scatter_kernel<<<p.t_cap2, 256, smem2, s>>>(a);
   CHS_LAUNCH_CHECK();
   if (keys_sorted) {
-    rebuild_keys_from_offsets_kernel<<<(unsigned)n_lin, 128, 0, s>>>(d.tiles, d.tile_bits, tile_offsets, vals_sorted, depths, keys_sorted);
+    rebuild_keys_from_offsets_kernel<<<(unsigned)n_lin, 128, 0, s>>>(d.tiles, d.tile_bits, tile_offsets, vals_sorted, depths, keys_sorted,
+                                                                     cfg->pose_fused ? d.n : 0, d.N);
     CHS_LAUNCH_CHECK();
   }
   return CHS_OK;

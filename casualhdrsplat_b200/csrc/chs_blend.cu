@@ -133,6 +133,7 @@ __device__ __forceinline__ P2 pair_power2(const float4 sa, float kc, float lo, f
 struct BlendFwdArgs {
   int N, n_virtual, W, H, tile_w, tiles;
   int crf_kind, crf_hidden, crf_before_average, rgbo_per_camera;
+  int fused;  // pose_fused: tile lists are per frame (entries frame * N + g); every pose of the frame walks the same list
   float bg[3];
   const float4* geom;
   const float* conic_c;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd_kernel(BlendFw
 // backward
 // ---------------------------------------------------------------------------------------------
 struct BlendBwdArgs {
-  int N, n_virtual, W, H, tile_w, tiles, v_hdr_per_camera, rgbo_per_camera;
+  int N, n_virtual, W, H, tile_w, tiles, v_hdr_per_camera, rgbo_per_camera, fused;
   float bg[3];
   const float4* geom;
   const float* conic_c;
@@ -871,8 +872,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
   for (int k = 0; k < a.n_virtual; ++k) {
     const int c = frame * a.n_virtual + k;
     const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;  // index of the camera's first record in rgbo
-    const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
-    const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
+    const int lc = a.fused ? frame : c;                     // whose tile list this camera walks
+    const int rec_shift = a.fused ? (c - frame) * a.N : 0;  // list entry frame * N + g -> record c * N + g
+    const uint32_t start = a.tile_offsets[(int64_t)lc * a.tiles + tile];
+    const uint32_t end = a.tile_offsets[(int64_t)lc * a.tiles + tile + 1];
     P2 T2 = p2s(1.f), acc_r2 = p2s(0.f), acc_g2 = p2s(0.f), acc_b2 = p2s(0.f);
     int lastA = 0, lastB = 0;
     // "done" is folded into the pixel's alpha threshold: a finished pixel has threshold +inf
@@ -882,7 +885,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
       // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
       if (__syncthreads_and(thrA == kInf && thrB == kInf)) break;
       const int cnt = min((uint32_t)kBatch, end - base);
-      for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[base + i], cam_base, a.geom, a.conic_c, a.rgbo);
+      for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[base + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
       __syncthreads();
       if (warp_done) continue;
       const int idx0 = (int)(base - start) + 1;
@@ -1093,8 +1096,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
   const float px = ix + 0.5f;
   const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 7.5f;
   const int64_t P = (int64_t)a.W * a.H;
-  const uint32_t start = a.tile_offsets[(int64_t)c * a.tiles + tile];
-  const uint32_t end = a.tile_offsets[(int64_t)c * a.tiles + tile + 1];
+  const int lc = a.fused ? frame : c;                          // whose tile list this camera walks
+  const int rec_shift = a.fused ? (c - frame) * a.N : 0;       // list entry frame * N + g -> record c * N + g
+  const uint32_t start = a.tile_offsets[(int64_t)lc * a.tiles + tile];
+  const uint32_t end = a.tile_offsets[(int64_t)lc * a.tiles + tile + 1];
   if (end <= start) return;
 
   const float inv_nv = 1.f / (float)a.n_virtual;
@@ -1145,7 +1150,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
     const int lo = max(0, hi - kB);
     const int cnt = hi - lo;
     __syncthreads();
-    for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[start + lo + i], cam_base, a.geom, a.conic_c, a.rgbo);
+    for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[start + lo + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
     __syncthreads();
     if (warp_last <= lo) continue;
     const int lrA = last[0] - lo - 1, lrB = last[1] - lo - 1;  // staged indices <= lr are inside the pixel's accumulated prefix
@@ -1248,6 +1253,8 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   a.N = d.N; a.n_virtual = d.n; a.W = d.W; a.H = d.H; a.tile_w = d.tile_w; a.tiles = d.tiles;
   a.crf_kind = cfg->crf_kind; a.crf_hidden = cfg->crf_hidden; a.crf_before_average = cfg->crf_before_average;
   a.rgbo_per_camera = cfg->rgbo_per_camera;
+  a.fused = cfg->pose_fused != 0;
+  CHS_REQUIRE(!a.fused || (cfg->tune_blend_fwd != 1 && cfg->tune_blend_fwd != 3 && cfg->tune_blend_fwd != 8), "chs_blend_fwd: pose_fused needs the round-2 kernel");
   a.bg[0] = cfg->background[0]; a.bg[1] = cfg->background[1]; a.bg[2] = cfg->background[2];
   a.geom = (const float4*)geom; a.conic_c = conic_c; a.rgbo = (const float4*)rgbo; a.vals = vals_sorted; a.tile_offsets = tile_offsets;
   a.exposure = exposure; a.crf_params = crf_params;
@@ -1296,6 +1303,11 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.final_T = final_T; a.last_id = last_id; a.v_hdr = v_hdr; a.v_alpha = v_alpha;
   a.v_hdr_per_camera = cfg->crf_before_average != 0;
   a.rgbo_per_camera = cfg->rgbo_per_camera;
+  a.fused = cfg->pose_fused != 0;
+  {
+    const int tb = cfg->tune_blend_bwd;
+    CHS_REQUIRE(!a.fused || tb == 0 || (tb >= 35 && tb <= 39), "chs_blend_bwd: pose_fused needs the round-2 kernel");
+  }
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
 #define CHS_BWD2_SMEM(S, B) (sizeof(SplatSmemT<B>) + 4 * sizeof(BwdWarpSmem<S>))

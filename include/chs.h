@@ -98,7 +98,11 @@ typedef struct chs_config {
                                * per frame into the union of its n per-pose tile rectangles and ordered by its depth at the frame's
                                * middle pose (k = n / 2); every pose still evaluates its own projection (mean2d, conic) per pixel.
                                * Binning work drops n-fold; images differ from pose_fused = 0 only where the depth order of two
-                               * overlapping Gaussians differs between the middle pose and pose k (oracle: pose_fused=True). */
+                               * overlapping Gaussians differs between the middle pose and pose k (oracle: pose_fused=True).
+                               * Shapes: tiles_touched [B,N] (size of the union rectangle), order / isect_offsets [B*N], list entries
+                               * frame * N + g, tile_offsets [B*tiles + 1]; last_id indexes the frame's list.  A pose that does not
+                               * see a Gaussian gets a record whose alpha is 0 everywhere.  Needs CHS_SORT_DEPTH_PRESORT with the
+                               * default binning route and the round-2 blend kernels. */
   /* Development knobs (0 = the measured-best default everywhere).  They select between bit-/tolerance-equivalent kernel
    * instantiations and never change results beyond atomics order; see DESIGN.md section 7. */
   int32_t tune_blend_fwd;     /* 1 / 3: 6 / 10 CTAs per SM */

@@ -701,3 +701,44 @@ def test_tight_bounds_keep_splats_with_half_extent_above_32767():
     assert torch.equal(_u32(st.tile_offsets), b["tile_offsets"])
     o_ldr, _, _ = oracle.rasterize(**kw, tight_bounds=True, projection_override=proj)
     assert rel(ldr, o_ldr) <= FWD_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# pose-fused binning: one tile list per (frame, tile)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tight", [False, True], ids=["square", "tight"])
+@pytest.mark.parametrize("name", ["tiny", "small", "c2"])
+def test_pose_fused_binning_and_parity(name, tight):
+    """chs_config.pose_fused against the oracle's definition (oracle.bin_tiles_fused / rasterize(pose_fused=True)): the fused
+    lists are bit-exact on the kernel's own fp32 projection, forward and every gradient inside the usual tolerances; and the
+    flagged model stays close to the per-pose model (the difference is depth-order swaps between poses millimetres apart)."""
+    sc = make_config(name)
+    ldr, alpha, meta, grads = cuda_run(sc, pose_fused=True, tight_bounds=tight, debug_keys=True)
+    st = meta["state"]
+    proj = cuda_projection(meta)
+    # culled (camera, Gaussian) pairs carry an "alpha = 0 everywhere" record; the oracle needs none (it skips them through `live`)
+    b = oracle.bin_tiles_fused(proj["means2d"], proj["radii"], proj["depths"], sc.width, sc.height, sc.n_virtual, tight=tight)
+    assert st.n_isect == b["n_isect"] and st.n_isect > 0
+    assert torch.equal(st.tiles_touched.cpu(), b["tiles_touched"])
+    assert torch.equal(st.vals_sorted.cpu()[: st.n_isect], b["vals_sorted"])
+    assert torch.equal(_u32(st.tile_offsets), b["tile_offsets"])
+    assert torch.equal(st.keys_sorted.cpu()[: st.n_isect], b["keys_sorted"])
+    o_ldr, o_alpha, o_meta, o_grads = oracle_run(sc, projection_override=proj, straight_through=True, tight_bounds=tight, pose_fused=True)
+    assert rel(ldr, o_ldr) <= FWD_TOL and rel(alpha, o_alpha) <= FWD_TOL
+    errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
+    assert all(e <= GRAD_TOL for e in errs.values()), errs
+    # against the per-pose model: n-fold fewer list entries, nearly the same frames
+    ldr_pp, _, meta_pp, _ = cuda_run(sc, with_grad=False, tight_bounds=tight)
+    n = sc.n_virtual
+    assert meta_pp["n_isect"] / n <= st.n_isect <= 1.6 * meta_pp["n_isect"] / n
+    assert rel(ldr, ldr_pp) < 5e-3, rel(ldr, ldr_pp)
+
+
+def test_pose_fused_static_camera_is_the_per_pose_model():
+    """Identical poses inside the exposure window: the fused lists are the per-pose lists, so the frames are the same bits."""
+    sc = make_config("small", static_camera=True)
+    a = cuda_run(sc)
+    b = cuda_run(sc, pose_fused=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for k in a[3]:
+        assert rel(b[3][k], a[3][k]) <= 1e-5, k  # atomics order only
