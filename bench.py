@@ -50,6 +50,8 @@ def parse():
                          "gradients, fewer intersections)")
     ap.add_argument("--host-sync", action="store_true", help="size the intersection buffers from a host read of M every frame (round-1 "
                     "behaviour) instead of the sync-free step (capacity from the previous step, count kept on the device)")
+    ap.add_argument("--pose-fused", action="store_true", help="chs_config.pose_fused: one tile list per (frame, tile) shared by the frame's "
+                    "virtual poses (a flagged variant of the model, SURVEY.md 8(f) row f1); the default is the per-pose model")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-tiles", type=int, default=48, help="tiles in the CPU-oracle sample")
@@ -270,7 +272,8 @@ def main():
         nonlocal flat
         layout, flat = formation_step(P if params is None else params, spline_meta, W, H, n, sc.crf_kind, ids, upstream, micro_batch=1, sort_mode=args.sort_mode,
                                       comm=comm, out=flat, stats=st, tight_bounds=tight if tight_bounds is None else tight_bounds,
-                                      state=step_state if tight_bounds is None else None)
+                                      state=step_state if tight_bounds is None else None,
+                                      pose_fused=args.pose_fused and tight_bounds is None)
         return layout
 
     def barrier():
@@ -302,6 +305,8 @@ def main():
         m_ref = m_emitted
     if not args.host_sync:
         # sync-free steps from here on: stage buffers from a pool, capacities from the previous step's M (+3 %), K2's count on the device
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the warm-up's allocator blocks would otherwise sit beside the pool (matters at c5: ~50 GB per frame)
         step_state = StepState()
         for _ in range(2):
             step(upstream_fixed, stats)
@@ -540,7 +545,7 @@ def main():
                 "config": {"workload": f"{args.workload}: BASELINE.json configs[{ {'c1': 0, 'c2': 1, 'c3': 2, 'c4': 3, 'c5': 4}.get(args.workload, '?') }] — {N} Gaussians, {W}x{H}, {n} virtual poses/frame, "
                                        f"global batch {B} frames sharded by frame, fwd+bwd incl. pose/exposure/CRF grads",
                            "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode, "tile_bounds": args.bounds,
-                           "host_syncs_per_step": len(ids) if args.host_sync else 0,
+                           "host_syncs_per_step": len(ids) if args.host_sync else 0, "pose_fused": bool(args.pose_fused),
                            "isects_emitted_per_frame": m_emitted / n_local,
                            "isects_per_frame": M_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
                            "collective": None if world == 1 else ("ncclAllReduce via libchs C ABI" if isinstance(comm, ChsComm) else

@@ -209,7 +209,8 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
                                tight_bounds=tight_bounds, pose_fused=pose_fused, tuning=tuning)
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
         cap = state.capacity(tuple(ids)) if state is not None else None
-        pool = state.pool if state is not None else None
+        # (the step that learns M sizes its buffers exactly, per frame batch: those do not go into the pool)
+        pool = state.pool if (state is not None and cap is not None) else None
         st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline, isect_capacity=cap, pool=pool)
         if state is not None:
             state.track(tuple(ids), st)

@@ -46,7 +46,7 @@ def _check_camera_binning(st, proj, sc, cams, tight):
         del b
 
 
-def _subset_parity(sc, n_tiles, tight, seed, check_cams):
+def _subset_parity(sc, n_tiles, tight, seed, check_cams, fused=False):
     """Forward + gradient parity on `n_tiles` random tiles of frame 0 (all its virtual poses); see the module docstring."""
     N = sc.means.shape[0]
     C = sc.n_frames * sc.n_virtual
@@ -56,20 +56,21 @@ def _subset_parity(sc, n_tiles, tight, seed, check_cams):
     pick = sorted(torch.randperm(tiles, generator=g)[:n_tiles].tolist())
     mask = tile_pixel_mask(sc.width, sc.height, pick)
     sc_m = dataclasses.replace(sc, v_ldr=sc.v_ldr * mask[None, :, :, None])
-    ldr, alpha, meta, grads = cuda_run(sc_m, tight_bounds=tight)
+    ldr, alpha, meta, grads = cuda_run(sc_m, tight_bounds=tight, pose_fused=fused)
     st = meta["state"]
     proj = cuda_projection(meta)
     _check_camera_binning(st, proj, sc, check_cams, tight)
-    g_idx = gaussians_of_tiles(st.vals_sorted[: st.n_isect], st.tile_offsets, N, C, tiles, pick)
+    L = sc.n_frames if fused else C  # number of tile-list owners: frames with pose_fused, cameras otherwise
+    g_idx = gaussians_of_tiles(st.vals_sorted[: st.n_isect], st.tile_offsets, N, L, tiles, pick)
     assert 0 < g_idx.numel() < N
     sub = subset_scene(sc_m, g_idx)
     o_ldr, o_alpha, o_meta, o_grads = oracle_run(sub, projection_override=subset_projection(proj, g_idx), straight_through=True,
-                                                 tight_bounds=tight, tile_subset=[(c, t) for c in range(C) for t in pick])
+                                                 tight_bounds=tight, pose_fused=fused, tile_subset=[(c, t) for c in range(C) for t in pick])
     # the oracle blended the same lists
     to_f, to_s = _u32(st.tile_offsets).tolist(), o_meta["bins"]["tile_offsets"].tolist()
     vals = st.vals_sorted.cpu().to(torch.int64)
     n_list = 0
-    for c in range(C):
+    for c in range(L):
         for t in pick:
             a = vals[to_f[c * tiles + t]:to_f[c * tiles + t + 1]] - c * N
             b = o_meta["bins"]["vals_sorted"][to_s[c * tiles + t]:to_s[c * tiles + t + 1]].long() - c * g_idx.numel()
@@ -128,3 +129,17 @@ def test_config5_one_frame_against_oracle():
     sc = make_config("c5", n_frames=1)
     r = _subset_parity(sc, 32, True, seed=9, check_cams=[0, 11])
     print("c5 subset parity", r)
+
+
+def test_config3_pose_fused_against_oracle_and_per_pose_model(c3_scene):
+    """chs_config.pose_fused at the headline size: 64-tile subset parity against the oracle's pose_fused definition, and the
+    distance of the flagged model from the per-pose model on the whole 1080p frame."""
+    r = _subset_parity(c3_scene, 64, True, seed=7, check_cams=[], fused=True)
+    print("c3 pose_fused subset parity", r)
+    ldr_f, _, meta_f, _ = cuda_run(c3_scene, with_grad=False, tight_bounds=True, pose_fused=True)
+    m_f = meta_f["n_isect"]
+    del meta_f
+    ldr_p, _, meta_p, _ = cuda_run(c3_scene, with_grad=False, tight_bounds=True)
+    e = rel(ldr_f, ldr_p)
+    print("c3 pose_fused vs per-pose model: rel", e, "list entries", m_f, "vs", meta_p["n_isect"])
+    assert e < 5e-3 and m_f < 0.2 * meta_p["n_isect"]
