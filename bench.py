@@ -547,7 +547,7 @@ def main():
                            "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode, "tile_bounds": args.bounds,
                            "host_syncs_per_step": len(ids) if args.host_sync else 0, "pose_fused": bool(args.pose_fused),
                            "isects_emitted_per_frame": m_emitted / n_local,
-                           "isects_per_frame": M_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
+                           "isects_per_frame": M_ref_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
                            "collective": None if world == 1 else ("ncclAllReduce via libchs C ABI" if isinstance(comm, ChsComm) else
                                                                  "NVLS multimem one-shot all-reduce kernel (libchs)" if isinstance(comm, NvlsComm)
                                                                  else "torch.distributed all_reduce"),
