@@ -24,7 +24,7 @@ class ChsConfig(ctypes.Structure):
         ("crf_kind", c_int32), ("crf_hidden", c_int32), ("crf_before_average", c_int32), ("ks_per_camera", c_int32),
         ("sort_mode", c_int32), ("background", c_float * 3), ("rgbo_per_camera", c_int32), ("tight_bounds", c_int32), ("pose_fused", c_int32),
         ("tune_blend_fwd", c_int32), ("tune_blend_bwd", c_int32), ("tune_crf_bwd", c_int32), ("tune_bin", c_int32),
-        ("tune_bin_chunk", c_int32), ("reserved", c_int32 * 2),
+        ("tune_bin_chunk", c_int32), ("tune_project_bwd", c_int32), ("reserved", c_int32 * 1),
     ]
 
 

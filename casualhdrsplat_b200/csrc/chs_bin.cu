@@ -1039,56 +1039,44 @@ __global__ void __launch_bounds__(256) tile_count_kernel(BandArgs a) {
   a.counts2[(size_t)threadIdx.x * a.t_cap2 + t] = hist[threadIdx.x];
 }
 
-// P2 scatter: every (record, tile) of the chunk straight to its final position in the tile's list
+// P2 scatter: every (record, tile) of the chunk straight to its final position in the tile's list.  Record-parallel threads set
+// bm[tile][record]; then the roles swap: thread = tile of the band walks its row of the bit matrix in record (= depth) order and
+// appends the pair id of every set bit at the tile's cursor.  The second pass touches exactly the chunk's intersections, is
+// balanced across the tiles of a band, and needs neither rank arithmetic nor a second expansion of the rectangles.
 __global__ void __launch_bounds__(256) tile_scatter_kernel(BandArgs a) {
   extern __shared__ uint32_t smem_tile[];
-  uint32_t* bm = smem_tile;                                                       // [256][kBandRow]
-  uint32_t* cursor = bm + 256 * kBandRow;                                         // [256]
-  unsigned short* pfx = reinterpret_cast<unsigned short*>(cursor + 256);          // [256][kBandWords + 2] (padded: conflict-free walk)
-  constexpr int kPfxRow = kBandWords + 2;
+  uint32_t* bm = smem_tile;                    // [256][kBandRow]
+  uint32_t* ids = bm + 256 * kBandRow;         // [kBandChunk] pair id of every record of the chunk
   const uint32_t t = blockIdx.x;
   const uint4 ds = a.desc[t];
   if (ds.x == 0xffffffffu) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  cursor[threadIdx.x] = a.base2[(size_t)ds.x * 256 + threadIdx.x] + a.counts2[(size_t)threadIdx.x * a.t_cap2 + t];
+  uint32_t cursor = a.base2[(size_t)ds.x * 256 + threadIdx.x] + a.counts2[(size_t)threadIdx.x * a.t_cap2 + t];
   for (int i = threadIdx.x; i < 256 * kBandRow; i += 256) bm[i] = 0u;
   __syncthreads();
-  uint2 rec[kBandChunk / 256];
 #pragma unroll
   for (int k = 0; k < kBandChunk / 256; ++k) {
     const uint32_t i = ds.y + k * 256 + threadIdx.x;  // record p = k * 256 + tid of the chunk: word k * 8 + warp, bit = lane
-    rec[k] = i < ds.z ? a.recs[i] : make_uint2(0u, 0xffffffffu);
     if (i < ds.z) {
-      const uint32_t box = rec[k].y;
+      const uint2 rec = a.recs[i];
+      ids[k * 256 + threadIdx.x] = rec.x;
+      const uint32_t box = rec.y;
       const int x0 = box & 0xff, x1 = (box >> 8) & 0xff, ry0 = (box >> 16) & 0xff, ry1 = box >> 24;
       for (int ry = ry0; ry <= ry1; ++ry)
         for (int x = x0; x <= x1; ++x) atomicOr(&bm[(ry * a.tile_w + x) * kBandRow + k * 8 + warp], 1u << lane);
     }
   }
   __syncthreads();
-  {  // thread = tile of the band: exclusive prefix of its row's word populations
-    uint32_t run = 0;
-#pragma unroll 8
-    for (int w = 0; w < kBandWords; ++w) {
-      pfx[threadIdx.x * kPfxRow + w] = (unsigned short)run;
-      run += __popc(bm[threadIdx.x * kBandRow + w]);
+  const uint32_t* row = bm + threadIdx.x * kBandRow;  // padded rows: the 32 lanes of a warp read 32 different banks
+#pragma unroll 4
+  for (int w = 0; w < kBandWords; ++w) {
+    uint32_t m = row[w];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (cursor < a.val_cap) a.vals[cursor] = (int32_t)ids[w * 32 + b];
+      ++cursor;
     }
-  }
-  __syncthreads();
-  const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int k = 0; k < kBandChunk / 256; ++k) {
-    const uint32_t i = ds.y + k * 256 + threadIdx.x;
-    if (i >= ds.z) continue;
-    const uint32_t box = rec[k].y;
-    const int w = k * 8 + warp;
-    const int x0 = box & 0xff, x1 = (box >> 8) & 0xff, ry0 = (box >> 16) & 0xff, ry1 = box >> 24;
-    for (int ry = ry0; ry <= ry1; ++ry)
-      for (int x = x0; x <= x1; ++x) {
-        const int tl = ry * a.tile_w + x;
-        const uint32_t dst = cursor[tl] + (uint32_t)pfx[tl * kPfxRow + w] + __popc(bm[tl * kBandRow + w] & lt);
-        if (dst < a.val_cap) a.vals[dst] = (int32_t)rec[k].x;
-      }
   }
 }
 
@@ -1337,7 +1325,7 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
   band_tile_offsets_kernel<<<grid_for(n_lin + 1), kThreads, 0, s>>>(n_lin, d.tiles, d.tile_w, p.g.BR, p.g.n_bands, base2,
                                                                      reinterpret_cast<const uint64_t*>(total), (uint32_t)cap, tile_offsets);
   CHS_LAUNCH_CHECK();
-  const size_t smem2 = (size_t)256 * kBandRow * 4 + 256 * 4 + (size_t)256 * (kBandWords + 2) * 2;
+  const size_t smem2 = (size_t)256 * kBandRow * 4 + (size_t)kBandChunk * 4;
   CHS_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   tile_scatter_kernel<<<p.t_cap2, 256, smem2, s>>>(a);
   CHS_LAUNCH_CHECK();

@@ -829,6 +829,40 @@ __device__ __forceinline__ bool splat_hits_block3(const Smem& sm, int slot, floa
   return chs_block_max_power(s, bx0, bx1, by0, by1) >= CHS_LOG2_ALPHA_MIN - 1e-3f;
 }
 
+// ---- asynchronous staging (cp.async = LDGSTS): the gathers of the NEXT batch's raw records travel while the current batch
+// is processed; each thread later transforms the record it fetched itself, so only its own copies have to be complete ----
+template <int kB>
+struct RawSmem {  // tile-list entries as gathered (36 bytes each); the record index stays in a register of the fetching thread
+  float4 gm[kB];   // geom: mean2d.x, mean2d.y, conic A, conic B
+  float4 col[kB];  // rgbo: r, g, b, opacity
+  float cc[kB];    // conic C
+};
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <class Raw>
+__device__ __forceinline__ void gather_raw_async(Raw& r, int slot, int32_t val, int cam_base, const float4* __restrict__ geom,
+                                                 const float* __restrict__ conic_c, const float4* __restrict__ rgbo) {
+  cp_async_16(&r.gm[slot], geom + val);
+  cp_async_16(&r.col[slot], rgbo + (val - cam_base));
+  cp_async_4(&r.cc[slot], conic_c + val);
+}
+template <class Smem, class Raw>
+__device__ __forceinline__ void stage_from_raw(Smem& sm, int slot, const Raw& r, int32_t val) {
+  const float4 gm = r.gm[slot], col = r.col[slot];
+  ChsSplat<float> s;
+  chs_make_splat(gm.x, gm.y, gm.z, gm.w, r.cc[slot], col.w, col.x, col.y, col.z, s);
+  sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.r);
+  sm.b[slot] = make_float4(s.kc, s.lo, s.cr, s.cg);
+  sm.c[slot] = make_float4(s.cb, s.inv_opac, __int_as_float(val), s.rbc);
+}
+
 __device__ __forceinline__ unsigned lanemask_lt_() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -841,9 +875,11 @@ __device__ __forceinline__ unsigned lanemask_gt_() {
 }
 
 // ---- forward ----
-template <int kMinBlocks, bool kPerPoseCrf>
+template <int kMinBlocks, bool kPerPoseCrf, bool kAsync>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendFwdArgs a) {
+  static_assert(kBatch == 2 * kThreads, "asynchronous staging: two tile-list entries per thread and batch");
   __shared__ SplatSmem3<kBatch> sm;
+  __shared__ RawSmem<kAsync ? kBatch : 1> raw;  // kAsync: the next batch's raw records, gathered with cp.async
   __shared__ int s_list[kThreads / 32][32];
   extern __shared__ float s_crf[];  // the CRF parameters [3, stride] when the CRF is learned
 
@@ -881,11 +917,40 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
     // "done" is folded into the pixel's alpha threshold: a finished pixel has threshold +inf
     float thrA = insideA ? CHS_LOG2_ALPHA_MIN : kInf, thrB = insideB ? CHS_LOG2_ALPHA_MIN : kInf;
     bool warp_done = __all_sync(CHS_FULL_MASK, thrA == kInf && thrB == kInf);
+    // kAsync pipeline: this thread's two entries of batch b + 1 are gathered (cp.async) while batch b is processed, and the
+    // tile-list values of batch b + 2 are already on their way in registers
+    int32_t val_cur[2] = {0, 0}, val_next[2] = {0, 0};
+    if (kAsync) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t i0 = start + h * kThreads + tid, i1 = i0 + kBatch;
+        if (i0 < end) {
+          val_cur[h] = a.vals[i0] + rec_shift;
+          gather_raw_async(raw, h * kThreads + tid, val_cur[h], cam_base, a.geom, a.conic_c, a.rgbo);
+        }
+        if (i1 < end) val_next[h] = a.vals[i1] + rec_shift;
+      }
+      cp_async_commit();
+    }
     for (uint32_t base = start; base < end; base += kBatch) {
+      if (kAsync) cp_async_wait_all();  // this thread's own gathers of the batch have landed
       // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
       if (__syncthreads_and(thrA == kInf && thrB == kInf)) break;
       const int cnt = min((uint32_t)kBatch, end - base);
-      for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[base + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+      if (kAsync) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int slot = h * kThreads + tid;
+          if (slot < cnt) stage_from_raw(sm, slot, raw, val_cur[h]);
+          val_cur[h] = val_next[h];
+          if (base + kBatch + slot < end) gather_raw_async(raw, slot, val_cur[h], cam_base, a.geom, a.conic_c, a.rgbo);
+          const uint32_t i2 = base + 2 * kBatch + slot;
+          if (i2 < end) val_next[h] = a.vals[i2] + rec_shift;
+        }
+        cp_async_commit();
+      } else {
+        for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[base + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+      }
       __syncthreads();
       if (warp_done) continue;
       const int idx0 = (int)(base - start) + 1;
@@ -935,6 +1000,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
       lastA = relA >= 0 ? idx0 + relA : lastA;
       lastB = relB >= 0 ? idx0 + relB : lastB;
     }
+    if (kAsync) cp_async_wait_all();  // (early exit) gathers of a batch nobody will read must land before the buffer is reused
     __syncthreads();  // the next pose restages shared memory
     if (insideA) {
       a.final_T[(int64_t)c * P + pixA] = p2lo(T2);
@@ -1078,11 +1144,14 @@ __device__ __forceinline__ void bwd_round3(const Smem& sm, const BwdWarp3<kSlots
   __syncwarp();  // the table is rewritten by the next round
 }
 
-template <int kSlots, int kB, int kMinBlocks, bool kPrefetch>
+template <int kSlots, int kB, int kMinBlocks, bool kAsync>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendBwdArgs a) {
+  static_assert(!kAsync || kB == kThreads, "asynchronous staging: one tile-list entry per thread and batch");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Smem = SplatSmem3<kB>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  // kAsync: raw records of the next batch (one per thread), behind the per-warp tables
+  RawSmem<kB>& raw = *reinterpret_cast<RawSmem<kB>*>(smem_raw + sizeof(Smem) + 4 * sizeof(BwdWarp3<kSlots>));
   __shared__ int s_max_last;
 
   const int tile = blockIdx.x, c = blockIdx.y;
@@ -1146,12 +1215,38 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
   constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = kSlots * kRow3 * 4;
   const uint32_t tab_end = tab0 + kSlots * kRowBytes;
   uint32_t tab = tab0;
+  // kAsync pipeline: this thread's entry of batch b + 1 is gathered (cp.async) while batch b is processed, and the tile-list
+  // value of batch b + 2 is already on its way in a register
+  int32_t val_cur = 0, val_next = 0;  // record index whose gather is in flight / of the batch after it
+  if (kAsync) {
+    const int lo0 = max(0, n_walk - kB);
+    if (tid < n_walk - lo0) {
+      val_cur = a.vals[start + lo0 + tid] + rec_shift;
+      gather_raw_async(raw, tid, val_cur, cam_base, a.geom, a.conic_c, a.rgbo);
+    }
+    cp_async_commit();
+    const int hi1 = n_walk - kB, lo1 = max(0, hi1 - kB);
+    if (hi1 > 0 && tid < hi1 - lo1) val_next = a.vals[start + lo1 + tid] + rec_shift;
+  }
   for (int hi = n_walk; hi > 0; hi -= kB) {
     const int lo = max(0, hi - kB);
     const int cnt = hi - lo;
-    __syncthreads();
-    for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[start + lo + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
-    __syncthreads();
+    if (kAsync) {
+      cp_async_wait_all();  // this thread's own gathers of the batch have landed
+      __syncthreads();      // every warp is done with the previous batch's records
+      if (tid < cnt) stage_from_raw(sm, tid, raw, val_cur);
+      const int hi1 = hi - kB, lo1 = max(0, hi1 - kB);
+      val_cur = val_next;
+      if (hi1 > 0 && tid < hi1 - lo1) gather_raw_async(raw, tid, val_cur, cam_base, a.geom, a.conic_c, a.rgbo);
+      cp_async_commit();
+      const int hi2 = hi1 - kB, lo2 = max(0, hi2 - kB);
+      if (hi2 > 0 && tid < hi2 - lo2) val_next = a.vals[start + lo2 + tid] + rec_shift;
+      __syncthreads();
+    } else {
+      __syncthreads();
+      for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[start + lo + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+      __syncthreads();
+    }
     if (warp_last <= lo) continue;
     const int lrA = last[0] - lo - 1, lrB = last[1] - lo - 1;  // staged indices <= lr are inside the pixel's accumulated prefix
     for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
@@ -1165,33 +1260,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
       if (hit) ws.list[__popc(mask & gt)] = j;  // descending: back to front
       __syncwarp();
       // ---- phase A over the survivors ----
-      // (the list has spare entries) kPrefetch: the next Gaussian's record is fetched while this one is processed, the index
-      // after it is already in flight; otherwise only the next index is fetched ahead
       int jn = ws.list[0];
-      float4 san = make_float4(0.f, 0.f, 0.f, 0.f), sbn = san;
-      if (kPrefetch) {
-        san = sm.a[jn];
-        sbn = sm.b[jn];
-        jn = ws.list[1];
-      }
-      int jcur = ws.list[0];
       for (int i = 0; i < n_surv; ++i) {
-        int jj;
-        float4 sa, sb;  // (mx, my, qa, r), (kc, log2(opacity), cr, cg)
-        if (kPrefetch) {
-          jj = jcur;
-          sa = san;
-          sb = sbn;
-          jcur = jn;
-          san = sm.a[jn];  // past the end: a stale (but in-bounds) staged index, never used
-          sbn = sm.b[jn];
-          jn = ws.list[i + 2];
-        } else {
-          jj = jn;
-          jn = ws.list[i + 1];
-          sa = sm.a[jj];
-          sb = sm.b[jj];
-        }
+        const int jj = jn;
+        jn = ws.list[i + 1];  // (the list has spare entries) the next index is in flight while this Gaussian is processed
+        const float4 sa = sm.a[jj];  // mx, my, qa, r
+        const float4 sb = sm.b[jj];  // kc, log2(opacity), cr, cg
         float dx;
         P2 dy2, u2;
         const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
@@ -1266,17 +1340,19 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
     if (cfg->tune_blend_fwd == 8)
       blend_fwd_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
     else
-      blend_fwd2_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
+      blend_fwd2_kernel<8, true, false><<<grid, kThreads, dyn, s>>>(a);
   } else {
     switch (cfg->tune_blend_fwd) {  // development knob (chs_config)
       case 1: blend_fwd_kernel<6, false><<<grid, kThreads, dyn, s>>>(a); break;
       case 3: blend_fwd_kernel<10, false><<<grid, kThreads, dyn, s>>>(a); break;
       case 8: blend_fwd_kernel<8, false><<<grid, kThreads, dyn, s>>>(a); break;  // the round-1 kernel (64 registers, 32 warps/SM)
-      case 26: blend_fwd2_kernel<6, false><<<grid, kThreads, dyn, s>>>(a); break;
-      case 28: blend_fwd2_kernel<8, false><<<grid, kThreads, dyn, s>>>(a); break;
+      case 26: blend_fwd2_kernel<6, false, false><<<grid, kThreads, dyn, s>>>(a); break;
+      case 28: blend_fwd2_kernel<8, false, false><<<grid, kThreads, dyn, s>>>(a); break;
+      case 29: blend_fwd2_kernel<7, false, true><<<grid, kThreads, dyn, s>>>(a); break;  // + cp.async staging
+      case 30: blend_fwd2_kernel<6, false, true><<<grid, kThreads, dyn, s>>>(a); break;
       // round 2: survivor list, T -= w.  r2e, c3 (ms per frame): 6 CTAs/SM 2.33 | 7 (72 registers) 2.21 | 8 (64 registers, spills) 2.26;
       // round-1 kernel 2.50
-      default: blend_fwd2_kernel<7, false><<<grid, kThreads, dyn, s>>>(a); break;
+      default: blend_fwd2_kernel<7, false, false><<<grid, kThreads, dyn, s>>>(a); break;
     }
   }
   CHS_LAUNCH_CHECK();
@@ -1325,12 +1401,13 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
     case 45: CHS_BWD2_LAUNCH(8, 128, 7, true); break;
     case 2: CHS_BWD2_LAUNCH(8, 128, 7, false); break;  // the round-1 default: tabled, 8 slots, 128-entry batches, 72 registers
 #define CHS_BWD3_SMEM(B) (sizeof(SplatSmem3<B>) + 4 * sizeof(BwdWarp3<8>))
+#define CHS_BWD3_SMEM_ASYNC(B) (CHS_BWD3_SMEM(B) + sizeof(RawSmem<B>))
 #define CHS_BWD3_LAUNCH(B, MB) blend_bwd3_kernel<8, B, MB, false><<<grid, kThreads, CHS_BWD3_SMEM(B), s>>>(a)
     case 36: CHS_BWD3_LAUNCH(128, 6); break;
     case 38: CHS_BWD3_LAUNCH(128, 8); break;
     case 37: CHS_BWD3_LAUNCH(64, 7); break;
-    case 39: blend_bwd3_kernel<8, 128, 7, true><<<grid, kThreads, CHS_BWD3_SMEM(128), s>>>(a); break;  // + record prefetch
-    case 35: blend_bwd3_kernel<8, 128, 6, true><<<grid, kThreads, CHS_BWD3_SMEM(128), s>>>(a); break;
+    case 39: blend_bwd3_kernel<8, 128, 7, true><<<grid, kThreads, CHS_BWD3_SMEM_ASYNC(128), s>>>(a); break;  // + cp.async staging
+    case 35: blend_bwd3_kernel<8, 128, 6, true><<<grid, kThreads, CHS_BWD3_SMEM_ASYNC(128), s>>>(a); break;
     // round 2: division-free colour state, survivor list, running table pointer.  r2e, c3 (ms per frame of 8 poses): batch 128 /
     // 7 CTAs per SM 4.03 (default) | 128 / 6: 4.19 | 128 / 8 (64 registers): 4.24 | 64 / 7: 4.17; round-1 tabled kernel 4.97
     default: CHS_BWD3_LAUNCH(128, 7); break;

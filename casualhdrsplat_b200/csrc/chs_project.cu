@@ -136,7 +136,8 @@ struct ProjectBwdArgs {
   double* v_cam_acc;  // [C, 12] = v_R (9) | v_t (3)
 };
 
-__global__ void __launch_bounds__(kThreads) project_bwd_kernel(ProjectBwdArgs a) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) project_bwd_kernel(ProjectBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* s_cam = smem;
   float* s_vcam = s_cam + ((a.C * kCamFloats + 3) & ~3);  // [C,12] block partial sums
@@ -294,8 +295,20 @@ extern "C" int chs_project_bwd(const chs_config* cfg, const float* means, const 
     a.quat_section_aligned = ((uintptr_t)(grads_flat + 3 * (size_t)d.N)) % 16 == 0;
     size_t smem = ((((size_t)d.C * kCamFloats + 3) & ~(size_t)3) + (((size_t)d.C * 12 + 3) & ~(size_t)3)) * 4 + 3 * kThreads * 3 * 4;
     int blocks = (d.N + kThreads - 1) / kThreads;
-    if (smem > 48 * 1024) CHS_CUDA(cudaFuncSetAttribute(project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    project_bwd_kernel<<<blocks, kThreads, smem, s>>>(a);
+    // resident blocks per SM (chs_config.tune_project_bwd).  The kernel is latency-bound, so occupancy beats spills (r2p, c3):
+    // 2 (115 registers, no spills) 0.450 ms | 3 (80 registers) 0.346 | 4 (64 registers, 176 B of spills) 0.318 (default)
+    const int mb = cfg->tune_project_bwd ? cfg->tune_project_bwd : 4;
+    if (smem > 48 * 1024) {
+      CHS_CUDA(cudaFuncSetAttribute(project_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CHS_CUDA(cudaFuncSetAttribute(project_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CHS_CUDA(cudaFuncSetAttribute(project_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (mb == 3)
+      project_bwd_kernel<3><<<blocks, kThreads, smem, s>>>(a);
+    else if (mb == 4)
+      project_bwd_kernel<4><<<blocks, kThreads, smem, s>>>(a);
+    else
+      project_bwd_kernel<2><<<blocks, kThreads, smem, s>>>(a);
     CHS_LAUNCH_CHECK();
   }
   finalize_viewmat_grads<<<(d.C * 16 + 255) / 256, 256, 0, s>>>(acc, v_viewmats, d.C);

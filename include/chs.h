@@ -111,7 +111,8 @@ typedef struct chs_config {
   int32_t tune_bin;           /* CHS_SORT_DEPTH_PRESORT routes.  0: banded placement (default); 3: hand-written two-pass radix multisplit
                                * over emitted intersections; 1: cub::DeviceRadixSort baseline; 2: round-1 counting placement */
   int32_t tune_bin_chunk;     /* counting placement: pairs per chunk */
-  int32_t reserved[2];
+  int32_t tune_project_bwd;   /* resident blocks per SM of K9 (2, 3, 4) */
+  int32_t reserved[1];
 } chs_config;
 
 typedef struct chs_workspace_sizes {
