@@ -185,12 +185,24 @@ namespace {
 __global__ void __launch_bounds__(256) nvls_allreduce_kernel(float* mc, uint64_t begin4, uint64_t end4, uint64_t tail_begin,
                                                              uint64_t tail_end) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = begin4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += stride) {
-    float* p = mc + i * 4;
-    float a, b, c, d;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p) : "memory");
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  // four switch reductions in flight per thread before the first broadcast store: the loop is latency-bound (a multimem.ld_reduce
+  // is a round trip through the NVSwitch), so memory-level parallelism per thread is what sets the time
+  constexpr int kU = 4;
+  for (uint64_t i0 = begin4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * kU) {
+    float4 v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t i = i0 + u * stride;
+      if (i < end4)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + i * 4) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t i = i0 + u * stride;
+      if (i < end4)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + i * 4), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+    }
   }
   // scalar tail (count % 4 floats), owned by the last rank
   for (uint64_t i = tail_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tail_end; i += stride) {
@@ -212,7 +224,7 @@ extern "C" int chs_nvls_allreduce(float* mc_ptr, uint64_t count, int32_t rank, i
   const uint64_t e4 = b4 + per < n4 ? b4 + per : n4;
   const uint64_t tb = rank == world - 1 ? n4 * 4 : count, te = count;
   uint64_t work = (e4 - b4) > (te - tb) ? (e4 - b4) : (te - tb);
-  int blocks = (int)((work + 255) / 256);
+  int blocks = (int)((work + 4 * 256 - 1) / (4 * 256));  // four float4 per thread and trip
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   nvls_allreduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mc_ptr, b4, e4, tb, te);
