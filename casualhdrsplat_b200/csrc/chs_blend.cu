@@ -800,10 +800,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd2_kernel(BlendB
 //     sums stay packed to the end; sum vs.u is derived as sum vs.dx + r sum vs.dy instead of being accumulated per pixel.
 // =================================================================================================
 template <int kB>
-struct SplatSmem3 {
+struct SplatSmem3 {  // what the block culling reads (a, b.xyz) is two conflict-free 128-bit loads per lane
   float4 a[kB];  // mx, my, qa, r
-  float4 b[kB];  // kc, lo, cr, cg
-  float4 c[kB];  // cb, 1/opacity, val (int bits; c * N + g), rbc
+  float4 b[kB];  // kc, lo, rbc, cr
+  float4 c[kB];  // cg, cb, 1/opacity, val (int bits; c * N + g)
 };
 
 template <class Smem>
@@ -815,17 +815,17 @@ __device__ __forceinline__ void stage_splat3(Smem& sm, int slot, int32_t val, in
   ChsSplat<float> s;
   chs_make_splat(gm.x, gm.y, gm.z, gm.w, cc, col.w, col.x, col.y, col.z, s);
   sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.r);
-  sm.b[slot] = make_float4(s.kc, s.lo, s.cr, s.cg);
-  sm.c[slot] = make_float4(s.cb, s.inv_opac, __int_as_float(val), s.rbc);
+  sm.b[slot] = make_float4(s.kc, s.lo, s.rbc, s.cr);
+  sm.c[slot] = make_float4(s.cg, s.cb, s.inv_opac, __int_as_float(val));
 }
 
 template <class Smem>
 __device__ __forceinline__ bool splat_hits_block3(const Smem& sm, int slot, float bx0, float bx1, float by0, float by1) {
   const float4 a = sm.a[slot];
-  const float2 b = *reinterpret_cast<const float2*>(&sm.b[slot]);
+  const float4 b = sm.b[slot];
   ChsSplat<float> s;
   s.mx = a.x; s.my = a.y; s.qa = a.z; s.r = a.w;
-  s.kc = b.x; s.lo = b.y; s.rbc = sm.c[slot].w;
+  s.kc = b.x; s.lo = b.y; s.rbc = b.z;
   return chs_block_max_power(s, bx0, bx1, by0, by1) >= CHS_LOG2_ALPHA_MIN - 1e-3f;
 }
 
@@ -859,8 +859,8 @@ __device__ __forceinline__ void stage_from_raw(Smem& sm, int slot, const Raw& r,
   ChsSplat<float> s;
   chs_make_splat(gm.x, gm.y, gm.z, gm.w, r.cc[slot], col.w, col.x, col.y, col.z, s);
   sm.a[slot] = make_float4(s.mx, s.my, s.qa, s.r);
-  sm.b[slot] = make_float4(s.kc, s.lo, s.cr, s.cg);
-  sm.c[slot] = make_float4(s.cb, s.inv_opac, __int_as_float(val), s.rbc);
+  sm.b[slot] = make_float4(s.kc, s.lo, s.rbc, s.cr);
+  sm.c[slot] = make_float4(s.cg, s.cb, s.inv_opac, __int_as_float(val));
 }
 
 __device__ __forceinline__ unsigned lanemask_lt_() {
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
         for (int i = 0; i < n_surv; ++i) {
           const int jj = list[i];
           const float4 sa = sm.a[jj];
-          const float4 sb = sm.b[jj];  // kc, log2(opacity), cr, cg
+          const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
           float dx;
           P2 dy2, u2;
           const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
@@ -982,10 +982,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
             thrA = (actA && !accA) ? kInf : thrA;
             thrB = (actB && !accB) ? kInf : thrB;
             const P2 w2 = p2(accA ? p2lo(wq2) : 0.f, accB ? p2hi(wq2) : 0.f);
-            const float cb = sm.c[jj].x;
-            acc_r2 = fma2(p2s(sb.z), w2, acc_r2);
-            acc_g2 = fma2(p2s(sb.w), w2, acc_g2);
-            acc_b2 = fma2(p2s(cb), w2, acc_b2);
+            const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
+            acc_r2 = fma2(p2s(sb.w), w2, acc_r2);
+            acc_g2 = fma2(p2s(cgb.x), w2, acc_g2);
+            acc_b2 = fma2(p2s(cgb.y), w2, acc_b2);
             T2 = T2 - w2;
             relA = accA ? jj : relA;
             relB = accB ? jj : relB;
@@ -1095,9 +1095,9 @@ __device__ __forceinline__ void bwd_round3(const Smem& sm, const BwdWarp3<kSlots
     const int jj = __float_as_int(ws.nvs[k][64]);
     sa = sm.a[jj];  // mx, my, qa, r
     kc = sm.b[jj].x;
-    const float4 sc = sm.c[jj];  // cb, 1/opacity, val, rbc
-    inv_opac = sc.y;
-    val = (uint32_t)__float_as_int(sc.z);
+    const float2 sc = *reinterpret_cast<const float2*>(&sm.c[jj].z);  // 1/opacity, val
+    inv_opac = sc.x;
+    val = (uint32_t)__float_as_int(sc.y);
     const float dxb = sa.x - bxc;  // mean - centre of pixel column 0
     dy_lo = sa.y - (byc + (float)part);
     const float* rv = &ws.nvs[k][16 * part];
@@ -1265,7 +1265,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
         const int jj = jn;
         jn = ws.list[i + 1];  // (the list has spare entries) the next index is in flight while this Gaussian is processed
         const float4 sa = sm.a[jj];  // mx, my, qa, r
-        const float4 sb = sm.b[jj];  // kc, log2(opacity), cr, cg
+        const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
         float dx;
         P2 dy2, u2;
         const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
@@ -1273,7 +1273,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
         const bool validA = (jj <= lrA) && pA >= CHS_LOG2_ALPHA_MIN;
         const bool validB = (jj <= lrB) && pB >= CHS_LOG2_ALPHA_MIN;
         if (!__any_sync(CHS_FULL_MASK, validA || validB)) continue;
-        const float cb = sm.c[jj].x;
+        const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
         const float auA = validA ? chs_exp2_fast(pA) : 0.f;
         const float auB = validB ? chs_exp2_fast(pB) : 0.f;
         // packed chs_pair_bwd_scalars_r with na = -alpha: a pixel that does not contribute runs with alpha = 0, which leaves
@@ -1282,7 +1282,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
         const P2 om2 = p2s(1.f) + na2;
         Tr2 = Tr2 * p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));  // transmittance before this Gaussian
         const P2 nf2 = na2 * Tr2;
-        const P2 s2 = fma2(p2s(cb), vh_b2, fma2(p2s(sb.w), vh_g2, p2s(sb.z) * vh_r2));
+        const P2 s2 = fma2(p2s(cgb.y), vh_b2, fma2(p2s(cgb.x), vh_g2, p2s(sb.w) * vh_r2));
         const P2 e2 = R2 - s2;
         R2 = fma2(na2, e2, R2);
         // no gradient through the 0.999 clamp
