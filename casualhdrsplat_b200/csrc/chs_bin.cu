@@ -1080,6 +1080,58 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BandArgs a) {
   }
 }
 
+// P2 scatter, warp-per-tile output (chs_config.tune_bin_chunk = 1 on the banded route).  Same bit matrix; the walk differs: a warp
+// takes one tile at a time, lane w owns word w of the tile's row, a warp scan of the word populations gives every lane its
+// offset in the tile's run, and the lanes append their set bits side by side.  All addresses of one store instruction then fall
+// into the tile's run of this chunk (a few sectors) instead of 32 different lists (32 sectors).
+__global__ void __launch_bounds__(256) tile_scatter_warp_kernel(BandArgs a) {
+  extern __shared__ uint32_t smem_tile[];
+  uint32_t* bm = smem_tile;                    // [256][kBandRow]
+  uint32_t* ids = bm + 256 * kBandRow;         // [kBandChunk] pair id of every record of the chunk
+  uint32_t* cur0 = ids + kBandChunk;           // [256] start of every tile's run
+  const uint32_t t = blockIdx.x;
+  const uint4 ds = a.desc[t];
+  if (ds.x == 0xffffffffu) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cur0[threadIdx.x] = a.base2[(size_t)ds.x * 256 + threadIdx.x] + a.counts2[(size_t)threadIdx.x * a.t_cap2 + t];
+  for (int i = threadIdx.x; i < 256 * kBandRow; i += 256) bm[i] = 0u;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kBandChunk / 256; ++k) {
+    const uint32_t i = ds.y + k * 256 + threadIdx.x;  // record p = k * 256 + tid of the chunk: word k * 8 + warp, bit = lane
+    if (i < ds.z) {
+      const uint2 rec = a.recs[i];
+      ids[k * 256 + threadIdx.x] = rec.x;
+      const uint32_t box = rec.y;
+      const int x0 = box & 0xff, x1 = (box >> 8) & 0xff, ry0 = (box >> 16) & 0xff, ry1 = box >> 24;
+      for (int ry = ry0; ry <= ry1; ++ry)
+        for (int x = x0; x <= x1; ++x) atomicOr(&bm[(ry * a.tile_w + x) * kBandRow + k * 8 + warp], 1u << lane);
+    }
+  }
+  __syncthreads();
+  static_assert(kBandWords == 32, "one lane per word of a bit-matrix row");
+  const int n_tiles = a.BR * a.tile_w;
+  for (int tl = warp; tl < n_tiles; tl += 8) {
+    uint32_t m = bm[tl * kBandRow + lane];
+    if (!__any_sync(CHS_FULL_MASK, m != 0u)) continue;
+    const uint32_t cnt = __popc(m);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(CHS_FULL_MASK, incl, o);
+      if (lane >= o) incl += u;
+    }
+    uint32_t cursor = cur0[tl] + incl - cnt;
+    const uint32_t* my_ids = ids + lane * 32;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (cursor < a.val_cap) a.vals[cursor] = (int32_t)my_ids[b];
+      ++cursor;
+    }
+  }
+}
+
 // K5 of the banded route: list starts of every (camera, tile) from the scanned column totals of P2 (clamped to the capacity of
 // the value buffer, so that a step whose M outgrew it walks truncated lists instead of reading past the end)
 __global__ void __launch_bounds__(kThreads) band_tile_offsets_kernel(int64_t n_lin, int tiles, int tile_w, int BR, int n_bands,
@@ -1326,8 +1378,13 @@ int band_bin_sort(const chs_config* cfg, const ChsDims& d, uint64_t cap, const f
                                                                      reinterpret_cast<const uint64_t*>(total), (uint32_t)cap, tile_offsets);
   CHS_LAUNCH_CHECK();
   const size_t smem2 = (size_t)256 * kBandRow * 4 + (size_t)kBandChunk * 4;
-  CHS_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  tile_scatter_kernel<<<p.t_cap2, 256, smem2, s>>>(a);
+  if (cfg->tune_bin_chunk == 1) {  // development knob: warp-per-tile output
+    CHS_CUDA(cudaFuncSetAttribute(tile_scatter_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem2 + 1024)));
+    tile_scatter_warp_kernel<<<p.t_cap2, 256, smem2 + 1024, s>>>(a);
+  } else {
+    CHS_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    tile_scatter_kernel<<<p.t_cap2, 256, smem2, s>>>(a);
+  }
   CHS_LAUNCH_CHECK();
   if (keys_sorted) {
     rebuild_keys_from_offsets_kernel<<<(unsigned)n_lin, 128, 0, s>>>(d.tiles, d.tile_bits, tile_offsets, vals_sorted, depths, keys_sorted,

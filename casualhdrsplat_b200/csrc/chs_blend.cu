@@ -875,12 +875,20 @@ __device__ __forceinline__ unsigned lanemask_gt_() {
 }
 
 // ---- forward ----
-template <int kMinBlocks, bool kPerPoseCrf, bool kAsync>
+// kGroup (round 2, second half; the default): the warp first culls the WHOLE staged batch into its survivor list, pads the list
+// to a multiple of four with the index of a null record (log2 opacity = -inf: alpha = 0 everywhere), and then walks it in
+// groups of four.  A group evaluates the four alphas (independent of the transmittance), runs the transmittance chain
+// T <- T - alpha T speculatively and takes ONE vote "did any pixel of the warp cross the 1e-4 stop threshold in this group?".
+// Almost always nobody did: the colour sums take the four products as they are and nothing per Gaussian is spent on the
+// stop logic (r2r source page of the ungrouped loop: 2 FSETP + 2 FSEL + 2 MOV + the reconvergence of a per-lane branch that
+// 96 % of the iterations took anyway, per Gaussian).  If somebody did, the same four alphas go through the exact sequential
+// code of the ungrouped loop, so results are bit-identical to it.
+template <int kMinBlocks, bool kPerPoseCrf, bool kAsync, bool kGroup = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendFwdArgs a) {
   static_assert(kBatch == 2 * kThreads, "asynchronous staging: two tile-list entries per thread and batch");
-  __shared__ SplatSmem3<kBatch> sm;
+  __shared__ SplatSmem3<kBatch + (kGroup ? 1 : 0)> sm;  // kGroup: entry kBatch is the null record
   __shared__ RawSmem<kAsync ? kBatch : 1> raw;  // kAsync: the next batch's raw records, gathered with cp.async
-  __shared__ int s_list[kThreads / 32][32];
+  __shared__ __align__(16) int s_list[kThreads / 32][kGroup ? kBatch + 4 : 32];
   extern __shared__ float s_crf[];  // the CRF parameters [3, stride] when the CRF is learned
 
   const int tile = blockIdx.x, frame = blockIdx.y;
@@ -900,6 +908,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
 
   const int crf_stride = chs_crf_stride(a.crf_kind, a.crf_hidden);  // 0 for the identity CRF
   for (int i = tid; i < 3 * crf_stride; i += kThreads) s_crf[i] = a.crf_params[i];
+  if constexpr (kGroup) if (tid == 0) {  // the null record (made visible by the first barrier of the batch loop)
+    sm.a[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.b[kBatch] = make_float4(0.f, -kInf, 0.f, 0.f);
+    sm.c[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   constexpr bool per_pose_crf = kPerPoseCrf;
   const float dt = a.exposure[frame];
@@ -955,6 +968,82 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
       if (warp_done) continue;
       const int idx0 = (int)(base - start) + 1;
       int relA = -1, relB = -1;  // staged index of the last Gaussian accumulated from this batch
+      if constexpr (kGroup) {
+        int n_surv = 0;
+        for (int sub = 0; sub < cnt; sub += 32) {
+          const int j = sub + lane;
+          const bool hit = (j < cnt) && splat_hits_block3(sm, j, bx0, bx1, by0, by1);
+          const unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+          if (hit) list[n_surv + __popc(mask & lt)] = j;  // ascending: front to back
+          n_surv += __popc(mask);
+        }
+        if (lane < 3) list[n_surv + lane] = kBatch;  // padding: the null record
+        __syncwarp();
+        for (int i = 0; i < n_surv; i += 4) {
+          const int4 j4 = *reinterpret_cast<const int4*>(list + i);
+          const int js[4] = {j4.x, j4.y, j4.z, j4.w};
+          P2 al2[4], wq2[4];
+          float cr[4];
+          int srelA = relA, srelB = relB;  // speculative: committed when nobody stops in this group
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 sa = sm.a[js[u]];
+            const float4 sb = sm.b[js[u]];  // kc, log2(opacity), rbc, cr
+            float dx;
+            P2 dy2, u2;
+            const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+            const float pA = p2lo(pw2), pB = p2hi(pw2);
+            const bool actA = pA >= thrA, actB = pB >= thrB;
+            al2[u] = p2(actA ? fminf(CHS_ALPHA_MAX, chs_exp2_fast(pA)) : 0.f, actB ? fminf(CHS_ALPHA_MAX, chs_exp2_fast(pB)) : 0.f);
+            cr[u] = sb.w;
+            srelA = actA ? js[u] : srelA;
+            srelB = actB ? js[u] : srelB;
+          }
+          P2 Tq2 = T2;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            wq2[u] = al2[u] * Tq2;
+            Tq2 = Tq2 - wq2[u];  // = T (1 - alpha)
+          }
+          const bool cross = fminf(p2lo(Tq2), p2hi(Tq2)) <= CHS_T_STOP;
+          if (!__any_sync(CHS_FULL_MASK, cross)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[js[u]]);  // cg, cb
+              acc_r2 = fma2(p2s(cr[u]), wq2[u], acc_r2);
+              acc_g2 = fma2(p2s(cgb.x), wq2[u], acc_g2);
+              acc_b2 = fma2(p2s(cgb.y), wq2[u], acc_b2);
+            }
+            T2 = Tq2;
+            relA = srelA;
+            relB = srelB;
+          } else {  // somebody stops inside this group: the ungrouped loop's exact sequence on the same alphas
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              // a pixel that stopped earlier in the group ignores the rest of it (its threshold is +inf from then on)
+              const float alA = thrA == kInf ? 0.f : p2lo(al2[u]), alB = thrB == kInf ? 0.f : p2hi(al2[u]);
+              const bool actA = alA != 0.f, actB = alB != 0.f;
+              const P2 wq = p2(alA, alB) * T2;
+              const P2 Tn2 = T2 - wq;
+              const bool accA = actA && p2lo(Tn2) > CHS_T_STOP, accB = actB && p2hi(Tn2) > CHS_T_STOP;
+              thrA = (actA && !accA) ? kInf : thrA;
+              thrB = (actB && !accB) ? kInf : thrB;
+              const P2 w2 = p2(accA ? p2lo(wq) : 0.f, accB ? p2hi(wq) : 0.f);
+              const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[js[u]]);  // cg, cb
+              acc_r2 = fma2(p2s(cr[u]), w2, acc_r2);
+              acc_g2 = fma2(p2s(cgb.x), w2, acc_g2);
+              acc_b2 = fma2(p2s(cgb.y), w2, acc_b2);
+              T2 = T2 - w2;
+              relA = accA ? js[u] : relA;
+              relB = accB ? js[u] : relB;
+            }
+            if (__all_sync(CHS_FULL_MASK, thrA == kInf && thrB == kInf)) {
+              warp_done = true;
+              break;
+            }
+          }
+        }
+      } else
       for (int sub = 0; sub < cnt; sub += 32) {
         const int j = sub + lane;
         const bool hit = (j < cnt) && splat_hits_block3(sm, j, bx0, bx1, by0, by1);
@@ -1074,7 +1163,9 @@ struct __align__(16) BwdWarp3 {
   float nvs[kSlots][kRow3];  // -dL/dsigma of (slot, pixel id); column 64: staged-batch index of the slot's Gaussian (int bits)
   float nf[kSlots][kRow3];   // -alpha * T of (slot, pixel id)
   float vh[3][64];           // dL/dH of the warp's pixels by pixel id (r, g, b planes)
-  int list[36];              // survivors of the current 32-entry sub-batch, back to front (+ spare entries: the loop reads one ahead)
+  int list[32];              // survivors of the current 32-entry sub-batch, back to front
+  int ent[kSlots];           // staged-batch index of every tabled slot's Gaussian
+  int pad_[4 - kSlots % 4];
 };
 
 // phase B for the n_slots tabled Gaussians of this warp.  Lane = (slot k = lane % 8, part = lane / 8); a part covers the two
@@ -1092,7 +1183,7 @@ __device__ __forceinline__ void bwd_round3(const Smem& sm, const BwdWarp3<kSlots
   float kc = 0.f, inv_opac = 0.f, dy_lo = 0.f;
   uint32_t val = 0;
   if (active) {
-    const int jj = __float_as_int(ws.nvs[k][64]);
+    const int jj = ws.ent[k];
     sa = sm.a[jj];  // mx, my, qa, r
     kc = sm.b[jj].x;
     const float2 sc = *reinterpret_cast<const float2*>(&sm.c[jj].z);  // 1/opacity, val
@@ -1194,8 +1285,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) ws.vh[ch][2 * lane + h] = v[h][ch];  // pixel id = 2 lane + h  <->  (x, y) = (lane & 7, (lane >> 3) + 4 h)
   }
-  ws.list[lane] = 0;  // entries read ahead of the valid ones must always be in-bounds staged indices
-  if (lane < 4) ws.list[32 + lane] = 0;
   const P2 py2 = p2(iy0 + 0.5f, iy0 + 4.5f);
   P2 Tr2 = p2(Tf[0], Tf[1]);
   P2 R2 = p2(r0[0], r0[1]);
@@ -1213,8 +1302,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
   // next free row): one add per tabled Gaussian, no address arithmetic from the thread id inside the loop.
   const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(&ws.nvs[0][0]) + 8u * (uint32_t)lane;
   constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = kSlots * kRow3 * 4;
-  const uint32_t tab_end = tab0 + kSlots * kRowBytes;
   uint32_t tab = tab0;
+  int slots_left = kSlots;  // free rows of the table (a down-counter: one subtract-and-test per tabled Gaussian)
   // kAsync pipeline: this thread's entry of batch b + 1 is gathered (cp.async) while batch b is processed, and the tile-list
   // value of batch b + 2 is already on its way in a register
   int32_t val_cur = 0, val_next = 0;  // record index whose gather is in flight / of the batch after it
@@ -1259,49 +1348,57 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
       const int n_surv = __popc(mask);
       if (hit) ws.list[__popc(mask & gt)] = j;  // descending: back to front
       __syncwarp();
-      // ---- phase A over the survivors ----
-      int jn = ws.list[0];
-      for (int i = 0; i < n_surv; ++i) {
-        const int jj = jn;
-        jn = ws.list[i + 1];  // (the list has spare entries) the next index is in flight while this Gaussian is processed
-        const float4 sa = sm.a[jj];  // mx, my, qa, r
-        const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
-        float dx;
-        P2 dy2, u2;
-        const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
-        const float pA = p2lo(pw2), pB = p2hi(pw2);
-        const bool validA = (jj <= lrA) && pA >= CHS_LOG2_ALPHA_MIN;
-        const bool validB = (jj <= lrB) && pB >= CHS_LOG2_ALPHA_MIN;
-        if (!__any_sync(CHS_FULL_MASK, validA || validB)) continue;
-        const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
-        const float auA = validA ? chs_exp2_fast(pA) : 0.f;
-        const float auB = validB ? chs_exp2_fast(pB) : 0.f;
-        // packed chs_pair_bwd_scalars_r with na = -alpha: a pixel that does not contribute runs with alpha = 0, which leaves
-        // T and R untouched and tables zeros
-        const P2 na2 = p2(fmaxf(-CHS_ALPHA_MAX, -auA), fmaxf(-CHS_ALPHA_MAX, -auB));
-        const P2 om2 = p2s(1.f) + na2;
-        Tr2 = Tr2 * p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));  // transmittance before this Gaussian
-        const P2 nf2 = na2 * Tr2;
-        const P2 s2 = fma2(p2s(cgb.y), vh_b2, fma2(p2s(cgb.x), vh_g2, p2s(sb.w) * vh_r2));
-        const P2 e2 = R2 - s2;
-        R2 = fma2(na2, e2, R2);
-        // no gradient through the 0.999 clamp
-        const P2 gate2 = p2(auA <= CHS_ALPHA_MAX ? 1.f : 0.f, auB <= CHS_ALPHA_MAX ? 1.f : 0.f);
-        const P2 nvs2 = (nf2 * e2) * gate2;
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab), "f"(p2lo(nvs2)), "f"(p2hi(nvs2)) : "memory");
-        asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(tab), "f"(p2lo(nf2)), "f"(p2hi(nf2)), "n"(kFOffBytes) : "memory");
-        if (lane == 0) asm volatile("st.shared.b32 [%0+256], %1;" ::"r"(tab), "r"(jj) : "memory");  // lane 0: tab = start of the row
-        tab += kRowBytes;
-        if (tab == tab_end) {
+      // ---- phase A over the survivors, in chunks that fit the free rows of the table: the inner loop has no table-full test,
+      // no call and no vote (r2r source page: 99 % of the survivors have a contributing pixel in the warp, so the "any valid"
+      // vote + branch cost more than the iterations they skipped), which lets the compiler unroll it ----
+      int i = 0;
+      while (i < n_surv) {
+        const int m = min(n_surv - i, slots_left);
+        if (lane < m) ws.ent[kSlots - slots_left + lane] = ws.list[i + lane];  // staged indices of the chunk's Gaussians, for phase B
+#pragma unroll 4
+        for (int q = 0; q < m; ++q) {
+          const int jj = ws.list[i + q];
+          const float4 sa = sm.a[jj];  // mx, my, qa, r
+          const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
+          float dx;
+          P2 dy2, u2;
+          const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+          const float pA = p2lo(pw2), pB = p2hi(pw2);
+          const bool validA = (jj <= lrA) && pA >= CHS_LOG2_ALPHA_MIN;
+          const bool validB = (jj <= lrB) && pB >= CHS_LOG2_ALPHA_MIN;
+          const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
+          const float auA = validA ? chs_exp2_fast(pA) : 0.f;
+          const float auB = validB ? chs_exp2_fast(pB) : 0.f;
+          // packed chs_pair_bwd_scalars_r with na = -alpha: a pixel that does not contribute runs with alpha = 0, which leaves
+          // T and R untouched and tables zeros
+          const P2 na2 = p2(fmaxf(-CHS_ALPHA_MAX, -auA), fmaxf(-CHS_ALPHA_MAX, -auB));
+          const P2 om2 = p2s(1.f) + na2;
+          Tr2 = Tr2 * p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));  // transmittance before this Gaussian
+          const P2 nf2 = na2 * Tr2;
+          const P2 s2 = fma2(p2s(cgb.y), vh_b2, fma2(p2s(cgb.x), vh_g2, p2s(sb.w) * vh_r2));
+          const P2 e2 = R2 - s2;
+          R2 = fma2(na2, e2, R2);
+          // no gradient through the 0.999 clamp
+          const P2 gate2 = p2(auA <= CHS_ALPHA_MAX ? 1.f : 0.f, auB <= CHS_ALPHA_MAX ? 1.f : 0.f);
+          const P2 nvs2 = (nf2 * e2) * gate2;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab), "f"(p2lo(nvs2)), "f"(p2hi(nvs2)) : "memory");
+          asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(tab), "f"(p2lo(nf2)), "f"(p2hi(nf2)), "n"(kFOffBytes) : "memory");
+          tab += kRowBytes;
+        }
+        i += m;
+        slots_left -= m;
+        if (slots_left == 0) {
           bwd_round3<kSlots>(sm, ws, kSlots, lane, bx0, by0, a);
           tab = tab0;
+          slots_left = kSlots;
         }
       }
       __syncwarp();  // the list is rewritten by the next sub-batch
     }
-    if (tab != tab0) {  // the staged batch is about to be replaced
-      bwd_round3<kSlots>(sm, ws, (int)((tab - tab0) / kRowBytes), lane, bx0, by0, a);
+    if (slots_left != kSlots) {  // the staged batch is about to be replaced
+      bwd_round3<kSlots>(sm, ws, kSlots - slots_left, lane, bx0, by0, a);
       tab = tab0;
+      slots_left = kSlots;
     }
   }
 }
@@ -1352,7 +1449,11 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
       case 30: blend_fwd2_kernel<6, false, true><<<grid, kThreads, dyn, s>>>(a); break;
       // round 2: survivor list, T -= w.  r2e, c3 (ms per frame): 6 CTAs/SM 2.33 | 7 (72 registers) 2.21 | 8 (64 registers, spills) 2.26;
       // round-1 kernel 2.50
-      default: blend_fwd2_kernel<7, false, false><<<grid, kThreads, dyn, s>>>(a); break;
+      case 27: blend_fwd2_kernel<7, false, false><<<grid, kThreads, dyn, s>>>(a); break;  // the ungrouped round-2 loop
+      case 46: blend_fwd2_kernel<6, false, false, true><<<grid, kThreads, dyn, s>>>(a); break;
+      case 48: blend_fwd2_kernel<8, false, false, true><<<grid, kThreads, dyn, s>>>(a); break;
+      // grouped pair loop (speculative transmittance chain, one stop vote per four Gaussians)
+      default: blend_fwd2_kernel<7, false, false, true><<<grid, kThreads, dyn, s>>>(a); break;
     }
   }
   CHS_LAUNCH_CHECK();
