@@ -33,6 +33,10 @@
 // Negative results kept out of the code (r1g, c3): prefetching the next survivor's staged record inside the
 // forward pair loop (to hide the bit-scan -> address -> LDS chain) made K6 2.55 -> 2.95 ms at 64 registers and
 // 3.00 ms at 72; software-pipelining phase A of the tabled backward cost +0.5 ms.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "chs_common.cuh"
 
 namespace {
@@ -1403,6 +1407,309 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
   }
 }
 
+
+// =================================================================================================
+// Backward with phase B on the tensor cores (blend_bwd4_kernel; chs_config.tune_blend_bwd = 47).
+//
+// ncu of blend_bwd3_kernel (profiles/r2_ncu_blend.csv): l1tex__data_pipe_lsu_wavefronts 85 % of peak, shared-memory
+// wavefronts 75 % — the kernel is bound by the shared-memory pipe, not by instruction issue (cutting phase A from 59 to 40
+// instructions per pair moved it from 3.90 to 3.80 ms).  Of the ~22 wavefronts per (warp, Gaussian) pair, 6 were phase B
+// re-reading the warp's dL/dH for every tabled Gaussian and 2.3 its 18 reduction shuffles.  Phase B is a contraction over
+// the warp's 64 pixels,
+//     S[slot][m] = sum_pix nvs[slot][pix] * mono_m(pix),  mono = (1, x, y, x^2, x y, y^2) relative to the block origin,
+//     G[slot][c] = sum_pix nf[slot][pix] * v_c[pix],
+// i.e. [8 slots x 64 pixels] x [64 pixels x 8 columns] products with a constant right-hand side: mma.sync.m16n8k16 (fp16 in,
+// fp32 accumulate), four k-steps of 16 pixels.  fp32 accuracy is kept by splitting every tabled value into fp16 hi + lo, which
+// ride in rows 0-7 / 8-15 of the SAME A operand (the two halves of the accumulator are added afterwards), and v_c into hi + lo
+// in neighbouring COLUMNS of the same B operand; the monomials are small integers, exact in fp16.  fp16 has five exponent bits,
+// so everything is scaled by powers of two into its range: v by the warp's max |v|, alpha T by 2^14 (carried in the
+// transmittance register), and dL/dsigma by a bound that cannot be exceeded: |nvs| <= |R - s| <= 2 max(|R0|, max_j |s_j|) with
+// |s_j| <= (|cr| + |cg| + |cb|) max|v| over every Gaussian staged so far (a running maximum kept by the staging code; R is a
+// convex combination of R0 and earlier s_j).  hi + lo then resolves 2^-25 of that bound: tests/test_hostsim_math.py
+// (test_tensor_core_phase_b_precision) pins geometry gradients at the accuracy of the fp32 table and colours at 1e-6.
+// The sums come out per (slot, column pair) on the lanes of a quad, five shuffles gather what the three reducing lanes need,
+// chs_shift_moments moves the origin-relative sums to the Gaussian's mean, and the REDs go out as before.
+// Per pair: shared-memory wavefronts ~22 -> ~16, phase B instructions 24 -> 9, phase A 40 -> 52 (the four conversions).
+// =================================================================================================
+constexpr int kRow4 = 72;  // halves per table row: 64 pixel ids + 8 (144-byte rows: the 8 rows of an ldmatrix tile hit 8 different 16-byte bank groups)
+
+template <int kB>
+struct __align__(16) BwdWarp4 {
+  __half tbl[4][8][kRow4];  // [nvs hi | nvs lo | nf hi | nf lo][slot][pixel id = 2 lane + h]
+  uint2 vfrag[4 * 32];      // B operand of the colour product per k-step and lane: columns 2..7 = (r hi, r lo, g hi, g lo, b hi, b lo)
+  uint8_t list[kB + 4];     // survivors of the staged batch, back to front, padded to a multiple of four with kB (the null record)
+};
+
+__device__ __forceinline__ uint32_t f16x2_of(float lo, float hi) {  // {hi, lo} -> packed halves, lo in bits 0..15
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ P2 f16x2_to_p2(uint32_t v) {
+  float a, b;
+  asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(a), "=f"(b) : "r"(v));
+  return p2(a, b);
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_f16(float d[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// 2^(k) as a float for an integer exponent already clamped to the normal range
+__device__ __forceinline__ float pow2i(int k) { return __int_as_float((k + 127) << 23); }
+__device__ __forceinline__ int expo_of(float x) { return (int)((__float_as_uint(x) >> 23) & 0xffu) - 126; }  // x = f 2^e, f in [0.5, 1)
+
+// phase B for the slots [0, n_slots) of this warp's table; slot g's Gaussian is staged record ents[g].
+// Lane = (slot g = lane >> 2, column pair t = lane & 3).  Geometry columns: (x, x^2 | 1, y | x y, y^2 | 1, y); colour columns:
+// (0, 0 | r hi, r lo | g hi, g lo | b hi, b lo).  Lane t = 0 sends v_geom, t = 1 v_cogr, t = 3 v_blue.
+template <int kB, class Smem>
+__device__ __forceinline__ void bwd_round4(const Smem& sm, uint32_t a_addr, const uint2* __restrict__ mono, const uint2* __restrict__ vfrag,
+                                           const uint8_t* __restrict__ ents, int n_slots, int lane, float bxc, float byc, float inv_sn,
+                                           float inv_sc, const BlendBwdArgs& a) {
+  __syncwarp();
+  float dg[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    uint32_t a0, a1, a2, a3;
+    ldmatrix_x4(a_addr + 32 * s, a0, a1, a2, a3);  // rows: nvs hi (slots) | nvs lo; 16 pixel ids of the k-step
+    const uint2 bm = mono[s * 32 + lane];
+    mma_f16(dg, a0, a1, a2, a3, bm.x, bm.y);
+    ldmatrix_x4(a_addr + 2 * 8 * kRow4 * 2 + 32 * s, a0, a1, a2, a3);  // rows: nf hi | nf lo
+    const uint2 bv = vfrag[s * 32 + lane];
+    mma_f16(dc, a0, a1, a2, a3, bv.x, bv.y);
+  }
+  const int g = lane >> 2, t = lane & 3;
+  const float P = dg[0] + dg[2], Q = dg[1] + dg[3];          // hi rows + lo rows
+  const float C = (dc[0] + dc[2]) + (dc[1] + dc[3]);         // t = 1: sum nf v_r, t = 2: v_g, t = 3: v_b (hi + lo columns)
+  const float P1 = __shfl_xor_sync(CHS_FULL_MASK, P, 1), Q1 = __shfl_xor_sync(CHS_FULL_MASK, Q, 1);
+  const float P2x = __shfl_xor_sync(CHS_FULL_MASK, P, 2);
+  const float Q3 = __shfl_xor_sync(CHS_FULL_MASK, Q, 3), C3 = __shfl_xor_sync(CHS_FULL_MASK, C, 3);
+  const int jj = ents[g];
+  if (g < n_slots && jj != kB && t != 2) {
+    const float4 sa = sm.a[jj];  // mx, my, qa, r
+    const float X = sa.x - bxc, Y = sa.y - byc;
+    const float2 sc = *reinterpret_cast<const float2*>(&sm.c[jj].z);  // 1/opacity, val
+    const uint32_t val = (uint32_t)__float_as_int(sc.y);
+    if (t == 0) {  // P, Q = Sx, Sxx;  P1, Q1 = S1, Sy;  P2x = Sxy
+      float m[6];
+      chs_shift_moments(P1, P, Q1, Q, P2x, 0.f, X, Y, sa.w, m);
+      ChsSplat<float> sp;
+      sp.qa = sa.z; sp.r = sa.w; sp.kc = sm.b[jj].x; sp.inv_opac = 0.f;
+      float t9[9] = {m[0] * inv_sn, m[1] * inv_sn, m[2] * inv_sn, m[3] * inv_sn, 0.f, 0.f, 0.f, 0.f, 0.f}, gr[9];
+      chs_moments_to_grads_neg(sp, t9, gr);
+      atomicAdd(a.v_geom + val, make_float4(gr[0], gr[1], gr[2], gr[3]));
+    } else if (t == 1) {  // P, Q = S1, Sy;  Q3 = Syy;  C = sum nf v_r, C3 = sum nf v_g
+      const float sdy = Y * P - Q;
+      const float m4 = (Y * (sdy - Q) + Q3) * inv_sn, m5 = P * inv_sn;
+      atomicAdd(a.v_cogr + val, make_float4(-0.5f * m4, m5 * sc.x, -C * inv_sc, -C3 * inv_sc));
+    } else {  // t == 3: C = sum nf v_b
+      atomicAdd(a.v_blue + val, -C * inv_sc);
+    }
+  }
+  __syncwarp();  // the table is rewritten by the next round
+}
+
+template <int kB, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd4_kernel(BlendBwdArgs a) {
+  static_assert(kB == kThreads && kB < 255, "one tile-list entry per thread and batch; staged indices fit a byte");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Smem = SplatSmem3<kB + 1>;  // entry kB: the null record
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  uint2* mono = reinterpret_cast<uint2*>(smem_raw + sizeof(Smem));  // [4 k-steps][32 lanes] B operand of the geometry product
+  __shared__ int s_max_last;
+  __shared__ unsigned s_cbnd;  // running max of |cr| + |cg| + |cb| over every staged Gaussian (float bits; non-negative)
+
+  const int tile = blockIdx.x, c = blockIdx.y;
+  const int frame = c / a.n_virtual;
+  const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;
+  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  BwdWarp4<kB>& ws = reinterpret_cast<BwdWarp4<kB>*>(smem_raw + sizeof(Smem) + 4 * 32 * sizeof(uint2))[warp];
+  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 8;
+  const int ix = bx + (lane & 7), iy0 = by + (lane >> 3);
+  const float px = ix + 0.5f;
+  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 7.5f;
+  const int64_t P = (int64_t)a.W * a.H;
+  const int lc = a.fused ? frame : c;                     // whose tile list this camera walks
+  const int rec_shift = a.fused ? (c - frame) * a.N : 0;  // list entry frame * N + g -> record c * N + g
+  const uint32_t start = a.tile_offsets[(int64_t)lc * a.tiles + tile];
+  const uint32_t end = a.tile_offsets[(int64_t)lc * a.tiles + tile + 1];
+  if (end <= start) return;
+
+  const float kInf = __int_as_float(0x7f800000);
+  if (tid == 0) {
+    s_max_last = 0;
+    s_cbnd = 0u;
+    sm.a[kB] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.b[kB] = make_float4(0.f, -kInf, 0.f, 0.f);
+    sm.c[kB] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  {  // geometry B operand: k-step s, lane (g, t): b0 = column g at pixels (x = t, y = s), (t, s + 4); b1 = the same at x = t + 4
+    const int s = tid >> 5, g = lane >> 2, t = lane & 3;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x = (float)(t + 4 * (q >> 1)), y = (float)(s + 4 * (q & 1));
+      v[q] = g == 0 ? x : g == 1 ? x * x : (g == 2 || g == 6) ? 1.f : (g == 3 || g == 7) ? y : g == 4 ? x * y : y * y;
+    }
+    mono[tid] = make_uint2(f16x2_of(v[0], v[1]), f16x2_of(v[2], v[3]));
+  }
+
+  const float inv_nv = 1.f / (float)a.n_virtual;
+  const int vimg = a.v_hdr_per_camera ? c : frame;
+  int last[2];
+  int warp_last = 0;
+  float Tf[2] = {1.f, 1.f}, v[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, r0[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int iy = iy0 + 4 * h;
+    last[h] = 0;
+    if (ix < a.W && iy < a.H) {
+      const int64_t pix = (int64_t)iy * a.W + ix;
+      Tf[h] = a.final_T[(int64_t)c * P + pix];
+      last[h] = a.last_id[(int64_t)c * P + pix];
+      const int64_t o = ((int64_t)vimg * P + pix) * 3;
+      v[h][0] = a.v_hdr[o]; v[h][1] = a.v_hdr[o + 1]; v[h][2] = a.v_hdr[o + 2];
+      const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] * inv_nv : 0.f;
+      // behind the last accumulated Gaussian lies the background: R = bg . v_H - v_alpha (chs_pair_bwd_scalars_r)
+      r0[h] = (a.bg[0] * v[h][0] + a.bg[1] * v[h][1] + a.bg[2] * v[h][2]) - v_al;
+    }
+    warp_last = max(warp_last, last[h]);
+  }
+  // power-of-two scales of this warp: v_H into [0, 1), and the two magnitudes the dL/dsigma bound is made of
+  float vmax = 0.f, r0max = fmaxf(fabsf(r0[0]), fabsf(r0[1]));
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) vmax = fmaxf(vmax, fabsf(v[h][ch]));
+  vmax = __uint_as_float(__reduce_max_sync(CHS_FULL_MASK, __float_as_uint(vmax)));
+  r0max = __uint_as_float(__reduce_max_sync(CHS_FULL_MASK, __float_as_uint(r0max)));
+  const int ev = min(max(expo_of(vmax), -100), 100);
+  const float sv = pow2i(-ev);
+  const float inv_sc = pow2i(ev - 14);  // undoes sv and the 2^14 carried by alpha T
+  {  // colour B operand: this lane's pixel pair is k = (2 t, 2 t + 1) of register q >> 2 in k-step lane >> 3, t = lane & 3
+    const int s = lane >> 3, q = lane & 7, t = q & 3;
+    uint32_t* vf = reinterpret_cast<uint32_t*>(ws.vfrag) + (q >> 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane < 8) ws.vfrag[k * 32 + lane] = make_uint2(0u, 0u);  // columns 0 and 1
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const uint32_t hi = f16x2_of(v[0][ch] * sv, v[1][ch] * sv);
+      const P2 res = p2(v[0][ch] * sv, v[1][ch] * sv) - f16x2_to_p2(hi);
+      vf[2 * (s * 32 + (2 + 2 * ch) * 4 + t)] = hi;
+      vf[2 * (s * 32 + (3 + 2 * ch) * 4 + t)] = f16x2_of(p2lo(res), p2hi(res));
+    }
+  }
+  const P2 py2 = p2(iy0 + 0.5f, iy0 + 4.5f);
+  P2 Tr2 = p2(Tf[0] * 16384.f, Tf[1] * 16384.f);  // 2^14 x transmittance: alpha T lands in fp16's normal range
+  P2 R2 = p2(r0[0], r0[1]);
+  const P2 vh_r2 = p2(v[0][0], v[1][0]), vh_g2 = p2(v[0][1], v[1][1]), vh_b2 = p2(v[0][2], v[1][2]);
+  __syncthreads();
+  warp_last = __reduce_max_sync(CHS_FULL_MASK, warp_last);
+  if (lane == 0 && warp_last > 0) atomicMax(&s_max_last, warp_last);
+  __syncthreads();
+  const int n_walk = s_max_last;
+
+  const unsigned gt = lanemask_gt_();
+  const uint32_t tbl0 = (uint32_t)__cvta_generic_to_shared(&ws.tbl[0][0][0]);
+  const uint32_t tab0 = tbl0 + 4u * (uint32_t)lane;  // this lane's pixel pair in row 0
+  // ldmatrix row address of this lane: matrix i = lane >> 3 = (hi | lo) x (k 0-7 | k 8-15), row = slot lane & 7
+  const uint32_t a_addr = tbl0 + (uint32_t)(((lane >> 3) & 1) * 8 * kRow4 * 2 + (lane & 7) * kRow4 * 2 + (lane >> 4) * 16);
+  constexpr uint32_t kRowB = kRow4 * 2, kArrB = 8 * kRow4 * 2;
+  for (int hi = n_walk; hi > 0; hi -= kB) {
+    const int lo = max(0, hi - kB);
+    const int cnt = hi - lo;
+    __syncthreads();  // every warp is done with the previous batch's records
+    {
+      float csum = 0.f;
+      if (tid < cnt) {
+        const int32_t val = a.vals[start + lo + tid] + rec_shift;
+        stage_splat3(sm, tid, val, cam_base, a.geom, a.conic_c, a.rgbo);
+        const float4 sb = sm.b[tid];
+        const float2 sc = *reinterpret_cast<const float2*>(&sm.c[tid]);
+        csum = fabsf(sb.w) + fabsf(sc.x) + fabsf(sc.y);
+      }
+      const unsigned cm = __reduce_max_sync(CHS_FULL_MASK, __float_as_uint(csum));
+      if (lane == 0) atomicMax(&s_cbnd, cm);
+    }
+    __syncthreads();
+    if (warp_last <= lo) continue;
+    // |nvs| <= 2 max(|R0|, cbnd vmax): scaled into [0, 2^14)
+    const float bound = 2.f * fmaxf(r0max, __uint_as_float(s_cbnd) * vmax);
+    const int eb = min(max(expo_of(bound), -100), 100);
+    const float gate_on = pow2i(-eb);  // = sn / 2^14 with sn = 2^(14 - eb): alpha T already carries the 2^14
+    const float inv_sn = pow2i(eb - 14);
+    const int lrA = last[0] - lo - 1, lrB = last[1] - lo - 1;  // staged indices <= lr are inside the pixel's accumulated prefix
+    // ---- cull the whole batch, back to front ----
+    int n_surv = 0;
+    for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
+      const int sub_lo = max(0, sub_hi - 32);
+      if (warp_last <= lo + sub_lo) continue;
+      const int j = sub_lo + lane;
+      const bool hit = (j < sub_hi) && (lo + j < warp_last) && splat_hits_block3(sm, j, bx0, bx1, by0, by1);
+      const unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+      if (hit) ws.list[n_surv + __popc(mask & gt)] = (uint8_t)j;  // descending
+      n_surv += __popc(mask);
+    }
+    if (lane < 3) ws.list[n_surv + lane] = (uint8_t)kB;  // padding: the null record (alpha = 0: tables zeros)
+    __syncwarp();
+    // ---- phase A in groups of four table rows; phase B every eight ----
+    for (int i = 0; i < n_surv; i += 4) {
+      const uint32_t j4 = *reinterpret_cast<const uint32_t*>(ws.list + i);
+      const uint32_t tab = tab0 + (uint32_t)(i & 4) * kRowB;
+      auto pair = [&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        const int jj = (int)((j4 >> (8 * u)) & 0xffu);
+        const float4 sa = sm.a[jj];  // mx, my, qa, r
+        const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
+        float dx;
+        P2 dy2, u2;
+        const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+        const float pA = p2lo(pw2), pB = p2hi(pw2);
+        const bool validA = (jj <= lrA) && pA >= CHS_LOG2_ALPHA_MIN;
+        const bool validB = (jj <= lrB) && pB >= CHS_LOG2_ALPHA_MIN;
+        const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
+        const float auA = validA ? chs_exp2_fast(pA) : 0.f;
+        const float auB = validB ? chs_exp2_fast(pB) : 0.f;
+        // packed chs_pair_bwd_scalars_r with na = -alpha (and T carrying 2^14): a pixel that does not contribute runs with
+        // alpha = 0, which leaves T and R untouched and tables zeros
+        const P2 na2 = p2(fmaxf(-CHS_ALPHA_MAX, -auA), fmaxf(-CHS_ALPHA_MAX, -auB));
+        const P2 om2 = p2s(1.f) + na2;
+        Tr2 = Tr2 * p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));  // transmittance before this Gaussian
+        const P2 nf2 = na2 * Tr2;
+        const P2 s2 = fma2(p2s(cgb.y), vh_b2, fma2(p2s(cgb.x), vh_g2, p2s(sb.w) * vh_r2));
+        const P2 e2 = R2 - s2;
+        R2 = fma2(na2, e2, R2);
+        // no gradient through the 0.999 clamp; the gate carries the scale of the dL/dsigma table
+        const P2 gate2 = p2(auA <= CHS_ALPHA_MAX ? gate_on : 0.f, auB <= CHS_ALPHA_MAX ? gate_on : 0.f);
+        const P2 nvs2 = (nf2 * e2) * gate2;
+        const uint32_t vhi = f16x2_of(p2lo(nvs2), p2hi(nvs2));
+        const P2 vres = nvs2 - f16x2_to_p2(vhi);
+        const uint32_t vlo = f16x2_of(p2lo(vres), p2hi(vres));
+        const uint32_t fhi = f16x2_of(p2lo(nf2), p2hi(nf2));
+        const P2 fres = nf2 - f16x2_to_p2(fhi);
+        const uint32_t flo = f16x2_of(p2lo(fres), p2hi(fres));
+        asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(tab), "r"(vhi), "n"(u * kRowB));
+        asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(tab), "r"(vlo), "n"(u * kRowB + kArrB));
+        asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(tab), "r"(fhi), "n"(u * kRowB + 2 * kArrB));
+        asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(tab), "r"(flo), "n"(u * kRowB + 3 * kArrB));
+      };
+      pair(std::integral_constant<int, 0>{});
+      pair(std::integral_constant<int, 1>{});
+      pair(std::integral_constant<int, 2>{});
+      pair(std::integral_constant<int, 3>{});
+      if (i & 4) bwd_round4<kB>(sm, a_addr, mono, ws.vfrag, ws.list + (i - 4), 8, lane, bx0, by0, inv_sn, inv_sc, a);
+    }
+    if (((n_surv + 3) >> 2) & 1)  // an odd number of groups: the last one sits alone in rows 0-3
+      bwd_round4<kB>(sm, a_addr, mono, ws.vfrag, ws.list + ((n_surv - 1) & ~3), 4, lane, bx0, by0, inv_sn, inv_sc, a);
+  }
+}
+
 }  // namespace
 
 static size_t crf_smem_bytes(const chs_config* cfg) {
@@ -1483,7 +1790,7 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.fused = cfg->pose_fused != 0;
   {
     const int tb = cfg->tune_blend_bwd;
-    CHS_REQUIRE(!a.fused || tb == 0 || (tb >= 35 && tb <= 39), "chs_blend_bwd: pose_fused needs the round-2 kernel");
+    CHS_REQUIRE(!a.fused || tb == 0 || (tb >= 35 && tb <= 39) || (tb >= 46 && tb <= 48), "chs_blend_bwd: pose_fused needs a round-2 kernel");
   }
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
@@ -1510,7 +1817,16 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
     case 39: blend_bwd3_kernel<8, 128, 7, true><<<grid, kThreads, CHS_BWD3_SMEM_ASYNC(128), s>>>(a); break;  // + cp.async staging
     case 35: blend_bwd3_kernel<8, 128, 6, true><<<grid, kThreads, CHS_BWD3_SMEM_ASYNC(128), s>>>(a); break;
     // round 2: division-free colour state, survivor list, running table pointer.  r2e, c3 (ms per frame of 8 poses): batch 128 /
-    // 7 CTAs per SM 4.03 (default) | 128 / 6: 4.19 | 128 / 8 (64 registers): 4.24 | 64 / 7: 4.17; round-1 tabled kernel 4.97
+    // 7 CTAs per SM 4.03 | 128 / 6: 4.19 | 128 / 8 (64 registers): 4.24 | 64 / 7: 4.17; round-1 tabled kernel 4.97
+#define CHS_BWD4_SMEM (sizeof(SplatSmem3<129>) + 4 * 32 * sizeof(uint2) + 4 * sizeof(BwdWarp4<128>))
+#define CHS_BWD4_LAUNCH(MB)                                                                                                   \
+  CHS_CUDA(cudaFuncSetAttribute(blend_bwd4_kernel<128, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHS_BWD4_SMEM)); \
+  blend_bwd4_kernel<128, MB><<<grid, kThreads, CHS_BWD4_SMEM, s>>>(a)
+    // phase B on the tensor cores (mma.sync m16n8k16, fp16 hi + lo tables): parity-green, measured r2v on c3: 7 CTAs per SM 4.00 ms |
+    // 6: 3.92 | 8: 3.98 against 3.83 for the default below
+    case 46: CHS_BWD4_LAUNCH(6); break;
+    case 47: CHS_BWD4_LAUNCH(7); break;
+    case 48: CHS_BWD4_LAUNCH(8); break;
     default: CHS_BWD3_LAUNCH(128, 7); break;
   }
   CHS_LAUNCH_CHECK();

@@ -546,6 +546,21 @@ template <class T> CHS_HD void chs_moments_to_grads_neg(const ChsSplat<T>& s, co
   g[8] = -m[8];
 }
 
+// Tensor-core phase B (blend_bwd4_kernel): the sums over a warp's 8x8 pixel block are taken against pixel monomials relative to
+// the block ORIGIN (x, y in 0 .. 7, exactly representable in fp16), S = sum nvs * (1, x, y, x^2, x y, y^2), as one small matrix
+// product.  This shifts them to the mean-relative sums chs_pair_moments accumulates, with (X, Y) = mean2d - centre of the block's
+// pixel (0, 0), i.e. dx = X - x, dy = Y - y, u = dx + r dy:
+//   m = (sum nvs u, sum nvs dy, sum nvs dx^2, sum nvs dx dy, sum nvs dy^2, sum nvs)
+template <class T> CHS_HD void chs_shift_moments(T S1, T Sx, T Sy, T Sxx, T Sxy, T Syy, T X, T Y, T r, T m[6]) {
+  const T sdx = X * S1 - Sx, sdy = Y * S1 - Sy;
+  m[0] = sdx + r * sdy;
+  m[1] = sdy;
+  m[2] = X * (sdx - Sx) + Sxx;         // X^2 S1 - 2 X Sx + Sxx
+  m[3] = X * sdy - Y * Sx + Sxy;       // X Y S1 - X Sy - Y Sx + Sxy
+  m[4] = Y * (sdy - Sy) + Syy;         // Y^2 S1 - 2 Y Sy + Syy
+  m[5] = S1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // A.7 camera response curve, MLP kind [D6]: per channel z = ln(X + 1e-5), h = relu(w1 z + b1),
 // y = sigmoid(w2 . h + b2).  params = [w1 (Hd) | b1 (Hd) | w2 (Hd) | b2].

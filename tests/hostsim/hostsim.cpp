@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "../../casualhdrsplat_b200/csrc/chs_math.cuh"
@@ -88,6 +89,30 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
   }
   const T thr = (T)log2(1.0 / 255.0);
   std::memset(v_params, 0, sizeof(T) * n_list * 9);
+  // tabled == 5: blend_bwd4_kernel's tensor-core phase B.  Per 8x8 pixel block (a warp): v_H scaled by a power of two into fp16
+  // range and split hi + lo, nvs scaled and split hi + lo in fp16, nf rounded to fp16; origin-relative monomial sums and colour
+  // sums accumulated per (Gaussian, block), shifted to the mean (chs_shift_moments) and unscaled.
+  auto h16 = [](T v) { return (T)(float)(_Float16)(float)v; };
+  auto block_of = [&](int p) {
+    const int bx = (int)floor((pix_xy[p * 2] - T(0.5)) / 8), by = (int)floor((pix_xy[p * 2 + 1] - T(0.5)) / 8);
+    return by * 4096 + bx;
+  };
+  std::map<int, T> blk_vmax, blk_ebound;
+  std::map<int, std::vector<T>> blk_sums;  // block -> [n_list][9] (S1, Sx, Sy, Sxx, Sxy, Syy, Gr, Gg, Gb), scaled
+  if (tabled >= 5) {
+    T cbnd = 0;  // the kernel keeps a running bound over the staged batches; one batch here
+    for (int j = 0; j < n_list; ++j) cbnd = chs_max(cbnd, (T)(fabs((double)sp[j].cr) + fabs((double)sp[j].cg) + fabs((double)sp[j].cb)));
+    for (int p = 0; p < n_pix; ++p) {
+      T& m = blk_vmax[block_of(p)];
+      for (int ch = 0; ch < 3; ++ch) m = chs_max(m, (T)fabs((double)v_hdr[p * 3 + ch]));
+    }
+    for (int p = 0; p < n_pix; ++p) {  // |e| = |R - s| <= 2 max(|R0|, max_j |s_j|),  |s_j| <= (|cr| + |cg| + |cb|) vmax
+      const int b = block_of(p);
+      const T r0 = (T)fabs((double)((bg[0] * v_hdr[p * 3] + bg[1] * v_hdr[p * 3 + 1] + bg[2] * v_hdr[p * 3 + 2]) - v_alpha[p]));
+      T& eb = blk_ebound[b];
+      eb = chs_max(eb, 2 * chs_max(r0, cbnd * blk_vmax[b]));
+    }
+  }
   for (int p = 0; p < n_pix; ++p) {
     T px = pix_xy[p * 2], py = pix_xy[p * 2 + 1];
     T Tr = 1, acc[3] = {0, 0, 0};
@@ -128,6 +153,29 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
         chs_pair_moments(nvs, nf, dx, dy, u, vh, &moments[(size_t)j * 9]);
         continue;
       }
+      if (tabled >= 5) {  // 6: the kernel (alpha T as fp16 hi + lo); what-ifs: 5: alpha T single fp16; 7: alpha T and v_H single
+        T nvs, nf;
+        chs_pair_bwd_scalars_r(sp[j], au, chs_min(ChsK<T>::alpha_max, au), Tr, Rn, vh, nvs, nf);
+        const int b = block_of(p);
+        int e;
+        frexp((double)blk_vmax[b], &e);              // vmax = f 2^e, f in [0.5, 1)
+        const T sv = (T)ldexp(1.0, -e);              // scale of v_H: |v_H| sv < 1
+        frexp((double)blk_ebound[b], &e);
+        const T sn = (T)ldexp(1.0, 14 - e);          // scale of nvs: |nvs| sn <= |e| sn < 2^14
+        std::vector<T>& S = blk_sums[b];
+        if (S.empty()) S.assign((size_t)n_list * 9, T(0));
+        const T x = px - (floor((px - T(0.5)) / 8) * 8 + T(0.5)), y = py - (floor((py - T(0.5)) / 8) * 8 + T(0.5));
+        const T hi = h16(nvs * sn), lo = h16(nvs * sn - hi), q = hi + lo;
+        const T mono[6] = {T(1), x, y, x * x, x * y, y * y};
+        for (int k = 0; k < 6; ++k) S[(size_t)j * 9 + k] += q * mono[k];
+        const T fs = nf * T(16384);
+        const T fhi = h16(fs), flo = tabled == 6 ? h16(fs - fhi) : T(0);
+        for (int ch = 0; ch < 3; ++ch) {
+          const T vhi = h16(vh[ch] * sv), vlo = tabled == 7 ? T(0) : h16(vh[ch] * sv - vhi);
+          S[(size_t)j * 9 + 6 + ch] += (fhi * vhi + fhi * vlo) + (flo * vhi + flo * vlo);
+        }
+        continue;
+      }
       if (tabled) {
         T vs, f;
         chs_pair_bwd_scalars(sp[j], au, chs_min(ChsK<T>::alpha_max, au), Tr, buf, vh, va_t, vs, f);
@@ -156,7 +204,25 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
       for (int k = 0; k < 9; ++k) v_params[j * 9 + k] += g[k];
     }
   }
-  if (tabled == 4)
+  if (tabled >= 5) {
+    for (auto& kv : blk_sums) {
+      const int b = kv.first;
+      const T bxc = (T)(b % 4096) * 8 + T(0.5), byc = (T)(b / 4096) * 8 + T(0.5);
+      int e;
+      frexp((double)blk_vmax[b], &e);
+      const T inv_sv = (T)ldexp(1.0, e - 14);  // also undoes the 2^14 of nf
+      frexp((double)blk_ebound[b], &e);
+      const T inv_sn = (T)ldexp(1.0, e - 14);
+      for (int j = 0; j < n_list; ++j) {
+        const T* S = &kv.second[(size_t)j * 9];
+        T m[6];
+        chs_shift_moments(S[0], S[1], S[2], S[3], S[4], S[5], sp[j].mx - bxc, sp[j].my - byc, sp[j].r, m);
+        for (int k = 0; k < 6; ++k) moments[(size_t)j * 9 + k] += m[k] * inv_sn;
+        for (int ch = 0; ch < 3; ++ch) moments[(size_t)j * 9 + 6 + ch] += S[6 + ch] * inv_sv;
+      }
+    }
+    for (int j = 0; j < n_list; ++j) chs_moments_to_grads_neg(sp[j], &moments[(size_t)j * 9], v_params + (size_t)j * 9);
+  } else if (tabled == 4)
     for (int j = 0; j < n_list; ++j) chs_moments_to_grads_neg(sp[j], &moments[(size_t)j * 9], v_params + (size_t)j * 9);
   else if (tabled)
     for (int j = 0; j < n_list; ++j) chs_moments_to_grads(sp[j], &moments[(size_t)j * 9], v_params + (size_t)j * 9);
@@ -205,6 +271,15 @@ void hs_blend_tabled_f32(int n_list, const float* params, int n_pix, const float
 void hs_blend_tabled_r_f64(int n_list, const double* params, int n_pix, const double* pix_xy, const double* bg, const double* v_hdr,
                            const double* v_alpha, double* out_hdr, double* out_alpha, int32_t* out_last, double* v_params) {
   blend_impl<double>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 4);
+}
+void hs_blend_tabled_mma_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
+                             const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {
+  blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, 6);  // the kernel's form
+}
+void hs_blend_tabled_mma_variant_f32(int mode, int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg,
+                                     const float* v_hdr, const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last,
+                                     float* v_params) {
+  blend_impl<float>(n_list, params, n_pix, pix_xy, bg, v_hdr, v_alpha, out_hdr, out_alpha, out_last, v_params, mode);
 }
 void hs_blend_tabled_r_f32(int n_list, const float* params, int n_pix, const float* pix_xy, const float* bg, const float* v_hdr,
                            const float* v_alpha, float* out_hdr, float* out_alpha, int32_t* out_last, float* v_params) {

@@ -287,6 +287,41 @@ def test_design_study_low_precision_table():
     assert worst["fp32"] < 5e-6 and 5e-5 < worst["fp16"] < 1e-3 and worst["bf16"] > 1e-3, worst
 
 
+@pytest.mark.parametrize("scale", [1.0, 1e-7, 3e4])
+def test_tensor_core_phase_b_precision(scale):
+    """blend_bwd4_kernel's phase B as arithmetic: fp16 hi + lo splits of the scaled dL/dsigma and alpha T tables and of the
+    upstream gradient, sums against block-origin pixel monomials, shift to the mean (chs_shift_moments).  Must match the fp32
+    table whatever the magnitude of the upstream gradient (power-of-two scaling per 8x8 block)."""
+    m, conic, o, col, pix, bg = _tile_case()
+    m = m + torch.tensor([40.0, -25.0]) * (torch.arange(m.shape[0]) % 3 == 0)[:, None]  # some means far outside the tile
+    n_list, n_pix = m.shape[0], pix.shape[0]
+    leaves = [t.clone().requires_grad_(True) for t in (m, conic, o, col)]
+    hdr, alpha, _ = oracle.blend(leaves[0][None], leaves[1][None], leaves[2], leaves[3], torch.arange(n_list, dtype=torch.int32),
+                                 torch.tensor([0, n_list]), n_list, 16, 16, background=bg)
+    g = torch.Generator().manual_seed(3)
+    vh, va = torch.randn(16, 16, 3, generator=g) * scale, torch.randn(16, 16, generator=g) * scale
+    vh[:8, :8] *= 1e-3  # blocks of very different magnitude
+    grads = torch.autograd.grad((hdr[0] * vh).sum() + (alpha[0] * va).sum(), leaves)
+    ref = torch.cat([grads[0], grads[1], grads[2][:, None], grads[3]], 1).numpy()
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np.float32))
+    params = arr(torch.cat([m, conic, o[:, None], col], 1))
+    errs = {}
+    for name in ["tabled_r", "tabled_mma"]:
+        o_h = np.zeros((n_pix, 3), np.float32); o_a = np.zeros(n_pix, np.float32); o_l = np.zeros(n_pix, np.int32)
+        o_v = np.zeros((n_list, 9), np.float32)
+        getattr(HS, f"hs_blend_{name}_f32")(n_list, _p(params), n_pix, _p(arr(pix)), _p(arr(bg)), _p(arr(vh.reshape(-1, 3))),
+                                            _p(arr(va.reshape(-1))), _p(o_h), _p(o_a), _p(o_l), _p(o_v))
+        errs[name] = [np.linalg.norm(o_v[:, k] - ref[:, k]) / np.linalg.norm(ref[:, k]) for k in range(9)]
+    # as accurate as the fp32 table of blend_bwd3_kernel
+    assert max(errs["tabled_mma"]) < 3 * max(max(errs["tabled_r"]), 1e-6), errs
+    # what-if kept for the record: alpha T as a single fp16 would put the colour gradients at 4e-4, too close to the 1e-3 bar
+    o_v = np.zeros((n_list, 9), np.float32)
+    HS.hs_blend_tabled_mma_variant_f32(5, n_list, _p(params), n_pix, _p(arr(pix)), _p(arr(bg)), _p(arr(vh.reshape(-1, 3))),
+                                       _p(arr(va.reshape(-1))), _p(o_h), _p(o_a), _p(o_l), _p(o_v))
+    single = max(np.linalg.norm(o_v[:, k] - ref[:, k]) / np.linalg.norm(ref[:, k]) for k in range(6, 9))
+    assert 5e-5 < single < 1e-3, single
+
+
 def test_block_cull_bound_is_conservative_and_tight():
     """chs_block_max_power >= max over the block's pixel centres (never culls a live pair) and is tight."""
     g = torch.Generator().manual_seed(9)
