@@ -78,17 +78,26 @@ class BufferPool:
             t = self._bufs[key] = torch.empty(tuple(shape), dtype=dtype, device=device)
         return t
 
+    def get_pinned(self, name, shape, dtype):
+        """A pinned host buffer, allocated once per name (CUDA-graph capture cannot allocate pinned memory)."""
+        key = ("pinned", name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        return t
+
     def bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+        return sum(t.numel() * t.element_size() for t in self._bufs.values() if t.is_cuda)
 
 
 def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposure, crf_params, cfg, spline=None,
-                   want_keys=False, sh=None, sh_degree=0, isect_capacity=None, pool=None) -> _State:
+                   want_keys=False, sh=None, sh_degree=0, isect_capacity=None, pool=None, pinned_name=None) -> _State:
     """Run K0-K6 through the C ABI. All tensors CUDA fp32 contiguous. Returns the stage buffers.
     With ``sh`` [N,K,3] the colours are view dependent (chs_sh_fwd, per-camera records) and ``colors`` is ignored.
     ``isect_capacity``: size the intersection buffers for that many entries and never synchronise with the host (K2's count
     stays on the device, chs_bin_sort_dev reads it there; ``st.n_isect`` / ``st.overflowed`` resolve it lazily).
-    ``pool``: a BufferPool to take the stage buffers from instead of allocating them."""
+    ``pool``: a BufferPool to take the stage buffers from instead of allocating them.  ``pinned_name``: take the pinned
+    landing buffer of M from the pool under that name (required inside a CUDA-graph capture, see parallel.GraphedStep)."""
     L = _lib.lib()
     dev = means.device
 
@@ -150,10 +159,14 @@ def forward_stages(means, quats, scales, opacities, colors, viewmats, Ks, exposu
                               None, ptr(work), work.numel(), s), "chs_bin_count")
         M = st.isect_capacity
         st._n_isect = None
-        st._n_pinned = torch.empty((1,), dtype=torch.int64).pin_memory()
+        capturing = torch.cuda.is_current_stream_capturing()
+        # (under CUDA-graph capture the copy becomes a node of the graph and lands in a buffer that outlives it)
+        st._n_pinned = pool.get_pinned(pinned_name or "n_isect", (1,), torch.int64) if (pool is not None and (capturing or pinned_name)) \
+            else torch.empty((1,), dtype=torch.int64).pin_memory()
         st._n_pinned.copy_(n_dev, non_blocking=True)
-        st._n_event = torch.cuda.Event()
-        st._n_event.record()
+        if not capturing:
+            st._n_event = torch.cuda.Event()
+            st._n_event.record()
     # K3-K5
     ws = _lib.workspace_sizes(cfg, M, st.n_knots)
     work = _empty((max(int(ws.bin_sort_bytes), 256),), torch.uint8, dev)

@@ -1743,8 +1743,10 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
   if (cfg->crf_before_average) {
     if (cfg->tune_blend_fwd == 8)
       blend_fwd_kernel<8, true><<<grid, kThreads, dyn, s>>>(a);
-    else
+    else if (cfg->tune_blend_fwd == 27)
       blend_fwd2_kernel<8, true, false><<<grid, kThreads, dyn, s>>>(a);
+    else
+      blend_fwd2_kernel<7, true, false, true><<<grid, kThreads, dyn, s>>>(a);
   } else {
     switch (cfg->tune_blend_fwd) {  // development knob (chs_config)
       case 1: blend_fwd_kernel<6, false><<<grid, kThreads, dyn, s>>>(a); break;

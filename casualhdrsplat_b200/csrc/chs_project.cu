@@ -297,6 +297,8 @@ extern "C" int chs_project_bwd(const chs_config* cfg, const float* means, const 
     int blocks = (d.N + kThreads - 1) / kThreads;
     // resident blocks per SM (chs_config.tune_project_bwd).  The kernel is latency-bound, so occupancy beats spills (r2p, c3):
     // 2 (115 registers, no spills) 0.450 ms | 3 (80 registers) 0.346 | 4 (64 registers, 176 B of spills) 0.318 (default)
+    // r2x negative result: requesting the next camera's 40 bytes before this camera's arithmetic (software prefetch) made it
+    // slower at every occupancy (0.412 | 0.349 | 0.355): the extra live registers cost more than the overlap gains
     const int mb = cfg->tune_project_bwd ? cfg->tune_project_bwd : 4;
     if (smem > 48 * 1024) {
       CHS_CUDA(cudaFuncSetAttribute(project_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

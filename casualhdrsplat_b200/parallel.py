@@ -199,9 +199,12 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
     first = True
     ids_all = list(frame_ids)
     n_isect_total, m_g_total = 0, 0
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing and state is None:
+        raise RuntimeError("formation_step: CUDA-graph capture needs a warmed-up StepState (see GraphedStep)")
     for s in range(0, len(ids_all), micro_batch):
         ids = ids_all[s:s + micro_batch]
-        idx = torch.as_tensor(ids, device=dev)
+        idx = state.index(tuple(ids), dev) if state is not None else torch.as_tensor(ids, device=dev)
         ft, ex, Ks = params["frame_times"][idx].contiguous(), params["exposure_times"][idx].contiguous(), params["Ks"][idx].contiguous()
         cfg = _lib.make_config(N, len(ids), n_virtual, width, height, crf_kind=crf_kind,
                                crf_hidden=_lib.crf_size(crf_kind, crf_params),
@@ -209,10 +212,15 @@ def formation_step(params: Dict[str, torch.Tensor], spline_meta: dict, width: in
                                tight_bounds=tight_bounds, pose_fused=pose_fused, tuning=tuning)
         spline = (knots, float(spline_meta["knot_t0"]), float(spline_meta["knot_dt"]), ft, int(spline_meta["kind"]))
         cap = state.capacity(tuple(ids)) if state is not None else None
+        if capturing and cap is None:
+            raise RuntimeError("formation_step: capture before the StepState has learnt the intersection counts")
         # (the step that learns M sizes its buffers exactly, per frame batch: those do not go into the pool)
         pool = state.pool if (state is not None and cap is not None) else None
-        st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline, isect_capacity=cap, pool=pool)
-        if state is not None:
+        st = forward_stages(means, quats, scales, opacities, colors, None, Ks, ex, crf_params, cfg, spline, isect_capacity=cap, pool=pool,
+                            pinned_name=f"n_isect{tuple(ids)}" if capturing else None)
+        if capturing:
+            state.graph_counts.append((tuple(ids), st._n_pinned, cap))  # checked by GraphedStep.verify after a replay
+        elif state is not None:
             state.track(tuple(ids), st)
         v_ldr = upstream(ids, st.ldr).contiguous()
         # the first micro-batch writes K9's output straight into the flat buffer (which may be symmetric memory)
@@ -323,9 +331,18 @@ class StepState:
         self._last = {}      # frame ids -> last resolved M
         self._pending = []   # (frame ids, forward state) of steps not verified yet
         self.overflows = []  # (frame ids, M, capacity) of frames that outgrew their buffers
+        self._idx = {}       # frame ids -> device index tensor (made once: a capture cannot copy from pageable memory)
+        self.graph_counts = []  # (frame ids, pinned M, capacity) of a captured step
+
+    def index(self, ids, device):
+        t = self._idx.get(ids)
+        if t is None:
+            t = self._idx[ids] = torch.as_tensor(list(ids), device=device)
+        return t
 
     def capacity(self, ids):
-        self._resolve(keep_last=True)
+        if not torch.cuda.is_current_stream_capturing():  # (a capture may not query events; GraphedStep resolves beforehand)
+            self._resolve(keep_last=True)
         if self._cap.get(ids) is None:
             return None
         # one capacity for all frame batches (rounded up to 1 Mi entries), so that the pooled buffers have one shape
@@ -363,3 +380,43 @@ class StepState:
 
     def last_total(self) -> int:
         return int(sum(self._last.values()))
+
+
+class GraphedStep:
+    """``formation_step`` of one rank captured in a CUDA graph and replayed (single process; the all-reduce stays outside).
+
+    The sync-free step launches ~70 kernels per frame from Python; for small scenes (BASELINE configs[1]: 100k Gaussians, 800 x 800,
+    4 poses) the host cannot feed the GPU fast enough.  Construction runs ``warmup`` eager steps (they learn every frame's
+    intersection count and fill the buffer pool), then captures one more step; ``replay()`` re-runs it with whatever the
+    parameter tensors hold NOW (same storage, same shapes).  ``upstream`` must be capturable (device work only, no host reads).
+    ``verify()`` waits for the replay and raises if a frame needed more intersections than the captured capacity.
+    """
+
+    def __init__(self, params, spline_meta, width, height, n_virtual, crf_kind, frame_ids, upstream, warmup: int = 2, **kw):
+        if kw.get("comm") is not None:
+            raise RuntimeError("GraphedStep captures the local step only; all-reduce the returned buffer after replay()")
+        self.state = kw.pop("state", None) or StepState()
+        args = (params, spline_meta, width, height, n_virtual, crf_kind, frame_ids, upstream)
+        for _ in range(max(warmup, 2)):
+            formation_step(*args, state=self.state, **kw)
+        self.state.verify()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # one more eager step on the capture stream: every lazy initialisation happens outside the graph
+            formation_step(*args, state=self.state, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        self.state.verify()
+        self.state.graph_counts = []
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.layout, self.flat = formation_step(*args, state=self.state, **kw)
+
+    def replay(self):
+        self.graph.replay()
+        return self.layout, self.flat
+
+    def verify(self) -> None:
+        torch.cuda.current_stream().synchronize()
+        bad = [(ids, int(p.item()), cap) for ids, p, cap in self.state.graph_counts if int(p.item()) > cap]
+        if bad:
+            raise RuntimeError(f"GraphedStep: intersection buffers overflowed for {bad}; rebuild the graph")

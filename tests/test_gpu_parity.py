@@ -742,3 +742,34 @@ def test_pose_fused_static_camera_is_the_per_pose_model():
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     for k in a[3]:
         assert rel(b[3][k], a[3][k]) <= 1e-5, k  # atomics order only
+
+
+def test_graphed_step_matches_eager_and_survives_parameter_updates():
+    """the sync-free step is capturable in a CUDA graph.  A replay equals the eager step (atomics order
+    aside), follows in-place parameter updates, and its intersection counts are checked after the fact."""
+    from casualhdrsplat_b200.parallel import GraphedStep, StepState, formation_step
+
+    sc = make_scene(6000, 192, 128, n_frames=3, n_virtual=3, crf_hidden=32, scale_mult=5.0)
+    dev = torch.device("cuda", 0)
+    names = ["means", "quats", "scales", "opacities", "colors", "knots", "frame_times", "exposure_times", "Ks", "crf_params"]
+    P = {k: getattr(sc, k).to(dev).contiguous() for k in names}
+    v = sc.v_ldr.to(dev)
+    idx = {i: torch.tensor([i], device=dev) for i in range(sc.n_frames)}
+    up = lambda f, ldr: torch.cat([v.index_select(0, idx[i]) for i in f])  # noqa: E731  (device-only: capturable)
+    meta = {"knot_t0": sc.knot_t0, "knot_dt": sc.knot_dt, "kind": sc.spline_kind}
+    args = (P, meta, sc.width, sc.height, sc.n_virtual, sc.crf_kind, list(range(sc.n_frames)), up)
+    kw = dict(micro_batch=1, tight_bounds=True)
+    gs = GraphedStep(*args, **kw)
+    for trial in range(2):
+        lay, flat = gs.replay()
+        gs.verify()
+        got = flat.clone()
+        _, ref = formation_step(*args, state=StepState(), **kw)
+        torch.cuda.synchronize()
+        for name, view in lay.views(got).items():
+            want = lay.views(ref)[name]
+            err = float((view - want).norm() / want.norm().clamp(min=1e-30))
+            assert err < 1e-5, (trial, name, err)
+        assert float(got.abs().sum()) > 0
+        P["means"].add_(0.003 * torch.randn_like(P["means"]))  # an optimiser step: same storage, new values
+        P["colors"].mul_(1.01)
