@@ -52,6 +52,8 @@ def parse():
                     "behaviour) instead of the sync-free step (capacity from the previous step, count kept on the device)")
     ap.add_argument("--pose-fused", action="store_true", help="chs_config.pose_fused: one tile list per (frame, tile) shared by the frame's "
                     "virtual poses (a flagged variant of the model, SURVEY.md 8(f) row f1); the default is the per-pose model")
+    ap.add_argument("--micro-batch", type=int, default=0, help="frames per launch of every kernel (0 = as many of the rank's frames as fit "
+                    "in 60 %% of the free HBM: 8 for c4, 1 for c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-tiles", type=int, default=48, help="tiles in the CPU-oracle sample")
@@ -267,10 +269,11 @@ def main():
     tight = args.bounds == "tight"
 
     step_state = None  # created after the warm-up that measures M
+    mb = 1             # frames per launch; chosen after the first warm-up step has shown what one frame needs
 
     def step(upstream, st=None, params=None, tight_bounds=None):
         nonlocal flat
-        layout, flat = formation_step(P if params is None else params, spline_meta, W, H, n, sc.crf_kind, ids, upstream, micro_batch=1, sort_mode=args.sort_mode,
+        layout, flat = formation_step(P if params is None else params, spline_meta, W, H, n, sc.crf_kind, ids, upstream, micro_batch=mb, sort_mode=args.sort_mode,
                                       comm=comm, out=flat, stats=st, tight_bounds=tight if tight_bounds is None else tight_bounds,
                                       state=step_state if tight_bounds is None else None,
                                       pose_fused=args.pose_fused and tight_bounds is None)
@@ -293,10 +296,28 @@ def main():
     # The algorithmic unit count M is the number of intersections of the reference binning (3-sigma square bounds); with
     # --bounds tight fewer are emitted, so one extra untimed step in square mode measures M itself.
     m_ref = None
+    torch.cuda.synchronize()
+    mem0 = torch.cuda.memory_allocated()
+    torch.cuda.reset_peak_memory_stats()
     if tight:
         ref_stats = {"count_pairs": False}
         step(upstream_fixed, ref_stats, tight_bounds=False)
         m_ref = ref_stats["n_isect"]
+    else:
+        step(upstream_fixed, {"count_pairs": False})
+    # Frames per launch.  Batching the rank's frames into one launch of every kernel amortises the ~70 small launches per frame
+    # and the tail of the per-frame grids (r2y, c4: 8.25 -> 7.55 ms per frame at 8 frames per launch); it costs memory
+    # (every stage buffer is per camera), so the batch is what fits beside the rest
+    torch.cuda.synchronize()
+    per_frame = max(torch.cuda.max_memory_allocated() - mem0, 1)
+    free_b, _total_b = torch.cuda.mem_get_info()
+    torch.cuda.empty_cache()
+    free_b, _total_b = torch.cuda.mem_get_info()
+    mb = args.micro_batch if args.micro_batch > 0 else max(1, min(len(ids), int(0.6 * free_b / per_frame)))
+    if world > 1:  # one choice for all ranks (the kernels' grids differ otherwise, nothing else)
+        t_mb = torch.tensor([mb], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_mb, op=dist.ReduceOp.MIN)
+        mb = int(t_mb.item())
     for _ in range(max(args.warmup, 3)):
         layout = step(upstream_fixed, stats)
     stats["count_pairs"] = False
@@ -497,7 +518,8 @@ def main():
     def k8_bytes(m):
         return 40 * m + 36 * Mg_f + 8 * n * Ppix + 12 * 1 * Ppix
 
-    bwd_bytes = k8_bytes(M_f)
+    fpl = len(ids) / max(len(bwd_calls) / max(args.steps, 1), 1)  # frames per K8 launch (= the micro-batch)
+    bwd_bytes = k8_bytes(M_f) * fpl
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
     # static facts of one K8 launch from the committed ncu capture of this kernel revision (not re-measured per run)
     prof, prof_src = {}, None
@@ -509,16 +531,20 @@ def main():
     sm_hz = (clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965) * 1e6
     issue_frac = None
     if prof.get("warp_inst_per_launch") and bwd_ms > 0 and args.workload in ("c3", "c4"):
-        issue_frac = prof["warp_inst_per_launch"] / (148 * 4 * sm_hz * bwd_ms * 1e-3)
+        issue_frac = prof["warp_inst_per_launch"] * fpl / (148 * 4 * sm_hz * bwd_ms * 1e-3)
+    static_ok = args.workload in ("c3", "c4")
     roofline = {"bound": "hbm", "kernel": "blend_bwd3_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch") if args.workload in ("c3", "c4") else None,
+                "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch") * fpl if (static_ok and prof) else None,
                 "traffic_source": prof_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
-                "launch_ms": bwd_ms, "isects_per_launch": M_f,
-                "frac_at_reference_isects": k8_bytes(M_ref_f) / (bwd_ms * 1e-3) / 1e9 / peak if bwd_ms > 0 else 0.0,
-                "reference_isects_per_launch": M_ref_f,
-                "issue_frac": issue_frac, "issue_frac_note": "warp instructions of one launch (static, ncu) / (148 SMs x 4 schedulers x SM clock x "
-                "launch time): the kernel is issue-bound, not HBM-bound (DRAM traffic is below the algorithmic bytes: the per-camera records "
-                "stay in L2)"}
+                "launch_ms": bwd_ms, "frames_per_launch": fpl, "isects_per_launch": M_f * fpl,
+                "frac_at_reference_isects": k8_bytes(M_ref_f) * fpl / (bwd_ms * 1e-3) / 1e9 / peak if bwd_ms > 0 else 0.0,
+                "reference_isects_per_launch": M_ref_f * fpl,
+                "issue_frac": issue_frac,
+                "smem_pipe_frac": prof.get("lsu_wavefronts_pct_of_peak", 0.0) / 100.0 if (static_ok and prof) else None,
+                "competing_bounds_note": "issue_frac = warp instructions of the launch (static, ncu, scaled by frames per launch) / (148 SMs x 4 "
+                "schedulers x SM clock x launch time); smem_pipe_frac = l1tex__data_pipe_lsu_wavefronts of the committed ncu capture as a "
+                "fraction of its peak (static).  The kernel is bound by the shared-memory data pipe and instruction issue together, not by "
+                "HBM: its DRAM traffic is 4x below the algorithmic bytes (the per-camera records stay in L2)"}
     # bytes the EXECUTED algorithm must move per frame (not the 7-pass 64-bit sort A.4 specifies): K2 = 4 passes of 8-byte pairs over
     # the C*N depth keys + the gathered scan; K3-K5 = emit (6 B) + two multisplit passes (count 2 + 11 B, count 1 + 9 B)
     Cn = n
@@ -544,7 +570,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload}: BASELINE.json configs[{ {'c1': 0, 'c2': 1, 'c3': 2, 'c4': 3, 'c5': 4}.get(args.workload, '?') }] — {N} Gaussians, {W}x{H}, {n} virtual poses/frame, "
                                        f"global batch {B} frames sharded by frame, fwd+bwd incl. pose/exposure/CRF grads",
-                           "frames_per_gpu": len(ids), "micro_batch_frames": 1, "sort_mode": args.sort_mode, "tile_bounds": args.bounds,
+                           "frames_per_gpu": len(ids), "micro_batch_frames": mb, "sort_mode": args.sort_mode, "tile_bounds": args.bounds,
                            "host_syncs_per_step": len(ids) if args.host_sync else 0, "pose_fused": bool(args.pose_fused),
                            "isects_emitted_per_frame": m_emitted / n_local,
                            "isects_per_frame": M_ref_f, "l2": "inputs larger than L2 (per-frame working set > 1 GB vs 126 MB L2)",
