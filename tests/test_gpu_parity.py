@@ -773,3 +773,32 @@ def test_graphed_step_matches_eager_and_survives_parameter_updates():
         assert float(got.abs().sum()) > 0
         P["means"].add_(0.003 * torch.randn_like(P["means"]))  # an optimiser step: same storage, new values
         P["colors"].mul_(1.01)
+
+
+KERNEL_VARIANTS = {
+    "bwd_tensor_core": {"blend_bwd": 47},       # blend_bwd4_kernel: phase B as mma.sync over fp16 hi + lo tables
+    "bwd_tensor_core_8": {"blend_bwd": 48},
+    "fwd_ungrouped": {"blend_fwd": 27},         # the pair loop without the speculative group of four
+    "scatter_warp_per_tile": {"bin_chunk": 1},  # P2 scatter with a warp per tile
+}
+
+
+@pytest.mark.parametrize("variant", sorted(KERNEL_VARIANTS))
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_opt_in_kernel_variants_match_the_oracle(name, variant):
+    """Every kernel instantiation kept behind a chs_config.tune_* knob (measured alternatives of the defaults) meets the same
+    bars: forward 1e-4, every gradient 1e-3, identical intersection count."""
+    sc = make_config(name)
+    g = torch.Generator().manual_seed(11)
+    v_alpha = torch.randn(sc.n_frames, sc.height, sc.width, 1, generator=g, dtype=torch.float32)
+    ldr, _, meta, grads = cuda_run(sc, v_alpha=v_alpha, tuning=KERNEL_VARIANTS[variant], tight_bounds=True)
+    o_ldr, _, o_meta, o_grads = oracle_run(sc, v_alpha=v_alpha, projection_override=cuda_projection(meta), straight_through=True,
+                                           tight_bounds=True)
+    assert rel(ldr, o_ldr) <= FWD_TOL
+    errs = {k: rel(grads[k], o_grads[k]) for k in grads if float(o_grads[k].norm()) > 0}
+    bad = {k: e for k, e in errs.items() if not e <= GRAD_TOL}
+    assert not bad, f"{variant}: gradient rel errors above {GRAD_TOL}: {bad} (all: {errs})"
+    ldr0, _, meta0, grads0 = cuda_run(sc, v_alpha=v_alpha, tight_bounds=True)
+    assert meta0["n_isect"] == meta["n_isect"]
+    if variant != "bwd_tensor_core" and variant != "bwd_tensor_core_8":
+        assert torch.equal(ldr0, ldr)  # forward and binning variants are bit-identical to the defaults
