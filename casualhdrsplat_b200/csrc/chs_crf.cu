@@ -187,6 +187,174 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_kernel(CrfBwdArg
     if (s_g[i] != 0.f) atomicAdd(&a.acc_crf[i], (double)s_g[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// MLP CRF, interval form (default since r3b).  With a scalar input z the network  sum_j w2_j relu(w1_j z + b1_j) + b2  is
+// piecewise linear in z: unit j switches at t_j = -b1_j / w1_j.  Per block the Hd breakpoints of a channel are ranked once
+// (Hd^2 compares), and for each of the Hd + 1 intervals the slope A_I = sum_{j on} w2_j w1_j and offset B_I = b2 + sum_{j on}
+// w2_j b1_j are tabulated.  A pixel then costs a binary search and one fma instead of Hd units (phase 1 of crf_bwd_kernel: 4 Hd
+// instructions per pixel and channel), and the parameter gradients need only two sums per INTERVAL,
+//     H_I = sum_{pix in I} g,   HZ_I = sum_{pix in I} g z          (g = v_y y (1 - y)),
+// because "unit j is on at this pixel" is a statement about the pixel's interval:  S_j = sum_{I: j on} H_I,  SZ_j likewise, and
+//     dL/dw2_j = w1_j SZ_j + b1_j S_j,   dL/dw1_j = w2_j SZ_j,   dL/db1_j = w2_j S_j,   dL/db2 = sum_I H_I.
+// Neighbouring pixels fall into the same one to three intervals, so a warp adds its 32 values per distinct interval with one
+// shuffle reduction and a plain store into a warp-private table (no atomics, no per-unit loop: phase 2 of crf_bwd_kernel was
+// 15 instructions per pixel and channel).  A unit whose pre-activation is within rounding of zero may be classified differently
+// from the forward's `pre > 0`; its contribution to the value is continuous there and the affected pixels have measure zero.
+// ---------------------------------------------------------------------------------------------
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_interval_kernel(CrfBwdArgs a) {
+  extern __shared__ float smem[];
+  const int hd = a.hd, stride = 3 * hd + 1, nI = hd + 1;
+  float* s_p = smem;                      // parameters [3, stride]
+  float* s_g = s_p + 3 * stride;          // block-partial parameter gradients [3, stride]
+  float* s_bp = s_g + 3 * stride;         // sorted breakpoints [3][hd]
+  float* s_A = s_bp + 3 * hd;             // [3][nI] slope of the interval
+  float* s_B = s_A + 3 * nI;              // [3][nI] offset
+  int* s_key = reinterpret_cast<int*>(s_B + 3 * nI);  // [3][hd] unit j is on in interval I  <=>  sgn_j * I + off_j >= 0 (key = off_j * 2 + (sgn_j < 0))
+  float* s_H = reinterpret_cast<float*>(s_key + 3 * hd);  // [warps][3][nI][2] warp-private interval sums (g, g z)
+  const int img = blockIdx.y;
+  const int frame = img / a.imgs_per_frame;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 3 * stride; i += kThreads) {
+    s_p[i] = a.crf_params[i];
+    s_g[i] = 0.f;
+  }
+  for (int i = tid; i < (kThreads / 32) * 3 * nI * 2; i += kThreads) s_H[i] = 0.f;
+  __syncthreads();
+  const float kInf = __int_as_float(0x7f800000);
+  // rank of every unit's breakpoint inside its channel (ties by unit index); units with w1 = 0 never switch: breakpoint +inf
+  for (int i = tid; i < 3 * hd; i += kThreads) {
+    const int ch = i / hd, j = i - ch * hd;
+    const float* p = s_p + ch * stride;
+    const float w1 = p[j], b1 = p[hd + j];
+    const float t = w1 != 0.f ? -b1 / w1 : kInf;
+    int r = 0;
+    for (int k = 0; k < hd; ++k) {
+      const float wk = p[k];
+      const float tk = wk != 0.f ? -p[hd + k] / wk : kInf;
+      r += (tk < t || (tk == t && k < j)) ? 1 : 0;
+    }
+    s_bp[ch * hd + r] = t;
+    // w1 > 0: on  <=>  z > t_j  <=>  I >= r + 1;   w1 < 0: on  <=>  z < t_j  <=>  I <= r;   w1 = 0: on  <=>  b1 > 0 (every interval)
+    int sgn = 1, off = -(r + 1);
+    if (w1 < 0.f) { sgn = -1; off = r; }
+    if (w1 == 0.f) { sgn = 1; off = b1 > 0.f ? 0 : -(hd + 1); }
+    s_key[i] = off * 2 + (sgn < 0 ? 1 : 0);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * nI; i += kThreads) {
+    const int ch = i / nI, I = i - ch * nI;
+    const float* p = s_p + ch * stride;
+    float A = 0.f, B = p[3 * hd];
+    for (int j = 0; j < hd; ++j) {
+      const int key = s_key[ch * hd + j];
+      const int d = (key & 1) ? (key >> 1) - I : I + (key >> 1);
+      if (d >= 0) {
+        A = fmaf(p[2 * hd + j], p[j], A);
+        B = fmaf(p[2 * hd + j], p[hd + j], B);
+      }
+    }
+    s_A[i] = A;
+    s_B[i] = B;
+  }
+  __syncthreads();
+  const float dt = a.exposure[frame];
+  const float scale = dt / a.vh_div;
+  float v_dt = 0.f;
+  float* myH = s_H + warp * (3 * nI * 2);
+  const int64_t n_chunks = (a.P + (int64_t)kPix * kThreads - 1) / ((int64_t)kPix * kThreads);
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) {
+      const int64_t pix = chunk * (kPix * kThreads) + q * kThreads + tid;
+      const bool live = pix < a.P;
+      const int64_t o_img = ((int64_t)img * a.P + (live ? pix : 0)) * 3, o_frm = ((int64_t)frame * a.P + (live ? pix : 0)) * 3;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float h = live ? a.hdr_mean[o_img + ch] : 0.f;
+        const float vy = live ? a.v_ldr[o_frm + ch] * a.vy_scale : 0.f;
+        const float xe = fmaxf(dt * h, 0.f) + CHS_CRF_EPS;  // X clamped to >= 0 (chs_crf_mlp_fwd)
+        const float z = logf(xe);
+        const float* bp = s_bp + ch * hd;
+        int lo = 0, n = hd;  // I = number of breakpoints < z
+        while (n > 0) {
+          const int half = n >> 1;
+          const bool right = bp[lo + half] < z;
+          lo = right ? lo + half + 1 : lo;
+          n = right ? n - half - 1 : half;
+        }
+        const int I = lo;
+        const float A = s_A[ch * nI + I];
+        const float acc = fmaf(A, z, s_B[ch * nI + I]);
+        const float y = 1.f / (1.f + expf(-acc));
+        const float g = vy * y * (1.f - y);  // 0 for pixels past the end
+        const float vx = dt * h >= 0.f ? g * A / xe : 0.f;  // zero gradient below the clamp
+        if (live) {
+          v_dt = fmaf(vx, h, v_dt);
+          a.v_hdr[o_img + ch] = vx * scale;
+        }
+        // the warp's 32 (I, g, g z) triples, one shuffle reduction per distinct interval
+        const float gz = g * z;
+        unsigned todo = __ballot_sync(CHS_FULL_MASK, g != 0.f);
+        while (todo) {
+          const int leader = __ffs(todo) - 1;
+          const int Ib = __shfl_sync(CHS_FULL_MASK, I, leader);
+          const bool mine = (I == Ib) && g != 0.f;
+          const float sg = chs_warp_sum(mine ? g : 0.f), sgz = chs_warp_sum(mine ? gz : 0.f);
+          if (lane == leader) {
+            float* hrow = myH + (ch * nI + Ib) * 2;
+            hrow[0] += sg;
+            hrow[1] += sgz;
+          }
+          todo &= ~__ballot_sync(CHS_FULL_MASK, mine);
+          __syncwarp();  // the next leader may be another lane adding to the same interval
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // interval sums of the block, then the per-unit sums over the intervals where the unit is on
+  for (int i = tid; i < 3 * nI * 2; i += kThreads) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += s_H[w * (3 * nI * 2) + i];
+    s_H[i] = t;  // (warp 0's table becomes the block's: every thread rewrites only the entry it summed)
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * hd; i += kThreads) {
+    const int ch = i / hd, j = i - ch * hd;
+    const float* p = s_p + ch * stride;
+    const int key = s_key[i];
+    float S = 0.f, SZ = 0.f;
+    for (int I = 0; I < nI; ++I) {
+      const int d = (key & 1) ? (key >> 1) - I : I + (key >> 1);
+      if (d >= 0) {
+        S += s_H[(ch * nI + I) * 2];
+        SZ += s_H[(ch * nI + I) * 2 + 1];
+      }
+    }
+    s_g[ch * stride + j] = p[2 * hd + j] * SZ;                        // dL/dw1
+    s_g[ch * stride + hd + j] = p[2 * hd + j] * S;                    // dL/db1
+    s_g[ch * stride + 2 * hd + j] = fmaf(p[j], SZ, p[hd + j] * S);    // dL/dw2
+  }
+  if (tid < 3) {
+    float t = 0.f;
+    for (int I = 0; I < nI; ++I) t += s_H[(tid * nI + I) * 2];
+    s_g[tid * stride + 3 * hd] = t;  // dL/db2
+  }
+  __syncthreads();
+  v_dt = chs_warp_sum(v_dt);
+  __shared__ float s_dt[kThreads / 32];
+  if (lane == 0) s_dt[warp] = v_dt;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += s_dt[w];
+    atomicAdd(&a.acc_exposure[frame], (double)t);
+  }
+  for (int i = tid; i < 3 * stride; i += kThreads)
+    if (s_g[i] != 0.f) atomicAdd(&a.acc_crf[i], (double)s_g[i]);
+}
+
 __global__ void finalize_f64_to_f32(const double* src, float* dst, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (float)src[i];
@@ -224,12 +392,21 @@ extern "C" int chs_crf_bwd(const chs_config* cfg, const float* hdr_mean, const f
     a.acc_crf = acc; a.acc_exposure = acc + n_par;
     const int64_t n_chunks = (d.P + (int64_t)kThreads * kPix - 1) / ((int64_t)kThreads * kPix);
     const int n_img = per_pose ? d.C : d.B;
-    const int mb = cfg->tune_crf_bwd ? cfg->tune_crf_bwd : 4;  // development knob (chs_config): resident blocks per SM  // r1g, c3: 2 -> 0.306 ms, 3 -> 0.296, 4 -> 0.280 (previous phase-1 loop order: 0.317)
+    const int mb = cfg->tune_crf_bwd ? cfg->tune_crf_bwd % 10 : 4;  // development knob (chs_config): resident blocks per SM  // r1g, c3: 2 -> 0.306 ms, 3 -> 0.296, 4 -> 0.280 (previous phase-1 loop order: 0.317)
     int gx = (148 * mb + n_img - 1) / n_img;  // one wave of resident blocks over all images
     if (gx > n_chunks) gx = (int)n_chunks;
     dim3 grid((unsigned)gx, n_img);
     size_t smem = mlp ? ((size_t)2 * n_par + (size_t)6 * kThreads * kPix) * sizeof(float) : (size_t)2 * n_par * sizeof(float) + 16;
-    if (mb == 4)
+    if (mlp && cfg->tune_crf_bwd < 10) {  // interval form; tune_crf_bwd = 12 / 13 / 14: the per-unit kernel at 2 / 3 / 4 blocks per SM
+      const int hd = cfg->crf_hidden, nI = hd + 1;
+      const size_t smem_i = ((size_t)2 * n_par + 3 * hd + 6 * nI + 3 * hd + (size_t)(kThreads / 32) * 3 * nI * 2) * sizeof(float);
+      if (mb == 2)
+        crf_bwd_interval_kernel<2><<<grid, kThreads, smem_i, s>>>(a);
+      else if (mb == 3)
+        crf_bwd_interval_kernel<3><<<grid, kThreads, smem_i, s>>>(a);
+      else
+        crf_bwd_interval_kernel<4><<<grid, kThreads, smem_i, s>>>(a);
+    } else if (mb == 4)
       crf_bwd_kernel<4><<<grid, kThreads, smem, s>>>(a);
     else if (mb == 2)
       crf_bwd_kernel<2><<<grid, kThreads, smem, s>>>(a);

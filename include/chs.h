@@ -107,7 +107,7 @@ typedef struct chs_config {
    * instantiations and never change results beyond atomics order; see DESIGN.md section 7. */
   int32_t tune_blend_fwd;     /* 1 / 3: 6 / 10 CTAs per SM */
   int32_t tune_blend_bwd;     /* 1: direct kernel; 22: direct, four pixels per thread; 40 / 41: tabled, 16 slots */
-  int32_t tune_crf_bwd;       /* resident blocks per SM (2, 3, 4) */
+  int32_t tune_crf_bwd;       /* resident blocks per SM (2, 3, 4); + 10: the per-unit MLP kernel instead of the interval form */
   int32_t tune_bin;           /* CHS_SORT_DEPTH_PRESORT routes.  0: banded placement (default); 3: hand-written two-pass radix multisplit
                                * over emitted intersections; 1: cub::DeviceRadixSort baseline; 2: round-1 counting placement */
   int32_t tune_bin_chunk;     /* counting placement: pairs per chunk */

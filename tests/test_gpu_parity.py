@@ -780,6 +780,7 @@ KERNEL_VARIANTS = {
     "bwd_tensor_core_8": {"blend_bwd": 48},
     "fwd_ungrouped": {"blend_fwd": 27},         # the pair loop without the speculative group of four
     "scatter_warp_per_tile": {"bin_chunk": 1},  # P2 scatter with a warp per tile
+    "crf_per_unit": {"crf_bwd": 14},            # crf_bwd_kernel: the MLP CRF backward unit by unit (the default walks intervals)
 }
 
 
