@@ -533,7 +533,7 @@ def main():
     if prof.get("warp_inst_per_launch") and bwd_ms > 0 and args.workload in ("c3", "c4"):
         issue_frac = prof["warp_inst_per_launch"] * fpl / (148 * 4 * sm_hz * bwd_ms * 1e-3)
     static_ok = args.workload in ("c3", "c4")
-    roofline = {"bound": "hbm", "kernel": "blend_bwd3_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "blend_bwd5_kernel (K8)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch") * fpl if (static_ok and prof) else None,
                 "traffic_source": prof_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
                 "launch_ms": bwd_ms, "frames_per_launch": fpl, "isects_per_launch": M_f * fpl,

@@ -1175,19 +1175,19 @@ struct __align__(16) BwdWarp3 {
 // phase B for the n_slots tabled Gaussians of this warp.  Lane = (slot k = lane % 8, part = lane / 8); a part covers the two
 // pixel rows y0 = part and y0 + 4 of the warp's 8x8 block: pixel ids 16 part .. 16 part + 15, i.e. four 128-bit chunks
 // [(x, y0), (x, y0 + 4), (x + 1, y0), (x + 1, y0 + 4)] for x = 0, 2, 4, 6.
-template <int kSlots, class Smem>
-__device__ __forceinline__ void bwd_round3(const Smem& sm, const BwdWarp3<kSlots>& ws, int n_slots, int lane, float bxc, float byc,
-                                           const BlendBwdArgs& a) {
+template <int kSlots, class Smem, class Warp, class EntT>
+__device__ __forceinline__ void bwd_round3(const Smem& sm, const Warp& ws, const EntT* __restrict__ ents, int null_ent, int n_slots,
+                                           int lane, float bxc, float byc, const BlendBwdArgs& a) {
   static_assert(kSlots == 8, "phase B assigns one lane per (slot, row pair): 8 slots x 4 parts");
   __syncwarp();
   const int k = lane & 7, part = lane >> 3;
-  const bool active = k < n_slots;
+  const bool active = k < n_slots && (int)ents[k] != null_ent;
   P2 rowvs = p2s(0.f), rowt = p2s(0.f), S_xx = p2s(0.f), G6 = p2s(0.f), G7 = p2s(0.f), G8 = p2s(0.f);
   float4 sa = make_float4(0.f, 0.f, 0.f, 0.f);
   float kc = 0.f, inv_opac = 0.f, dy_lo = 0.f;
   uint32_t val = 0;
   if (active) {
-    const int jj = ws.ent[k];
+    const int jj = (int)ents[k];
     sa = sm.a[jj];  // mx, my, qa, r
     kc = sm.b[jj].x;
     const float2 sc = *reinterpret_cast<const float2*>(&sm.c[jj].z);  // 1/opacity, val
@@ -1392,7 +1392,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
         i += m;
         slots_left -= m;
         if (slots_left == 0) {
-          bwd_round3<kSlots>(sm, ws, kSlots, lane, bx0, by0, a);
+          bwd_round3<kSlots>(sm, ws, ws.ent, -1, kSlots, lane, bx0, by0, a);
           tab = tab0;
           slots_left = kSlots;
         }
@@ -1400,13 +1400,164 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
       __syncwarp();  // the list is rewritten by the next sub-batch
     }
     if (slots_left != kSlots) {  // the staged batch is about to be replaced
-      bwd_round3<kSlots>(sm, ws, kSlots - slots_left, lane, bx0, by0, a);
+      bwd_round3<kSlots>(sm, ws, ws.ent, -1, kSlots - slots_left, lane, bx0, by0, a);
       tab = tab0;
       slots_left = kSlots;
     }
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// blend_bwd5_kernel (r3c): the fp32-table backward with phase A written for instruction-level parallelism.  ncu of
+// blend_bwd3_kernel: every issued instruction waits 2.0 cycles on a fixed-latency dependency and 2.4 on a shared-memory /
+// MUFU result, because one Gaussian's chain (record load -> exponent -> ex2 -> rcp -> T -> table store) runs start to finish
+// before the next one's begins.  Here the warp culls the whole staged batch into a byte list padded with the null record
+// (as the grouped forward does) and takes the survivors four at a time in two stages: stage 1 evaluates everything that does
+// not depend on the running state for all four (alpha, 1 / (1 - alpha), c . v, the clamp gate: four independent streams),
+// stage 2 runs the two short recurrences (T: one multiply, R: subtract + fma) and stores the table rows.  Phase B is
+// bwd_round3 after every second group.
+// ---------------------------------------------------------------------------------------------
+template <int kB>
+struct __align__(16) BwdWarp5 {
+  float nvs[8][kRow3];   // -dL/dsigma of (slot, pixel id)
+  float nf[8][kRow3];    // -alpha * T of (slot, pixel id)
+  float vh[3][64];       // dL/dH of the warp's pixels by pixel id (r, g, b planes)
+  uint8_t list[kB + 4];  // survivors of the staged batch, back to front, padded to a multiple of four with kB (the null record)
+};
+
+template <int kB, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendBwdArgs a) {
+  static_assert(kB == kThreads && kB < 255, "one tile-list entry per thread and batch; staged indices fit a byte");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Smem = SplatSmem3<kB + 1>;  // entry kB: the null record
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  __shared__ int s_max_last;
+
+  const int tile = blockIdx.x, c = blockIdx.y;
+  const int frame = c / a.n_virtual;
+  const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;
+  const int tx = tile % a.tile_w, ty = tile / a.tile_w;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  BwdWarp5<kB>& ws = reinterpret_cast<BwdWarp5<kB>*>(smem_raw + sizeof(Smem))[warp];
+  const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 8;
+  const int ix = bx + (lane & 7), iy0 = by + (lane >> 3);
+  const float px = ix + 0.5f;
+  const float bx0 = bx + 0.5f, bx1 = bx + 7.5f, by0 = by + 0.5f, by1 = by + 7.5f;
+  const int64_t P = (int64_t)a.W * a.H;
+  const int lc = a.fused ? frame : c;
+  const int rec_shift = a.fused ? (c - frame) * a.N : 0;
+  const uint32_t start = a.tile_offsets[(int64_t)lc * a.tiles + tile];
+  const uint32_t end = a.tile_offsets[(int64_t)lc * a.tiles + tile + 1];
+  if (end <= start) return;
+
+  if (tid == 0) {
+    s_max_last = 0;
+    sm.a[kB] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.b[kB] = make_float4(0.f, -__int_as_float(0x7f800000), 0.f, 0.f);
+    sm.c[kB] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_nv = 1.f / (float)a.n_virtual;
+  const int vimg = a.v_hdr_per_camera ? c : frame;
+  int last[2];
+  int warp_last = 0;
+  float Tf[2] = {1.f, 1.f}, v[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, r0[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int iy = iy0 + 4 * h;
+    last[h] = 0;
+    if (ix < a.W && iy < a.H) {
+      const int64_t pix = (int64_t)iy * a.W + ix;
+      Tf[h] = a.final_T[(int64_t)c * P + pix];
+      last[h] = a.last_id[(int64_t)c * P + pix];
+      const int64_t o = ((int64_t)vimg * P + pix) * 3;
+      v[h][0] = a.v_hdr[o]; v[h][1] = a.v_hdr[o + 1]; v[h][2] = a.v_hdr[o + 2];
+      const float v_al = a.v_alpha ? a.v_alpha[(int64_t)frame * P + pix] * inv_nv : 0.f;
+      r0[h] = (a.bg[0] * v[h][0] + a.bg[1] * v[h][1] + a.bg[2] * v[h][2]) - v_al;
+    }
+    warp_last = max(warp_last, last[h]);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) ws.vh[ch][2 * lane + h] = v[h][ch];  // pixel id = 2 lane + h
+  }
+  const P2 py2 = p2(iy0 + 0.5f, iy0 + 4.5f);
+  P2 Tr2 = p2(Tf[0], Tf[1]);
+  P2 R2 = p2(r0[0], r0[1]);
+  const P2 vh_r2 = p2(v[0][0], v[1][0]), vh_g2 = p2(v[0][1], v[1][1]), vh_b2 = p2(v[0][2], v[1][2]);
+  __syncthreads();
+  warp_last = __reduce_max_sync(CHS_FULL_MASK, warp_last);
+  if (lane == 0 && warp_last > 0) atomicMax(&s_max_last, warp_last);
+  __syncthreads();
+  const int n_walk = s_max_last;
+
+  const unsigned gt = lanemask_gt_();
+  const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(&ws.nvs[0][0]) + 8u * (uint32_t)lane;
+  constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = 8 * kRow3 * 4;
+  for (int hi = n_walk; hi > 0; hi -= kB) {
+    const int lo = max(0, hi - kB);
+    const int cnt = hi - lo;
+    __syncthreads();
+    if (tid < cnt) stage_splat3(sm, tid, a.vals[start + lo + tid] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+    __syncthreads();
+    if (warp_last <= lo) continue;
+    const int lrA = last[0] - lo - 1, lrB = last[1] - lo - 1;
+    int n_surv = 0;
+    for (int sub_hi = cnt; sub_hi > 0; sub_hi -= 32) {
+      const int sub_lo = max(0, sub_hi - 32);
+      if (warp_last <= lo + sub_lo) continue;
+      const int j = sub_lo + lane;
+      const bool hit = (j < sub_hi) && (lo + j < warp_last) && splat_hits_block3(sm, j, bx0, bx1, by0, by1);
+      const unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
+      if (hit) ws.list[n_surv + __popc(mask & gt)] = (uint8_t)j;  // descending: back to front
+      n_surv += __popc(mask);
+    }
+    if (lane < 3) ws.list[n_surv + lane] = (uint8_t)kB;
+    __syncwarp();
+    for (int i = 0; i < n_surv; i += 4) {
+      const uint32_t j4 = *reinterpret_cast<const uint32_t*>(ws.list + i);
+      const uint32_t tab = tab0 + (uint32_t)(i & 4) * kRowBytes;
+      // ---- stage 1: what does not depend on T or R, for the four Gaussians ----
+      P2 na2[4], ra2[4], s2[4], gate2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = (int)((j4 >> (8 * u)) & 0xffu);
+        const float4 sa = sm.a[jj];  // mx, my, qa, r
+        const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
+        const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
+        float dx;
+        P2 dy2, u2;
+        const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
+        const float pA = p2lo(pw2), pB = p2hi(pw2);
+        const bool validA = (jj <= lrA) && pA >= CHS_LOG2_ALPHA_MIN;
+        const bool validB = (jj <= lrB) && pB >= CHS_LOG2_ALPHA_MIN;
+        const float auA = validA ? chs_exp2_fast(pA) : 0.f;
+        const float auB = validB ? chs_exp2_fast(pB) : 0.f;
+        na2[u] = p2(fmaxf(-CHS_ALPHA_MAX, -auA), fmaxf(-CHS_ALPHA_MAX, -auB));
+        const P2 om2 = p2s(1.f) + na2[u];
+        ra2[u] = p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));
+        s2[u] = fma2(p2s(cgb.y), vh_b2, fma2(p2s(cgb.x), vh_g2, p2s(sb.w) * vh_r2));
+        gate2[u] = p2(auA <= CHS_ALPHA_MAX ? 1.f : 0.f, auB <= CHS_ALPHA_MAX ? 1.f : 0.f);  // no gradient through the 0.999 clamp
+      }
+      // ---- stage 2: the two recurrences (chs_pair_bwd_scalars_r) and the table rows ----
+      auto row = [&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        Tr2 = Tr2 * ra2[u];  // transmittance before this Gaussian
+        const P2 nf2 = na2[u] * Tr2;
+        const P2 e2 = R2 - s2[u];
+        R2 = fma2(na2[u], e2, R2);
+        const P2 nvs2 = (nf2 * e2) * gate2[u];
+        asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(tab), "f"(p2lo(nvs2)), "f"(p2hi(nvs2)), "n"(u * kRowBytes));
+        asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(tab), "f"(p2lo(nf2)), "f"(p2hi(nf2)), "n"(u * kRowBytes + kFOffBytes));
+      };
+      row(std::integral_constant<int, 0>{});
+      row(std::integral_constant<int, 1>{});
+      row(std::integral_constant<int, 2>{});
+      row(std::integral_constant<int, 3>{});
+      if (i & 4) bwd_round3<8>(sm, ws, ws.list + (i - 4), kB, 8, lane, bx0, by0, a);
+    }
+    if (((n_surv + 3) >> 2) & 1)  // an odd number of groups: the last one sits alone in rows 0-3
+      bwd_round3<8>(sm, ws, ws.list + ((n_surv - 1) & ~3), kB, 4, lane, bx0, by0, a);
+  }
+}
 
 // =================================================================================================
 // Backward with phase B on the tensor cores (blend_bwd4_kernel; chs_config.tune_blend_bwd = 47).
@@ -1662,32 +1813,37 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd4_kernel(BlendB
     for (int i = 0; i < n_surv; i += 4) {
       const uint32_t j4 = *reinterpret_cast<const uint32_t*>(ws.list + i);
       const uint32_t tab = tab0 + (uint32_t)(i & 4) * kRowB;
-      auto pair = [&](auto uc) {
-        constexpr int u = decltype(uc)::value;
+      // ---- stage 1: what does not depend on T or R, for the four Gaussians (independent streams: blend_bwd5_kernel) ----
+      P2 na2[4], ra2[4], s2[4], gate2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
         const int jj = (int)((j4 >> (8 * u)) & 0xffu);
         const float4 sa = sm.a[jj];  // mx, my, qa, r
         const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
+        const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
         float dx;
         P2 dy2, u2;
         const P2 pw2 = pair_power2(sa, sb.x, sb.y, px, py2, dx, dy2, u2);
         const float pA = p2lo(pw2), pB = p2hi(pw2);
         const bool validA = (jj <= lrA) && pA >= CHS_LOG2_ALPHA_MIN;
         const bool validB = (jj <= lrB) && pB >= CHS_LOG2_ALPHA_MIN;
-        const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
         const float auA = validA ? chs_exp2_fast(pA) : 0.f;
         const float auB = validB ? chs_exp2_fast(pB) : 0.f;
-        // packed chs_pair_bwd_scalars_r with na = -alpha (and T carrying 2^14): a pixel that does not contribute runs with
-        // alpha = 0, which leaves T and R untouched and tables zeros
-        const P2 na2 = p2(fmaxf(-CHS_ALPHA_MAX, -auA), fmaxf(-CHS_ALPHA_MAX, -auB));
-        const P2 om2 = p2s(1.f) + na2;
-        Tr2 = Tr2 * p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));  // transmittance before this Gaussian
-        const P2 nf2 = na2 * Tr2;
-        const P2 s2 = fma2(p2s(cgb.y), vh_b2, fma2(p2s(cgb.x), vh_g2, p2s(sb.w) * vh_r2));
-        const P2 e2 = R2 - s2;
-        R2 = fma2(na2, e2, R2);
+        na2[u] = p2(fmaxf(-CHS_ALPHA_MAX, -auA), fmaxf(-CHS_ALPHA_MAX, -auB));
+        const P2 om2 = p2s(1.f) + na2[u];
+        ra2[u] = p2(chs_rcp_fast(p2lo(om2)), chs_rcp_fast(p2hi(om2)));
+        s2[u] = fma2(p2s(cgb.y), vh_b2, fma2(p2s(cgb.x), vh_g2, p2s(sb.w) * vh_r2));
         // no gradient through the 0.999 clamp; the gate carries the scale of the dL/dsigma table
-        const P2 gate2 = p2(auA <= CHS_ALPHA_MAX ? gate_on : 0.f, auB <= CHS_ALPHA_MAX ? gate_on : 0.f);
-        const P2 nvs2 = (nf2 * e2) * gate2;
+        gate2[u] = p2(auA <= CHS_ALPHA_MAX ? gate_on : 0.f, auB <= CHS_ALPHA_MAX ? gate_on : 0.f);
+      }
+      // ---- stage 2: the recurrences (T carries 2^14), the fp16 hi + lo splits and the table rows ----
+      auto pair = [&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        Tr2 = Tr2 * ra2[u];  // transmittance before this Gaussian
+        const P2 nf2 = na2[u] * Tr2;
+        const P2 e2 = R2 - s2[u];
+        R2 = fma2(na2[u], e2, R2);
+        const P2 nvs2 = (nf2 * e2) * gate2[u];
         const uint32_t vhi = f16x2_of(p2lo(nvs2), p2hi(nvs2));
         const P2 vres = nvs2 - f16x2_to_p2(vhi);
         const uint32_t vlo = f16x2_of(p2lo(vres), p2hi(vres));
@@ -1792,7 +1948,7 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.fused = cfg->pose_fused != 0;
   {
     const int tb = cfg->tune_blend_bwd;
-    CHS_REQUIRE(!a.fused || tb == 0 || (tb >= 35 && tb <= 39) || (tb >= 46 && tb <= 48), "chs_blend_bwd: pose_fused needs a round-2 kernel");
+    CHS_REQUIRE(!a.fused || tb == 0 || tb == 3 || (tb >= 35 && tb <= 39) || (tb >= 46 && tb <= 48) || (tb >= 56 && tb <= 58), "chs_blend_bwd: pose_fused needs a round-2 kernel");
   }
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
@@ -1826,10 +1982,16 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   blend_bwd4_kernel<128, MB><<<grid, kThreads, CHS_BWD4_SMEM, s>>>(a)
     // phase B on the tensor cores (mma.sync m16n8k16, fp16 hi + lo tables): parity-green, measured r2v on c3: 7 CTAs per SM 4.00 ms |
     // 6: 3.92 | 8: 3.98 against 3.83 for the default below
+#define CHS_BWD5_SMEM (sizeof(SplatSmem3<129>) + 4 * sizeof(BwdWarp5<128>))
+#define CHS_BWD5_LAUNCH(MB) blend_bwd5_kernel<128, MB><<<grid, kThreads, CHS_BWD5_SMEM, s>>>(a)
+    // r3c, c3 (ms per frame of 8 poses): 6 CTAs per SM 3.45 | 7: 3.45 (default) | 8 (64 registers): 3.65; blend_bwd3_kernel 3.87
+    case 56: CHS_BWD5_LAUNCH(6); break;
+    case 58: CHS_BWD5_LAUNCH(8); break;
+    case 3: CHS_BWD3_LAUNCH(128, 7); break;  // the chunked, unstaged phase A (the default until r3c)
     case 46: CHS_BWD4_LAUNCH(6); break;
     case 47: CHS_BWD4_LAUNCH(7); break;
     case 48: CHS_BWD4_LAUNCH(8); break;
-    default: CHS_BWD3_LAUNCH(128, 7); break;
+    default: CHS_BWD5_LAUNCH(7); break;  // fp32 table, phase A staged for instruction-level parallelism
   }
   CHS_LAUNCH_CHECK();
   return CHS_OK;
