@@ -1418,16 +1418,87 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd3_kernel(BlendB
 // stage 2 runs the two short recurrences (T: one multiply, R: subtract + fma) and stores the table rows.  Phase B is
 // bwd_round3 after every second group.
 // ---------------------------------------------------------------------------------------------
-template <int kB>
+template <int kB, int kRows>
 struct __align__(16) BwdWarp5 {
-  float nvs[8][kRow3];   // -dL/dsigma of (slot, pixel id)
-  float nf[8][kRow3];    // -alpha * T of (slot, pixel id)
-  float vh[3][64];       // dL/dH of the warp's pixels by pixel id (r, g, b planes)
-  uint8_t list[kB + 4];  // survivors of the staged batch, back to front, padded to a multiple of four with kB (the null record)
+  float nvs[kRows][kRow3];  // -dL/dsigma of (slot, pixel id)
+  float nf[kRows][kRow3];   // -alpha * T of (slot, pixel id)
+  float vh[3][64];          // dL/dH of the warp's pixels by pixel id (r, g, b planes)
+  uint8_t list[kB + 4];     // survivors of the staged batch, back to front, padded to a multiple of four with kB (the null record)
 };
 
-template <int kB, int kMinBlocks>
+// phase B over kSets x 8 tabled slots: lane = (k = lane % 8, part = lane / 8) sums the slots k, k + 8, ... over the part's two pixel
+// rows.  With two sets the warp's dL/dH (a quarter of phase B's shared-memory wavefronts) is read once for two Gaussians.
+template <int kSets, class Smem, class Warp, class EntT>
+__device__ __forceinline__ void bwd_round5(const Smem& sm, const Warp& ws, const EntT* __restrict__ ents, int null_ent, int n_slots,
+                                           int lane, float bxc, float byc, const BlendBwdArgs& a) {
+  __syncwarp();
+  const int k = lane & 7, part = lane >> 3;
+  bool active[kSets];
+  P2 rowvs[kSets], rowt[kSets], S_xx[kSets], G6[kSets], G7[kSets], G8[kSets];
+  float dxb[kSets];
+  int jj[kSets];
+#pragma unroll
+  for (int s = 0; s < kSets; ++s) {
+    jj[s] = k + 8 * s < n_slots ? (int)ents[k + 8 * s] : null_ent;
+    active[s] = jj[s] != null_ent;
+    rowvs[s] = rowt[s] = S_xx[s] = G6[s] = G7[s] = G8[s] = p2s(0.f);
+    dxb[s] = sm.a[jj[s]].x - bxc;  // (the null record is a valid staged entry) mean - centre of pixel column 0
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 r4 = *reinterpret_cast<const float4*>(&ws.vh[0][16 * part + 4 * c]);
+    const float4 g4 = *reinterpret_cast<const float4*>(&ws.vh[1][16 * part + 4 * c]);
+    const float4 b4 = *reinterpret_cast<const float4*>(&ws.vh[2][16 * part + 4 * c]);
+#pragma unroll
+    for (int s = 0; s < kSets; ++s) {
+      const float4 vs4 = *reinterpret_cast<const float4*>(&ws.nvs[k + 8 * s][16 * part + 4 * c]);
+      const float4 f4 = *reinterpret_cast<const float4*>(&ws.nf[k + 8 * s][16 * part + 4 * c]);
+      const P2 vA = p2(vs4.x, vs4.y), vB = p2(vs4.z, vs4.w);  // columns 2c and 2c + 1, rows (y0, y0 + 4)
+      const P2 dxa = p2s(dxb[s] - (float)(2 * c)), dxc = p2s(dxb[s] - (float)(2 * c + 1));
+      const P2 tA = vA * dxa, tB = vB * dxc;
+      rowvs[s] = rowvs[s] + (vA + vB);
+      rowt[s] = rowt[s] + (tA + tB);
+      S_xx[s] = fma2(tA, dxa, S_xx[s]);
+      S_xx[s] = fma2(tB, dxc, S_xx[s]);
+      const P2 fA = p2(f4.x, f4.y), fB = p2(f4.z, f4.w);
+      G6[s] = fma2(fA, p2(r4.x, r4.y), G6[s]); G6[s] = fma2(fB, p2(r4.z, r4.w), G6[s]);
+      G7[s] = fma2(fA, p2(g4.x, g4.y), G7[s]); G7[s] = fma2(fB, p2(g4.z, g4.w), G7[s]);
+      G8[s] = fma2(fA, p2(b4.x, b4.y), G8[s]); G8[s] = fma2(fB, p2(b4.z, b4.w), G8[s]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kSets; ++s) {
+    const float4 sa = sm.a[jj[s]];  // mx, my, qa, r
+    const float dy_lo = sa.y - (byc + (float)part);
+    // the two halves of every packed sum are the rows y0 (dy = dy_lo) and y0 + 4 (dy = dy_lo - 4)
+    const P2 dyv = p2(dy_lo, dy_lo - 4.f);
+    const P2 S_dy = rowvs[s] * dyv, S_xy = rowt[s] * dyv;
+    const P2 S_yy = S_dy * dyv;
+    const float s_dy = p2sum(S_dy);
+    float t[9] = {fmaf(sa.w, s_dy, p2sum(rowt[s])), s_dy, p2sum(S_xx[s]), p2sum(S_xy), p2sum(S_yy), p2sum(rowvs[s]), p2sum(G6[s]),
+                  p2sum(G7[s]), p2sum(G8[s])};
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1)
+#pragma unroll
+      for (int i = 0; i < 9; ++i) t[i] += __shfl_xor_sync(CHS_FULL_MASK, t[i], o);
+    if (active[s]) {
+      const float2 sc = *reinterpret_cast<const float2*>(&sm.c[jj[s]].z);  // 1/opacity, val
+      const uint32_t val = (uint32_t)__float_as_int(sc.y);
+      ChsSplat<float> sp;
+      sp.qa = sa.z; sp.r = sa.w; sp.kc = sm.b[jj[s]].x; sp.inv_opac = sc.x;
+      float g[9];
+      chs_moments_to_grads_neg(sp, t, g);  // csrc/chs_math.cuh, checked on the host against chs_pair_bwd and the oracle
+      if (part == 0) atomicAdd(a.v_geom + val, make_float4(g[0], g[1], g[2], g[3]));
+      if (part == 1) atomicAdd(a.v_cogr + val, make_float4(g[4], g[5], g[6], g[7]));
+      if (part == 2) atomicAdd(a.v_blue + val, g[8]);
+    }
+  }
+  __syncwarp();  // the table is rewritten by the next round
+}
+
+template <int kB, int kMinBlocks, int kSets>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendBwdArgs a) {
+  constexpr int kRows = 8 * kSets;  // table rows = Gaussians per phase-B round
   static_assert(kB == kThreads && kB < 255, "one tile-list entry per thread and batch; staged indices fit a byte");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Smem = SplatSmem3<kB + 1>;  // entry kB: the null record
@@ -1439,7 +1510,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendB
   const int cam_base = a.rgbo_per_camera ? 0 : c * a.N;
   const int tx = tile % a.tile_w, ty = tile / a.tile_w;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  BwdWarp5<kB>& ws = reinterpret_cast<BwdWarp5<kB>*>(smem_raw + sizeof(Smem))[warp];
+  BwdWarp5<kB, kRows>& ws = reinterpret_cast<BwdWarp5<kB, kRows>*>(smem_raw + sizeof(Smem))[warp];
   const int bx = tx * CHS_TILE + (warp & 1) * 8, by = ty * CHS_TILE + (warp >> 1) * 8;
   const int ix = bx + (lane & 7), iy0 = by + (lane >> 3);
   const float px = ix + 0.5f;
@@ -1491,7 +1562,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendB
 
   const unsigned gt = lanemask_gt_();
   const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(&ws.nvs[0][0]) + 8u * (uint32_t)lane;
-  constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = 8 * kRow3 * 4;
+  constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = kRows * kRow3 * 4;
   for (int hi = n_walk; hi > 0; hi -= kB) {
     const int lo = max(0, hi - kB);
     const int cnt = hi - lo;
@@ -1514,7 +1585,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendB
     __syncwarp();
     for (int i = 0; i < n_surv; i += 4) {
       const uint32_t j4 = *reinterpret_cast<const uint32_t*>(ws.list + i);
-      const uint32_t tab = tab0 + (uint32_t)(i & 4) * kRowBytes;
+      const uint32_t tab = tab0 + (uint32_t)(i & (kRows - 4)) * kRowBytes;
       // ---- stage 1: what does not depend on T or R, for the four Gaussians ----
       P2 na2[4], ra2[4], s2[4], gate2[4];
 #pragma unroll
@@ -1552,10 +1623,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendB
       row(std::integral_constant<int, 1>{});
       row(std::integral_constant<int, 2>{});
       row(std::integral_constant<int, 3>{});
-      if (i & 4) bwd_round3<8>(sm, ws, ws.list + (i - 4), kB, 8, lane, bx0, by0, a);
+      if ((i & (kRows - 4)) == kRows - 4) bwd_round5<kSets>(sm, ws, ws.list + (i + 4 - kRows), kB, kRows, lane, bx0, by0, a);
     }
-    if (((n_surv + 3) >> 2) & 1)  // an odd number of groups: the last one sits alone in rows 0-3
-      bwd_round3<8>(sm, ws, ws.list + ((n_surv - 1) & ~3), kB, 4, lane, bx0, by0, a);
+    const int n_pad = (n_surv + 3) & ~3;
+    if (n_pad & (kRows - 4))  // groups left in the table when the batch ends
+      bwd_round5<kSets>(sm, ws, ws.list + (n_pad & ~(kRows - 1)), kB, n_pad & (kRows - 1), lane, bx0, by0, a);
   }
 }
 
@@ -1948,7 +2020,7 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.fused = cfg->pose_fused != 0;
   {
     const int tb = cfg->tune_blend_bwd;
-    CHS_REQUIRE(!a.fused || tb == 0 || tb == 3 || (tb >= 35 && tb <= 39) || (tb >= 46 && tb <= 48) || (tb >= 56 && tb <= 58), "chs_blend_bwd: pose_fused needs a round-2 kernel");
+    CHS_REQUIRE(!a.fused || tb == 0 || tb == 3 || (tb >= 35 && tb <= 39) || (tb >= 46 && tb <= 48) || (tb >= 56 && tb <= 58) || tb == 64 || tb == 65, "chs_blend_bwd: pose_fused needs a round-2 kernel");
   }
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
@@ -1982,8 +2054,13 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   blend_bwd4_kernel<128, MB><<<grid, kThreads, CHS_BWD4_SMEM, s>>>(a)
     // phase B on the tensor cores (mma.sync m16n8k16, fp16 hi + lo tables): parity-green, measured r2v on c3: 7 CTAs per SM 4.00 ms |
     // 6: 3.92 | 8: 3.98 against 3.83 for the default below
-#define CHS_BWD5_SMEM (sizeof(SplatSmem3<129>) + 4 * sizeof(BwdWarp5<128>))
-#define CHS_BWD5_LAUNCH(MB) blend_bwd5_kernel<128, MB><<<grid, kThreads, CHS_BWD5_SMEM, s>>>(a)
+#define CHS_BWD5_SMEM(SETS) (sizeof(SplatSmem3<129>) + 4 * sizeof(BwdWarp5<128, 8 * SETS>))
+#define CHS_BWD5_LAUNCH(MB) blend_bwd5_kernel<128, MB, 1><<<grid, kThreads, CHS_BWD5_SMEM(1), s>>>(a)
+#define CHS_BWD5_LAUNCH2(MB)                                                                                                          \
+  CHS_CUDA(cudaFuncSetAttribute(blend_bwd5_kernel<128, MB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHS_BWD5_SMEM(2))); \
+  blend_bwd5_kernel<128, MB, 2><<<grid, kThreads, CHS_BWD5_SMEM(2), s>>>(a)
+    case 64: CHS_BWD5_LAUNCH2(4); break;  // 16 table rows, two Gaussians per phase-B lane
+    case 65: CHS_BWD5_LAUNCH2(5); break;
     // r3c, c3 (ms per frame of 8 poses): 6 CTAs per SM 3.45 | 7: 3.45 (default) | 8 (64 registers): 3.65; blend_bwd3_kernel 3.87
     case 56: CHS_BWD5_LAUNCH(6); break;
     case 58: CHS_BWD5_LAUNCH(8); break;
