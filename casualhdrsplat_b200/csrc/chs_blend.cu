@@ -823,6 +823,38 @@ __device__ __forceinline__ void stage_splat3(Smem& sm, int slot, int32_t val, in
   sm.c[slot] = make_float4(s.cg, s.cb, s.inv_opac, __int_as_float(val));
 }
 
+// two entries of one thread: both gathers are in flight before either record is transformed
+template <class Smem>
+__device__ __forceinline__ void stage_splat3_pair(Smem& sm, int slot0, bool on0, int32_t val0, int slot1, bool on1, int32_t val1, int cam_base,
+                                                  const float4* __restrict__ geom, const float* __restrict__ conic_c,
+                                                  const float4* __restrict__ rgbo) {
+  float4 gm0 = make_float4(0.f, 0.f, 1.f, 0.f), gm1 = gm0, col0 = make_float4(0.f, 0.f, 0.f, 1.f), col1 = col0;
+  float cc0 = 1.f, cc1 = 1.f;
+  if (on0) {
+    gm0 = __ldg(geom + val0);
+    cc0 = __ldg(conic_c + val0);
+    col0 = __ldg(rgbo + (val0 - cam_base));
+  }
+  if (on1) {
+    gm1 = __ldg(geom + val1);
+    cc1 = __ldg(conic_c + val1);
+    col1 = __ldg(rgbo + (val1 - cam_base));
+  }
+  ChsSplat<float> s;
+  if (on0) {
+    chs_make_splat(gm0.x, gm0.y, gm0.z, gm0.w, cc0, col0.w, col0.x, col0.y, col0.z, s);
+    sm.a[slot0] = make_float4(s.mx, s.my, s.qa, s.r);
+    sm.b[slot0] = make_float4(s.kc, s.lo, s.rbc, s.cr);
+    sm.c[slot0] = make_float4(s.cg, s.cb, s.inv_opac, __int_as_float(val0));
+  }
+  if (on1) {
+    chs_make_splat(gm1.x, gm1.y, gm1.z, gm1.w, cc1, col1.w, col1.x, col1.y, col1.z, s);
+    sm.a[slot1] = make_float4(s.mx, s.my, s.qa, s.r);
+    sm.b[slot1] = make_float4(s.kc, s.lo, s.rbc, s.cr);
+    sm.c[slot1] = make_float4(s.cg, s.cb, s.inv_opac, __int_as_float(val1));
+  }
+}
+
 template <class Smem>
 __device__ __forceinline__ bool splat_hits_block3(const Smem& sm, int slot, float bx0, float bx1, float by0, float by1) {
   const float4 a = sm.a[slot];
@@ -949,6 +981,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
       }
       cp_async_commit();
     }
+    int32_t vpre0 = 0, vpre1 = 0;  // kGroup: this thread's two tile-list entries of the batch about to be staged
+    if (kGroup && !kAsync) {
+      if (start + tid < end) vpre0 = a.vals[start + tid];
+      if (start + tid + kThreads < end) vpre1 = a.vals[start + tid + kThreads];
+    }
     for (uint32_t base = start; base < end; base += kBatch) {
       if (kAsync) cp_async_wait_all();  // this thread's own gathers of the batch have landed
       // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
@@ -965,6 +1002,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
           if (i2 < end) val_next[h] = a.vals[i2] + rec_shift;
         }
         cp_async_commit();
+      } else if (kGroup) {
+        // the thread's two list entries were requested during the previous batch; the next batch's are requested now
+        stage_splat3_pair(sm, tid, tid < cnt, vpre0 + rec_shift, tid + kThreads, tid + kThreads < cnt, vpre1 + rec_shift, cam_base, a.geom,
+                          a.conic_c, a.rgbo);
+        const uint32_t nb = base + kBatch + tid;
+        if (nb < end) vpre0 = a.vals[nb];
+        if (nb + kThreads < end) vpre1 = a.vals[nb + kThreads];
       } else {
         for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[base + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
       }
@@ -1563,11 +1607,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendB
   const unsigned gt = lanemask_gt_();
   const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(&ws.nvs[0][0]) + 8u * (uint32_t)lane;
   constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = kRows * kRow3 * 4;
+  // this thread's tile-list entry of the NEXT batch is requested while the current batch is processed: the staging of a batch
+  // then starts with the record gathers instead of a dependent list read
+  int32_t val_next = 0;
+  {
+    const int lo0 = max(0, n_walk - kB);
+    if (tid < n_walk - lo0) val_next = a.vals[start + lo0 + tid];
+  }
   for (int hi = n_walk; hi > 0; hi -= kB) {
     const int lo = max(0, hi - kB);
     const int cnt = hi - lo;
     __syncthreads();
-    if (tid < cnt) stage_splat3(sm, tid, a.vals[start + lo + tid] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+    if (tid < cnt) stage_splat3(sm, tid, val_next + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+    {
+      const int hi1 = lo, lo1 = max(0, hi1 - kB);
+      if (hi1 > 0 && tid < hi1 - lo1) val_next = a.vals[start + lo1 + tid];
+    }
     __syncthreads();
     if (warp_last <= lo) continue;
     const int lrA = last[0] - lo - 1, lrB = last[1] - lo - 1;
