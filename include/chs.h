@@ -105,8 +105,9 @@ typedef struct chs_config {
                                * default binning route and the round-2 blend kernels. */
   /* Development knobs (0 = the measured-best default everywhere).  They select between bit-/tolerance-equivalent kernel
    * instantiations and never change results beyond atomics order; see DESIGN.md section 7. */
-  int32_t tune_blend_fwd;     /* 1 / 3: 6 / 10 CTAs per SM */
-  int32_t tune_blend_bwd;     /* 1: direct kernel; 22: direct, four pixels per thread; 40 / 41: tabled, 16 slots */
+  int32_t tune_blend_fwd;     /* 27: ungrouped pair loop; 46 / 48: grouped at 6 / 8 CTAs per SM; 26 / 28: ungrouped at 6 / 8; 8: round-1 kernel */
+  int32_t tune_blend_bwd;     /* 56 / 58: default kernel at 6 / 8 CTAs per SM; 64 / 65: 16 table rows; 3: unstaged phase A; 46-48: phase B on the
+                               * tensor cores; 2: round-1 tabled kernel; 1 / 22: direct kernels */
   int32_t tune_crf_bwd;       /* resident blocks per SM (2, 3, 4); + 10: the per-unit MLP kernel instead of the interval form */
   int32_t tune_bin;           /* CHS_SORT_DEPTH_PRESORT routes.  0: banded placement (default); 3: hand-written two-pass radix multisplit
                                * over emitted intersections; 1: cub::DeviceRadixSort baseline; 2: round-1 counting placement */
