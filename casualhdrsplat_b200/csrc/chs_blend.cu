@@ -1467,7 +1467,8 @@ struct __align__(16) BwdWarp5 {
   float nvs[kRows][kRow3];  // -dL/dsigma of (slot, pixel id)
   float nf[kRows][kRow3];   // -alpha * T of (slot, pixel id)
   float vh[3][64];          // dL/dH of the warp's pixels by pixel id (r, g, b planes)
-  uint8_t list[kB + 4];     // survivors of the staged batch, back to front, padded to a multiple of four with kB (the null record)
+  typedef typename std::conditional<(kB < 255), uint8_t, uint16_t>::type ent_t;
+  ent_t list[kB + 4];       // survivors of the staged batch, back to front, padded to a multiple of four with kB (the null record)
 };
 
 // phase B over kSets x 8 tabled slots: lane = (k = lane % 8, part = lane / 8) sums the slots k, k + 8, ... over the part's two pixel
@@ -1543,7 +1544,9 @@ __device__ __forceinline__ void bwd_round5(const Smem& sm, const Warp& ws, const
 template <int kB, int kMinBlocks, int kSets>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendBwdArgs a) {
   constexpr int kRows = 8 * kSets;  // table rows = Gaussians per phase-B round
-  static_assert(kB == kThreads && kB < 255, "one tile-list entry per thread and batch; staged indices fit a byte");
+  static_assert(kB == kThreads || kB == 2 * kThreads, "one or two tile-list entries per thread and batch");
+  constexpr int kPer = kB / kThreads;  // tile-list entries a thread stages per batch
+  typedef typename BwdWarp5<kB, kRows>::ent_t ent_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Smem = SplatSmem3<kB + 1>;  // entry kB: the null record
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -1609,19 +1612,30 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendB
   constexpr uint32_t kRowBytes = kRow3 * 4, kFOffBytes = kRows * kRow3 * 4;
   // this thread's tile-list entry of the NEXT batch is requested while the current batch is processed: the staging of a batch
   // then starts with the record gathers instead of a dependent list read
-  int32_t val_next = 0;
+  int32_t val_next[kPer];
   {
     const int lo0 = max(0, n_walk - kB);
-    if (tid < n_walk - lo0) val_next = a.vals[start + lo0 + tid];
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      val_next[e] = 0;
+      if (tid + e * kThreads < n_walk - lo0) val_next[e] = a.vals[start + lo0 + tid + e * kThreads];
+    }
   }
   for (int hi = n_walk; hi > 0; hi -= kB) {
     const int lo = max(0, hi - kB);
     const int cnt = hi - lo;
     __syncthreads();
-    if (tid < cnt) stage_splat3(sm, tid, val_next + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+    if (kPer == 1) {
+      if (tid < cnt) stage_splat3(sm, tid, val_next[0] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+    } else {
+      stage_splat3_pair(sm, tid, tid < cnt, val_next[0] + rec_shift, tid + kThreads, tid + kThreads < cnt, val_next[kPer - 1] + rec_shift,
+                        cam_base, a.geom, a.conic_c, a.rgbo);
+    }
     {
       const int hi1 = lo, lo1 = max(0, hi1 - kB);
-      if (hi1 > 0 && tid < hi1 - lo1) val_next = a.vals[start + lo1 + tid];
+#pragma unroll
+      for (int e = 0; e < kPer; ++e)
+        if (hi1 > 0 && tid + e * kThreads < hi1 - lo1) val_next[e] = a.vals[start + lo1 + tid + e * kThreads];
     }
     __syncthreads();
     if (warp_last <= lo) continue;
@@ -1633,19 +1647,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_bwd5_kernel(BlendB
       const int j = sub_lo + lane;
       const bool hit = (j < sub_hi) && (lo + j < warp_last) && splat_hits_block3(sm, j, bx0, bx1, by0, by1);
       const unsigned mask = __ballot_sync(CHS_FULL_MASK, hit);
-      if (hit) ws.list[n_surv + __popc(mask & gt)] = (uint8_t)j;  // descending: back to front
+      if (hit) ws.list[n_surv + __popc(mask & gt)] = (ent_t)j;  // descending: back to front
       n_surv += __popc(mask);
     }
-    if (lane < 3) ws.list[n_surv + lane] = (uint8_t)kB;
+    if (lane < 3) ws.list[n_surv + lane] = (ent_t)kB;
     __syncwarp();
     for (int i = 0; i < n_surv; i += 4) {
-      const uint32_t j4 = *reinterpret_cast<const uint32_t*>(ws.list + i);
+      int js[4];
+      if (sizeof(ent_t) == 1) {
+        const uint32_t j4 = *reinterpret_cast<const uint32_t*>(ws.list + i);
+        js[0] = j4 & 0xffu; js[1] = (j4 >> 8) & 0xffu; js[2] = (j4 >> 16) & 0xffu; js[3] = j4 >> 24;
+      } else {
+        const uint2 j4 = *reinterpret_cast<const uint2*>(ws.list + i);
+        js[0] = j4.x & 0xffffu; js[1] = j4.x >> 16; js[2] = j4.y & 0xffffu; js[3] = j4.y >> 16;
+      }
       const uint32_t tab = tab0 + (uint32_t)(i & (kRows - 4)) * kRowBytes;
       // ---- stage 1: what does not depend on T or R, for the four Gaussians ----
       P2 na2[4], ra2[4], s2[4], gate2[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int jj = (int)((j4 >> (8 * u)) & 0xffu);
+        const int jj = js[u];
         const float4 sa = sm.a[jj];  // mx, my, qa, r
         const float4 sb = sm.b[jj];  // kc, log2(opacity), rbc, cr
         const float2 cgb = *reinterpret_cast<const float2*>(&sm.c[jj]);  // cg, cb
@@ -2075,7 +2096,7 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
   a.fused = cfg->pose_fused != 0;
   {
     const int tb = cfg->tune_blend_bwd;
-    CHS_REQUIRE(!a.fused || tb == 0 || tb == 3 || (tb >= 35 && tb <= 39) || (tb >= 46 && tb <= 48) || (tb >= 56 && tb <= 58) || tb == 64 || tb == 65, "chs_blend_bwd: pose_fused needs a round-2 kernel");
+    CHS_REQUIRE(!a.fused || tb == 0 || tb == 3 || (tb >= 35 && tb <= 39) || (tb >= 46 && tb <= 48) || (tb >= 56 && tb <= 58) || tb == 64 || tb == 65 || tb == 76 || tb == 77, "chs_blend_bwd: pose_fused needs a round-2 kernel");
   }
   a.v_geom = (float4*)v_geom; a.v_cogr = (float4*)v_cogr; a.v_blue = v_blue;
   dim3 grid(d.tiles, d.C);
@@ -2114,6 +2135,10 @@ extern "C" int chs_blend_bwd(const chs_config* cfg, const float* geom, const flo
 #define CHS_BWD5_LAUNCH2(MB)                                                                                                          \
   CHS_CUDA(cudaFuncSetAttribute(blend_bwd5_kernel<128, MB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHS_BWD5_SMEM(2))); \
   blend_bwd5_kernel<128, MB, 2><<<grid, kThreads, CHS_BWD5_SMEM(2), s>>>(a)
+#define CHS_BWD5_SMEM_B(B, SETS) (sizeof(SplatSmem3<B + 1>) + 4 * sizeof(BwdWarp5<B, 8 * SETS>))
+#define CHS_BWD5_LAUNCH_B256(MB) blend_bwd5_kernel<256, MB, 1><<<grid, kThreads, CHS_BWD5_SMEM_B(256, 1), s>>>(a)
+    case 76: CHS_BWD5_LAUNCH_B256(6); break;  // 256-entry batches (two list entries per thread), half as many CTA barriers: r3j 3.65-3.69 vs 3.43 ms
+    case 77: CHS_BWD5_LAUNCH_B256(7); break;
     case 64: CHS_BWD5_LAUNCH2(4); break;  // 16 table rows, two Gaussians per phase-B lane
     case 65: CHS_BWD5_LAUNCH2(5); break;
     // r3c, c3 (ms per frame of 8 poses): 6 CTAs per SM 3.45 | 7: 3.45 (default) | 8 (64 registers): 3.65; blend_bwd3_kernel 3.87
