@@ -221,25 +221,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_interval_kernel(
   }
   for (int i = tid; i < (kThreads / 32) * 3 * nI * 2; i += kThreads) s_H[i] = 0.f;
   __syncthreads();
-  const float kInf = __int_as_float(0x7f800000);
   // rank of every unit's breakpoint inside its channel (ties by unit index); units with w1 = 0 never switch: breakpoint +inf
   for (int i = tid; i < 3 * hd; i += kThreads) {
     const int ch = i / hd, j = i - ch * hd;
     const float* p = s_p + ch * stride;
     const float w1 = p[j], b1 = p[hd + j];
-    const float t = w1 != 0.f ? -b1 / w1 : kInf;
+    const float t = chs_crf_breakpoint(w1, b1);
     int r = 0;
     for (int k = 0; k < hd; ++k) {
-      const float wk = p[k];
-      const float tk = wk != 0.f ? -p[hd + k] / wk : kInf;
+      const float tk = chs_crf_breakpoint(p[k], p[hd + k]);
       r += (tk < t || (tk == t && k < j)) ? 1 : 0;
     }
     s_bp[ch * hd + r] = t;
-    // w1 > 0: on  <=>  z > t_j  <=>  I >= r + 1;   w1 < 0: on  <=>  z < t_j  <=>  I <= r;   w1 = 0: on  <=>  b1 > 0 (every interval)
-    int sgn = 1, off = -(r + 1);
-    if (w1 < 0.f) { sgn = -1; off = r; }
-    if (w1 == 0.f) { sgn = 1; off = b1 > 0.f ? 0 : -(hd + 1); }
-    s_key[i] = off * 2 + (sgn < 0 ? 1 : 0);
+    s_key[i] = chs_crf_unit_key(w1, b1, r, hd);
   }
   __syncthreads();
   for (int i = tid; i < 3 * nI; i += kThreads) {
@@ -247,9 +241,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_interval_kernel(
     const float* p = s_p + ch * stride;
     float A = 0.f, B = p[3 * hd];
     for (int j = 0; j < hd; ++j) {
-      const int key = s_key[ch * hd + j];
-      const int d = (key & 1) ? (key >> 1) - I : I + (key >> 1);
-      if (d >= 0) {
+      if (chs_crf_key_on(s_key[ch * hd + j], I)) {
         A = fmaf(p[2 * hd + j], p[j], A);
         B = fmaf(p[2 * hd + j], p[hd + j], B);
       }
@@ -275,15 +267,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_interval_kernel(
         const float vy = live ? a.v_ldr[o_frm + ch] * a.vy_scale : 0.f;
         const float xe = fmaxf(dt * h, 0.f) + CHS_CRF_EPS;  // X clamped to >= 0 (chs_crf_mlp_fwd)
         const float z = logf(xe);
-        const float* bp = s_bp + ch * hd;
-        int lo = 0, n = hd;  // I = number of breakpoints < z
-        while (n > 0) {
-          const int half = n >> 1;
-          const bool right = bp[lo + half] < z;
-          lo = right ? lo + half + 1 : lo;
-          n = right ? n - half - 1 : half;
-        }
-        const int I = lo;
+        const int I = chs_crf_interval_of(s_bp + ch * hd, hd, z);  // number of breakpoints below z
         const float A = s_A[ch * nI + I];
         const float acc = fmaf(A, z, s_B[ch * nI + I]);
         const float y = 1.f / (1.f + expf(-acc));
@@ -326,8 +310,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_interval_kernel(
     const int key = s_key[i];
     float S = 0.f, SZ = 0.f;
     for (int I = 0; I < nI; ++I) {
-      const int d = (key & 1) ? (key >> 1) - I : I + (key >> 1);
-      if (d >= 0) {
+      if (chs_crf_key_on(key, I)) {
         S += s_H[(ch * nI + I) * 2];
         SZ += s_H[(ch * nI + I) * 2 + 1];
       }

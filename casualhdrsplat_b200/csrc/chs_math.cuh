@@ -41,6 +41,33 @@ template <> struct ChsK<double> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// MLP CRF in interval form (crf_bwd_interval_kernel).  With a scalar input z the network is piecewise linear: unit j switches
+// at its breakpoint t_j = -b1_j / w1_j (+inf for w1_j = 0: it never switches).  Units are ranked by breakpoint inside a channel
+// (ties by index); interval I in [0, Hd] = "I breakpoints lie below z".  "Unit j is on in interval I" is the integer test
+// chs_crf_key_on(key_j, I) with key_j = chs_crf_unit_key(w1_j, b1_j, rank_j, Hd):
+//   w1 > 0: on <=> z > t_j <=> I >= rank + 1;   w1 < 0: on <=> z < t_j <=> I <= rank;   w1 = 0: on <=> b1 > 0, in every interval.
+// ---------------------------------------------------------------------------------------------
+template <class T> CHS_HD T chs_crf_breakpoint(T w1, T b1) { return w1 != T(0) ? -b1 / w1 : T(INFINITY); }
+template <class T> CHS_HD int chs_crf_unit_key(T w1, T b1, int rank, int hd) {
+  int sgn = 1, off = -(rank + 1);
+  if (w1 < T(0)) { sgn = -1; off = rank; }
+  if (w1 == T(0)) { sgn = 1; off = b1 > T(0) ? 0 : -(hd + 1); }
+  return off * 2 + (sgn < 0 ? 1 : 0);
+}
+CHS_HD bool chs_crf_key_on(int key, int I) { return ((key & 1) ? (key >> 1) - I : I + (key >> 1)) >= 0; }
+// number of sorted breakpoints below z (branch-free bisection)
+template <class T> CHS_HD int chs_crf_interval_of(const T* bp, int hd, T z) {
+  int lo = 0, n = hd;
+  while (n > 0) {
+    const int half = n >> 1;
+    const bool right = bp[lo + half] < z;
+    lo = right ? lo + half + 1 : lo;
+    n = right ? n - half - 1 : half;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
 template <class T> CHS_HD T chs_min(T a, T b) { return a < b ? a : b; }

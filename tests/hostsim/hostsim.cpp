@@ -228,6 +228,60 @@ static void blend_impl(int n_list, const T* params, int n_pix, const T* pix_xy, 
     for (int j = 0; j < n_list; ++j) chs_moments_to_grads(sp[j], &moments[(size_t)j * 9], v_params + (size_t)j * 9);
 }
 
+// CRF MLP in interval form, step by step as crf_bwd_interval_kernel does it (ranking, per-interval slope / offset, bisection,
+// two sums per interval, per-unit sums over the intervals where the unit is on).  Same outputs as hs_crf_f64.
+template <class T>
+static void crf_interval_impl(int n, const T* X, const T* p, int hd, const T* v_y, T* y, T* dydx, T* v_params) {
+  const int nI = hd + 1;
+  std::vector<T> bp(hd), A(nI), B(nI), H(nI, T(0)), HZ(nI, T(0));
+  std::vector<int> key(hd);
+  for (int j = 0; j < hd; ++j) {
+    const T t = chs_crf_breakpoint(p[j], p[hd + j]);
+    int r = 0;
+    for (int k = 0; k < hd; ++k) {
+      const T tk = chs_crf_breakpoint(p[k], p[hd + k]);
+      r += (tk < t || (tk == t && k < j)) ? 1 : 0;
+    }
+    bp[r] = t;
+    key[j] = chs_crf_unit_key(p[j], p[hd + j], r, hd);
+  }
+  for (int I = 0; I < nI; ++I) {
+    T a = 0, b = p[3 * hd];
+    for (int j = 0; j < hd; ++j)
+      if (chs_crf_key_on(key[j], I)) {
+        a = chs_fma(p[2 * hd + j], p[j], a);
+        b = chs_fma(p[2 * hd + j], p[hd + j], b);
+      }
+    A[I] = a;
+    B[I] = b;
+  }
+  for (int i = 0; i < n; ++i) {
+    const T xe = chs_max(X[i], T(0)) + ChsK<T>::crf_eps;
+    const T z = log(xe);
+    const int I = chs_crf_interval_of(bp.data(), hd, z);
+    const T acc = chs_fma(A[I], z, B[I]);
+    y[i] = T(1) / (T(1) + exp(-acc));
+    const T g = v_y[i] * y[i] * (T(1) - y[i]);
+    dydx[i] = X[i] >= T(0) ? y[i] * (T(1) - y[i]) * A[I] / xe : T(0);
+    H[I] += g;
+    HZ[I] += g * z;
+  }
+  T gb2 = 0;
+  for (int I = 0; I < nI; ++I) gb2 += H[I];
+  for (int j = 0; j < hd; ++j) {
+    T S = 0, SZ = 0;
+    for (int I = 0; I < nI; ++I)
+      if (chs_crf_key_on(key[j], I)) {
+        S += H[I];
+        SZ += HZ[I];
+      }
+    v_params[j] = p[2 * hd + j] * SZ;
+    v_params[hd + j] = p[2 * hd + j] * S;
+    v_params[2 * hd + j] = chs_fma(p[j], SZ, p[hd + j] * S);
+  }
+  v_params[3 * hd] = gb2;
+}
+
 extern "C" {
 
 void hs_project_fwd_f64(int N, int C, int W, int H, double near_p, double far_p, double eps2d, const double* means, const double* quats,
@@ -352,6 +406,12 @@ void hs_crf_f64(int n, const double* X, const double* params, int hd, const doub
     y[i] = chs_crf_mlp_fwd(X[i], params, hd);
     dydx[i] = chs_crf_mlp_bwd(X[i], params, hd, v_y[i], v_params);
   }
+}
+void hs_crf_interval_f64(int n, const double* X, const double* params, int hd, const double* v_y, double* y, double* dydx, double* v_params) {
+  crf_interval_impl<double>(n, X, params, hd, v_y, y, dydx, v_params);
+}
+void hs_crf_interval_f32(int n, const float* X, const float* params, int hd, const float* v_y, float* y, float* dydx, float* v_params) {
+  crf_interval_impl<float>(n, X, params, hd, v_y, y, dydx, v_params);
 }
 // CRF LUT: same contract; v_params has L + 2 entries (the two range entries stay 0)
 void hs_crf_lut_f64(int n, const double* X, const double* params, int L, const double* v_y, double* y, double* dydx, double* v_params) {

@@ -371,6 +371,46 @@ def test_crf_mlp_fwd_bwd():
         assert np.allclose(o_p, gp.numpy(), rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("hd", [8, 32, 64, 128])
+def test_crf_mlp_interval_form_matches_the_per_unit_form(hd):
+    """crf_bwd_interval_kernel's algorithm (ranked breakpoints, slope / offset per interval, two sums per interval) restated
+    serially with the kernel's own helper functions: same y, dy/dX and parameter gradients as the per-unit form and as the
+    oracle's autograd, also with zero weights, duplicated breakpoints and units that are on or off everywhere."""
+    from casualhdrsplat_b200.scene import gamma_crf_params
+    g = torch.Generator().manual_seed(40 + hd)
+    P = gamma_crf_params(hd).double()
+    p0 = P[1].clone()
+    p0[0] = 0.0                      # w1 = 0 with b1 > 0: on everywhere
+    p0[hd] = abs(float(p0[hd])) + 0.1
+    p0[1] = 0.0                      # w1 = 0 with b1 < 0: never on
+    p0[hd + 1] = -abs(float(p0[hd + 1])) - 0.1
+    p0[3], p0[hd + 3] = p0[2], p0[hd + 2]          # duplicated breakpoint
+    p0[4] = -abs(float(p0[4])) - 0.05               # a negative slope
+    n = 4000
+    X = torch.exp(torch.randn(n, generator=g, dtype=torch.float64) * 2.5 - 3)
+    X[::97] = -0.01                 # below the clamp: zero gradient
+    vy = torch.randn(n, generator=g, dtype=torch.float64)
+    p = p0.clone().requires_grad_(True)
+    Xl = X.clone().requires_grad_(True)
+    y = oracle.crf_apply(Xl[:, None].expand(-1, 3), oracle.CRF_MLP, torch.stack([p, p, p]))[:, 0]
+    gx, gp = torch.autograd.grad((y * vy).sum(), [Xl, p])
+    outs = {}
+    for name in ["hs_crf_f64", "hs_crf_interval_f64"]:
+        o_y = np.zeros(n); o_d = np.zeros(n); o_p = np.zeros(3 * hd + 1)
+        getattr(HS, name)(n, _p(X.numpy()), _p(np.ascontiguousarray(p0.numpy())), hd, _p(vy.numpy()), _p(o_y), _p(o_d), _p(o_p))
+        outs[name] = (o_y, o_d, o_p)
+        assert np.allclose(o_y, y.detach().numpy(), rtol=1e-11), name
+        assert np.allclose(o_d * vy.numpy(), gx.numpy(), rtol=1e-9, atol=1e-13), name
+        assert np.allclose(o_p, gp.numpy(), rtol=1e-9, atol=1e-10), name
+    # single precision, as the kernel runs it: within 1e-5 of the float64 result
+    f32 = lambda t: np.ascontiguousarray(np.asarray(t, dtype=np.float32))
+    o_y = np.zeros(n, np.float32); o_d = np.zeros(n, np.float32); o_p = np.zeros(3 * hd + 1, np.float32)
+    HS.hs_crf_interval_f32(n, _p(f32(X.numpy())), _p(f32(p0.numpy())), hd, _p(f32(vy.numpy())), _p(o_y), _p(o_d), _p(o_p))
+    assert np.abs(o_y - y.detach().numpy()).max() < 2e-5
+    ref = gp.numpy()
+    assert np.linalg.norm(o_p - ref) / np.linalg.norm(ref) < 1e-4
+
+
 def test_crf_lut_fwd_bwd():
     from casualhdrsplat_b200.scene import gamma_lut_params
     L = 48
