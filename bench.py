@@ -4,8 +4,9 @@
 Metric (BASELINE.json): blurred-LDR frames/s, forward+backward, 1M Gaussians, 1920x1080, 8 virtual
 poses per frame, on 1/2/4/8 B200.  Workload = BASELINE.json configs[3] ("c4"): a global batch of 8
 frames, sharded by frames across the ranks (strong scaling: the batch is fixed), replicated
-Gaussians, one NCCL all-reduce of the flat gradient buffer per step.  At N=1 the 8 frames run as 8
-micro-batches on the one GPU (this is configs[2] repeated per frame).
+Gaussians, one all-reduce of the flat gradient buffer per step (hand-written NVLS kernel; NCCL fallback).
+A rank's frames go through every kernel in ONE launch when their stage buffers fit in 60 % of the free HBM
+(--micro-batch; 8 frames per launch for c4 at N=1, 1 for c5), else frame by frame.
 
 A step = fwd+bwd of the whole batch (K0..K9 of SURVEY.md section 3.1) + the all-reduce.
     value : frames/s with every input resident in HBM (upstream gradient = the fixed seed-2 v_B)
@@ -18,7 +19,8 @@ A step = fwd+bwd of the whole batch (K0..K9 of SURVEY.md section 3.1) + the all-
     roofline : blend_bwd (K8), the dominant kernel; algorithmic bytes of the units
             the launch actually processes (emitted intersections) over its CUDA-event duration measured
             inside the timed region, against MEASURED_PEAKS.json; issue_frac = its warp instructions over
-            the SM issue slots of that duration (the bound that actually limits it)
+            the SM issue slots of that duration and smem_pipe_frac = its share of the shared-memory pipe's
+            peak wavefront rate (static facts of the committed ncu capture): the two bounds that limit it
     cpu_baseline : the float64 oracle on the host cores, on a bounded sample (stated), extrapolated
 `--impl reference` times that CPU oracle alone (the reference ships no implementation to run).
 """
