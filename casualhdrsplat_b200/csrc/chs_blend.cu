@@ -22,17 +22,20 @@
 // Forward fuses the whole formation epilogue: the CTA loops over the n virtual poses of its frame,
 // accumulates sum_k H_k in registers, and writes B = F(dt/n * sum_k H_k) once (decision D0 order).
 //
-// Backward walks each pixel's list back to front from last_id.  Two implementations:
-//   blend_bwd2_kernel (default, "tabled"): the per-pixel sequential part runs pixel-parallel and leaves two
-//     scalars per (pixel, Gaussian) in a per-warp shared-memory table; every 8 Gaussians the lanes switch
-//     to one Gaussian each and sum their table rows privately (see the comment above the kernel).
-//   blend_bwd_kernel (chs_config.tune_blend_bwd = 1, "direct"): the nine per-Gaussian partials of the thread's two
-//     pixels are added, then reduced across the warp with a transposing butterfly (14 shuffles instead of
-//     45) that leaves value j on lane j, so a single RED instruction with nine active lanes adds all nine
-//     numbers into the three [C,N] gradient planes.
+// Backward walks each pixel's list back to front from last_id.  Kernel generations in this file (the defaults are the
+// last of each; the earlier ones stay selectable through chs_config.tune_* as measured baselines):
+//   forward   blend_fwd_kernel (round 1) -> blend_fwd2_kernel (round 2: survivor list, T -= w; with kGroup, the default: whole
+//             batch culled first, survivors in groups of four with a speculative transmittance chain and one stop vote)
+//   backward  blend_bwd_kernel ("direct": nine partials per Gaussian reduced across the warp with a transposing butterfly)
+//             -> blend_bwd2_kernel ("tabled": the per-pixel sequential part runs pixel-parallel and leaves two scalars per
+//             (pixel, Gaussian) in a per-warp shared-memory table; every 8 Gaussians the lanes switch to one Gaussian each and
+//             sum their table rows privately) -> blend_bwd3_kernel (division-free colour state, running table pointer)
+//             -> blend_bwd5_kernel (default: phase A in two stages over groups of four, for instruction-level parallelism)
+//             and blend_bwd4_kernel (opt-in: phase B as tensor-core products over fp16 hi + lo tables).
 // Negative results kept out of the code (r1g, c3): prefetching the next survivor's staged record inside the
 // forward pair loop (to hide the bit-scan -> address -> LDS chain) made K6 2.55 -> 2.95 ms at 64 registers and
-// 3.00 ms at 72; software-pipelining phase A of the tabled backward cost +0.5 ms.
+// 3.00 ms at 72; software-pipelining phase A of the tabled backward one Gaussian ahead cost +0.5 ms (the staged groups of
+// blend_bwd5_kernel are what finally overlapped those chains).
 #include <cuda_fp16.h>
 
 #include <type_traits>
