@@ -33,3 +33,36 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_other_ranks_exit_silently():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The round's final bench lines under profiles/ (printed by bench.py on the B200 boxes) have every key the driver and the
+    judge read, consistent with each other: same metric / workload at every N, value = frames / time, frac = achieved / peak,
+    loss and gradient checksums equal across N (the sharded job computes the same step)."""
+    lines = {}
+    for n in (1, 2, 4, 8):
+        p = os.path.join(ROOT, "profiles", f"r2_final_bench_n{n}.json")
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        lines[n] = d
+        for k in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "extra"]:
+            assert k in d, (n, k)
+        assert d["n_gpus"] == n and d["unit"] == "frames/s" and d["scaling"] == "strong" and d["data"] == "synthetic"
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+        assert abs(d["value"] - 8 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+        r = d["roofline"]
+        for k in ["bound", "achieved", "peak", "unit", "frac", "traffic", "issue_frac", "smem_pipe_frac", "frames_per_launch"]:
+            assert k in r, (n, k)
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0 < r["frac"] < 1 and 0 < r["issue_frac"] < 1
+        assert r["frames_per_launch"] == d["config"]["micro_batch_frames"] == 8 // n
+        e = d["e2e"]
+        assert e["unit"] == "frames/s" and 0 < e["value"] <= d["value"] * 1.001 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert lines[1]["cpu_baseline"]["kind"] == "port" and lines[1]["cpu_baseline"]["cores"] >= 1
+    assert len({d["metric"] for d in lines.values()}) == 1
+    ref = lines[1]
+    for n, d in lines.items():
+        assert abs(d["e2e"]["loss_all_frames"] - ref["e2e"]["loss_all_frames"]) <= 1e-8 * abs(ref["e2e"]["loss_all_frames"])
+        for k in ("sum", "l2"):
+            assert abs(d["extra"]["grad_checksum"][k] - ref["extra"]["grad_checksum"][k]) <= 1e-6 * abs(ref["extra"]["grad_checksum"][k])
+        assert d["value"] > 0.85 * n * ref["value"]  # strong-scaling efficiency of the committed lines
