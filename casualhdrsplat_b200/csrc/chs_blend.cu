@@ -922,12 +922,12 @@ __device__ __forceinline__ unsigned lanemask_gt_() {
 // stop logic (r2r source page of the ungrouped loop: 2 FSETP + 2 FSEL + 2 MOV + the reconvergence of a per-lane branch that
 // 96 % of the iterations took anyway, per Gaussian).  If somebody did, the same four alphas go through the exact sequential
 // code of the ungrouped loop, so results are bit-identical to it.
-template <int kMinBlocks, bool kPerPoseCrf, bool kAsync, bool kGroup = false>
+template <int kMinBlocks, bool kPerPoseCrf, bool kAsync, bool kGroup = false, int kFB = kBatch>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendFwdArgs a) {
-  static_assert(kBatch == 2 * kThreads, "asynchronous staging: two tile-list entries per thread and batch");
-  __shared__ SplatSmem3<kBatch + (kGroup ? 1 : 0)> sm;  // kGroup: entry kBatch is the null record
-  __shared__ RawSmem<kAsync ? kBatch : 1> raw;  // kAsync: the next batch's raw records, gathered with cp.async
-  __shared__ __align__(16) int s_list[kThreads / 32][kGroup ? kBatch + 4 : 32];
+  static_assert(kFB == 2 * kThreads || (kFB == kThreads && kGroup && !kAsync), "two tile-list entries per thread and batch (one: grouped kernel only)");
+  __shared__ SplatSmem3<kFB + (kGroup ? 1 : 0)> sm;  // kGroup: entry kFB is the null record
+  __shared__ RawSmem<kAsync ? kFB : 1> raw;  // kAsync: the next batch's raw records, gathered with cp.async
+  __shared__ __align__(16) int s_list[kThreads / 32][kGroup ? kFB + 4 : 32];
   extern __shared__ float s_crf[];  // the CRF parameters [3, stride] when the CRF is learned
 
   const int tile = blockIdx.x, frame = blockIdx.y;
@@ -948,9 +948,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
   const int crf_stride = chs_crf_stride(a.crf_kind, a.crf_hidden);  // 0 for the identity CRF
   for (int i = tid; i < 3 * crf_stride; i += kThreads) s_crf[i] = a.crf_params[i];
   if constexpr (kGroup) if (tid == 0) {  // the null record (made visible by the first barrier of the batch loop)
-    sm.a[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
-    sm.b[kBatch] = make_float4(0.f, -kInf, 0.f, 0.f);
-    sm.c[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.a[kFB] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.b[kFB] = make_float4(0.f, -kInf, 0.f, 0.f);
+    sm.c[kFB] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   constexpr bool per_pose_crf = kPerPoseCrf;
@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
     if (kAsync) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const uint32_t i0 = start + h * kThreads + tid, i1 = i0 + kBatch;
+        const uint32_t i0 = start + h * kThreads + tid, i1 = i0 + kFB;
         if (i0 < end) {
           val_cur[h] = a.vals[i0] + rec_shift;
           gather_raw_async(raw, h * kThreads + tid, val_cur[h], cam_base, a.geom, a.conic_c, a.rgbo);
@@ -987,31 +987,35 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
     int32_t vpre0 = 0, vpre1 = 0;  // kGroup: this thread's two tile-list entries of the batch about to be staged
     if (kGroup && !kAsync) {
       if (start + tid < end) vpre0 = a.vals[start + tid];
-      if (start + tid + kThreads < end) vpre1 = a.vals[start + tid + kThreads];
+      if (kFB == 2 * kThreads && start + tid + kThreads < end) vpre1 = a.vals[start + tid + kThreads];
     }
-    for (uint32_t base = start; base < end; base += kBatch) {
+    for (uint32_t base = start; base < end; base += kFB) {
       if (kAsync) cp_async_wait_all();  // this thread's own gathers of the batch have landed
       // barrier + CTA-wide early exit; also protects the staged batch of the previous iteration
       if (__syncthreads_and(thrA == kInf && thrB == kInf)) break;
-      const int cnt = min((uint32_t)kBatch, end - base);
+      const int cnt = min((uint32_t)kFB, end - base);
       if (kAsync) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int slot = h * kThreads + tid;
           if (slot < cnt) stage_from_raw(sm, slot, raw, val_cur[h]);
           val_cur[h] = val_next[h];
-          if (base + kBatch + slot < end) gather_raw_async(raw, slot, val_cur[h], cam_base, a.geom, a.conic_c, a.rgbo);
-          const uint32_t i2 = base + 2 * kBatch + slot;
+          if (base + kFB + slot < end) gather_raw_async(raw, slot, val_cur[h], cam_base, a.geom, a.conic_c, a.rgbo);
+          const uint32_t i2 = base + 2 * kFB + slot;
           if (i2 < end) val_next[h] = a.vals[i2] + rec_shift;
         }
         cp_async_commit();
       } else if (kGroup) {
         // the thread's two list entries were requested during the previous batch; the next batch's are requested now
-        stage_splat3_pair(sm, tid, tid < cnt, vpre0 + rec_shift, tid + kThreads, tid + kThreads < cnt, vpre1 + rec_shift, cam_base, a.geom,
-                          a.conic_c, a.rgbo);
-        const uint32_t nb = base + kBatch + tid;
+        if (kFB == 2 * kThreads) {
+          stage_splat3_pair(sm, tid, tid < cnt, vpre0 + rec_shift, tid + kThreads, tid + kThreads < cnt, vpre1 + rec_shift, cam_base, a.geom,
+                            a.conic_c, a.rgbo);
+        } else if (tid < cnt) {
+          stage_splat3(sm, tid, vpre0 + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
+        }
+        const uint32_t nb = base + kFB + tid;
         if (nb < end) vpre0 = a.vals[nb];
-        if (nb + kThreads < end) vpre1 = a.vals[nb + kThreads];
+        if (kFB == 2 * kThreads && nb + kThreads < end) vpre1 = a.vals[nb + kThreads];
       } else {
         for (int i = tid; i < cnt; i += kThreads) stage_splat3(sm, i, a.vals[base + i] + rec_shift, cam_base, a.geom, a.conic_c, a.rgbo);
       }
@@ -1028,7 +1032,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) blend_fwd2_kernel(BlendF
           if (hit) list[n_surv + __popc(mask & lt)] = j;  // ascending: front to back
           n_surv += __popc(mask);
         }
-        if (lane < 3) list[n_surv + lane] = kBatch;  // padding: the null record
+        if (lane < 3) list[n_surv + lane] = kFB;  // padding: the null record
         __syncwarp();
         for (int i = 0; i < n_surv; i += 4) {
           const int4 j4 = *reinterpret_cast<const int4*>(list + i);
@@ -2067,6 +2071,9 @@ extern "C" int chs_blend_fwd(const chs_config* cfg, const float* geom, const flo
       // round-1 kernel 2.50
       case 27: blend_fwd2_kernel<7, false, false><<<grid, kThreads, dyn, s>>>(a); break;  // the ungrouped round-2 loop
       case 46: blend_fwd2_kernel<6, false, false, true><<<grid, kThreads, dyn, s>>>(a); break;
+      // 128-entry batches (one list entry per thread): r3m 1.997 (7 CTAs per SM) / 1.984 (8) vs 2.007 ms, inside the run-to-run noise
+      case 57: blend_fwd2_kernel<7, false, false, true, 128><<<grid, kThreads, dyn, s>>>(a); break;
+      case 58: blend_fwd2_kernel<8, false, false, true, 128><<<grid, kThreads, dyn, s>>>(a); break;
       case 48: blend_fwd2_kernel<8, false, false, true><<<grid, kThreads, dyn, s>>>(a); break;
       // grouped pair loop (speculative transmittance chain, one stop vote per four Gaussians)
       default: blend_fwd2_kernel<7, false, false, true><<<grid, kThreads, dyn, s>>>(a); break;

@@ -781,6 +781,7 @@ KERNEL_VARIANTS = {
     "bwd_16_rows": {"blend_bwd": 65},           # blend_bwd5_kernel with 16 table rows: two Gaussians per phase-B lane
     "bwd_batch_256": {"blend_bwd": 76},         # blend_bwd5_kernel with 256-entry batches (two list entries per thread)
     "bwd_unstaged": {"blend_bwd": 3},           # blend_bwd3_kernel: one Gaussian's chain after the other (the default until r3c)
+    "fwd_batch_128": {"blend_fwd": 57},         # grouped forward with 128-entry batches (one list entry per thread)
     "fwd_ungrouped": {"blend_fwd": 27},         # the pair loop without the speculative group of four
     "scatter_warp_per_tile": {"bin_chunk": 1},  # P2 scatter with a warp per tile
     "crf_per_unit": {"crf_bwd": 14},            # crf_bwd_kernel: the MLP CRF backward unit by unit (the default walks intervals)
