@@ -221,19 +221,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) crf_bwd_interval_kernel(
   }
   for (int i = tid; i < (kThreads / 32) * 3 * nI * 2; i += kThreads) s_H[i] = 0.f;
   __syncthreads();
-  // rank of every unit's breakpoint inside its channel (ties by unit index); units with w1 = 0 never switch: breakpoint +inf
+  // rank of every unit's breakpoint inside its channel (ties by unit index); units with w1 = 0 never switch: breakpoint +inf.
+  // The breakpoints are computed once (s_A is free until the ranks are known) so that the Hd^2 ranking loop only compares.
+  float* s_t = s_A;
   for (int i = tid; i < 3 * hd; i += kThreads) {
     const int ch = i / hd, j = i - ch * hd;
     const float* p = s_p + ch * stride;
-    const float w1 = p[j], b1 = p[hd + j];
-    const float t = chs_crf_breakpoint(w1, b1);
+    s_t[i] = chs_crf_breakpoint(p[j], p[hd + j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * hd; i += kThreads) {
+    const int ch = i / hd, j = i - ch * hd;
+    const float* p = s_p + ch * stride;
+    const float* tc = s_t + ch * hd;
+    const float t = tc[j];
     int r = 0;
     for (int k = 0; k < hd; ++k) {
-      const float tk = chs_crf_breakpoint(p[k], p[hd + k]);
+      const float tk = tc[k];
       r += (tk < t || (tk == t && k < j)) ? 1 : 0;
     }
     s_bp[ch * hd + r] = t;
-    s_key[i] = chs_crf_unit_key(w1, b1, r, hd);
+    s_key[i] = chs_crf_unit_key(p[j], p[hd + j], r, hd);
   }
   __syncthreads();
   for (int i = tid; i < 3 * nI; i += kThreads) {
