@@ -1,5 +1,5 @@
 """Full (not extrapolated) timing of the float64 CPU oracle on one BASELINE.json configuration, forward + backward.
-Usage: python tools/cpu_oracle_full.py [config=c2] [threads=all]   (result recorded in BASELINE.md)"""
+Usage: python tests/tools/cpu_oracle_full.py [config=c2] [threads=all]   (result recorded in BASELINE.md)"""
 import json
 import os
 import sys
@@ -7,7 +7,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from casualhdrsplat_b200.scene import make_config  # noqa: E402
 from tests.util import oracle_run  # noqa: E402

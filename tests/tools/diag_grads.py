@@ -1,11 +1,11 @@
-"""Stage-wise gradient error diagnosis against the oracle (development tool). Usage: python tools/diag_grads.py [config]"""
+"""Stage-wise gradient error diagnosis against the oracle (test infrastructure: it runs the oracle, so it lives under tests/). Usage: python tests/tools/diag_grads.py [config]"""
 import os
 import sys
 from ctypes import byref
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from casualhdrsplat_b200 import _lib, api  # noqa: E402
